@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py - candidate-sites/sec of the Clair forward path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): ONT-shape model, 1M synthetic candidate sites in
+predict-batches of 1000.  A "step" is one pass of the forward over a pool of `--batches-per-step`
+predict-batches (default 64 x 1000 sites = 270 MB of fp32 input, larger than the 126 MB L2, so
+every step re-reads its inputs from HBM); the default 16 steps are 1.024 M sites.
+  value : device-resident sites/s (inputs already in HBM, CUDA events on the launching stream)
+  e2e   : the same through the reference-facing call (Clair.predict_packed -> clairb_predict):
+          pinned HOST input, H2D + forward + D2H inside the timed region
+  roofline / cpu_baseline : see DESIGN.md section "Measurement"
+N>1 (launched by torchrun, one rank per GPU): every rank runs the same per-GPU workload on its own
+sites (weak scaling) and the packed [sites,90] probabilities are gathered to rank 0 with one NCCL
+collective per step, inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_SITE = 40386432            # 2 x 20,193,216 MAC
+BYTES_PER_SITE = 4584               # 4,224 in + 360 out
+LSTM2_FLOP_PER_SITE = 2 * 12976128  # SURVEY.md 8a row a7 (dominant kernel)
+LSTM1_FLOP_PER_SITE = 2 * 5406720
+KERNEL_FLOP_PER_SITE = {"lstm_layer2": LSTM2_FLOP_PER_SITE, "lstm_layer1": LSTM1_FLOP_PER_SITE,
+                        "l4_dense": 2 * 1474560, "l3_slice_dense": 2 * 253440, "tail_heads": 2 * (73728 + 8640)}
+BATCH = 1000                        # shared/param.py:16 predictBatchSize
+WORKLOAD = "ONT-shape model inference, 1M synthetic candidate sites, batch=1000, 1xB200"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batches-per-step", type=int, default=64)
+    ap.add_argument("--cpu-baseline-batches", type=int, default=0, help="0 = auto (about 10-20 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p.get("hbm_gbs", 6650.0), "bf16_burst": p.get("bf16_tflops", 1590.0),
+                "bf16_sustained": p.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return model, os.cpu_count() or 1
+
+
+def time_cpu_port(weights, pool, n_batches, warm=1):
+    """Oracle port (torch-CPU fp32, all host threads) on a bounded sample of the same workload."""
+    from oracle.clair_oracle_fast import FastOracle
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    fo = FastOracle(weights)
+    for i in range(warm):
+        fo.forward_packed(pool[i % len(pool)])
+    t0 = time.perf_counter()
+    for i in range(n_batches):
+        fo.forward_packed(pool[i % len(pool)])
+    dt = time.perf_counter() - t0
+    return n_batches * BATCH / dt, fo.threads, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path.  TensorFlow 1.13.2 cannot be installed here (no
+    wheel for Python 3.12, no network), so this times the oracle port - see DESIGN.md."""
+    if rank != 0:
+        return
+    import numpy as np
+    from clair_b200 import synth, weights as W
+    w = W.random_weights(seed=1234)
+    per_step = 2                                        # bounded sample: 2 predict-batches per step
+    pool = [synth.synthetic_tensors(BATCH, seed=20240607 + i) for i in range(4)]
+    from oracle.clair_oracle_fast import FastOracle
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    fo = FastOracle(w)
+    k = 0
+    for _ in range(args.warmup):
+        for _ in range(per_step):
+            fo.forward_packed(pool[k % 4]); k += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            fo.forward_packed(pool[k % 4]); k += 1
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step * BATCH / dt
+    model, cores = cpu_info()
+    sample = "%d steps x %d predict-batches x %d sites (of the 1M-site workload)" % (args.steps, per_step, BATCH)
+    print(json.dumps({
+        "impl": "reference", "metric": "candidate-sites/sec", "value": value, "unit": "sites/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch": BATCH, "sites_per_step": per_step * BATCH,
+                   "note": "reference CPU path = fp32 torch-CPU port of the reference graph (TensorFlow 1.13.2 not installable)"},
+        "cpu_baseline": {"value": value, "unit": "sites/s", "cores": fo.threads, "kind": "port", "sample": sample,
+                         "cpu_model": model, "host_cores": cores},
+        "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # direct invocation with --gpus N: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)]
+        cmd += sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from clair_b200 import _lib, synth, weights as W
+    from clair_b200.model import Clair, pinned_empty
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    bps = args.batches_per_step
+    sites = bps * BATCH
+    weights = W.random_weights(seed=1234)
+    m = Clair(device=local_rank, max_sites=sites, batch_sites=BATCH)
+    m.set_weights(weights)
+
+    # ---- synthetic pool: distinct per rank, 64 distinct predict-batches per step ----
+    X = pinned_empty((sites, 33, 8, 4), np.float32)
+    X[...] = synth.synthetic_tensors(sites, seed=20240607 + 1 + 1000 * rank)
+    out_host = pinned_empty((sites, _lib.N_OUT), np.float32)
+    xd = torch.from_numpy(X).cuda(non_blocking=False)
+    od = torch.empty((sites, _lib.N_OUT), dtype=torch.float32, device="cuda")
+    gather_bufs = [torch.empty_like(od) for _ in range(world)] if (world > 1 and rank == 0) else None
+    stream = torch.cuda.current_stream()
+
+    def device_step():
+        m.predict_device(xd.data_ptr(), _lib.DTYPE_F32, sites, od.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.gather(od, gather_list=gather_bufs, dst=0)     # the path's one exchange
+
+    # ---- parity spot check before any timing counts ----
+    if rank == 0:
+        from oracle import clair_oracle as O
+        chk = m.predict_packed(np.array(X[:200]))
+        ref = O.forward_packed(np.array(X[:200]), weights, np.float64)
+        assert np.abs(chk - ref).max() <= 1e-4, "parity check failed before timing"
+        for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
+            assert (chk[:, a:b].argmax(1) == ref[:, a:b].argmax(1)).all()
+
+    # ---- device-resident timing ----
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    m.set_profiling(True)
+    launches0 = m.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    launches = m.kernel_launches() - launches0
+    ms = ev0.elapsed_time(ev1)
+    profile = m.read_profile()
+    m.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * sites * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the reference-facing call: pinned host in, host out ----
+    for _ in range(2):
+        m._lib.clairb_predict(m._h, X.ctypes.data, _lib.DTYPE_F32, sites, out_host.ctypes.data)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = m.predict_packed(X)          # allocates the fresh result array like the reference
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * sites * args.steps / e2e_s
+    assert np.isfinite(out).all()
+
+    if rank == 0:
+        peaks = measured_peaks()
+        prof = {p["kernel"]: p for p in profile}
+        dom = max(profile, key=lambda p: p["ms"]) if profile else None
+        roofline = None
+        if dom is not None:
+            sites_per_launch = sites * args.steps / dom["launches"]
+            flop = KERNEL_FLOP_PER_SITE.get(dom["kernel"], 0) * sites_per_launch
+            avg_ms = dom["ms"] / dom["launches"]
+            achieved = flop / (avg_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": achieved,
+                        "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                        "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+                        "avg_launch_ms": avg_ms, "sites_per_launch": sites_per_launch,
+                        "whole_path_frac": value / world * FLOP_PER_SITE / 1e12 / peaks["bf16_sustained"],
+                        "kernel_share": {k: v["ms"] / max(1e-9, sum(p["ms"] for p in profile)) for k, v in prof.items()},
+                        "note": "logit tolerance 1e-4 needs the 3-term fp16 split: attainable ceiling is 1/3 of peak"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            nb = args.cpu_baseline_batches or 24
+            pool = [np.array(X[i * BATCH:(i + 1) * BATCH]) for i in range(min(8, bps))]
+            v, threads, dt = time_cpu_port(weights, pool, nb)
+            model, cores = cpu_info()
+            cpu = {"value": v, "unit": "sites/s", "cores": threads, "kind": "port",
+                   "sample": "%d predict-batches x %d sites of the same pool, %.1f s" % (nb, BATCH, dt),
+                   "cpu_model": model, "host_cores": cores}
+        engine = os.environ.get("CLAIRB_ENGINE", "default")
+        print(json.dumps({
+            "metric": "candidate-sites/sec", "value": value, "unit": "sites/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fp16 hi/lo split operands, f32 accumulate)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch": BATCH, "batches_per_step": bps, "sites_per_step": sites,
+                       "l2": "inputs larger than L2: %.0f MB of fp32 input re-read per step" % (sites * 4224 / 1e6),
+                       "weights": "random-init ONT-shape, seed 1234", "engine": engine,
+                       "parallelism": "sites sharded over %d GPU(s), one NCCL gather of [sites,90] per step" % world},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": sites * 4224,
+                    "d2h_bytes_per_step": sites * 360},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "kernels": profile,
+        }))
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

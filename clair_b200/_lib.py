@@ -1,0 +1,71 @@
+"""ctypes binding of libclair_b200.so (the C-ABI in include/clair_b200.h).
+
+There is no CPU fallback: if the shared library is missing this raises, and clairb_create
+itself refuses anything that is not an sm_100 device.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libclair_b200.so")
+
+OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, EWEIGHTS = range(6)
+DTYPE_F32, DTYPE_I16 = 0, 1
+N_OUT = 90
+SITE_ELEMS = 1056
+LAYER_LSTM1, LAYER_LSTM2, LAYER_L3, LAYER_L4, LAYER_LOGITS = 1, 2, 3, 4, 5
+
+# every symbol include/clair_b200.h declares: (restype, argtypes)
+_c = ctypes
+SYMBOLS = {
+    "clairb_create": (_c.c_int, [_c.c_int, _c.c_int64, _c.c_int, _c.POINTER(_c.c_void_p)]),
+    "clairb_set_weight": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.POINTER(_c.c_int64), _c.c_int]),
+    "clairb_finalize_weights": (_c.c_int, [_c.c_void_p]),
+    "clairb_predict": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p]),
+    "clairb_predict_device": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p]),
+    "clairb_get_layer": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int64]),
+    "clairb_host_alloc": (_c.c_int, [_c.POINTER(_c.c_void_p), _c.c_int64]),
+    "clairb_host_free": (_c.c_int, [_c.c_void_p]),
+    "clairb_kernel_launches": (_c.c_int64, [_c.c_void_p]),
+    "clairb_set_profiling": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "clairb_read_profile": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_int64]),
+    "clairb_version": (_c.c_char_p, []),
+    "clairb_last_error": (_c.c_char_p, [_c.c_void_p]),
+    "clairb_destroy": (_c.c_int, [_c.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library and attach prototypes.  Raises if it was never built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "clair_b200: %s not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error(handle=None):
+    msg = load().clairb_last_error(handle)
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc, handle=None, what=""):
+    if rc == OK:
+        return
+    msg = "%s: %s" % (what, last_error(handle)) if what else last_error(handle)
+    if rc in (EINVAL, EWEIGHTS):
+        raise ValueError(msg)
+    if rc == ENOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)

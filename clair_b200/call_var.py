@@ -1,0 +1,63 @@
+"""The batch loop that drives predict(): same contract as ``clair.call_var.call_variants``
+(reference clair/call_var.py:1312-1367).
+
+Per iteration three stages run concurrently and then meet at a barrier:
+  output(batch k-1)  ||  predict(batch k)  ||  load(batch k+1)
+exactly one predict is in flight, batches are handled in strict input order, and the output stage
+of an iteration is handed the ``m.prediction`` object that existed when the iteration was set up
+(call_var.py:1334-1338) - i.e. the result of the previous iteration's predict.
+The VCF decision logic (batch_output, call_var.py:1199-1236) is out of scope and is injected.
+"""
+import logging
+from threading import Thread
+from time import time
+
+from . import param, utils
+
+
+def run_batches(m, tensor_generator, output_stage, *output_args):
+    """Drive ``m.predict`` over every (X, infos) batch of ``tensor_generator``."""
+    to_predict = None      # batch loaded in the previous iteration
+    to_output = None       # batch predicted in the previous iteration
+    source_open = True
+
+    while True:
+        stages = []
+        if to_output is not None:
+            stages.append(Thread(target=output_stage, args=(to_output, m.prediction) + output_args))
+        predicted = None
+        if to_predict is not None:
+            stages.append(Thread(target=m.predict, kwargs={"batchX": to_predict[0]}))
+            predicted = to_predict
+        fetched = []
+        if source_open:
+            stages.append(Thread(target=lambda: fetched.extend(_take_one(tensor_generator))))
+        if not stages:
+            return
+        for s in stages:
+            s.start()
+        for s in stages:
+            s.join()
+        to_output = predicted
+        to_predict = fetched[0] if fetched else None
+        if source_open and not fetched:
+            source_open = False
+
+
+def _take_one(gen):
+    try:
+        return [next(gen)]
+    except StopIteration:
+        return []
+
+
+def call_variants(args, m, output_config, output_utilities, output_stage):
+    """Reference signature plus the output stage to run (the reference picks batch_output or
+    batch_output_for_ensemble itself, call_var.py:1320)."""
+    output_utilities.output_header()
+    tensor_generator = utils.tensor_generator_from(args.tensor_fn, param.predictBatchSize)
+    logging.info("Calling variants ...")
+    started = time()
+    run_batches(m, tensor_generator, output_stage, output_config, output_utilities)
+    logging.info("Total time elapsed: %.2f s" % (time() - started))
+    output_utilities.close_opened_files()

@@ -1,0 +1,638 @@
+// C-ABI + host orchestration of the clair_b200 forward path (see include/clair_b200.h).
+//
+// One engine drives one B200.  Weights arrive by TF variable name, are re-laid-out once in
+// clairb_finalize_weights and stay resident in HBM.  A predict call is cut into chunks of whole
+// predict-batches; each chunk is: async H2D -> forward kernels -> async D2H, with the copies of
+// neighbouring chunks overlapping the kernels on separate streams (double-buffered input/output).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/clair_b200.h"
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "tc_kernels.cuh"
+
+using namespace clairb;
+
+namespace {
+
+std::mutex g_err_mu;
+std::string g_create_error;
+
+const char* kHeadNames[4] = {"Y_base_change_logits", "Y_genotype_logits", "Y_indel_length_logits_1",
+                             "Y_indel_length_logits_2"};
+const int kHeadSize[4] = {21, 3, 33, 33};
+const int kHeadOffH[5] = {0, 21, 24, 57, 90};
+
+std::string lstm_name(int layer, int dir, const char* var) {
+  char buf[256];
+  snprintf(buf, sizeof buf, "LSTM%d/stack_bidirectional_rnn/cell_0/bidirectional_rnn/%s/cudnn_compatible_lstm_cell/%s",
+           layer, dir ? "bw" : "fw", var);
+  return buf;
+}
+
+struct HostWeight {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+enum EngineKind { ENGINE_SIMT = 0, ENGINE_TC = 1 };
+
+}  // namespace
+
+struct clairb_engine {
+  int device = 0;
+  int64_t max_sites = 0;
+  int batch = 1000;
+  int bp = 1024;
+  int64_t chunk_sites = 0;     // real sites per chunk (multiple of batch)
+  int64_t chunk_np = 0;        // padded sites per chunk
+  EngineKind kind = ENGINE_SIMT;
+  bool finalized = false;
+  std::string err;
+  int64_t launches = 0;
+
+  std::map<std::string, HostWeight> hw;
+
+  // device weights (SIMT layouts, fp32)
+  float *d_Wp[2] = {nullptr, nullptr}, *d_bp[2] = {nullptr, nullptr};   // per layer: [2][K][512], [2][512]
+  float *d_w3p = nullptr, *d_b3p = nullptr, *d_W4 = nullptr, *d_b4 = nullptr;
+  float *d_W5 = nullptr, *d_b5 = nullptr, *d_Whd = nullptr, *d_bhd = nullptr;
+  tc::Weights tcw;             // tensor-core operand layouts (fp16 hi/lo, tile-blocked)
+
+  // workspace (sized for one chunk)
+  float *d_xT = nullptr, *d_h1 = nullptr, *d_h2 = nullptr, *d_l3T = nullptr, *d_l4T = nullptr, *d_logits = nullptr;
+  tc::Workspace tcws;
+  void* d_x[2] = {nullptr, nullptr};
+  float* d_out[2] = {nullptr, nullptr};
+
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr;
+
+  SiteMap last_map{0, 1000, 1024, 0};
+  bool last_single_chunk = false;
+
+  // optional per-kernel CUDA-event timing (bench.py's roofline leg)
+  bool profiling = false;
+  struct ProfSpan { cudaEvent_t a, b; int id; };
+  std::vector<ProfSpan> prof_open;
+  std::vector<cudaEvent_t> prof_free;
+  std::map<int, std::pair<double, int64_t>> prof_acc;     // kernel id -> (ms, launches)
+};
+
+namespace {
+
+int fail(clairb_engine* e, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf;
+  else {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_create_error = buf;
+  }
+  return code;
+}
+
+#define CU_TRY(e, call)                                                                          \
+  do {                                                                                           \
+    cudaError_t _st = (call);                                                                    \
+    if (_st != cudaSuccess)                                                                      \
+      return fail((e), _st == cudaErrorMemoryAllocation ? CLAIRB_ENOMEM : CLAIRB_ECUDA,          \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), __FILE__, __LINE__);  \
+  } while (0)
+
+template <typename Tp>
+int dev_alloc(clairb_engine* e, Tp** p, size_t count) {
+  CU_TRY(e, cudaMalloc((void**)p, count * sizeof(Tp)));
+  return CLAIRB_OK;
+}
+
+template <typename Tp>
+int upload(clairb_engine* e, Tp** dptr, const std::vector<Tp>& h) {
+  int rc = dev_alloc(e, dptr, h.size());
+  if (rc) return rc;
+  CU_TRY(e, cudaMemcpy(*dptr, h.data(), h.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+  return CLAIRB_OK;
+}
+
+const HostWeight* find_weight(clairb_engine* e, const std::string& name, std::vector<int64_t> shape) {
+  auto it = e->hw.find(name);
+  if (it == e->hw.end()) {
+    fail(e, CLAIRB_EWEIGHTS, "variable %s was never set", name.c_str());
+    return nullptr;
+  }
+  if (it->second.shape != shape) {
+    fail(e, CLAIRB_EWEIGHTS, "variable %s has the wrong shape", name.c_str());
+    return nullptr;
+  }
+  return &it->second;
+}
+
+SiteMap make_map(const clairb_engine* e, int64_t n) {
+  SiteMap m;
+  m.n = n;
+  m.batch = e->batch;
+  m.bp = e->bp;
+  int64_t nb = (n + e->batch - 1) / e->batch;
+  m.np = nb * e->bp;
+  return m;
+}
+
+// ---- per-kernel event timing --------------------------------------------------------------------
+const char* kKernelNames[] = {"prep_input", "lstm_layer1", "lstm_layer2", "l3_slice_dense", "l4_dense",
+                              "tail_heads"};
+constexpr int kNumKernelNames = 6;
+
+void prof_fold(clairb_engine* e) {
+  for (auto& sp : e->prof_open) {
+    cudaEventSynchronize(sp.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+      auto& acc = e->prof_acc[sp.id];
+      acc.first += ms;
+      acc.second += 1;
+    }
+    e->prof_free.push_back(sp.a);
+    e->prof_free.push_back(sp.b);
+  }
+  e->prof_open.clear();
+}
+
+cudaEvent_t prof_event(clairb_engine* e) {
+  if (!e->prof_free.empty()) {
+    cudaEvent_t ev = e->prof_free.back();
+    e->prof_free.pop_back();
+    return ev;
+  }
+  cudaEvent_t ev = nullptr;
+  cudaEventCreate(&ev);
+  return ev;
+}
+
+struct ProfScope {
+  clairb_engine* e;
+  cudaStream_t st;
+  cudaEvent_t b = nullptr;
+  ProfScope(clairb_engine* e_, int id, cudaStream_t st_) : e(e_), st(st_) {
+    if (!e->profiling) return;
+    if (e->prof_open.size() >= 4096) prof_fold(e);
+    cudaEvent_t a = prof_event(e);
+    b = prof_event(e);
+    cudaEventRecord(a, st);
+    e->prof_open.push_back({a, b, id});
+  }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, st);
+  }
+};
+
+// ---- forward on one chunk, all launches on `st` ------------------------------------------------
+int forward_simt(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, float* out_dev, cudaStream_t st) {
+  const int64_t np = sm.np;
+  dim3 gprep((unsigned)(np / 32), 4);
+  {
+    ProfScope ps(e, 0, st);
+    if (dtype == CLAIRB_DTYPE_F32)
+      simt::prep_input<float><<<gprep, 256, 0, st>>>((const float*)x_dev, e->d_xT, sm);
+    else
+      simt::prep_input<int16_t><<<gprep, 256, 0, st>>>((const int16_t*)x_dev, e->d_xT, sm);
+  }
+  dim3 glstm((unsigned)(np / simt::LSTM_TM), 2);
+  {
+    ProfScope ps(e, 1, st);
+    simt::lstm_layer<F_IN><<<glstm, simt::LSTM_THREADS, simt::lstm_smem_bytes<F_IN>(), st>>>(
+        e->d_xT, e->d_Wp[0], e->d_bp[0], e->d_h1, np);
+  }
+  {
+    ProfScope ps(e, 2, st);
+    simt::lstm_layer<2 * H><<<glstm, simt::LSTM_THREADS, simt::lstm_smem_bytes<2 * H>(), st>>>(
+        e->d_h1, e->d_Wp[1], e->d_bp[1], e->d_h2, np);
+  }
+  dim3 gl3((unsigned)(np / 128), 2 * H / simt::L3_CPB);
+  {
+    ProfScope ps(e, 3, st);
+    simt::l3_slice_dense<<<gl3, 128, 0, st>>>(e->d_h2, e->d_w3p, e->d_b3p, e->d_l3T, np);
+  }
+  {
+    ProfScope ps(e, 4, st);
+    simt::l4_dense<<<(unsigned)(np / simt::L4_TM), 256, simt::l4_smem_bytes(), st>>>(e->d_l3T, e->d_W4, e->d_b4,
+                                                                                    e->d_l4T, np);
+  }
+  {
+    ProfScope ps(e, 5, st);
+    simt::tail_heads<<<(unsigned)(np / simt::TL_TM), 256, simt::tail_smem_bytes(), st>>>(
+        e->d_l4T, e->d_W5, e->d_b5, e->d_Whd, e->d_bhd, out_dev, e->d_logits, sm);
+  }
+  e->launches += 6;
+  CU_TRY(e, cudaGetLastError());
+  return CLAIRB_OK;
+}
+
+int forward_chunk(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, float* out_dev, cudaStream_t st) {
+  if (e->kind == ENGINE_TC) {
+    int nl = 0;
+    cudaError_t cst = tc::forward(e->tcw, e->tcws, x_dev, dtype, sm, out_dev, e->d_logits, st, &nl);
+    e->launches += nl;
+    if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "tensor-core forward failed: %s", cudaGetErrorString(cst));
+    return CLAIRB_OK;
+  }
+  return forward_simt(e, x_dev, dtype, sm, out_dev, st);
+}
+
+size_t elem_bytes(int dtype) { return dtype == CLAIRB_DTYPE_I16 ? 2 : 4; }
+
+void free_all(clairb_engine* e) {
+  cudaSetDevice(e->device);
+  prof_fold(e);
+  for (cudaEvent_t ev : e->prof_free) cudaEventDestroy(ev);
+  e->prof_free.clear();
+  for (int l = 0; l < 2; ++l) {
+    cudaFree(e->d_Wp[l]);
+    cudaFree(e->d_bp[l]);
+    cudaFree(e->d_x[l]);
+    cudaFree(e->d_out[l]);
+    if (e->ev_h2d[l]) cudaEventDestroy(e->ev_h2d[l]);
+    if (e->ev_comp[l]) cudaEventDestroy(e->ev_comp[l]);
+    if (e->ev_d2h[l]) cudaEventDestroy(e->ev_d2h[l]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  cudaFree(e->d_w3p); cudaFree(e->d_b3p); cudaFree(e->d_W4); cudaFree(e->d_b4);
+  cudaFree(e->d_W5); cudaFree(e->d_b5); cudaFree(e->d_Whd); cudaFree(e->d_bhd);
+  cudaFree(e->d_xT); cudaFree(e->d_h1); cudaFree(e->d_h2); cudaFree(e->d_l3T); cudaFree(e->d_l4T);
+  cudaFree(e->d_logits);
+  tc::free_weights(e->tcw);
+  tc::free_workspace(e->tcws);
+  if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+  if (e->s_comp) cudaStreamDestroy(e->s_comp);
+  if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* clairb_version(void) { return "clair_b200 0.1 sm_100a"; }
+
+const char* clairb_last_error(const clairb_engine* e) {
+  if (e) return e->err.c_str();
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  return g_create_error.c_str();
+}
+
+int64_t clairb_kernel_launches(const clairb_engine* e) { return e ? e->launches : 0; }
+
+int clairb_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return CLAIRB_EINVAL;
+  cudaError_t st = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable);
+  return st == cudaSuccess ? CLAIRB_OK : CLAIRB_ENOMEM;
+}
+
+int clairb_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? CLAIRB_OK : CLAIRB_ECUDA; }
+
+int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine** out) {
+  if (!out || max_sites <= 0 || batch_sites <= 0) return fail(nullptr, CLAIRB_EINVAL, "clairb_create: bad arguments");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(nullptr, CLAIRB_ENODEVICE, "clairb_create: CUDA device %d not available (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, CLAIRB_ENODEVICE,
+                "clairb_create: device %d is not compute capability 10.x (sm_100a only, no fallback)", device);
+  clairb_engine* e = new clairb_engine();
+  e->device = device;
+  e->max_sites = max_sites;
+  e->batch = batch_sites;
+  e->bp = (batch_sites + TILE - 1) / TILE * TILE;
+  const char* kind = getenv("CLAIRB_ENGINE");
+  e->kind = (kind && !strcmp(kind, "simt")) ? ENGINE_SIMT : (tc::available() ? ENGINE_TC : ENGINE_SIMT);
+  int64_t chunk_batches = 32;
+  if (const char* cb = getenv("CLAIRB_CHUNK_BATCHES")) chunk_batches = atoll(cb) > 0 ? atoll(cb) : chunk_batches;
+  int64_t nb_max = (max_sites + batch_sites - 1) / batch_sites;
+  if (chunk_batches > nb_max) chunk_batches = nb_max;
+  e->chunk_sites = chunk_batches * batch_sites;
+  e->chunk_np = chunk_batches * e->bp;
+  auto bail = [&](int rc) {
+    g_create_error = e->err;
+    free_all(e);
+    delete e;
+    return rc;
+  };
+#define CR_TRY(call)                                                                  \
+  do {                                                                                \
+    cudaError_t _st = (call);                                                         \
+    if (_st != cudaSuccess) {                                                         \
+      fail(e, CLAIRB_ECUDA, "%s failed: %s", #call, cudaGetErrorString(_st));         \
+      return bail(_st == cudaErrorMemoryAllocation ? CLAIRB_ENOMEM : CLAIRB_ECUDA);   \
+    }                                                                                 \
+  } while (0)
+  CR_TRY(cudaSetDevice(device));
+  CR_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+  CR_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+  CR_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CR_TRY(cudaEventCreateWithFlags(&e->ev_h2d[b], cudaEventDisableTiming));
+    CR_TRY(cudaEventCreateWithFlags(&e->ev_comp[b], cudaEventDisableTiming));
+    CR_TRY(cudaEventCreateWithFlags(&e->ev_d2h[b], cudaEventDisableTiming));
+    CR_TRY(cudaMalloc(&e->d_x[b], (size_t)e->chunk_sites * SITE_ELEMS * sizeof(float)));
+    CR_TRY(cudaMalloc((void**)&e->d_out[b], (size_t)e->chunk_sites * N_OUT * sizeof(float)));
+  }
+  CR_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  const size_t np = (size_t)e->chunk_np;
+  CR_TRY(cudaMalloc((void**)&e->d_logits, np * N_OUT * sizeof(float)));
+  CR_TRY(cudaMemset(e->d_logits, 0, np * N_OUT * sizeof(float)));
+  if (e->kind == ENGINE_SIMT) {
+    CR_TRY(cudaMalloc((void**)&e->d_xT, np * SITE_ELEMS * sizeof(float)));
+    CR_TRY(cudaMalloc((void**)&e->d_h1, np * T_STEPS * 2 * H * sizeof(float)));
+    CR_TRY(cudaMalloc((void**)&e->d_h2, np * T_STEPS * 2 * H * sizeof(float)));
+    CR_TRY(cudaMalloc((void**)&e->d_l3T, np * L3_K * sizeof(float)));
+    CR_TRY(cudaMalloc((void**)&e->d_l4T, np * L4_UNITS * sizeof(float)));
+    CR_TRY(cudaFuncSetAttribute(simt::lstm_layer<F_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)simt::lstm_smem_bytes<F_IN>()));
+    CR_TRY(cudaFuncSetAttribute(simt::lstm_layer<2 * H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)simt::lstm_smem_bytes<2 * H>()));
+    CR_TRY(cudaFuncSetAttribute(simt::l4_dense, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)simt::l4_smem_bytes()));
+    CR_TRY(cudaFuncSetAttribute(simt::tail_heads, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)simt::tail_smem_bytes()));
+  } else {
+    CR_TRY(tc::alloc_workspace(e->tcws, e->chunk_np));
+  }
+#undef CR_TRY
+  *out = e;
+  return CLAIRB_OK;
+}
+
+int clairb_set_weight(clairb_engine* e, const char* tf_name, const float* data, const int64_t* shape, int rank) {
+  if (!e) return CLAIRB_EINVAL;
+  if (!tf_name || !data || !shape || rank < 1 || rank > 2)
+    return fail(e, CLAIRB_EINVAL, "clairb_set_weight: bad arguments");
+  HostWeight w;
+  size_t count = 1;
+  for (int i = 0; i < rank; ++i) {
+    if (shape[i] <= 0) return fail(e, CLAIRB_EINVAL, "clairb_set_weight: non-positive dimension");
+    w.shape.push_back(shape[i]);
+    count *= (size_t)shape[i];
+  }
+  w.data.assign(data, data + count);
+  e->hw[tf_name] = std::move(w);
+  e->finalized = false;
+  return CLAIRB_OK;
+}
+
+int clairb_finalize_weights(clairb_engine* e) {
+  if (!e) return CLAIRB_EINVAL;
+  CU_TRY(e, cudaSetDevice(e->device));
+  // ---- gather + check every variable of the forward graph ----
+  const int fin[2] = {F_IN, 2 * H};
+  std::vector<float> Wp[2], bp[2];
+  for (int l = 0; l < 2; ++l) {
+    const int K = fin[l] + H;
+    Wp[l].assign((size_t)2 * K * G4, 0.f);
+    bp[l].assign((size_t)2 * G4, 0.f);
+    for (int d = 0; d < 2; ++d) {
+      const HostWeight* k = find_weight(e, lstm_name(l + 1, d, "kernel"), {K, G4});
+      const HostWeight* b = find_weight(e, lstm_name(l + 1, d, "bias"), {G4});
+      if (!k || !b) return CLAIRB_EWEIGHTS;
+      for (int g = 0; g < 4; ++g)
+        for (int u = 0; u < H; ++u) {
+          const int colp = (u / 64) * 256 + (u % 64) * 4 + g, col = g * H + u;
+          bp[l][(size_t)d * G4 + colp] = b->data[col];
+          for (int r = 0; r < K; ++r) Wp[l][((size_t)d * K + r) * G4 + colp] = k->data[(size_t)r * G4 + col];
+        }
+    }
+  }
+  std::vector<float> w3p((size_t)2 * H * T_STEPS * 32, 0.f), b3p((size_t)2 * H * 32, 0.f);
+  std::vector<float> w3((size_t)2 * H * T_STEPS * L3_UNITS), b3((size_t)2 * H * L3_UNITS);
+  for (int c = 0; c < 2 * H; ++c) {
+    char nm[64];
+    snprintf(nm, sizeof nm, "L3/Unit_%d/kernel", c);
+    const HostWeight* k = find_weight(e, nm, {T_STEPS, L3_UNITS});
+    snprintf(nm, sizeof nm, "L3/Unit_%d/bias", c);
+    const HostWeight* b = find_weight(e, nm, {L3_UNITS});
+    if (!k || !b) return CLAIRB_EWEIGHTS;
+    for (int t = 0; t < T_STEPS; ++t)
+      for (int o = 0; o < L3_UNITS; ++o) {
+        w3p[((size_t)c * T_STEPS + t) * 32 + o] = k->data[t * L3_UNITS + o];
+        w3[((size_t)c * T_STEPS + t) * L3_UNITS + o] = k->data[t * L3_UNITS + o];
+      }
+    for (int o = 0; o < L3_UNITS; ++o) {
+      b3p[(size_t)c * 32 + o] = b->data[o];
+      b3[(size_t)c * L3_UNITS + o] = b->data[o];
+    }
+  }
+  const HostWeight* W4 = find_weight(e, "L4/kernel", {L3_K, L4_UNITS});
+  const HostWeight* b4 = find_weight(e, "L4/bias", {L4_UNITS});
+  if (!W4 || !b4) return CLAIRB_EWEIGHTS;
+  std::vector<float> W5((size_t)L4_UNITS * L5_ALL), b5(L5_ALL), Whd((size_t)L5_UNITS * N_OUT), bhd(N_OUT);
+  for (int k = 0; k < 4; ++k) {
+    char nm[96];
+    snprintf(nm, sizeof nm, "L5_%d/kernel", k + 1);
+    const HostWeight* kk = find_weight(e, nm, {L4_UNITS, L5_UNITS});
+    snprintf(nm, sizeof nm, "L5_%d/bias", k + 1);
+    const HostWeight* bb = find_weight(e, nm, {L5_UNITS});
+    snprintf(nm, sizeof nm, "Prediction/%s/kernel", kHeadNames[k]);
+    const HostWeight* hk = find_weight(e, nm, {L5_UNITS, kHeadSize[k]});
+    snprintf(nm, sizeof nm, "Prediction/%s/bias", kHeadNames[k]);
+    const HostWeight* hb = find_weight(e, nm, {kHeadSize[k]});
+    if (!kk || !bb || !hk || !hb) return CLAIRB_EWEIGHTS;
+    for (int r = 0; r < L4_UNITS; ++r)
+      for (int j = 0; j < L5_UNITS; ++j) W5[(size_t)r * L5_ALL + k * L5_UNITS + j] = kk->data[r * L5_UNITS + j];
+    for (int j = 0; j < L5_UNITS; ++j) b5[k * L5_UNITS + j] = bb->data[j];
+    for (int j = 0; j < L5_UNITS; ++j)
+      for (int o = 0; o < kHeadSize[k]; ++o) Whd[(size_t)j * N_OUT + kHeadOffH[k] + o] = hk->data[j * kHeadSize[k] + o];
+    for (int o = 0; o < kHeadSize[k]; ++o) bhd[kHeadOffH[k] + o] = hb->data[o];
+  }
+  // ---- upload ----
+  auto drop = [](float*& p) { cudaFree(p); p = nullptr; };
+  for (int l = 0; l < 2; ++l) { drop(e->d_Wp[l]); drop(e->d_bp[l]); }
+  drop(e->d_w3p); drop(e->d_b3p); drop(e->d_W4); drop(e->d_b4);
+  drop(e->d_W5); drop(e->d_b5); drop(e->d_Whd); drop(e->d_bhd);
+  int rc = 0;
+  // small tail weights are shared by both engines
+  if ((rc = upload(e, &e->d_W5, W5)) || (rc = upload(e, &e->d_b5, b5)) || (rc = upload(e, &e->d_Whd, Whd)) ||
+      (rc = upload(e, &e->d_bhd, bhd)) || (rc = upload(e, &e->d_b4, b4->data)))
+    return rc;
+  if (e->kind == ENGINE_SIMT) {
+    for (int l = 0; l < 2; ++l)
+      if ((rc = upload(e, &e->d_Wp[l], Wp[l])) || (rc = upload(e, &e->d_bp[l], bp[l]))) return rc;
+    if ((rc = upload(e, &e->d_w3p, w3p)) || (rc = upload(e, &e->d_b3p, b3p)) || (rc = upload(e, &e->d_W4, W4->data)))
+      return rc;
+  } else {
+    tc::HostModel hm;
+    for (int l = 0; l < 2; ++l)
+      for (int d = 0; d < 2; ++d) {
+        hm.lstm_kernel[l][d] = e->hw[lstm_name(l + 1, d, "kernel")].data.data();
+        hm.lstm_bias[l][d] = e->hw[lstm_name(l + 1, d, "bias")].data.data();
+      }
+    hm.w3 = w3.data(); hm.b3 = b3.data();
+    hm.W4 = W4->data.data(); hm.b4 = b4->data.data();
+    hm.d_W5 = e->d_W5; hm.d_b5 = e->d_b5; hm.d_Whd = e->d_Whd; hm.d_bhd = e->d_bhd;
+    tc::free_weights(e->tcw);
+    cudaError_t cst = tc::build_weights(e->tcw, hm);
+    if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "tensor-core weight upload failed: %s", cudaGetErrorString(cst));
+  }
+  CU_TRY(e, cudaDeviceSynchronize());
+  e->finalized = true;
+  return CLAIRB_OK;
+}
+
+int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_t n, float* out_dev, void* stream) {
+  if (!e) return CLAIRB_EINVAL;
+  if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
+  if (!x_dev || !out_dev || n <= 0 || n > e->max_sites) return fail(e, CLAIRB_EINVAL, "predict_device: bad n or buffers");
+  if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(e, CLAIRB_EINVAL, "unknown dtype %d", dtype);
+  CU_TRY(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t eb = elem_bytes(dtype);
+  int64_t done = 0;
+  int nchunks = 0;
+  while (done < n) {
+    int64_t cn = n - done < e->chunk_sites ? n - done : e->chunk_sites;
+    SiteMap sm = make_map(e, cn);
+    int rc = forward_chunk(e, (const char*)x_dev + (size_t)done * SITE_ELEMS * eb, dtype, sm,
+                           out_dev + (size_t)done * N_OUT, st);
+    if (rc) return rc;
+    e->last_map = sm;
+    done += cn;
+    ++nchunks;
+  }
+  e->last_single_chunk = nchunks == 1;
+  return CLAIRB_OK;
+}
+
+int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_host) {
+  if (!e) return CLAIRB_EINVAL;
+  if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
+  if (!x_host || !out_host || n <= 0 || n > e->max_sites) return fail(e, CLAIRB_EINVAL, "predict: bad n or buffers");
+  if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(e, CLAIRB_EINVAL, "unknown dtype %d", dtype);
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t eb = elem_bytes(dtype);
+  int64_t done = 0;
+  int c = 0;
+  while (done < n) {
+    const int b = c & 1;
+    int64_t cn = n - done < e->chunk_sites ? n - done : e->chunk_sites;
+    SiteMap sm = make_map(e, cn);
+    // input buffer b is free once the forward of chunk c-2 has consumed it
+    CU_TRY(e, cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));
+    CU_TRY(e, cudaMemcpyAsync(e->d_x[b], (const char*)x_host + (size_t)done * SITE_ELEMS * eb,
+                              (size_t)cn * SITE_ELEMS * eb, cudaMemcpyHostToDevice, e->s_h2d));
+    CU_TRY(e, cudaEventRecord(e->ev_h2d[b], e->s_h2d));
+    CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_h2d[b], 0));
+    CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_d2h[b], 0));   // output buffer b drained
+    int rc = forward_chunk(e, e->d_x[b], dtype, sm, e->d_out[b], e->s_comp);
+    if (rc) return rc;
+    CU_TRY(e, cudaEventRecord(e->ev_comp[b], e->s_comp));
+    CU_TRY(e, cudaStreamWaitEvent(e->s_d2h, e->ev_comp[b], 0));
+    CU_TRY(e, cudaMemcpyAsync(out_host + (size_t)done * N_OUT, e->d_out[b], (size_t)cn * N_OUT * sizeof(float),
+                              cudaMemcpyDeviceToHost, e->s_d2h));
+    CU_TRY(e, cudaEventRecord(e->ev_d2h[b], e->s_d2h));
+    e->last_map = sm;
+    done += cn;
+    ++c;
+  }
+  e->last_single_chunk = c == 1;
+  // the caller reads out_host as soon as we return (call_var.py:1334-1338)
+  CU_TRY(e, cudaStreamSynchronize(e->s_d2h));
+  CU_TRY(e, cudaStreamSynchronize(e->s_comp));
+  return CLAIRB_OK;
+}
+
+int clairb_get_layer(clairb_engine* e, int layer, float* out_host, int64_t n) {
+  if (!e || !out_host) return CLAIRB_EINVAL;
+  if (!e->last_single_chunk || n != e->last_map.n)
+    return fail(e, CLAIRB_EINVAL, "get_layer: needs a preceding single-chunk predict of exactly n sites");
+  CU_TRY(e, cudaSetDevice(e->device));
+  CU_TRY(e, cudaDeviceSynchronize());
+  const SiteMap sm = e->last_map;
+  const size_t np = (size_t)sm.np;
+  if (layer == CLAIRB_LAYER_LOGITS) {
+    std::vector<float> buf(np * N_OUT);
+    CU_TRY(e, cudaMemcpy(buf.data(), e->d_logits, buf.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int64_t r = 0; r < n; ++r)
+      memcpy(out_host + r * N_OUT, buf.data() + sm.padded_row(r) * N_OUT, N_OUT * sizeof(float));
+    return CLAIRB_OK;
+  }
+  if (e->kind == ENGINE_TC) {
+    cudaError_t cst = tc::get_layer(e->tcws, layer, sm, out_host);
+    if (cst == cudaErrorInvalidValue) return fail(e, CLAIRB_EINVAL, "get_layer: unknown layer %d", layer);
+    if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "get_layer failed: %s", cudaGetErrorString(cst));
+    return CLAIRB_OK;
+  }
+  const float* src = nullptr;
+  size_t planes = 0;
+  switch (layer) {
+    case CLAIRB_LAYER_LSTM1: src = e->d_h1; planes = (size_t)T_STEPS * 2 * H; break;
+    case CLAIRB_LAYER_LSTM2: src = e->d_h2; planes = (size_t)T_STEPS * 2 * H; break;
+    case CLAIRB_LAYER_L3: src = e->d_l3T; planes = L3_K; break;
+    case CLAIRB_LAYER_L4: src = e->d_l4T; planes = L4_UNITS; break;
+    default: return fail(e, CLAIRB_EINVAL, "get_layer: unknown layer %d", layer);
+  }
+  std::vector<float> buf(planes * np);
+  CU_TRY(e, cudaMemcpy(buf.data(), src, buf.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int64_t r = 0; r < n; ++r) {
+    const size_t p = (size_t)sm.padded_row(r);
+    if (layer == CLAIRB_LAYER_LSTM1 || layer == CLAIRB_LAYER_LSTM2) {
+      // plane index t*256+f -> out[t][r][f]
+      for (int t = 0; t < T_STEPS; ++t)
+        for (int f = 0; f < 2 * H; ++f)
+          out_host[((size_t)t * n + r) * 2 * H + f] = buf[((size_t)t * 2 * H + f) * np + p];
+    } else {
+      // plane index k -> out[r][k]   (L3: k = o*256+c, i.e. [n,30,256] row-major)
+      for (size_t k = 0; k < planes; ++k) out_host[(size_t)r * planes + k] = buf[k * np + p];
+    }
+  }
+  return CLAIRB_OK;
+}
+
+int clairb_set_profiling(clairb_engine* e, int enabled) {
+  if (!e) return CLAIRB_EINVAL;
+  cudaSetDevice(e->device);
+  prof_fold(e);
+  e->prof_acc.clear();
+  e->profiling = enabled != 0;
+  return CLAIRB_OK;
+}
+
+int clairb_read_profile(clairb_engine* e, char* json, int64_t json_len) {
+  if (!e || !json || json_len < 64) return CLAIRB_EINVAL;
+  cudaSetDevice(e->device);
+  prof_fold(e);
+  std::string s = "[";
+  for (auto& kv : e->prof_acc) {
+    char buf[256];
+    const char* nm = kv.first < kNumKernelNames ? kKernelNames[kv.first] : "kernel";
+    snprintf(buf, sizeof buf, "%s{\"kernel\": \"%s\", \"launches\": %lld, \"ms\": %.6f}", s.size() > 1 ? ", " : "", nm,
+             (long long)kv.second.second, kv.second.first);
+    s += buf;
+  }
+  s += "]";
+  if ((int64_t)s.size() + 1 > json_len) return fail(e, CLAIRB_EINVAL, "read_profile: buffer too small");
+  memcpy(json, s.c_str(), s.size() + 1);
+  e->prof_acc.clear();
+  return CLAIRB_OK;
+}
+
+int clairb_destroy(clairb_engine* e) {
+  if (!e) return CLAIRB_EINVAL;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  free_all(e);
+  delete e;
+  return CLAIRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,16 @@
+"""Shape / batch constants of the hot path (mirror of reference shared/param.py:9-16).
+
+Only the values the forward path reads are kept; training hyper-parameters are out of scope.
+"""
+flankingBaseNum = 16          # shared/param.py:9
+matrixRow = 8                 # shared/param.py:10
+matrixNum = 4                 # shared/param.py:11
+predictBatchSize = 1000       # shared/param.py:16
+NUM_THREADS = 12              # shared/param.py:3 (kept for callers that mutate it: call_var.py:182-189)
+
+no_of_positions = 2 * flankingBaseNum + 1
+input_tensor_size = no_of_positions * matrixRow * matrixNum   # clair/utils.py:68-69
+
+
+def get_model_parameters():   # shared/param.py:51-56
+    return dict(flankingBaseNum=flankingBaseNum, matrixNum=matrixNum, expandReferenceRegion=1000000)

@@ -1,0 +1,119 @@
+/* clair_b200.h — C-ABI of the B200-native replacement for Clair's batched forward path.
+ *
+ * The reference (HKU-BAL/Clair) is pure Python over TensorFlow 1.13; the path replaced here is
+ *   Clair.__init__/init/restore_parameters/predict/close      reference clair/model.py:58,807,1016,946,872
+ *   (graph: clair/model.py:400-622, activation: clair/selu.py:26-30)
+ * i.e. everything `session.run(self.Y)` does for the "2BiLSTM" structure.  There is no FFI in the
+ * reference; this header is the boundary a maintainer binds with ctypes.
+ *
+ * Conventions: plain pointers and sizes only; every entry point returns 0 on success and a
+ * non-zero CLAIRB_E* code on failure (message via clairb_last_error); nothing here calls
+ * exit() or throws.  One handle drives one GPU.  A handle is not re-entrant: one call in flight
+ * per handle (the reference keeps exactly one predict in flight: clair/call_var.py:1340-1352),
+ * but calls may come from any host thread.
+ *
+ * Tensor layouts
+ *   input  x   : [n,33,8,4] row-major (position, ACGTacgt row, channel), already
+ *                channel-subtracted as clair/utils.py:96-98 yields it; dtype per CLAIRB_DTYPE_*.
+ *   output out : [n,90] float32 row-major = softmax probabilities of the four heads concatenated
+ *                21 (gt21) | 3 (genotype) | 33 (indel length 1) | 33 (indel length 2)
+ *                (clair/model.py:581-622, clair/task/main.py:10-29).
+ */
+#ifndef CLAIR_B200_H
+#define CLAIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLAIRB_OK            0
+#define CLAIRB_EINVAL        1   /* bad argument / shape / state            */
+#define CLAIRB_ECUDA         2   /* a CUDA runtime call or kernel failed     */
+#define CLAIRB_ENOMEM        3   /* host or device allocation failed         */
+#define CLAIRB_ENODEVICE     4   /* no sm_100 device visible                 */
+#define CLAIRB_EWEIGHTS      5   /* unknown / missing / mis-shaped variable  */
+
+#define CLAIRB_DTYPE_F32     0   /* what tensor_generator_from yields (clair/utils.py:84)     */
+#define CLAIRB_DTYPE_I16     1   /* compact transport of the same integer counts (lossless)   */
+
+#define CLAIRB_N_OUT         90  /* 21 + 3 + 33 + 33                                           */
+#define CLAIRB_SITE_ELEMS    1056 /* 33*8*4, clair/utils.py:68-69                              */
+
+/* stages of the forward graph whose activations can be read back for parity tests */
+#define CLAIRB_LAYER_LSTM1   1   /* [33,n,256]  clair/model.py:423-430 (time-major like TF)    */
+#define CLAIRB_LAYER_LSTM2   2   /* [33,n,256]  clair/model.py:443-450                          */
+#define CLAIRB_LAYER_L3      3   /* [n,30,256]  clair/model.py:464-471                          */
+#define CLAIRB_LAYER_L4      4   /* [n,192]     clair/model.py:482-488                          */
+#define CLAIRB_LAYER_LOGITS  5   /* [n,90]      post-SELU head outputs, clair/model.py:581-618  */
+
+typedef struct clairb_engine clairb_engine;
+
+/* Replaces Clair.__init__ + tf.Session creation (clair/model.py:58-192).
+ * device: CUDA ordinal.  max_sites: largest n any later call will pass (device workspace and
+ * pinned staging are sized once from it).  batch_sites: sites per predict-batch when a call
+ * carries several batches (param.predictBatchSize = 1000, shared/param.py:16); tiles never
+ * straddle a batch.  Fails with CLAIRB_ENODEVICE when the device is not compute capability 10.x
+ * — there is no CPU or other-architecture fallback. */
+int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine** out);
+
+/* Replaces tf.train.Saver.restore variable assignment (clair/model.py:1016-1020).
+ * tf_name is the TF-1.13 variable name (e.g. "L4/kernel", "L3/Unit_17/bias",
+ * "LSTM1/stack_bidirectional_rnn/cell_0/bidirectional_rnn/fw/cudnn_compatible_lstm_cell/kernel");
+ * data is float32 row-major of the given shape.  Copies the data. */
+int clairb_set_weight(clairb_engine* e, const char* tf_name, const float* data,
+                      const int64_t* shape, int rank);
+
+/* Checks that every variable of the forward graph was set, builds the device-side operand
+ * layouts (gate-column permutation, fp16 hi/lo split, tile blocking) and uploads them. */
+int clairb_finalize_weights(clairb_engine* e);
+
+/* Replaces Clair.predict (clair/model.py:946-966): host buffers in, host buffers out.
+ * x_host: n sites of dtype `dtype`; out_host: [n,90] float32.  Copies host->device, runs the
+ * forward, copies device->host and returns when out_host is fully written (the caller's next
+ * pipeline stage reads it immediately: clair/call_var.py:1334-1338).  n may be any value in
+ * [1, max_sites]; it is processed as ceil(n/batch_sites) predict-batches, several in flight.
+ * The library does not retain x_host or out_host. */
+int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_host);
+
+/* Same forward with both buffers already resident in device memory, enqueued on `stream`
+ * (a cudaStream_t; NULL = legacy default stream) without synchronising the host.  Used by
+ * bench.py for the device-resident number and by the multi-GPU shard path. */
+int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_t n,
+                          float* out_dev, void* stream);
+
+/* Parity hook: activations of the most recent clairb_predict* call at one stage of the graph,
+ * copied to host as float32 in the reference's own axis order (see CLAIRB_LAYER_*).
+ * out_host must hold layer_elems(layer) * n floats. */
+int clairb_get_layer(clairb_engine* e, int layer, float* out_host, int64_t n);
+
+/* Pinned host memory for async staging (replaces the pageable numpy buffers of
+ * clair/utils.py:85).  Buffers from here make clairb_predict's copies truly asynchronous. */
+int clairb_host_alloc(void** ptr, int64_t bytes);
+int clairb_host_free(void* ptr);
+
+/* Number of kernels this library launched on the handle since creation (bench.py reports the
+ * difference over the timed region as gpu_launches). */
+int64_t clairb_kernel_launches(const clairb_engine* e);
+
+/* Per-kernel device timing for the roofline report: while enabled, every kernel launch is
+ * bracketed by CUDA events on its own stream.  clairb_read_profile writes a JSON array
+ * [{"kernel": name, "launches": L, "ms": total}] into `json` and resets the counters. */
+int clairb_set_profiling(clairb_engine* e, int enabled);
+int clairb_read_profile(clairb_engine* e, char* json, int64_t json_len);
+
+/* Static description of the build: "clair_b200 <version> sm_100a <engine>" */
+const char* clairb_version(void);
+
+/* Message of the last failure on this handle (or of the last failed clairb_create when e is
+ * NULL).  The pointer stays valid until the next failing call. */
+const char* clairb_last_error(const clairb_engine* e);
+
+/* Replaces Clair.close / __del__ (clair/model.py:872,1149). */
+int clairb_destroy(clairb_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLAIR_B200_H */

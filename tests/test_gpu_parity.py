@@ -1,0 +1,192 @@
+"""Parity of the CUDA path against the oracle, through the C-ABI (python -m pytest -m gpu).
+
+Bar: |d| <= 1e-4 * max(1, |ref|) on the 90 post-SELU logits against the
+fp64 oracle AND identical arg-max on each of the four heads.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from clair_b200 import _lib, synth
+from oracle import clair_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def assert_parity(m, X, w, check_layers=False):
+    n = X.shape[0]
+    probs = m.predict(X)
+    ref_probs, im = O.forward(X.astype(np.float32), w, np.float64, intermediates=True)
+    logits = m.get_layer(_lib.LAYER_LOGITS, n)
+    ref_logits = np.concatenate(im["logits"], axis=1)
+    err = np.abs(logits - ref_logits) / np.maximum(1.0, np.abs(ref_logits))
+    assert err.max() <= TOL, "scaled logit error %g" % err.max()
+    assert [p.shape for p in probs] == [(n, 21), (n, 3), (n, 33), (n, 33)]
+    for k in range(4):
+        assert probs[k].dtype == np.float32
+        np.testing.assert_array_equal(probs[k].argmax(1), ref_probs[k].argmax(1))
+        assert np.abs(probs[k] - ref_probs[k]).max() <= TOL
+        np.testing.assert_allclose(probs[k].sum(1), 1.0, atol=1e-5)
+    if check_layers:
+        for layer, key in ((_lib.LAYER_LSTM1, "lstm1"), (_lib.LAYER_LSTM2, "lstm2"), (_lib.LAYER_L3, "l3"),
+                           (_lib.LAYER_L4, "l4")):
+            got = m.get_layer(layer, n)
+            ref = im[key]
+            assert got.shape == ref.shape
+            assert np.abs(got - ref).max() <= TOL, key
+    return err.max()
+
+
+def test_golden_vectors(gpu_model, weights1234, golden_forward):
+    g = golden_forward
+    probs = gpu_model.predict(g["X"])
+    logits = gpu_model.get_layer(_lib.LAYER_LOGITS, 8)
+    err = np.abs(logits - g["logits"]) / np.maximum(1.0, np.abs(g["logits"]))
+    assert err.max() <= TOL
+    packed = np.concatenate(probs, axis=1)
+    assert np.abs(packed - g["probs"]).max() <= TOL
+    for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
+        np.testing.assert_array_equal(packed[:, a:b].argmax(1), g["probs"][:, a:b].argmax(1))
+    for layer, key in ((_lib.LAYER_LSTM1, "lstm1"), (_lib.LAYER_LSTM2, "lstm2"), (_lib.LAYER_L3, "l3"), (_lib.LAYER_L4, "l4")):
+        assert np.abs(gpu_model.get_layer(layer, 8) - g[key]).max() <= TOL, key
+
+
+def test_config1_256_sites_every_layer(gpu_model, weights1234):
+    X = synth.synthetic_tensors(256, seed=20240607)
+    assert_parity(gpu_model, X, weights1234, check_layers=True)
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 1000, 1001, 2500])
+def test_ragged_batches(gpu_model, weights1234, n):
+    # n=1: smallest batch; 1001/2500: several predict-batches with a ragged last one (utils.py:105)
+    X = synth.synthetic_tensors(n, seed=1000 + n)
+    assert_parity(gpu_model, X, weights1234)
+
+
+def test_int16_transport_is_bit_identical(gpu_model):
+    counts = synth.synthetic_counts(300, seed=5).astype(np.int32)
+    counts[..., 1:] -= counts[..., 0:1]
+    xi = counts.astype(np.int16)
+    a = gpu_model.predict_packed(xi)
+    b = gpu_model.predict_packed(xi.astype(np.float32))
+    np.testing.assert_array_equal(a, b)
+
+
+def test_input_forms_and_fresh_outputs(gpu_model):
+    X = synth.synthetic_tensors(64, seed=9)
+    a = gpu_model.predict(X)
+    assert gpu_model.prediction is a
+    b = gpu_model.predict(np.asfortranarray(X.astype(np.float64)))      # non-contiguous float64
+    c = gpu_model.predict(X.reshape(64, -1))                             # flat rows
+    for k in range(4):
+        np.testing.assert_array_equal(a[k], b[k])
+        np.testing.assert_array_equal(a[k], c[k])
+        assert a[k] is not b[k] and not np.shares_memory(a[k], b[k])      # caller keeps the old ones
+    with pytest.raises(ValueError):
+        gpu_model.predict(np.zeros((4, 33, 8, 3), np.float32))
+    with pytest.raises(ValueError):
+        gpu_model.predict(np.zeros((0, 33, 8, 4), np.float32))
+
+
+def test_deterministic_and_site_independent(gpu_model):
+    X = synth.synthetic_tensors(1500, seed=21)
+    a = gpu_model.predict_packed(X)
+    b = gpu_model.predict_packed(X)
+    np.testing.assert_array_equal(a, b)
+    perm = np.random.default_rng(1).permutation(1500)
+    c = gpu_model.predict_packed(X[perm])
+    np.testing.assert_array_equal(a[perm], c)          # per-site: position in the batch is irrelevant
+
+
+def test_multi_chunk_equals_single_calls(gpu_model):
+    # 8192 sites = 9 predict-batches through the chunked, copy-overlapped host path
+    X = synth.synthetic_tensors(8192, seed=33)
+    full = gpu_model.predict_packed(X)
+    for s in (0, 3000, 8000):
+        part = gpu_model.predict_packed(X[s:s + 192])
+        np.testing.assert_array_equal(full[s:s + 192], part)
+    assert np.isfinite(full).all()
+
+
+def test_predict_from_worker_thread(gpu_model):
+    import threading
+    X = synth.synthetic_tensors(100, seed=2)
+    ref = gpu_model.predict_packed(X)
+    t = threading.Thread(target=gpu_model.predict, kwargs={"batchX": X})     # call_var.py:1343
+    t.start()
+    t.join()
+    np.testing.assert_array_equal(np.concatenate(gpu_model.prediction, 1), ref)
+
+
+def test_extreme_inputs_stay_finite(gpu_model, weights1234):
+    X = np.zeros((6, 33, 8, 4), np.float32)
+    X[1] = 2000.0
+    X[2] = -2000.0
+    X[3, :, :, 0] = 30000.0
+    X[4] = np.random.default_rng(0).normal(0, 3, X[4].shape)                 # non-integer input
+    X[5] = 0.125
+    assert_parity(gpu_model, X, weights1234)
+
+
+def test_zero_bias_reference_initialisation():
+    from clair_b200.model import Clair
+    from clair_b200 import weights as W
+    w = W.random_weights(seed=7, bias_std=0.0)                                # TF's own init has zero biases
+    m = Clair(max_sites=512)
+    m.set_weights(w)
+    X = synth.synthetic_tensors(130, seed=8)
+    assert_parity(m, X, w)
+    m.close()
+
+
+def test_pinned_staging_buffers(gpu_model):
+    from clair_b200.model import pinned_empty, pinned_free
+    X = synth.synthetic_tensors(500, seed=12)
+    buf = pinned_empty(X.shape, np.float32)
+    buf[...] = X
+    np.testing.assert_array_equal(gpu_model.predict_packed(buf), gpu_model.predict_packed(X))
+    pinned_free(buf)
+
+
+def test_device_resident_entry_point(gpu_model):
+    import torch
+    X = synth.synthetic_tensors(2100, seed=14)
+    ref = gpu_model.predict_packed(X)
+    xd = torch.from_numpy(X).cuda()
+    od = torch.empty((2100, 90), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream()
+    before = gpu_model.kernel_launches()
+    gpu_model.predict_device(xd.data_ptr(), _lib.DTYPE_F32, 2100, od.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert gpu_model.kernel_launches() > before
+    np.testing.assert_array_equal(od.cpu().numpy(), ref)
+
+
+def test_predict_before_weights_is_an_error():
+    from clair_b200.model import Clair
+    m = Clair(max_sites=256)
+    with pytest.raises(RuntimeError):
+        m.predict(np.zeros((1, 33, 8, 4), np.float32))
+    lib = _lib.load()
+    out = np.zeros((1, 90), np.float32)
+    x = np.zeros((1, 33, 8, 4), np.float32)
+    rc = lib.clairb_predict(m._h, x.ctypes.data_as(ctypes.c_void_p), 0, 1, out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == _lib.EINVAL and "finalize" in _lib.last_error(m._h)
+    m.close()
+
+
+def test_drop_in_batch_loop(gpu_model, weights1234):
+    from clair_b200 import call_var
+    sizes = [1000, 1000, 333]
+    Xs = [synth.synthetic_tensors(s, seed=50 + i) for i, s in enumerate(sizes)]
+    gen = ((X, [["c", str(j), "A" * 33] for j in range(len(X))]) for X in Xs)
+    got = []
+    call_var.run_batches(gpu_model, gen, lambda mb, Y: got.append((mb[0], [y.copy() for y in Y])))
+    assert len(got) == 3
+    for (X, Y), Xref in zip(got, Xs):
+        assert X is Xref
+        ref = O.forward(Xref, weights1234, np.float32)
+        for k in range(4):
+            np.testing.assert_array_equal(Y[k].argmax(1), ref[k].argmax(1))
