@@ -45,6 +45,7 @@ struct HostWeight {
 };
 
 enum EngineKind { ENGINE_SIMT = 0, ENGINE_TC = 1 };
+constexpr int TC_PAIR_SITES = 256;
 
 }  // namespace
 
@@ -143,6 +144,13 @@ const HostWeight* find_weight(clairb_engine* e, const std::string& name, std::ve
 SiteMap make_map(const clairb_engine* e, int64_t n) {
   SiteMap m;
   m.n = n;
+  if (e->kind == ENGINE_TC) {
+    // sites are independent, so the tensor-core path tiles straight through predict-batch boundaries:
+    // padded row == real row, padded up to a whole CTA pair (256 sites)
+    m.batch = m.bp = TC_PAIR_SITES;
+    m.np = (n + TC_PAIR_SITES - 1) / TC_PAIR_SITES * TC_PAIR_SITES;
+    return m;
+  }
   m.batch = e->batch;
   m.bp = e->bp;
   int64_t nb = (n + e->batch - 1) / e->batch;
@@ -152,8 +160,8 @@ SiteMap make_map(const clairb_engine* e, int64_t n) {
 
 // ---- per-kernel event timing --------------------------------------------------------------------
 const char* kKernelNames[] = {"prep_input", "lstm_layer1", "lstm_layer2", "l3_slice_dense", "l4_dense",
-                              "tail_heads"};
-constexpr int kNumKernelNames = 6;
+                              "tail_heads", "prep_tiles", "xproj1", "lstm_rec1", "xproj2", "lstm_rec2"};
+constexpr int kNumKernelNames = 11;
 
 void prof_fold(clairb_engine* e) {
   for (auto& sp : e->prof_open) {
@@ -199,6 +207,8 @@ struct ProfScope {
 };
 
 // ---- forward on one chunk, all launches on `st` ------------------------------------------------
+int forward_tail(clairb_engine* e, SiteMap sm, float* out_dev, cudaStream_t st);
+
 int forward_simt(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, float* out_dev, cudaStream_t st) {
   const int64_t np = sm.np;
   dim3 gprep((unsigned)(np / 32), 4);
@@ -220,6 +230,12 @@ int forward_simt(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, flo
     simt::lstm_layer<2 * H><<<glstm, simt::LSTM_THREADS, simt::lstm_smem_bytes<2 * H>(), st>>>(
         e->d_h1, e->d_Wp[1], e->d_bp[1], e->d_h2, np);
   }
+  return forward_tail(e, sm, out_dev, st);
+}
+
+// slice-dense L3 -> L4 -> L5/heads/softmax from the h2 planes (shared by both engines for now)
+int forward_tail(clairb_engine* e, SiteMap sm, float* out_dev, cudaStream_t st) {
+  const int64_t np = sm.np;
   dim3 gl3((unsigned)(np / 128), 2 * H / simt::L3_CPB);
   {
     ProfScope ps(e, 3, st);
@@ -235,7 +251,7 @@ int forward_simt(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, flo
     simt::tail_heads<<<(unsigned)(np / simt::TL_TM), 256, simt::tail_smem_bytes(), st>>>(
         e->d_l4T, e->d_W5, e->d_b5, e->d_Whd, e->d_bhd, out_dev, e->d_logits, sm);
   }
-  e->launches += 6;
+  e->launches += 3;
   CU_TRY(e, cudaGetLastError());
   return CLAIRB_OK;
 }
@@ -243,10 +259,15 @@ int forward_simt(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, flo
 int forward_chunk(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, float* out_dev, cudaStream_t st) {
   if (e->kind == ENGINE_TC) {
     int nl = 0;
-    cudaError_t cst = tc::forward(e->tcw, e->tcws, x_dev, dtype, sm, out_dev, e->d_logits, st, &nl);
+    ProfScope* open = nullptr;
+    auto hook = [&](int id, bool begin) {
+      if (begin) open = new ProfScope(e, 6 + id, st);
+      else { delete open; open = nullptr; }
+    };
+    cudaError_t cst = tc::forward_lstm(e->tcw, e->tcws, x_dev, dtype == CLAIRB_DTYPE_I16, sm.n, sm.np, e->d_h2, st, &nl, hook);
     e->launches += nl;
     if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "tensor-core forward failed: %s", cudaGetErrorString(cst));
-    return CLAIRB_OK;
+    return forward_tail(e, sm, out_dev, st);
   }
   return forward_simt(e, x_dev, dtype, sm, out_dev, st);
 }
@@ -283,7 +304,7 @@ void free_all(clairb_engine* e) {
 
 extern "C" {
 
-const char* clairb_version(void) { return "clair_b200 0.1 sm_100a"; }
+const char* clairb_version(void) { return "clair_b200 0.2 sm_100a (tcgen05 BiLSTM)"; }
 
 const char* clairb_last_error(const clairb_engine* e) {
   if (e) return e->err.c_str();
@@ -318,12 +339,13 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
   e->bp = (batch_sites + TILE - 1) / TILE * TILE;
   const char* kind = getenv("CLAIRB_ENGINE");
   e->kind = (kind && !strcmp(kind, "simt")) ? ENGINE_SIMT : (tc::available() ? ENGINE_TC : ENGINE_SIMT);
-  int64_t chunk_batches = 32;
+  int64_t chunk_batches = e->kind == ENGINE_TC ? 37 : 32;   // TC: 145 CTA pairs x 2 directions ~ 3.9 waves of 74 pairs
   if (const char* cb = getenv("CLAIRB_CHUNK_BATCHES")) chunk_batches = atoll(cb) > 0 ? atoll(cb) : chunk_batches;
   int64_t nb_max = (max_sites + batch_sites - 1) / batch_sites;
   if (chunk_batches > nb_max) chunk_batches = nb_max;
   e->chunk_sites = chunk_batches * batch_sites;
-  e->chunk_np = chunk_batches * e->bp;
+  e->chunk_np = e->kind == ENGINE_TC ? (e->chunk_sites + TC_PAIR_SITES - 1) / TC_PAIR_SITES * TC_PAIR_SITES
+                                     : chunk_batches * e->bp;
   auto bail = [&](int rc) {
     g_create_error = e->err;
     free_all(e);
@@ -353,22 +375,21 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
   const size_t np = (size_t)e->chunk_np;
   CR_TRY(cudaMalloc((void**)&e->d_logits, np * N_OUT * sizeof(float)));
   CR_TRY(cudaMemset(e->d_logits, 0, np * N_OUT * sizeof(float)));
+  CR_TRY(cudaMalloc((void**)&e->d_h2, np * T_STEPS * 2 * H * sizeof(float)));
+  CR_TRY(cudaMalloc((void**)&e->d_l3T, np * L3_K * sizeof(float)));
+  CR_TRY(cudaMalloc((void**)&e->d_l4T, np * L4_UNITS * sizeof(float)));
+  CR_TRY(cudaFuncSetAttribute(simt::l4_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt::l4_smem_bytes()));
+  CR_TRY(cudaFuncSetAttribute(simt::tail_heads, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)simt::tail_smem_bytes()));
   if (e->kind == ENGINE_SIMT) {
     CR_TRY(cudaMalloc((void**)&e->d_xT, np * SITE_ELEMS * sizeof(float)));
     CR_TRY(cudaMalloc((void**)&e->d_h1, np * T_STEPS * 2 * H * sizeof(float)));
-    CR_TRY(cudaMalloc((void**)&e->d_h2, np * T_STEPS * 2 * H * sizeof(float)));
-    CR_TRY(cudaMalloc((void**)&e->d_l3T, np * L3_K * sizeof(float)));
-    CR_TRY(cudaMalloc((void**)&e->d_l4T, np * L4_UNITS * sizeof(float)));
     CR_TRY(cudaFuncSetAttribute(simt::lstm_layer<F_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)simt::lstm_smem_bytes<F_IN>()));
     CR_TRY(cudaFuncSetAttribute(simt::lstm_layer<2 * H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)simt::lstm_smem_bytes<2 * H>()));
-    CR_TRY(cudaFuncSetAttribute(simt::l4_dense, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)simt::l4_smem_bytes()));
-    CR_TRY(cudaFuncSetAttribute(simt::tail_heads, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)simt::tail_smem_bytes()));
   } else {
-    CR_TRY(tc::alloc_workspace(e->tcws, e->chunk_np));
+    CR_TRY(tc::alloc_workspace(e->tcws, e->chunk_np, device));
   }
 #undef CR_TRY
   *out = e;
@@ -465,11 +486,11 @@ int clairb_finalize_weights(clairb_engine* e) {
   if ((rc = upload(e, &e->d_W5, W5)) || (rc = upload(e, &e->d_b5, b5)) || (rc = upload(e, &e->d_Whd, Whd)) ||
       (rc = upload(e, &e->d_bhd, bhd)) || (rc = upload(e, &e->d_b4, b4->data)))
     return rc;
+  if ((rc = upload(e, &e->d_w3p, w3p)) || (rc = upload(e, &e->d_b3p, b3p)) || (rc = upload(e, &e->d_W4, W4->data)))
+    return rc;
   if (e->kind == ENGINE_SIMT) {
     for (int l = 0; l < 2; ++l)
       if ((rc = upload(e, &e->d_Wp[l], Wp[l])) || (rc = upload(e, &e->d_bp[l], bp[l]))) return rc;
-    if ((rc = upload(e, &e->d_w3p, w3p)) || (rc = upload(e, &e->d_b3p, b3p)) || (rc = upload(e, &e->d_W4, W4->data)))
-      return rc;
   } else {
     tc::HostModel hm;
     for (int l = 0; l < 2; ++l)
@@ -477,9 +498,6 @@ int clairb_finalize_weights(clairb_engine* e) {
         hm.lstm_kernel[l][d] = e->hw[lstm_name(l + 1, d, "kernel")].data.data();
         hm.lstm_bias[l][d] = e->hw[lstm_name(l + 1, d, "bias")].data.data();
       }
-    hm.w3 = w3.data(); hm.b3 = b3.data();
-    hm.W4 = W4->data.data(); hm.b4 = b4->data.data();
-    hm.d_W5 = e->d_W5; hm.d_b5 = e->d_b5; hm.d_Whd = e->d_Whd; hm.d_bhd = e->d_bhd;
     tc::free_weights(e->tcw);
     cudaError_t cst = tc::build_weights(e->tcw, hm);
     if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "tensor-core weight upload failed: %s", cudaGetErrorString(cst));
@@ -566,9 +584,8 @@ int clairb_get_layer(clairb_engine* e, int layer, float* out_host, int64_t n) {
       memcpy(out_host + r * N_OUT, buf.data() + sm.padded_row(r) * N_OUT, N_OUT * sizeof(float));
     return CLAIRB_OK;
   }
-  if (e->kind == ENGINE_TC) {
-    cudaError_t cst = tc::get_layer(e->tcws, layer, sm, out_host);
-    if (cst == cudaErrorInvalidValue) return fail(e, CLAIRB_EINVAL, "get_layer: unknown layer %d", layer);
+  if (e->kind == ENGINE_TC && layer == CLAIRB_LAYER_LSTM1) {
+    cudaError_t cst = tc::get_lstm1(e->tcws, n, sm.np, out_host);
     if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "get_layer failed: %s", cudaGetErrorString(cst));
     return CLAIRB_OK;
   }

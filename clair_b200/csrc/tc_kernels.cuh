@@ -1,14 +1,617 @@
-// placeholder until the tcgen05 path lands
+// Tensor-core (tcgen05 / TMEM / bulk-async-copy) kernels of the forward path for sm_100a.
+//
+// Numerics: every contraction runs on fp16 operands split hi/lo (x = hi + lo, both fp16) with the three products
+// hi*hi + lo*hi + hi*lo accumulated in fp32 in TMEM (kind::f16).  That keeps ~22 mantissa bits per operand, which the
+// <=1e-4 logit gate needs (single fp16/bf16/tf32 operands fail it: SURVEY.md section 7).
+//
+// One bidirectional LSTM layer (reference clair/model.py:265-312) is two kernels:
+//   xproj_pair  Gx[t,site,dir,512] = x_t . W_x + b          one large GEMM over all 33 steps (no time dependence)
+//   lstm_rec    gates = Gx[t] + h_{t-1} . W_h ; (c,h) update  33 dependent steps, W_h resident in shared memory
+// Both run on CTA pairs (cta_group::2): a pair owns 256 sites, each CTA holds its 128 rows of the A operand and one
+// half of the gate columns of the B operand, so the 256 KB fp16 hi/lo recurrent kernel of one direction is split
+// 128 KB + 128 KB over the two SMs and never re-read from L2.
+//
+// Operand tiles live in global memory already in the UMMA canonical K-major no-swizzle order
+// [k/8][row][8] (see tc_common.cuh), so they move with plain 1-D bulk copies in both directions.
+//
+// Gate column order inside a direction: j = unit*4 + gate, gate in TF LSTMBlockCell order (i, c, f, o), so the four
+// pre-activations of one hidden unit are one float4 of Gx and four adjacent TMEM columns.
 #pragma once
+#include <cuda_fp16.h>
+
+#include <vector>
+
 #include "common.cuh"
-namespace clairb { namespace tc {
-struct Weights {}; struct Workspace {};
-struct HostModel { const float* lstm_kernel[2][2]; const float* lstm_bias[2][2]; const float *w3, *b3, *W4, *b4; float *d_W5, *d_b5, *d_Whd, *d_bhd; };
-inline bool available() { return false; }
-inline cudaError_t build_weights(Weights&, const HostModel&) { return cudaErrorNotSupported; }
-inline void free_weights(Weights&) {}
-inline cudaError_t alloc_workspace(Workspace&, int64_t) { return cudaErrorNotSupported; }
-inline void free_workspace(Workspace&) {}
-inline cudaError_t forward(const Weights&, Workspace&, const void*, int, SiteMap, float*, float*, cudaStream_t, int*) { return cudaErrorNotSupported; }
-inline cudaError_t get_layer(Workspace&, int, SiteMap, float*) { return cudaErrorNotSupported; }
-}}
+#include "tc_common.cuh"
+
+namespace clairb {
+namespace tc {
+
+// ---- sizes --------------------------------------------------------------------------------------
+constexpr int KCH = 1024;                      // halves per k-chunk of a 128-row tile: 128 rows x 8
+constexpr int KCH_BYTES = 2048;
+constexpr int GX_TILE_FLOATS = 2 * 128 * 128 * 4;   // per (t, tile): [dir][unit 128][row 128][gate 4]
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// split 8 floats into fp16 hi / lo chunks (16 bytes each)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    float2 back = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+  }
+  hi = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                  *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+  lo = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
+                  *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: x[n][33][32] (f32 or i16; clair/utils.py:95 order) -> A tiles of the layer-1 input projection
+//   X16[(t*NT + tile)][hl][kc 4][row 128][8] fp16   (model.py:403-418: reshape + time-major transpose)
+// grid = (NT, 33), block 128: thread = one site of the tile.  Padding rows are zero.
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(128) prep_tiles(const TIn* __restrict__ x, __half* __restrict__ X16, int64_t n, int NT) {
+  const int tile = blockIdx.x, t = blockIdx.y, r = threadIdx.x;
+  const int64_t site = (int64_t)tile * 128 + r;
+  float v[32];
+  if (site < n) {
+    const TIn* src = x + site * SITE_ELEMS + t * F_IN;
+    if constexpr (sizeof(TIn) == 4) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 q = *reinterpret_cast<const float4*>(src + 4 * i);
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = (float)src[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  }
+  __half* base = X16 + ((size_t)t * NT + tile) * (2 * 4 * KCH);
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    uint4 hi, lo;
+    split8(v + 8 * kc, hi, lo);
+    *reinterpret_cast<uint4*>(base + kc * KCH + r * 8) = hi;
+    *reinterpret_cast<uint4*>(base + 4 * KCH + kc * KCH + r * 8) = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// xproj_pair<KC>: Gx[a][dir][unit][row][gate] = A[a] . Wx[:, dir, unit*4+gate] + b      (a = t*NT + tile)
+//   A tiles  : [a][hl][KC][128][8] fp16          (KC = K/8: 4 for layer 1, 32 for layer 2)
+//   Wx       : [nb 4][q 2][hl][KC][128][8] fp16  N-block nb = dir*2 + half covers gate columns half*256..+256 of `dir`;
+//              CTA q of the pair supplies rows q*128..+128 of the block
+//   bias     : [nb 4][256] fp32 in the same column order
+// Persistent CTA pairs: a pair keeps ONE N-block of Wx resident in shared memory (B operand, <=128 KB per CTA) and
+// streams row-pairs (256 rows = two A tiles) through a ring of K=32 stages.  Pairs 4g..4g+3 walk the same row-pairs
+// with the four different N-blocks at the same time, so each A tile is read from HBM once and hit in L2 three times.
+// Warp roles: 0 = A producer, 1 = MMA issuer (leader) / stage relay (peer), 2..5 = epilogue (TMEM -> +bias -> Gx).
+// ---------------------------------------------------------------------------------------------
+constexpr int XP_RING = 6;
+constexpr int XP_STAGE_BYTES = 2 * 4 * KCH_BYTES;     // [hl][4 kc][128][8] = 16 KB
+constexpr int XP_THREADS = 192;
+
+template <int KC>
+constexpr size_t xproj_smem_bytes() {
+  return (size_t)2 * KC * KCH_BYTES + (size_t)XP_RING * XP_STAGE_BYTES + 256 * 4 + 256 + 1024;
+}
+
+template <int KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XP_THREADS, 1)
+xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const float* __restrict__ bias,
+           float* __restrict__ Gx, int num_row_pairs) {
+  constexpr int NST = KC / 4;                          // K=32 stages per row tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* Bs = smem;                                  // [hl][KC][128][8]
+  uint8_t* ring = Bs + 2 * KC * KCH_BYTES;
+  float* bias_s = (float*)(ring + XP_RING * XP_STAGE_BYTES);
+  uint64_t* bars = (uint64_t*)(bias_s + 256);
+  uint64_t* full = bars;                               // [XP_RING] this CTA's stage landed (tx bytes)
+  uint64_t* peer_full = bars + XP_RING;                // [XP_RING] (leader) peer's stage landed
+  uint64_t* empty = bars + 2 * XP_RING;                // [XP_RING] stage consumed (MMA commit, both CTAs)
+  uint64_t* acc_full = bars + 3 * XP_RING;             // [2] accumulator buffer complete (MMA commit, both CTAs)
+  uint64_t* acc_empty = acc_full + 2;                  // [2] (leader) drained by all 8 epilogue warps of the pair
+  uint64_t* b_full = acc_empty + 2;                    // [1] resident B landed
+  uint32_t* tmem_slot = (uint32_t*)(b_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int nb = cid & 3, grp = cid >> 2, ngrp = ncl >> 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < XP_RING; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&peer_full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8);
+    }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+    // resident B: this CTA's 128 rows of N-block nb
+    const __half* src = Wx + ((size_t)nb * 2 + rank) * (2 * KC * KCH);
+    mbar_expect_tx(b_full, 2 * KC * KCH_BYTES);
+    for (int i = 0; i < 2 * KC * KCH_BYTES; i += 16384) bulk_g2s(Bs + i, (const uint8_t*)src + i, 16384, b_full);
+  }
+  if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
+  for (int i = threadIdx.x; i < 256; i += XP_THREADS) bias_s[i] = bias[nb * 256 + i];
+  mbar_wait(b_full, 0);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- A producer (each CTA loads its own 128 rows) ----
+      uint32_t use = 0;
+      for (int rp = grp; rp < num_row_pairs; rp += ngrp) {
+        const __half* at = A + ((size_t)rp * 2 + rank) * (2 * KC * KCH);
+        for (int ks = 0; ks < NST; ++ks, ++use) {
+          const int slot = use % XP_RING;
+          mbar_wait(&empty[slot], ((use / XP_RING) & 1) ^ 1);
+          uint8_t* dst = ring + slot * XP_STAGE_BYTES;
+          mbar_expect_tx(&full[slot], XP_STAGE_BYTES);
+          bulk_g2s(dst, at + (size_t)ks * 4 * KCH, 4 * KCH_BYTES, &full[slot]);
+          bulk_g2s(dst + 4 * KCH_BYTES, at + (size_t)KC * KCH + (size_t)ks * 4 * KCH, 4 * KCH_BYTES, &full[slot]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (rank == 1) {
+        // ---- relay: tell the leader when this CTA's stage has landed ----
+        uint32_t use = 0;
+        for (int rp = grp; rp < num_row_pairs; rp += ngrp)
+          for (int ks = 0; ks < NST; ++ks, ++use) {
+            const int slot = use % XP_RING;
+            mbar_wait(&full[slot], (use / XP_RING) & 1);
+            mbar_arrive_cluster(map_to_cta(smem_u32(&peer_full[slot]), 0));
+          }
+      } else {
+        // ---- MMA issuer ----
+        const uint32_t idesc = make_idesc_f16(256, 256);
+        const uint32_t b_base = smem_u32(Bs);
+        uint32_t use = 0, it = 0;
+        for (int rp = grp; rp < num_row_pairs; rp += ngrp, ++it) {
+          const uint32_t buf = it & 1;
+          mbar_wait_cluster(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem + buf * 256;
+          for (int ks = 0; ks < NST; ++ks, ++use) {
+            const int slot = use % XP_RING;
+            const uint32_t par = (use / XP_RING) & 1;
+            mbar_wait(&full[slot], par);
+            mbar_wait_cluster(&peer_full[slot], par);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(ring + slot * XP_STAGE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t a_hi = make_smem_desc(a_base + kk * 2 * KCH_BYTES, KCH_BYTES, 128);
+              const uint64_t a_lo = make_smem_desc(a_base + 4 * KCH_BYTES + kk * 2 * KCH_BYTES, KCH_BYTES, 128);
+              const uint32_t bo = (ks * 4 + kk * 2) * KCH_BYTES;
+              const uint64_t b_hi = make_smem_desc(b_base + bo, KCH_BYTES, 128);
+              const uint64_t b_lo = make_smem_desc(b_base + KC * KCH_BYTES + bo, KCH_BYTES, 128);
+              umma_f16_pair(d, a_hi, b_hi, idesc, (ks | kk) != 0);
+              umma_f16_pair(d, a_lo, b_hi, idesc, 1);
+              umma_f16_pair(d, a_hi, b_lo, idesc, 1);
+            }
+            umma_commit_pair(&empty[slot], 0b11);
+          }
+          umma_commit_pair(&acc_full[buf], 0b11);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: TMEM -> + bias -> Gx (float4 per hidden unit, 512 B per warp store) ----
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int dir = nb >> 1, unit0 = (nb & 1) * 64;
+    uint32_t it = 0;
+    for (int rp = grp; rp < num_row_pairs; rp += ngrp, ++it) {
+      const uint32_t buf = it & 1;
+      mbar_wait_cluster(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      float* out = Gx + ((size_t)rp * 2 + rank) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) +
+                   (size_t)unit0 * 512 + r * 4;
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+#pragma unroll 2
+      for (int c = 0; c < 256; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float4 o = make_float4(v[4 * u] + bias_s[c + 4 * u], v[4 * u + 1] + bias_s[c + 4 * u + 1],
+                                 v[4 * u + 2] + bias_s[c + 4 * u + 2], v[4 * u + 3] + bias_s[c + 4 * u + 3]);
+          *reinterpret_cast<float4*>(out + (size_t)(c / 4 + u) * 512) = o;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&acc_empty[buf]), 0));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// lstm_rec<OUT>: the 33 dependent steps of one direction of one BiLSTM layer for a pair of site tiles.
+//   grid = (2 * pairs, 2 directions), cluster (2,1,1); CTA rank q owns tile 2*pair+q (128 sites) and the gate
+//   columns {n*256 + q*128 .. +128 : n = 0,1} of the recurrent kernel.
+//   Wh   : [dir][q][hl][n 2][kc 16][128][8] fp16 (128 KB per CTA, loaded once, resident)
+//   Gx   : see xproj_pair (bias already folded in)
+//   OUT == 0: h_t -> A tiles of the next layer's input projection  Hout[(t*NT+tile)][hl][kc 32][128][8] fp16,
+//             direction d fills kc d*16..+16 (model.py:306-312: out[t] = concat(fw_t, bw_t)), moved by the bulk-copy
+//             engine straight from the shared-memory operand tile
+//   OUT == 1: h_t -> fp32 planes  Hout[(t*256 + dir*128 + unit)][np]  (input of the slice-dense kernel)
+// Per step the leader's control thread issues 2 x 24 pair-MMAs (gate blocks n = 0,1: 8 k-steps x 3 split terms) and
+// commits each block to both CTAs; the 8 epilogue warps of each CTA turn block 0 into (c,h) while block 1 is still in
+// the tensor pipe, then block 1, write h_t (fp16 hi/lo) back into the operand tile and signal the leader.
+// c lives in registers for all 33 steps (64 units per thread).
+// ---------------------------------------------------------------------------------------------
+constexpr int REC_EPI_WARPS = 8;
+constexpr int REC_THREADS = 32 * (1 + REC_EPI_WARPS);
+constexpr int REC_W_BYTES = 2 * 2 * 16 * KCH_BYTES;     // 131072
+constexpr int REC_H_BYTES = 2 * 16 * KCH_BYTES;         // 65536
+constexpr size_t rec_smem_bytes() { return (size_t)REC_W_BYTES + REC_H_BYTES + 256 + 1024; }
+
+template <int OUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(REC_THREADS, 1)
+lstm_rec(const __half* __restrict__ Wh, const float* __restrict__ Gx, void* __restrict__ Hout, int NT, int64_t np) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* Ws = smem;                                  // [hl][n][kc 16][128][8]
+  uint8_t* Hs = smem + REC_W_BYTES;                    // [hl][kc 16][128][8]
+  uint64_t* bars = (uint64_t*)(Hs + REC_H_BYTES);
+  uint64_t* gates_full = bars;                         // [2] block n complete (MMA commit, both CTAs)
+  uint64_t* h_ready = bars + 2;                        // (leader) h_t of both CTAs written, TMEM drained
+  uint64_t* h_local = bars + 3;                        // h_t of this CTA written
+  uint64_t* hbuf_free = bars + 4;                      // bulk store of h_{t-1} has finished reading Hs
+  uint64_t* w_full = bars + 5;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int dir = blockIdx.y;
+  const int tile = blockIdx.x;                         // = 2*pair + rank
+
+  if (threadIdx.x == 0) {
+    mbar_init(&gates_full[0], 1);
+    mbar_init(&gates_full[1], 1);
+    mbar_init(h_ready, 2 * REC_EPI_WARPS);
+    mbar_init(h_local, REC_EPI_WARPS);
+    mbar_init(hbuf_free, 1);
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+    const uint8_t* src = (const uint8_t*)(Wh + ((size_t)dir * 2 + rank) * (REC_W_BYTES / 2));
+    mbar_expect_tx(w_full, REC_W_BYTES);
+    for (int i = 0; i < REC_W_BYTES; i += 32768) bulk_g2s(Ws + i, src + i, 32768, w_full);
+  }
+  if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
+  mbar_wait(w_full, 0);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- control thread: MMA issue (leader) and h_t write-out (both CTAs) ----
+      const uint32_t idesc = make_idesc_f16(256, 256);
+      const uint32_t w_base = smem_u32(Ws), h_base = smem_u32(Hs);
+      for (int s = 1; s <= T_STEPS; ++s) {
+        // h_{s-1} complete?
+        if (rank == 0) mbar_wait_cluster(h_ready, (s - 1) & 1);
+        else mbar_wait(h_local, (s - 1) & 1);
+        tc_fence_after();
+        if (OUT == 0) {
+          const int tp = dir ? (T_STEPS - s) : (s - 1);          // time index of step s-1
+          __half* dst = (__half*)Hout + ((size_t)tp * NT + tile) * (2 * 32 * KCH) + (size_t)dir * 16 * KCH;
+          bulk_s2g(dst, Hs, 16 * KCH_BYTES);
+          bulk_s2g(dst + 32 * KCH, Hs + 16 * KCH_BYTES, 16 * KCH_BYTES);
+          bulk_commit();
+        }
+        if (rank == 0 && s < T_STEPS) {
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t a_hi = make_smem_desc(h_base + j * 2 * KCH_BYTES, KCH_BYTES, 128);
+              const uint64_t a_lo = make_smem_desc(h_base + 16 * KCH_BYTES + j * 2 * KCH_BYTES, KCH_BYTES, 128);
+              const uint32_t bo = n * 16 * KCH_BYTES + j * 2 * KCH_BYTES;
+              const uint64_t b_hi = make_smem_desc(w_base + bo, KCH_BYTES, 128);
+              const uint64_t b_lo = make_smem_desc(w_base + 2 * 16 * KCH_BYTES + bo, KCH_BYTES, 128);
+              umma_f16_pair(tmem + n * 256, a_hi, b_hi, idesc, j != 0);
+              umma_f16_pair(tmem + n * 256, a_lo, b_hi, idesc, 1);
+              umma_f16_pair(tmem + n * 256, a_hi, b_lo, idesc, 1);
+            }
+            umma_commit_pair(&gates_full[n], 0b11);
+          }
+        }
+        if (OUT == 0) {
+          bulk_wait_read0();
+          mbar_arrive(hbuf_free);
+        }
+      }
+      if (OUT == 0) bulk_wait0();
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue warps ----
+    const int ew = warp - 1;
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+    const int colhalf = ew >> 2;                       // which 128 columns of each 256-column gate block
+    const int r = quarter * 32 + lane;
+    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + colhalf * 128;
+    const uint32_t leader_h_ready = map_to_cta(smem_u32(h_ready), 0);
+    float c[2][32];
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) c[n][i] = 0.f;
+
+    for (int s = 0; s < T_STEPS; ++s) {
+      const int t = dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
+      const float* gx = Gx + ((size_t)t * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) + r * 4;
+      uint4 keep_hi[4], keep_lo[4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int unit0 = n * 64 + colhalf * 32;
+        if (s > 0) {
+          mbar_wait_cluster(&gates_full[n], (s - 1) & 1);
+          tc_fence_after();
+        }
+        float hv[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 gq[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gq[k] = ld_stream4(gx + (size_t)(unit0 + 4 * g + k) * 512);
+          float v[16];
+          if (s > 0) {
+            tmem_ld16(taddr + n * 256 + g * 16, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float zi = v[4 * k] + gq[k].x, zg = v[4 * k + 1] + gq[k].y;
+            const float zf = v[4 * k + 2] + gq[k].z, zo = v[4 * k + 3] + gq[k].w;
+            const float cn = fast_tanh(zg) * fast_sigmoid(zi) + c[n][4 * g + k] * fast_sigmoid(zf);
+            c[n][4 * g + k] = cn;
+            hv[4 * g + k] = fast_tanh(cn) * fast_sigmoid(zo);
+          }
+        }
+        if (OUT == 1) {
+          float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + unit0) * np + (size_t)tile * 128 + r;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) out[(size_t)i * np] = hv[i];
+        }
+        if (n == 0) {
+          // block 1 is still reading h_{t-1}: park block 0's h_t in registers
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split8(hv + 8 * q, keep_hi[q], keep_lo[q]);
+        } else {
+          if (OUT == 0 && s > 0) mbar_wait(hbuf_free, (s - 1) & 1);
+          // all MMAs of this step are complete (gates_full[1]): the operand tile may be overwritten
+          uint8_t* h0 = Hs + (size_t)((colhalf * 32) / 8) * KCH_BYTES + r * 16;            // units of block 0
+          uint8_t* h1 = Hs + (size_t)((64 + colhalf * 32) / 8) * KCH_BYTES + r * 16;       // units of block 1
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 hi, lo;
+            split8(hv + 8 * q, hi, lo);
+            *reinterpret_cast<uint4*>(h0 + q * KCH_BYTES) = keep_hi[q];
+            *reinterpret_cast<uint4*>(h0 + 16 * KCH_BYTES + q * KCH_BYTES) = keep_lo[q];
+            *reinterpret_cast<uint4*>(h1 + q * KCH_BYTES) = hi;
+            *reinterpret_cast<uint4*>(h1 + 16 * KCH_BYTES + q * KCH_BYTES) = lo;
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(h_local);
+        mbar_arrive_cluster(leader_h_ready);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct HostModel {
+  const float* lstm_kernel[2][2];   // [layer][dir] TF layout [(Kx+128)][512], rows x first, columns gate-major i,c,f,o
+  const float* lstm_bias[2][2];     // [512]
+};
+
+struct Weights {
+  __half* Wx[2] = {nullptr, nullptr};      // per layer: [nb 4][q 2][hl][KC][128][8]
+  float* bx[2] = {nullptr, nullptr};       // per layer: [nb 4][256]
+  __half* Wh[2] = {nullptr, nullptr};      // per layer: [dir][q][hl][n][kc 16][128][8]
+};
+
+struct Workspace {
+  int64_t np_max = 0;
+  __half* X16 = nullptr;     // [33*NT][hl][4][128][8]
+  float* Gx = nullptr;       // [33*NT][dir][unit][row][4]
+  __half* H1 = nullptr;      // [33*NT][hl][32][128][8]
+  int sm_count = 148;
+};
+
+inline bool available() { return true; }
+
+inline void split_half(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+// gate column j (unit*4+gate) of a direction -> TF kernel column (gate*128+unit)
+inline int tf_col(int j) { return (j & 3) * H + (j >> 2); }
+
+inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
+  const int kx[2] = {F_IN, 2 * H};
+  for (int l = 0; l < 2; ++l) {
+    const int KC = kx[l] / 8;
+    std::vector<__half> wx((size_t)4 * 2 * 2 * KC * KCH);
+    std::vector<float> bx((size_t)4 * 256);
+    std::vector<__half> wh((size_t)2 * 2 * 2 * 2 * 16 * KCH);
+    for (int dir = 0; dir < 2; ++dir) {
+      const float* K = hm.lstm_kernel[l][dir];
+      const float* B = hm.lstm_bias[l][dir];
+      for (int half = 0; half < 2; ++half) {
+        const int nb = dir * 2 + half;
+        for (int c = 0; c < 256; ++c) bx[(size_t)nb * 256 + c] = B[tf_col(half * 256 + c)];
+        for (int q = 0; q < 2; ++q)
+          for (int row = 0; row < 128; ++row) {
+            const int col = tf_col(half * 256 + q * 128 + row);
+            // input projection rows (x first in the TF kernel)
+            for (int k = 0; k < kx[l]; ++k) {
+              __half hi, lo;
+              split_half(K[(size_t)k * G4 + col], hi, lo);
+              const size_t base = (((size_t)nb * 2 + q) * 2) * KC * KCH + (size_t)(k / 8) * KCH + row * 8 + k % 8;
+              wx[base] = hi;
+              wx[base + (size_t)KC * KCH] = lo;
+            }
+            // recurrent rows: block n == half
+            for (int k = 0; k < H; ++k) {
+              __half hi, lo;
+              split_half(K[(size_t)(kx[l] + k) * G4 + col], hi, lo);
+              const size_t cta = ((size_t)dir * 2 + q) * (2 * 2 * 16 * KCH);
+              const size_t off = (size_t)half * 16 * KCH + (size_t)(k / 8) * KCH + row * 8 + k % 8;
+              wh[cta + off] = hi;
+              wh[cta + (size_t)2 * 16 * KCH + off] = lo;
+            }
+          }
+      }
+    }
+    cudaError_t st;
+    if ((st = cudaMalloc((void**)&w.Wx[l], wx.size() * 2)) != cudaSuccess) return st;
+    if ((st = cudaMalloc((void**)&w.bx[l], bx.size() * 4)) != cudaSuccess) return st;
+    if ((st = cudaMalloc((void**)&w.Wh[l], wh.size() * 2)) != cudaSuccess) return st;
+    if ((st = cudaMemcpy(w.Wx[l], wx.data(), wx.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
+    if ((st = cudaMemcpy(w.bx[l], bx.data(), bx.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
+    if ((st = cudaMemcpy(w.Wh[l], wh.data(), wh.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
+  }
+  return cudaSuccess;
+}
+
+inline void free_weights(Weights& w) {
+  for (int l = 0; l < 2; ++l) {
+    cudaFree(w.Wx[l]); cudaFree(w.bx[l]); cudaFree(w.Wh[l]);
+    w.Wx[l] = nullptr; w.bx[l] = nullptr; w.Wh[l] = nullptr;
+  }
+}
+
+inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
+  ws.np_max = np_max;
+  const size_t NT = (size_t)np_max / 128;
+  cudaError_t st;
+  if ((st = cudaMalloc((void**)&ws.X16, (size_t)T_STEPS * NT * 2 * 4 * KCH * 2)) != cudaSuccess) return st;
+  if ((st = cudaMalloc((void**)&ws.Gx, (size_t)T_STEPS * NT * GX_TILE_FLOATS * 4)) != cudaSuccess) return st;
+  if ((st = cudaMalloc((void**)&ws.H1, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
+  cudaDeviceGetAttribute(&ws.sm_count, cudaDevAttrMultiProcessorCount, device);
+  if ((st = cudaFuncSetAttribute(xproj_pair<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<4>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(xproj_pair<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<32>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_rec<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem_bytes())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_rec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem_bytes())) != cudaSuccess) return st;
+  return cudaSuccess;
+}
+
+inline void free_workspace(Workspace& ws) {
+  cudaFree(ws.X16); cudaFree(ws.Gx); cudaFree(ws.H1);
+  ws.X16 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr;
+}
+
+// Both BiLSTM layers for np padded sites (np % 256 == 0): x -> h2 planes [33*256][np] fp32.
+// `hook(id)` brackets every launch for the per-kernel event timing (id: 0 prep, 1 xproj1, 2 rec1, 3 xproj2, 4 rec2).
+template <typename Hook>
+inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_dev, int dtype_is_i16, int64_t n, int64_t np,
+                                float* h2_planes, cudaStream_t st, int* launches, Hook&& hook) {
+  const int NT = (int)(np / 128);
+  const int num_row_pairs = T_STEPS * NT / 2;
+  // persistent input-projection grid: whole groups of 4 CTA pairs (one pair per N-block), one pair per 2 SMs
+  int ncl = (ws.sm_count / 2) / 4 * 4;
+  if (ncl > 4 * num_row_pairs) ncl = 4 * num_row_pairs;
+  if (ncl < 4) ncl = 4;
+  dim3 gprep((unsigned)NT, T_STEPS);
+  hook(0, true);
+  if (dtype_is_i16) prep_tiles<int16_t><<<gprep, 128, 0, st>>>((const int16_t*)x_dev, ws.X16, n, NT);
+  else prep_tiles<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X16, n, NT);
+  hook(0, false);
+  hook(1, true);
+  xproj_pair<4><<<2 * ncl, XP_THREADS, xproj_smem_bytes<4>(), st>>>(ws.X16, w.Wx[0], w.bx[0], ws.Gx, num_row_pairs);
+  hook(1, false);
+  dim3 grec((unsigned)NT, 2);
+  hook(2, true);
+  lstm_rec<0><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[0], ws.Gx, ws.H1, NT, np);
+  hook(2, false);
+  hook(3, true);
+  xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs);
+  hook(3, false);
+  hook(4, true);
+  lstm_rec<1><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, h2_planes, NT, np);
+  hook(4, false);
+  *launches += 5;
+  return cudaGetLastError();
+}
+
+// parity hook: LSTM1 output [33][n][256] fp32 rebuilt from the hi/lo operand tiles
+inline cudaError_t get_lstm1(const Workspace& ws, int64_t n, int64_t np, float* out_host) {
+  const size_t NT = (size_t)np / 128;
+  std::vector<__half> buf((size_t)T_STEPS * NT * 2 * 32 * KCH);
+  cudaError_t st = cudaMemcpy(buf.data(), ws.H1, buf.size() * 2, cudaMemcpyDeviceToHost);
+  if (st != cudaSuccess) return st;
+  for (int t = 0; t < T_STEPS; ++t)
+    for (int64_t s = 0; s < n; ++s) {
+      const size_t base = ((size_t)t * NT + (size_t)(s / 128)) * (2 * 32 * KCH);
+      const int r = (int)(s % 128);
+      for (int f = 0; f < 2 * H; ++f) {
+        const size_t off = (size_t)(f / 8) * KCH + r * 8 + f % 8;
+        out_host[((size_t)t * n + s) * 2 * H + f] =
+            __half2float(buf[base + off]) + __half2float(buf[base + (size_t)32 * KCH + off]);
+      }
+    }
+  return cudaSuccess;
+}
+
+}  // namespace tc
+}  // namespace clairb
