@@ -58,6 +58,7 @@ struct clairb_engine {
   int64_t chunk_np = 0;        // padded sites per chunk
   EngineKind kind = ENGINE_SIMT;
   bool finalized = false;
+  bool fuse_tail = false;      // TC engine: slice-dense + L4 on tensor cores (l3l4_fused)
   std::string err;
   int64_t launches = 0;
 
@@ -160,8 +161,8 @@ SiteMap make_map(const clairb_engine* e, int64_t n) {
 
 // ---- per-kernel event timing --------------------------------------------------------------------
 const char* kKernelNames[] = {"prep_input", "lstm_layer1", "lstm_layer2", "l3_slice_dense", "l4_dense",
-                              "tail_heads", "prep_tiles", "xproj1", "lstm_rec1", "xproj2", "lstm_rec2"};
-constexpr int kNumKernelNames = 11;
+                              "tail_heads", "prep_tiles", "xproj1", "lstm_rec1", "xproj2", "lstm_rec2", "l3l4_fused", "transpose_h2"};
+constexpr int kNumKernelNames = 13;
 
 void prof_fold(clairb_engine* e) {
   for (auto& sp : e->prof_open) {
@@ -208,6 +209,7 @@ struct ProfScope {
 
 // ---- forward on one chunk, all launches on `st` ------------------------------------------------
 int forward_tail(clairb_engine* e, SiteMap sm, float* out_dev, cudaStream_t st);
+int forward_heads(clairb_engine* e, SiteMap sm, float* out_dev, cudaStream_t st);
 
 int forward_simt(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, float* out_dev, cudaStream_t st) {
   const int64_t np = sm.np;
@@ -246,12 +248,19 @@ int forward_tail(clairb_engine* e, SiteMap sm, float* out_dev, cudaStream_t st) 
     simt::l4_dense<<<(unsigned)(np / simt::L4_TM), 256, simt::l4_smem_bytes(), st>>>(e->d_l3T, e->d_W4, e->d_b4,
                                                                                     e->d_l4T, np);
   }
+  e->launches += 2;
+  return forward_heads(e, sm, out_dev, st);
+}
+
+// L5_1..4 -> heads -> softmax from the l4T planes
+int forward_heads(clairb_engine* e, SiteMap sm, float* out_dev, cudaStream_t st) {
+  const int64_t np = sm.np;
   {
     ProfScope ps(e, 5, st);
     simt::tail_heads<<<(unsigned)(np / simt::TL_TM), 256, simt::tail_smem_bytes(), st>>>(
         e->d_l4T, e->d_W5, e->d_b5, e->d_Whd, e->d_bhd, out_dev, e->d_logits, sm);
   }
-  e->launches += 3;
+  e->launches += 1;
   CU_TRY(e, cudaGetLastError());
   return CLAIRB_OK;
 }
@@ -264,9 +273,11 @@ int forward_chunk(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, fl
       if (begin) open = new ProfScope(e, 6 + id, st);
       else { delete open; open = nullptr; }
     };
-    cudaError_t cst = tc::forward_lstm(e->tcw, e->tcws, x_dev, dtype == CLAIRB_DTYPE_I16, sm.n, sm.np, e->d_h2, st, &nl, hook);
+    cudaError_t cst = tc::forward_lstm(e->tcw, e->tcws, x_dev, dtype == CLAIRB_DTYPE_I16, sm.n, sm.np, e->d_h2, e->d_l4T,
+                                       e->fuse_tail, st, &nl, hook);
     e->launches += nl;
     if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "tensor-core forward failed: %s", cudaGetErrorString(cst));
+    if (e->fuse_tail) return forward_heads(e, sm, out_dev, st);
     return forward_tail(e, sm, out_dev, st);
   }
   return forward_simt(e, x_dev, dtype, sm, out_dev, st);
@@ -339,6 +350,10 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
   e->bp = (batch_sites + TILE - 1) / TILE * TILE;
   const char* kind = getenv("CLAIRB_ENGINE");
   e->kind = (kind && !strcmp(kind, "simt")) ? ENGINE_SIMT : (tc::available() ? ENGINE_TC : ENGINE_SIMT);
+  if (e->kind == ENGINE_TC) {
+    const char* ft = getenv("CLAIRB_FUSED_TAIL");
+    e->fuse_tail = !(ft && !strcmp(ft, "0"));
+  }
   int64_t chunk_batches = e->kind == ENGINE_TC ? 37 : 32;   // TC: 145 CTA pairs x 2 directions ~ 3.9 waves of 74 pairs
   if (const char* cb = getenv("CLAIRB_CHUNK_BATCHES")) chunk_batches = atoll(cb) > 0 ? atoll(cb) : chunk_batches;
   int64_t nb_max = (max_sites + batch_sites - 1) / batch_sites;
@@ -498,7 +513,9 @@ int clairb_finalize_weights(clairb_engine* e) {
         hm.lstm_kernel[l][d] = e->hw[lstm_name(l + 1, d, "kernel")].data.data();
         hm.lstm_bias[l][d] = e->hw[lstm_name(l + 1, d, "bias")].data.data();
       }
+    hm.w3 = w3.data(); hm.b3 = b3.data(); hm.W4 = W4->data.data();
     tc::free_weights(e->tcw);
+    e->tcw.b4 = e->d_b4;
     cudaError_t cst = tc::build_weights(e->tcw, hm);
     if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "tensor-core weight upload failed: %s", cudaGetErrorString(cst));
   }
@@ -582,6 +599,16 @@ int clairb_get_layer(clairb_engine* e, int layer, float* out_host, int64_t n) {
     CU_TRY(e, cudaMemcpy(buf.data(), e->d_logits, buf.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int64_t r = 0; r < n; ++r)
       memcpy(out_host + r * N_OUT, buf.data() + sm.padded_row(r) * N_OUT, N_OUT * sizeof(float));
+    return CLAIRB_OK;
+  }
+  if (e->kind == ENGINE_TC && e->fuse_tail && layer == CLAIRB_LAYER_L3) {
+    // the fused path keeps L3 on chip: replay the fused kernel on the retained LSTM2 tiles with the debug sink set
+    cudaError_t cst = tc::dump_l3(e->tcw, e->tcws, sm.np, e->d_l4T, e->d_l3T);
+    if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "get_layer(L3) replay failed: %s", cudaGetErrorString(cst));
+  }
+  if (e->kind == ENGINE_TC && e->fuse_tail && layer == CLAIRB_LAYER_LSTM2) {
+    cudaError_t cst = tc::get_lstm2(e->tcws, n, sm.np, out_host);
+    if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "get_layer failed: %s", cudaGetErrorString(cst));
     return CLAIRB_OK;
   }
   if (e->kind == ENGINE_TC && layer == CLAIRB_LAYER_LSTM1) {

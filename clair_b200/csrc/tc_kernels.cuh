@@ -31,9 +31,40 @@ namespace tc {
 constexpr int KCH = 1024;                      // halves per k-chunk of a 128-row tile: 128 rows x 8
 constexpr int KCH_BYTES = 2048;
 constexpr int GX_TILE_FLOATS = 2 * 128 * 128 * 4;   // per (t, tile): [dir][unit 128][row 128][gate 4]
+constexpr int L3_TG = 5;                                  // time groups of 8 kept per channel (t = 0..39, 33..39 zero)
+constexpr int L3A_HALVES = 2 * L3_TG * 1024;              // per (tile, channel): [hl][tg][16 site groups][8 t][8 sites]
+constexpr int L3A_BYTES = L3A_HALVES * 2;                 // 20480
+// per-channel weight blob of l3l4_fused: W3_c hi|lo ([6 kc][32 o][8 t]) , W4_c hi|lo ([4 kc][192 n][8 o]) , b3_c[32]
+constexpr int L3W_BYTES = 6 * 32 * 16;                    // 3072
+constexpr int L4W_BYTES = 4 * 192 * 16;                   // 12288
+constexpr int L3L4_BLOB_BYTES = 2 * L3W_BYTES + 2 * L4W_BYTES + 128;   // 30848
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+constexpr float LOG2E = 1.4426950408889634f;
+// Gate pre-activations reach the epilogue pre-scaled (the scale is folded into W and b on the host):
+//   pi = -log2e*zi, pg = -2*log2e*zg, pf = -log2e*zf, po = -log2e*zo      so that 2^p = e^-z (resp. e^-2z)
+constexpr float GATE_SCALE[4] = {-LOG2E, -2.f * LOG2E, -LOG2E, -LOG2E};
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// TF LSTMBlockCell (forget_bias 0, no clip, no peephole; model.py:299-305):
+//   c' = tanh(zg)*sigmoid(zi) + c*sigmoid(zf),  h = tanh(c')*sigmoid(zo)
+// written over common denominators: with a=e^-zi, b=e^-2zg, d=e^-zf:
+//   c' = [(1-b)(1+d) + c(1+a)(1+b)] / [(1+a)(1+b)(1+d)]          3 ex2 + 1 rcp
+//   h  = (1-e) / [(1+e)(1+f)],  e=e^-2c', f=e^-zo                 2 ex2 + 1 rcp
+// Exponent arguments are clamped at 2^40 so the denominators stay finite (sigmoid(-27.7) ~ 1e-12).
+__device__ __forceinline__ float lstm_cell(float pi, float pg, float pf, float po, float& c) {
+  const float a = ex2f(fminf(pi, 40.f)), b = ex2f(fminf(pg, 40.f)), d = ex2f(fminf(pf, 40.f));
+  const float A = 1.f + a, B = 1.f + b, D = 1.f + d;
+  const float AB = A * B;
+  const float cn = fmaf(c, AB, (1.f - b) * D) * rcpf(AB * D);
+  c = cn;
+  const float e = ex2f(fminf(cn * (-2.f * LOG2E), 40.f)), f = ex2f(fminf(po, 40.f));
+  return (1.f - e) * rcpf((1.f + e) * (1.f + f));
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
 
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
   float4 r;
@@ -162,6 +193,7 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
   }
   if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
   for (int i = threadIdx.x; i < 256; i += XP_THREADS) bias_s[i] = bias[nb * 256 + i];
+  __syncthreads();                                     // barrier inits visible before anyone polls them
   mbar_wait(b_full, 0);
   tc_fence_before();
   cluster_sync_all();
@@ -203,14 +235,14 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
         uint32_t use = 0, it = 0;
         for (int rp = grp; rp < num_row_pairs; rp += ngrp, ++it) {
           const uint32_t buf = it & 1;
-          mbar_wait_cluster(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+          mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d = tmem + buf * 256;
           for (int ks = 0; ks < NST; ++ks, ++use) {
             const int slot = use % XP_RING;
             const uint32_t par = (use / XP_RING) & 1;
             mbar_wait(&full[slot], par);
-            mbar_wait_cluster(&peer_full[slot], par);
+            mbar_wait(&peer_full[slot], par);
             tc_fence_after();
             const uint32_t a_base = smem_u32(ring + slot * XP_STAGE_BYTES);
 #pragma unroll
@@ -239,7 +271,7 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
     uint32_t it = 0;
     for (int rp = grp; rp < num_row_pairs; rp += ngrp, ++it) {
       const uint32_t buf = it & 1;
-      mbar_wait_cluster(&acc_full[buf], (it >> 1) & 1);
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
       float* out = Gx + ((size_t)rp * 2 + rank) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) +
                    (size_t)unit0 * 512 + r * 4;
@@ -275,7 +307,7 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
 //   OUT == 0: h_t -> A tiles of the next layer's input projection  Hout[(t*NT+tile)][hl][kc 32][128][8] fp16,
 //             direction d fills kc d*16..+16 (model.py:306-312: out[t] = concat(fw_t, bw_t)), moved by the bulk-copy
 //             engine straight from the shared-memory operand tile
-//   OUT == 1: h_t -> fp32 planes  Hout[(t*256 + dir*128 + unit)][np]  (input of the slice-dense kernel)
+//   OUT == 1: h_t -> fp32 planes  Hout[(t*256 + dir*128 + unit)][np]  (input of the CUDA-core slice-dense kernel)
 // Per step the leader's control thread issues 2 x 24 pair-MMAs (gate blocks n = 0,1: 8 k-steps x 3 split terms) and
 // commits each block to both CTAs; the 8 epilogue warps of each CTA turn block 0 into (c,h) while block 1 is still in
 // the tensor pipe, then block 1, write h_t (fp16 hi/lo) back into the operand tile and signal the leader.
@@ -320,6 +352,7 @@ lstm_rec(const __half* __restrict__ Wh, const float* __restrict__ Gx, void* __re
     for (int i = 0; i < REC_W_BYTES; i += 32768) bulk_g2s(Ws + i, src + i, 32768, w_full);
   }
   if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
+  __syncthreads();                                     // barrier inits visible before anyone polls them
   mbar_wait(w_full, 0);
   tc_fence_before();
   cluster_sync_all();
@@ -331,11 +364,22 @@ lstm_rec(const __half* __restrict__ Wh, const float* __restrict__ Gx, void* __re
       // ---- control thread: MMA issue (leader) and h_t write-out (both CTAs) ----
       const uint32_t idesc = make_idesc_f16(256, 256);
       const uint32_t w_base = smem_u32(Ws), h_base = smem_u32(Hs);
+      for (int sp = 0; sp < 2; ++sp) {
+        const int tn = dir ? (T_STEPS - 1 - sp) : sp;
+        const float* g = Gx + ((size_t)tn * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2);
+        for (int i = 0; i < 4; ++i) bulk_prefetch_l2(g + i * 16384, 65536);
+      }
       for (int s = 1; s <= T_STEPS; ++s) {
         // h_{s-1} complete?
-        if (rank == 0) mbar_wait_cluster(h_ready, (s - 1) & 1);
+        if (rank == 0) mbar_wait(h_ready, (s - 1) & 1);
         else mbar_wait(h_local, (s - 1) & 1);
         tc_fence_after();
+        if (s + 1 < T_STEPS) {
+          // pull the Gx tile of step s+1 (256 KB, written by the previous kernel) from HBM into L2
+          const int tn = dir ? (T_STEPS - 2 - s) : (s + 1);
+          const float* g = Gx + ((size_t)tn * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2);
+          for (int i = 0; i < 4; ++i) bulk_prefetch_l2(g + i * 16384, 65536);
+        }
         if (OUT == 0) {
           const int tp = dir ? (T_STEPS - s) : (s - 1);          // time index of step s-1
           __half* dst = (__half*)Hout + ((size_t)tp * NT + tile) * (2 * 32 * KCH) + (size_t)dir * 16 * KCH;
@@ -382,23 +426,38 @@ lstm_rec(const __half* __restrict__ Wh, const float* __restrict__ Gx, void* __re
 #pragma unroll
       for (int i = 0; i < 32; ++i) c[n][i] = 0.f;
 
-    for (int s = 0; s < T_STEPS; ++s) {
+    // Gx of (step s, block n, group g): four float4 (one per hidden unit), prefetched one group ahead
+    auto gx_ptr = [&](int s) {
       const int t = dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
-      const float* gx = Gx + ((size_t)t * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) + r * 4;
+      return Gx + ((size_t)t * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) +
+             (size_t)(colhalf * 32) * 512 + r * 4;
+    };
+    const float* gx = gx_ptr(0);
+    float4 gq[2][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gq[0][k] = ld_stream4(gx + (size_t)k * 512);
+
+    for (int s = 0; s < T_STEPS; ++s) {
+      const int t = dir ? (T_STEPS - 1 - s) : s;
+      const float* gx_next = gx_ptr(s + 1 < T_STEPS ? s + 1 : s);
       uint4 keep_hi[4], keep_lo[4];
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
         const int unit0 = n * 64 + colhalf * 32;
         if (s > 0) {
-          mbar_wait_cluster(&gates_full[n], (s - 1) & 1);
+          mbar_wait(&gates_full[n], (s - 1) & 1);
           tc_fence_after();
         }
         float hv[32];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          float4 gq[4];
+          // prefetch the next group's pre-activations (next block / next step at the boundaries)
+          {
+            const float* nx = g < 7 ? gx + (size_t)(n * 64 + 4 * (g + 1)) * 512
+                                    : (n == 0 ? gx + (size_t)64 * 512 : gx_next);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) gq[k] = ld_stream4(gx + (size_t)(unit0 + 4 * g + k) * 512);
+            for (int k = 0; k < 4; ++k) gq[(g + 1) & 1][k] = ld_stream4(nx + (size_t)k * 512);
+          }
           float v[16];
           if (s > 0) {
             tmem_ld16(taddr + n * 256 + g * 16, v);
@@ -409,11 +468,9 @@ lstm_rec(const __half* __restrict__ Wh, const float* __restrict__ Gx, void* __re
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float zi = v[4 * k] + gq[k].x, zg = v[4 * k + 1] + gq[k].y;
-            const float zf = v[4 * k + 2] + gq[k].z, zo = v[4 * k + 3] + gq[k].w;
-            const float cn = fast_tanh(zg) * fast_sigmoid(zi) + c[n][4 * g + k] * fast_sigmoid(zf);
-            c[n][4 * g + k] = cn;
-            hv[4 * g + k] = fast_tanh(cn) * fast_sigmoid(zo);
+            const float4 q = gq[g & 1][k];
+            hv[4 * g + k] = lstm_cell(v[4 * k] + q.x, v[4 * k + 1] + q.y, v[4 * k + 2] + q.z, v[4 * k + 3] + q.w,
+                                      c[n][4 * g + k]);
           }
         }
         if (OUT == 1) {
@@ -441,6 +498,7 @@ lstm_rec(const __half* __restrict__ Wh, const float* __restrict__ Gx, void* __re
           }
         }
       }
+      gx = gx_next;
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -456,17 +514,253 @@ lstm_rec(const __half* __restrict__ Wh, const float* __restrict__ Gx, void* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// transpose_h2: K-major operand tiles of LSTM2's output  H2[(t*NT+tile)][hl][kc 32][row 128][8 units]
+//            -> MN-major tiles for the slice-dense MMA     H2t[tile][c][hl][t/8 (5)][row/8 (16)][t%8][row%8]
+// (model.py:461 transposes [33,B,256] -> [B,33,256]; here the contraction axis of L3 -- time -- becomes the K axis.)
+// One CTA per (tile, kc, hl, time group of 8): 16 KB in, 16 KB out, both fully coalesced; the 8x8 fp16 transposes run
+// on ldmatrix.trans.  t = 33..39 are written as zeros.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_h2(const __half* __restrict__ H2, __half* __restrict__ H2t, int NT) {
+  __shared__ __align__(128) uint8_t in_s[8 * KCH_BYTES];      // [t%8][row 128][8 units]
+  __shared__ __align__(128) uint8_t out_s[8 * 2048];          // [unit 8][row/8 16][t%8][row%8]
+  const int tile = blockIdx.x, kc = blockIdx.y >> 1, hl = blockIdx.y & 1, tg = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // load: 8 time steps x 2 KB
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + i * 256;                 // 16-byte chunk index, 128 per time step
+    const int tl = idx >> 7, t = tg * 8 + tl;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (t < T_STEPS)
+      v = *reinterpret_cast<const uint4*>(H2 + (((size_t)t * NT + tile) * 2 + hl) * (32 * KCH) + (size_t)kc * KCH + (idx & 127) * 8);
+    reinterpret_cast<uint4*>(in_s)[idx] = v;
+  }
+  __syncthreads();
+  // warp = time step within the group; 4 x ldmatrix.x4.trans cover the 16 row groups
+  {
+    const int tl = warp;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int mg = j * 4 + (lane >> 3);          // lanes 8m..8m+7 give the row addresses of matrix m
+      const uint32_t addr = smem_u32(in_s + tl * KCH_BYTES + (mg * 8 + (lane & 7)) * 16);
+      uint32_t q[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(addr));
+      // lane holds, for unit lane/4, rows 2*(lane%4), +1 of row group j*4+m in q[m]
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        *reinterpret_cast<uint32_t*>(out_s + (lane >> 2) * 2048 + (j * 4 + m) * 128 + tl * 16 + (lane & 3) * 4) = q[m];
+    }
+  }
+  __syncthreads();
+  // store: unit u -> 2 KB run at H2t[tile][kc*8+u][hl][tg]
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + i * 256;
+    const int u = idx >> 7;
+    __half* dst = H2t + ((size_t)tile * 2 * H + kc * 8 + u) * L3A_HALVES + (size_t)hl * (L3A_HALVES / 2) + (size_t)tg * 1024;
+    reinterpret_cast<uint4*>(dst)[idx & 127] = reinterpret_cast<const uint4*>(out_s)[idx];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// l3l4_fused: slice-dense L3 (model.py:225-244, 464-471) chained into dense L4 (model.py:482-488) per 128-site tile.
+//   for every channel c (256):  S_c[128 x 32] = selu(A_c[128 x t] . W3_c[t x o] + b3_c)      (o padded 30 -> 32)
+//                               D4[128 x 192] += S_c . W4[(o,c), :]                          (L4 rows regrouped by channel)
+//   then l4[128 x 192] = selu(D4 + b4) -> planes l4T[192][np] fp32 for the heads kernel.
+// The [B,30,256] -> [B,7680] flatten (model.py:474-478, index o*256+c) never materialises: S_c goes TMEM -> registers ->
+// fp16 hi/lo operand tile in shared memory -> next MMA.  A_c arrives MN-major (K = time) from transpose_h2; the k-group
+// t = 40..47 of the third k-step points at a shared zero block through the descriptor's leading-dimension offset.
+// Warp roles: 0 = producer (one A tile + one weight blob per channel, 3-stage ring), 1 = MMA issuer,
+// 2..9 = epilogue: group g = (warp-2)/4 owns channels c = g mod 2 with its own D3 / S_c buffers.
+// ---------------------------------------------------------------------------------------------
+constexpr int LF_STAGES = 3;
+constexpr int LF_STAGE_BYTES = L3A_BYTES + L3L4_BLOB_BYTES;          // 51328
+constexpr int LF_A4_BYTES = 2 * 4 * KCH_BYTES;                       // [hl][4 kc][128][8] = 16384
+constexpr int LF_THREADS = 320;
+constexpr size_t l3l4_smem_bytes() { return (size_t)LF_STAGES * LF_STAGE_BYTES + 2 * LF_A4_BYTES + 2048 + 256 + 1024; }
+
+__global__ void __launch_bounds__(LF_THREADS, 1)
+l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, const float* __restrict__ b4,
+           float* __restrict__ l4T, int64_t np, float* __restrict__ l3_dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stages = smem;
+  uint8_t* A4 = stages + LF_STAGES * LF_STAGE_BYTES;   // [g 2][hl][4 kc][128][8]
+  uint8_t* zero = A4 + 2 * LF_A4_BYTES;                // 2 KB of zeros (k-group t = 40..47)
+  uint64_t* bars = (uint64_t*)(zero + 2048);
+  uint64_t* stage_full = bars;          // [3]
+  uint64_t* stage_empty = bars + 3;     // [3]
+  uint64_t* d3_full = bars + 6;         // [2]
+  uint64_t* d3_empty = bars + 8;        // [2]
+  uint64_t* a4_full = bars + 10;        // [2]
+  uint64_t* a4_empty = bars + 12;       // [2]
+  uint64_t* d4_full = bars + 14;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LF_STAGES; ++i) { mbar_init(&stage_full[i], 1); mbar_init(&stage_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d3_full[i], 1); mbar_init(&d3_empty[i], 4);
+      mbar_init(&a4_full[i], 4); mbar_init(&a4_empty[i], 1);
+    }
+    mbar_init(d4_full, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2048 / 16; i += LF_THREADS) reinterpret_cast<uint4*>(zero)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;     // cols 0..191: D4, 192..223: D3[0], 224..255: D3[1]
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint8_t* a_src = (const uint8_t*)(H2t + (size_t)tile * 2 * H * L3A_HALVES);
+      for (int c = 0; c < 2 * H; ++c) {
+        const int st = c % LF_STAGES;
+        mbar_wait(&stage_empty[st], ((c / LF_STAGES) & 1) ^ 1);
+        uint8_t* dst = stages + st * LF_STAGE_BYTES;
+        mbar_expect_tx(&stage_full[st], LF_STAGE_BYTES);
+        bulk_g2s(dst, a_src + (size_t)c * L3A_BYTES, L3A_BYTES, &stage_full[st]);
+        bulk_g2s(dst + L3A_BYTES, blobs + (size_t)c * L3L4_BLOB_BYTES, L3L4_BLOB_BYTES, &stage_full[st]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc3 = make_idesc_f16_amn(128, 32);
+      const uint32_t idesc4 = make_idesc_f16(128, 192);
+      const uint32_t zero_addr = smem_u32(zero);
+      auto issue_l4 = [&](int cc) {
+        const int g = cc & 1, use = cc >> 1, st = cc % LF_STAGES;
+        mbar_wait(&a4_full[g], use & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(A4 + g * LF_A4_BYTES);
+        const uint32_t w_base = smem_u32(stages + st * LF_STAGE_BYTES + L3A_BYTES + 2 * L3W_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint64_t a_hi = make_smem_desc(a_base + kk * 2 * KCH_BYTES, KCH_BYTES, 128);
+          const uint64_t a_lo = make_smem_desc(a_base + 4 * KCH_BYTES + kk * 2 * KCH_BYTES, KCH_BYTES, 128);
+          const uint64_t b_hi = make_smem_desc(w_base + kk * 2 * (192 * 16), 192 * 16, 128);
+          const uint64_t b_lo = make_smem_desc(w_base + L4W_BYTES + kk * 2 * (192 * 16), 192 * 16, 128);
+          umma_f16(tmem, a_hi, b_hi, idesc4, (cc | kk) != 0);
+          umma_f16(tmem, a_lo, b_hi, idesc4, 1);
+          umma_f16(tmem, a_hi, b_lo, idesc4, 1);
+        }
+        umma_commit(&a4_empty[g]);
+        umma_commit(&stage_empty[st]);
+      };
+      for (int c = 0; c < 2 * H; ++c) {
+        const int g = c & 1, use = c >> 1, st = c % LF_STAGES;
+        mbar_wait(&stage_full[st], (c / LF_STAGES) & 1);
+        mbar_wait(&d3_empty[g], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(stages + st * LF_STAGE_BYTES);
+        const uint32_t w_base = a_base + L3A_BYTES;
+        const uint32_t d3 = tmem + 192 + g * 32;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          // MN-major A: LBO = distance between the two time groups of this k-step, SBO = site-group stride
+          const uint32_t a_hi_addr = a_base + j * 2 * 2048, a_lo_addr = a_base + L3A_BYTES / 2 + j * 2 * 2048;
+          const uint64_t a_hi = j < 2 ? make_smem_desc(a_hi_addr, 2048, 128) : make_smem_desc(a_hi_addr, zero_addr - a_hi_addr, 128);
+          const uint64_t a_lo = j < 2 ? make_smem_desc(a_lo_addr, 2048, 128) : make_smem_desc(a_lo_addr, zero_addr - a_lo_addr, 128);
+          const uint64_t b_hi = make_smem_desc(w_base + j * 2 * 512, 512, 128);
+          const uint64_t b_lo = make_smem_desc(w_base + L3W_BYTES + j * 2 * 512, 512, 128);
+          umma_f16(d3, a_hi, b_hi, idesc3, j != 0);
+          umma_f16(d3, a_lo, b_hi, idesc3, 1);
+          umma_f16(d3, a_hi, b_lo, idesc3, 1);
+        }
+        umma_commit(&d3_full[g]);
+        if (c >= 1) issue_l4(c - 1);
+      }
+      issue_l4(2 * H - 1);
+      umma_commit(d4_full);
+    }
+    __syncwarp();
+  } else {
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* a4 = A4 + g * LF_A4_BYTES + r * 16;
+    for (int c = g; c < 2 * H; c += 2) {
+      const int use = c >> 1, st = c % LF_STAGES;
+      mbar_wait(&d3_full[g], use & 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld16(lane_addr + 192 + g * 32, v);
+      tmem_ld16(lane_addr + 192 + g * 32 + 16, v + 16);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d3_empty[g]);
+      const float* b3 = reinterpret_cast<const float*>(stages + st * LF_STAGE_BYTES + L3A_BYTES + 2 * L3W_BYTES + 2 * L4W_BYTES);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = v[i] + b3[i];
+        v[i] = x >= 0.f ? SELU_SCALE * x : (SELU_SCALE * SELU_ALPHA) * (__expf(x) - 1.f);
+      }
+      if (l3_dbg != nullptr) {
+        // parity hook only (clairb_get_layer): the [n,30,256] activations the production path never materialises
+#pragma unroll
+        for (int i = 0; i < L3_UNITS; ++i) l3_dbg[((size_t)i * 2 * H + c) * np + (size_t)tile * 128 + r] = v[i];
+      }
+      uint4 hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) split8(v + 8 * q, hi[q], lo[q]);
+      mbar_wait(&a4_empty[g], (use & 1) ^ 1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        *reinterpret_cast<uint4*>(a4 + q * KCH_BYTES) = hi[q];
+        *reinterpret_cast<uint4*>(a4 + 4 * KCH_BYTES + q * KCH_BYTES) = lo[q];
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a4_full[g]);
+    }
+    // ---- L4 epilogue: group g takes columns g*96..+96 ----
+    mbar_wait(d4_full, 0);
+    tc_fence_after();
+    float* out = l4T + (size_t)tile * 128 + r;
+#pragma unroll
+    for (int cb = 0; cb < 96; cb += 16) {
+      const int col0 = g * 96 + cb;
+      float v[16];
+      tmem_ld16(lane_addr + col0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float x = v[i] + __ldg(b4 + col0 + i);
+        out[(size_t)(col0 + i) * np] = x >= 0.f ? SELU_SCALE * x : (SELU_SCALE * SELU_ALPHA) * (__expf(x) - 1.f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 struct HostModel {
   const float* lstm_kernel[2][2];   // [layer][dir] TF layout [(Kx+128)][512], rows x first, columns gate-major i,c,f,o
   const float* lstm_bias[2][2];     // [512]
+  const float* w3;                  // [256][33][30]  (L3/Unit_c/kernel)
+  const float* b3;                  // [256][30]
+  const float* W4;                  // [7680][192], row = o*256 + c
 };
 
 struct Weights {
   __half* Wx[2] = {nullptr, nullptr};      // per layer: [nb 4][q 2][hl][KC][128][8]
   float* bx[2] = {nullptr, nullptr};       // per layer: [nb 4][256]
   __half* Wh[2] = {nullptr, nullptr};      // per layer: [dir][q][hl][n][kc 16][128][8]
+  uint8_t* l3l4 = nullptr;                 // [256] per-channel blobs (L3L4_BLOB_BYTES each)
+  const float* b4 = nullptr;               // [192] (owned by the engine)
 };
 
 struct Workspace {
@@ -474,6 +768,8 @@ struct Workspace {
   __half* X16 = nullptr;     // [33*NT][hl][4][128][8]
   float* Gx = nullptr;       // [33*NT][dir][unit][row][4]
   __half* H1 = nullptr;      // [33*NT][hl][32][128][8]
+  __half* H2 = nullptr;      // [33*NT][hl][32][128][8]      LSTM2 output, same tile format as H1
+  __half* H2t = nullptr;     // [NT][256][hl][5][16][8][8]   the same, MN-major per channel (t = 33..39 zero)
   int sm_count = 148;
 };
 
@@ -499,14 +795,15 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
       const float* B = hm.lstm_bias[l][dir];
       for (int half = 0; half < 2; ++half) {
         const int nb = dir * 2 + half;
-        for (int c = 0; c < 256; ++c) bx[(size_t)nb * 256 + c] = B[tf_col(half * 256 + c)];
+        for (int c = 0; c < 256; ++c) bx[(size_t)nb * 256 + c] = B[tf_col(half * 256 + c)] * GATE_SCALE[c & 3];
         for (int q = 0; q < 2; ++q)
           for (int row = 0; row < 128; ++row) {
             const int col = tf_col(half * 256 + q * 128 + row);
+            const float gs = GATE_SCALE[row & 3];                 // fold the exp2 scaling of this gate into W
             // input projection rows (x first in the TF kernel)
             for (int k = 0; k < kx[l]; ++k) {
               __half hi, lo;
-              split_half(K[(size_t)k * G4 + col], hi, lo);
+              split_half(K[(size_t)k * G4 + col] * gs, hi, lo);
               const size_t base = (((size_t)nb * 2 + q) * 2) * KC * KCH + (size_t)(k / 8) * KCH + row * 8 + k % 8;
               wx[base] = hi;
               wx[base + (size_t)KC * KCH] = lo;
@@ -514,7 +811,7 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
             // recurrent rows: block n == half
             for (int k = 0; k < H; ++k) {
               __half hi, lo;
-              split_half(K[(size_t)(kx[l] + k) * G4 + col], hi, lo);
+              split_half(K[(size_t)(kx[l] + k) * G4 + col] * gs, hi, lo);
               const size_t cta = ((size_t)dir * 2 + q) * (2 * 2 * 16 * KCH);
               const size_t off = (size_t)half * 16 * KCH + (size_t)(k / 8) * KCH + row * 8 + k % 8;
               wh[cta + off] = hi;
@@ -531,10 +828,39 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
     if ((st = cudaMemcpy(w.bx[l], bx.data(), bx.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
     if ((st = cudaMemcpy(w.Wh[l], wh.data(), wh.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
   }
+  // ---- slice-dense + L4 blobs ----
+  {
+    std::vector<uint8_t> blob((size_t)2 * H * L3L4_BLOB_BYTES, 0);
+    for (int c = 0; c < 2 * H; ++c) {
+      uint8_t* b = blob.data() + (size_t)c * L3L4_BLOB_BYTES;
+      __half* w3hi = (__half*)b;
+      __half* w3lo = (__half*)(b + L3W_BYTES);
+      __half* w4hi = (__half*)(b + 2 * L3W_BYTES);
+      __half* w4lo = (__half*)(b + 2 * L3W_BYTES + L4W_BYTES);
+      float* bb = (float*)(b + 2 * L3W_BYTES + 2 * L4W_BYTES);
+      for (int t = 0; t < T_STEPS; ++t)
+        for (int o = 0; o < L3_UNITS; ++o) {
+          const size_t idx = (size_t)(t / 8) * 32 * 8 + o * 8 + t % 8;
+          split_half(hm.w3[((size_t)c * T_STEPS + t) * L3_UNITS + o], w3hi[idx], w3lo[idx]);
+        }
+      for (int o = 0; o < L3_UNITS; ++o) {
+        bb[o] = hm.b3[(size_t)c * L3_UNITS + o];
+        for (int n = 0; n < L4_UNITS; ++n) {
+          const size_t idx = (size_t)(o / 8) * 192 * 8 + n * 8 + o % 8;
+          split_half(hm.W4[((size_t)o * 2 * H + c) * L4_UNITS + n], w4hi[idx], w4lo[idx]);
+        }
+      }
+    }
+    cudaError_t st;
+    if ((st = cudaMalloc((void**)&w.l3l4, blob.size())) != cudaSuccess) return st;
+    if ((st = cudaMemcpy(w.l3l4, blob.data(), blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return st;
+  }
   return cudaSuccess;
 }
 
 inline void free_weights(Weights& w) {
+  cudaFree(w.l3l4);
+  w.l3l4 = nullptr;
   for (int l = 0; l < 2; ++l) {
     cudaFree(w.Wx[l]); cudaFree(w.bx[l]); cudaFree(w.Wh[l]);
     w.Wx[l] = nullptr; w.bx[l] = nullptr; w.Wh[l] = nullptr;
@@ -548,24 +874,30 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
   if ((st = cudaMalloc((void**)&ws.X16, (size_t)T_STEPS * NT * 2 * 4 * KCH * 2)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.Gx, (size_t)T_STEPS * NT * GX_TILE_FLOATS * 4)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H1, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
+  if ((st = cudaMalloc((void**)&ws.H2, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
+  if ((st = cudaMalloc((void**)&ws.H2t, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
   cudaDeviceGetAttribute(&ws.sm_count, cudaDevAttrMultiProcessorCount, device);
   if ((st = cudaFuncSetAttribute(xproj_pair<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<4>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(xproj_pair<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<32>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_rec<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem_bytes())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_rec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem_bytes())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(l3l4_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3l4_smem_bytes())) != cudaSuccess) return st;
   return cudaSuccess;
 }
 
 inline void free_workspace(Workspace& ws) {
-  cudaFree(ws.X16); cudaFree(ws.Gx); cudaFree(ws.H1);
-  ws.X16 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr;
+  cudaFree(ws.X16); cudaFree(ws.Gx); cudaFree(ws.H1); cudaFree(ws.H2); cudaFree(ws.H2t);
+  ws.X16 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr; ws.H2 = nullptr; ws.H2t = nullptr;
 }
 
-// Both BiLSTM layers for np padded sites (np % 256 == 0): x -> h2 planes [33*256][np] fp32.
-// `hook(id)` brackets every launch for the per-kernel event timing (id: 0 prep, 1 xproj1, 2 rec1, 3 xproj2, 4 rec2).
+// Both BiLSTM layers for np padded sites (np % 256 == 0).
+//   fuse_tail = false: x -> h2 planes [33*256][np] fp32 (CUDA-core slice-dense / L4 follow)
+//   fuse_tail = true : x -> l4T planes [192][np] fp32 through transpose_h2 + l3l4_fused
+// `hook(id)` brackets every launch for the per-kernel event timing
+// (id: 0 prep, 1 xproj1, 2 rec1, 3 xproj2, 4 rec2, 5 l3l4_fused, 6 transpose_h2).
 template <typename Hook>
 inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_dev, int dtype_is_i16, int64_t n, int64_t np,
-                                float* h2_planes, cudaStream_t st, int* launches, Hook&& hook) {
+                                float* h2_planes, float* l4T, bool fuse_tail, cudaStream_t st, int* launches, Hook&& hook) {
   const int NT = (int)(np / 128);
   const int num_row_pairs = T_STEPS * NT / 2;
   // persistent input-projection grid: whole groups of 4 CTA pairs (one pair per N-block), one pair per 2 SMs
@@ -588,9 +920,20 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs);
   hook(3, false);
   hook(4, true);
-  lstm_rec<1><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, h2_planes, NT, np);
+  if (fuse_tail) lstm_rec<0><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, ws.H2, NT, np);
+  else lstm_rec<1><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, h2_planes, NT, np);
   hook(4, false);
   *launches += 5;
+  if (fuse_tail) {
+    hook(6, true);
+    transpose_h2<<<dim3((unsigned)NT, 64, L3_TG), 256, 0, st>>>(ws.H2, ws.H2t, NT);
+    hook(6, false);
+    *launches += 1;
+    hook(5, true);
+    l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, np, nullptr);
+    hook(5, false);
+    *launches += 1;
+  }
   return cudaGetLastError();
 }
 
@@ -608,6 +951,32 @@ inline cudaError_t get_lstm1(const Workspace& ws, int64_t n, int64_t np, float* 
         const size_t off = (size_t)(f / 8) * KCH + r * 8 + f % 8;
         out_host[((size_t)t * n + s) * 2 * H + f] =
             __half2float(buf[base + off]) + __half2float(buf[base + (size_t)32 * KCH + off]);
+      }
+    }
+  return cudaSuccess;
+}
+
+// parity hook: re-run the fused slice-dense on the retained H2t with the L3 activations written out as planes
+inline cudaError_t dump_l3(const Weights& w, const Workspace& ws, int64_t np, float* l4T, float* l3_planes) {
+  l3l4_fused<<<(unsigned)(np / 128), LF_THREADS, l3l4_smem_bytes(), 0>>>(ws.H2t, w.l3l4, w.b4, l4T, np, l3_planes);
+  cudaError_t st = cudaGetLastError();
+  return st != cudaSuccess ? st : cudaDeviceSynchronize();
+}
+
+// parity hook: LSTM2 output [33][n][256] fp32 rebuilt from the MN-major hi/lo tiles
+inline cudaError_t get_lstm2(const Workspace& ws, int64_t n, int64_t np, float* out_host) {
+  const size_t NT = (size_t)np / 128;
+  std::vector<__half> buf(NT * 2 * H * (size_t)L3A_HALVES);
+  cudaError_t st = cudaMemcpy(buf.data(), ws.H2t, buf.size() * 2, cudaMemcpyDeviceToHost);
+  if (st != cudaSuccess) return st;
+  for (int t = 0; t < T_STEPS; ++t)
+    for (int64_t s = 0; s < n; ++s) {
+      const int r = (int)(s % 128);
+      for (int f = 0; f < 2 * H; ++f) {
+        const size_t base = ((size_t)(s / 128) * 2 * H + f) * L3A_HALVES;
+        const size_t off = (size_t)(t >> 3) * 1024 + (r >> 3) * 64 + (t & 7) * 8 + (r & 7);
+        out_host[((size_t)t * n + s) * 2 * H + f] =
+            __half2float(buf[base + off]) + __half2float(buf[base + L3A_HALVES / 2 + off]);
       }
     }
   return cudaSuccess;
