@@ -19,6 +19,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -514,6 +516,310 @@ lstm_rec(const __half* __restrict__ Wh, const float* __restrict__ Gx, void* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// lstm_seq<FUSE_X, OUT>: second-generation recurrent kernel.  Differences from lstm_rec:
+//   * h_t never touches shared memory: the epilogue packs it to fp16 hi/lo and writes it with tcgen05.st into
+//     tensor memory, from where the next step's MMAs read it as the A operand (".ts" form).  Two h buffers
+//     (2 x 128 columns) + two 128-column gate accumulators fill the 512 TMEM columns.
+//   * a step is four gate blocks of 32 hidden units (N = 128 per pair); the accumulators ping-pong, so block b+1 is in
+//     the tensor pipe while the epilogue turns block b into (c, h); nothing has to be parked in registers.
+//   * FUSE_X (layer 1): the input projection x_t . W_x + b runs inside the kernel (K = 32 + 16: x_t, then two
+//     constant-one columns that pick up the bias hi/lo rows of W_x), so Gx of layer 1 never exists in HBM.
+//     x_t tiles arrive through a 2-stage bulk-copy ring.  !FUSE_X (layer 2): Gx (from xproj_pair) is added in the
+//     epilogue, L2-prefetched two steps ahead and register double-buffered.
+//   * h_t leaves for the next layer straight from registers: 16-byte stores, 512 contiguous bytes per warp.
+//   Wh   : [dir][q][hl][b 4][kc 16][64 rows][8]  (row r of CTA q, block b = gate column b*128 + q*64 + r)
+//   Wx   : [dir][q][hl][b 4][kc 6][64 rows][8]   (FUSE_X only; k = 32, 33 hold bias hi / lo)
+//   X48  : [(t*NT+tile)][hl][kc 6][128][8]       (FUSE_X only; k = 32, 33 are 1.0)
+// Warps: 0 = MMA issuer (leader CTA), 1..8 = epilogue, 9 = x_t ring (FUSE_X).
+// ---------------------------------------------------------------------------------------------
+constexpr int SEQ_THREADS = 320;
+constexpr int SEQ_W_BYTES = 2 * 4 * 16 * 1024;          // 131072
+constexpr int SEQ_WX_BYTES = 2 * 4 * 6 * 1024;          // 49152
+constexpr int SEQ_X_STAGE = 2 * 6 * KCH_BYTES;          // 24576
+constexpr int X48_TILE_HALVES = 2 * 6 * KCH;
+template <bool FUSE_X>
+constexpr size_t seq_smem_bytes() {
+  return (size_t)SEQ_W_BYTES + (FUSE_X ? SEQ_WX_BYTES + 2 * SEQ_X_STAGE : 0) + 256 + 1024;
+}
+
+template <bool FUSE_X, int OUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SEQ_THREADS, 1)
+lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __half* __restrict__ X48,
+         const float* __restrict__ Gx, void* __restrict__ Hout, int NT, int64_t np) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* Ws = smem;                                            // [hl][b][kc 16][64][8]
+  uint8_t* Wxs = smem + SEQ_W_BYTES;                             // [hl][b][kc 6][64][8]
+  uint8_t* Xs = Wxs + (FUSE_X ? SEQ_WX_BYTES : 0);               // [2 stages][hl][kc 6][128][8]
+  uint64_t* bars = (uint64_t*)(Xs + (FUSE_X ? 2 * SEQ_X_STAGE : 0));
+  uint64_t* acc_full = bars;           // [2] gate block complete (MMA commit, both CTAs)
+  uint64_t* acc_empty = bars + 2;      // [2] (leader) accumulator drained by all 16 epilogue warps of the pair
+  uint64_t* h_ready = bars + 4;        // (leader) h_t of both CTAs is in tensor memory
+  uint64_t* x_full = bars + 5;         // [2] this CTA's x_t tile landed
+  uint64_t* x_peer = bars + 7;         // [2] (leader) the peer's x_t tile landed
+  uint64_t* x_empty = bars + 9;        // [2] x_t tile consumed (MMA commit, both CTAs)
+  uint64_t* w_full = bars + 11;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int dir = blockIdx.y;
+  const int tile = blockIdx.x;                                   // = 2*pair + rank
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 16);
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_peer[i], 1);
+      mbar_init(&x_empty[i], 1);
+    }
+    mbar_init(h_ready, 16);
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+    const uint8_t* src = (const uint8_t*)Wh + ((size_t)dir * 2 + rank) * SEQ_W_BYTES;
+    mbar_expect_tx(w_full, SEQ_W_BYTES + (FUSE_X ? SEQ_WX_BYTES : 0));
+    for (int i = 0; i < SEQ_W_BYTES; i += 32768) bulk_g2s(Ws + i, src + i, 32768, w_full);
+    if (FUSE_X) {
+      const uint8_t* sx = (const uint8_t*)Wx + ((size_t)dir * 2 + rank) * SEQ_WX_BYTES;
+      for (int i = 0; i < SEQ_WX_BYTES; i += 16384) bulk_g2s(Wxs + i, sx + i, 16384, w_full);
+    }
+  }
+  if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
+  __syncthreads();                                     // barrier inits visible before anyone polls them
+  mbar_wait(w_full, 0);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;    // cols 0..127 acc0, 128..255 acc1, 256..383 h buffer 0 (hi 64 | lo 64), 384..511 h buffer 1
+
+  if (warp == 0) {
+    if (lane == 0 && rank == 0) {
+      // ---- MMA issuer ----
+      const uint32_t idesc = make_idesc_f16(256, 128);
+      const uint32_t w_base = smem_u32(Ws), wx_base = smem_u32(Wxs);
+      uint32_t use0 = 0, use1 = 0;
+      for (int s = 0; s < T_STEPS; ++s) {
+        if (!FUSE_X && s == 0) continue;               // h_{-1} = 0 and no x part: nothing to accumulate
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = b & 1;
+          uint32_t& use = i ? use1 : use0;
+          mbar_wait(&acc_empty[i], (use & 1) ^ 1);
+          ++use;
+          tc_fence_after();
+          const uint32_t d = tmem + i * 128;
+          if (FUSE_X) {
+            const int st = s & 1;
+            if (b == 0) {
+              mbar_wait(&x_full[st], (s >> 1) & 1);
+              mbar_wait(&x_peer[st], (s >> 1) & 1);
+              tc_fence_after();
+            }
+            const uint32_t x_base = smem_u32(Xs + st * SEQ_X_STAGE);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const uint64_t a_hi = make_smem_desc(x_base + j * 2 * KCH_BYTES, KCH_BYTES, 128);
+              const uint64_t a_lo = make_smem_desc(x_base + 6 * KCH_BYTES + j * 2 * KCH_BYTES, KCH_BYTES, 128);
+              const uint32_t bo = b * 6 * 1024 + j * 2 * 1024;
+              const uint64_t b_hi = make_smem_desc(wx_base + bo, 1024, 128);
+              const uint64_t b_lo = make_smem_desc(wx_base + 4 * 6 * 1024 + bo, 1024, 128);
+              umma_f16_pair(d, a_hi, b_hi, idesc, j != 0);
+              umma_f16_pair(d, a_lo, b_hi, idesc, 1);
+              umma_f16_pair(d, a_hi, b_lo, idesc, 1);
+            }
+          }
+          if (s > 0) {
+            if (b == 0) {
+              mbar_wait(h_ready, (s - 1) & 1);
+              tc_fence_after();
+            }
+            const uint32_t h_hi = tmem + 256 + ((s - 1) & 1) * 128, h_lo = h_hi + 64;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t bo = b * 16 * 1024 + j * 2 * 1024;
+              const uint64_t b_hi = make_smem_desc(w_base + bo, 1024, 128);
+              const uint64_t b_lo = make_smem_desc(w_base + 4 * 16 * 1024 + bo, 1024, 128);
+              umma_f16_pair_ts(d, h_hi + j * 8, b_hi, idesc, (FUSE_X || j != 0) ? 1u : 0u);
+              umma_f16_pair_ts(d, h_lo + j * 8, b_hi, idesc, 1);
+              umma_f16_pair_ts(d, h_hi + j * 8, b_lo, idesc, 1);
+            }
+          }
+          umma_commit_pair(&acc_full[i], 0b11);
+        }
+        if (FUSE_X) umma_commit_pair(&x_empty[s & 1], 0b11);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    if (lane == 0) {
+      if (FUSE_X) {
+        // ---- x_t ring: each CTA loads its own 128 rows; the peer tells the leader when its tile has landed ----
+        for (int s = 0; s < T_STEPS; ++s) {
+          const int st = s & 1, t = dir ? (T_STEPS - 1 - s) : s;
+          mbar_wait(&x_empty[st], ((s >> 1) & 1) ^ 1);
+          mbar_expect_tx(&x_full[st], SEQ_X_STAGE);
+          bulk_g2s(Xs + st * SEQ_X_STAGE, X48 + ((size_t)t * NT + tile) * X48_TILE_HALVES, SEQ_X_STAGE, &x_full[st]);
+          if (rank == 1) {
+            mbar_wait(&x_full[st], (s >> 1) & 1);
+            mbar_arrive_cluster(map_to_cta(smem_u32(&x_peer[st]), 0));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue warps ----
+    const int ew = warp - 1;
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+    const int half = ew >> 2;                          // which 16 of the 32 hidden units of a gate block
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t leader_h_ready = map_to_cta(smem_u32(h_ready), 0);
+    const uint32_t leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
+    const uint32_t leader_acc_empty1 = map_to_cta(smem_u32(&acc_empty[1]), 0);
+    float c[4][16];
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) c[b][i] = 0.f;
+
+    auto gx_ptr = [&](int s) {
+      const int t = dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
+      return Gx + ((size_t)t * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) + (size_t)(half * 16) * 512 + r * 4;
+    };
+    const float* gx = FUSE_X ? nullptr : gx_ptr(0);
+    float4 gq[2][4];
+    if (!FUSE_X) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gq[0][k] = ld_stream4(gx + (size_t)k * 512);
+    }
+    uint32_t use0 = 0, use1 = 0;
+    // Gx tiles (written by xproj_pair, HBM-resident) are pulled into L2 two steps ahead, paced by the step loop
+    auto prefetch_gx = [&](int sp) {
+      const int tp = dir ? (T_STEPS - 1 - sp) : sp;
+      const float* g = Gx + ((size_t)tp * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2);
+      for (int i = 0; i < 4; ++i) bulk_prefetch_l2(g + i * 16384, 65536);
+    };
+    if (!FUSE_X && ew == 0 && lane == 0) {
+      prefetch_gx(0);
+      prefetch_gx(1);
+    }
+
+    for (int s = 0; s < T_STEPS; ++s) {
+      const int t = dir ? (T_STEPS - 1 - s) : s;
+      const float* gx_next = FUSE_X ? nullptr : gx_ptr(s + 1 < T_STEPS ? s + 1 : s);
+      const bool have_acc = FUSE_X || s > 0;
+      if (!FUSE_X && ew == 0 && lane == 0 && s + 2 < T_STEPS) prefetch_gx(s + 2);
+      const uint32_t h_st = lane_base + 256 + (s & 1) * 128;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = b & 1;
+        if (have_acc) {
+          uint32_t& use = i ? use1 : use0;
+          mbar_wait(&acc_full[i], use & 1);
+          ++use;
+          tc_fence_after();
+        }
+        float hv[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (!FUSE_X) {
+            // prefetch the next group's pre-activations (next block / next step at the boundaries)
+            const float* nx = g < 3 ? gx + (size_t)(b * 32 + 4 * (g + 1)) * 512
+                                    : (b < 3 ? gx + (size_t)((b + 1) * 32) * 512 : gx_next);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gq[(g + 1) & 1][k] = ld_stream4(nx + (size_t)k * 512);
+          }
+          float v[16];
+          if (have_acc) {
+            tmem_ld16(lane_base + i * 128 + half * 64 + g * 16, v);
+            tmem_ld_wait();
+            if (g == 3) {
+              // the accumulator is fully in registers: hand it back to the MMA issuer
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(i ? leader_acc_empty1 : leader_acc_empty0);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float pi = v[4 * k], pg = v[4 * k + 1], pf = v[4 * k + 2], po = v[4 * k + 3];
+            if (!FUSE_X) {
+              const float4 q = gq[g & 1][k];
+              pi += q.x; pg += q.y; pf += q.z; po += q.w;
+            }
+            hv[4 * g + k] = lstm_cell(pi, pg, pf, po, c[b][4 * g + k]);
+          }
+        }
+        // h_t of these 16 units: fp16 hi/lo words (two units per word), to tensor memory and to the next layer
+        uint4 hi[2], lo[2];
+        split8(hv, hi[0], lo[0]);
+        split8(hv + 8, hi[1], lo[1]);
+        {
+          const uint32_t col = (uint32_t)(b * 32 + half * 16) >> 1;
+          const uint32_t whi[8] = {hi[0].x, hi[0].y, hi[0].z, hi[0].w, hi[1].x, hi[1].y, hi[1].z, hi[1].w};
+          const uint32_t wlo[8] = {lo[0].x, lo[0].y, lo[0].z, lo[0].w, lo[1].x, lo[1].y, lo[1].z, lo[1].w};
+          tmem_st8(h_st + col, whi);
+          tmem_st8(h_st + 64 + col, wlo);
+        }
+        if (OUT == 0) {
+          __half* out = (__half*)Hout + ((size_t)t * NT + tile) * (2 * 32 * KCH) + (size_t)(dir * 16 + b * 4 + half * 2) * KCH + r * 8;
+          *reinterpret_cast<uint4*>(out) = hi[0];
+          *reinterpret_cast<uint4*>(out + KCH) = hi[1];
+          *reinterpret_cast<uint4*>(out + 32 * KCH) = lo[0];
+          *reinterpret_cast<uint4*>(out + 33 * KCH) = lo[1];
+        } else {
+          float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + b * 32 + half * 16) * np + (size_t)tile * 128 + r;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) out[(size_t)k * np] = hv[k];
+        }
+      }
+      gx = gx_next;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_h_ready);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
+// prep for the fused layer-1 kernel: like prep_tiles but K = 48 (k = 32, 33 are the constant-one bias columns)
+template <typename TIn>
+__global__ void __launch_bounds__(128) prep_tiles48(const TIn* __restrict__ x, __half* __restrict__ X48, int64_t n, int NT) {
+  const int tile = blockIdx.x, t = blockIdx.y, r = threadIdx.x;
+  const int64_t site = (int64_t)tile * 128 + r;
+  float v[32];
+  if (site < n) {
+    const TIn* src = x + site * SITE_ELEMS + t * F_IN;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (float)src[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  }
+  __half* base = X48 + ((size_t)t * NT + tile) * X48_TILE_HALVES;
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    uint4 hi, lo;
+    split8(v + 8 * kc, hi, lo);
+    *reinterpret_cast<uint4*>(base + kc * KCH + r * 8) = hi;
+    *reinterpret_cast<uint4*>(base + 6 * KCH + kc * KCH + r * 8) = lo;
+  }
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  *reinterpret_cast<uint4*>(base + 4 * KCH + r * 8) = make_uint4(0x3C003C00u, 0, 0, 0);     // k = 32, 33: fp16 1.0
+  *reinterpret_cast<uint4*>(base + 5 * KCH + r * 8) = zero;
+  *reinterpret_cast<uint4*>(base + 10 * KCH + r * 8) = zero;
+  *reinterpret_cast<uint4*>(base + 11 * KCH + r * 8) = zero;
+}
+
+// ---------------------------------------------------------------------------------------------
 // transpose_h2: K-major operand tiles of LSTM2's output  H2[(t*NT+tile)][hl][kc 32][row 128][8 units]
 //            -> MN-major tiles for the slice-dense MMA     H2t[tile][c][hl][t/8 (5)][row/8 (16)][t%8][row%8]
 // (model.py:461 transposes [33,B,256] -> [B,33,256]; here the contraction axis of L3 -- time -- becomes the K axis.)
@@ -759,6 +1065,8 @@ struct Weights {
   __half* Wx[2] = {nullptr, nullptr};      // per layer: [nb 4][q 2][hl][KC][128][8]
   float* bx[2] = {nullptr, nullptr};       // per layer: [nb 4][256]
   __half* Wh[2] = {nullptr, nullptr};      // per layer: [dir][q][hl][n][kc 16][128][8]
+  __half* Whs[2] = {nullptr, nullptr};     // lstm_seq, per layer: [dir][q][hl][b 4][kc 16][64][8]
+  __half* Wxf = nullptr;                   // lstm_seq<FUSE_X>, layer 1: [dir][q][hl][b 4][kc 6][64][8] (k 32,33 = bias hi,lo)
   uint8_t* l3l4 = nullptr;                 // [256] per-channel blobs (L3L4_BLOB_BYTES each)
   const float* b4 = nullptr;               // [192] (owned by the engine)
 };
@@ -767,7 +1075,9 @@ struct Workspace {
   int64_t np_max = 0;
   __half* X16 = nullptr;     // [33*NT][hl][4][128][8]
   float* Gx = nullptr;       // [33*NT][dir][unit][row][4]
+  __half* X48 = nullptr;     // [33*NT][hl][6][128][8]      layer-1 input tiles with the bias columns (lstm_seq<FUSE_X>)
   __half* H1 = nullptr;      // [33*NT][hl][32][128][8]
+  bool use_seq = true;       // second-generation recurrent kernel (h in tensor memory, fused layer-1 projection)
   __half* H2 = nullptr;      // [33*NT][hl][32][128][8]      LSTM2 output, same tile format as H1
   __half* H2t = nullptr;     // [NT][256][hl][5][16][8][8]   the same, MN-major per channel (t = 33..39 zero)
   int sm_count = 148;
@@ -828,6 +1138,53 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
     if ((st = cudaMemcpy(w.bx[l], bx.data(), bx.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
     if ((st = cudaMemcpy(w.Wh[l], wh.data(), wh.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
   }
+  // ---- lstm_seq layouts: gate blocks of 128 columns, 64 rows per CTA ----
+  for (int l = 0; l < 2; ++l) {
+    std::vector<__half> whs((size_t)2 * 2 * 2 * 4 * 16 * 512);
+    std::vector<__half> wxf(l == 0 ? (size_t)2 * 2 * 2 * 4 * 6 * 512 : 0, __float2half_rn(0.f));
+    for (int dir = 0; dir < 2; ++dir) {
+      const float* K = hm.lstm_kernel[l][dir];
+      const float* B = hm.lstm_bias[l][dir];
+      for (int q = 0; q < 2; ++q)
+        for (int b = 0; b < 4; ++b)
+          for (int row = 0; row < 64; ++row) {
+            const int col = tf_col(b * 128 + q * 64 + row);
+            const float gs = GATE_SCALE[row & 3];
+            const size_t cta = ((size_t)dir * 2 + q);
+            for (int k = 0; k < H; ++k) {
+              __half hi, lo;
+              split_half(K[(size_t)(kx[l] + k) * G4 + col] * gs, hi, lo);
+              const size_t off = cta * (2 * 4 * 16 * 512) + ((size_t)b * 16 + k / 8) * 512 + row * 8 + k % 8;
+              whs[off] = hi;
+              whs[off + (size_t)4 * 16 * 512] = lo;
+            }
+            if (l == 0) {
+              for (int k = 0; k < F_IN + 2; ++k) {
+                __half hi, lo;
+                if (k < F_IN) {
+                  split_half(K[(size_t)k * G4 + col] * gs, hi, lo);
+                } else {
+                  // bias rides on two constant-one input columns: row 32 = fp16(b), row 33 = fp16(b - fp16(b))
+                  __half bh, bl;
+                  split_half(B[col] * gs, bh, bl);
+                  hi = k == F_IN ? bh : bl;
+                  lo = __float2half_rn(0.f);
+                }
+                const size_t off = cta * (2 * 4 * 6 * 512) + ((size_t)b * 6 + k / 8) * 512 + row * 8 + k % 8;
+                wxf[off] = hi;
+                wxf[off + (size_t)4 * 6 * 512] = lo;
+              }
+            }
+          }
+    }
+    cudaError_t st;
+    if ((st = cudaMalloc((void**)&w.Whs[l], whs.size() * 2)) != cudaSuccess) return st;
+    if ((st = cudaMemcpy(w.Whs[l], whs.data(), whs.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
+    if (l == 0) {
+      if ((st = cudaMalloc((void**)&w.Wxf, wxf.size() * 2)) != cudaSuccess) return st;
+      if ((st = cudaMemcpy(w.Wxf, wxf.data(), wxf.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
+    }
+  }
   // ---- slice-dense + L4 blobs ----
   {
     std::vector<uint8_t> blob((size_t)2 * H * L3L4_BLOB_BYTES, 0);
@@ -859,8 +1216,8 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
 }
 
 inline void free_weights(Weights& w) {
-  cudaFree(w.l3l4);
-  w.l3l4 = nullptr;
+  cudaFree(w.l3l4); cudaFree(w.Wxf); cudaFree(w.Whs[0]); cudaFree(w.Whs[1]);
+  w.l3l4 = nullptr; w.Wxf = nullptr; w.Whs[0] = w.Whs[1] = nullptr;
   for (int l = 0; l < 2; ++l) {
     cudaFree(w.Wx[l]); cudaFree(w.bx[l]); cudaFree(w.Wh[l]);
     w.Wx[l] = nullptr; w.bx[l] = nullptr; w.Wh[l] = nullptr;
@@ -874,6 +1231,11 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
   if ((st = cudaMalloc((void**)&ws.X16, (size_t)T_STEPS * NT * 2 * 4 * KCH * 2)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.Gx, (size_t)T_STEPS * NT * GX_TILE_FLOATS * 4)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H1, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
+  if ((st = cudaMalloc((void**)&ws.X48, (size_t)T_STEPS * NT * X48_TILE_HALVES * 2)) != cudaSuccess) return st;
+  if (const char* rk = getenv("CLAIRB_REC")) ws.use_seq = strcmp(rk, "v1") != 0;
+  if ((st = cudaFuncSetAttribute(lstm_seq<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H2, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H2t, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
   cudaDeviceGetAttribute(&ws.sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -886,8 +1248,8 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
 }
 
 inline void free_workspace(Workspace& ws) {
-  cudaFree(ws.X16); cudaFree(ws.Gx); cudaFree(ws.H1); cudaFree(ws.H2); cudaFree(ws.H2t);
-  ws.X16 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr; ws.H2 = nullptr; ws.H2t = nullptr;
+  cudaFree(ws.X16); cudaFree(ws.Gx); cudaFree(ws.H1); cudaFree(ws.H2); cudaFree(ws.H2t); cudaFree(ws.X48);
+  ws.X16 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr; ws.H2 = nullptr; ws.H2t = nullptr; ws.X48 = nullptr;
 }
 
 // Both BiLSTM layers for np padded sites (np % 256 == 0).
@@ -905,25 +1267,44 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   if (ncl > 4 * num_row_pairs) ncl = 4 * num_row_pairs;
   if (ncl < 4) ncl = 4;
   dim3 gprep((unsigned)NT, T_STEPS);
-  hook(0, true);
-  if (dtype_is_i16) prep_tiles<int16_t><<<gprep, 128, 0, st>>>((const int16_t*)x_dev, ws.X16, n, NT);
-  else prep_tiles<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X16, n, NT);
-  hook(0, false);
-  hook(1, true);
-  xproj_pair<4><<<2 * ncl, XP_THREADS, xproj_smem_bytes<4>(), st>>>(ws.X16, w.Wx[0], w.bx[0], ws.Gx, num_row_pairs);
-  hook(1, false);
   dim3 grec((unsigned)NT, 2);
-  hook(2, true);
-  lstm_rec<0><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[0], ws.Gx, ws.H1, NT, np);
-  hook(2, false);
-  hook(3, true);
-  xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs);
-  hook(3, false);
-  hook(4, true);
-  if (fuse_tail) lstm_rec<0><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, ws.H2, NT, np);
-  else lstm_rec<1><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, h2_planes, NT, np);
-  hook(4, false);
-  *launches += 5;
+  if (ws.use_seq) {
+    // layer 1: input projection fused into the recurrent kernel (no Gx round trip)
+    hook(0, true);
+    if (dtype_is_i16) prep_tiles48<int16_t><<<gprep, 128, 0, st>>>((const int16_t*)x_dev, ws.X48, n, NT);
+    else prep_tiles48<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X48, n, NT);
+    hook(0, false);
+    hook(2, true);
+    lstm_seq<true, 0><<<grec, SEQ_THREADS, seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np);
+    hook(2, false);
+    hook(3, true);
+    xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs);
+    hook(3, false);
+    hook(4, true);
+    if (fuse_tail) lstm_seq<false, 0><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2, NT, np);
+    else lstm_seq<false, 1><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np);
+    hook(4, false);
+    *launches += 4;
+  } else {
+    hook(0, true);
+    if (dtype_is_i16) prep_tiles<int16_t><<<gprep, 128, 0, st>>>((const int16_t*)x_dev, ws.X16, n, NT);
+    else prep_tiles<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X16, n, NT);
+    hook(0, false);
+    hook(1, true);
+    xproj_pair<4><<<2 * ncl, XP_THREADS, xproj_smem_bytes<4>(), st>>>(ws.X16, w.Wx[0], w.bx[0], ws.Gx, num_row_pairs);
+    hook(1, false);
+    hook(2, true);
+    lstm_rec<0><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[0], ws.Gx, ws.H1, NT, np);
+    hook(2, false);
+    hook(3, true);
+    xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs);
+    hook(3, false);
+    hook(4, true);
+    if (fuse_tail) lstm_rec<0><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, ws.H2, NT, np);
+    else lstm_rec<1><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, h2_planes, NT, np);
+    hook(4, false);
+    *launches += 5;
+  }
   if (fuse_tail) {
     hook(6, true);
     transpose_h2<<<dim3((unsigned)NT, 64, L3_TG), 256, 0, st>>>(ws.H2, ws.H2t, NT);
