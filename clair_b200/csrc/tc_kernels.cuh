@@ -141,11 +141,11 @@ __global__ void __launch_bounds__(128) prep_tiles(const TIn* __restrict__ x, __h
 // Persistent CTA pairs: a pair keeps ONE N-block of Wx resident in shared memory (B operand, <=128 KB per CTA) and
 // streams row-pairs (256 rows = two A tiles) through a ring of K=32 stages.  Pairs 4g..4g+3 walk the same row-pairs
 // with the four different N-blocks at the same time, so each A tile is read from HBM once and hit in L2 three times.
-// Warp roles: 0 = A producer, 1 = MMA issuer (leader) / stage relay (peer), 2..5 = epilogue (TMEM -> +bias -> Gx).
+// Warp roles: 0 = A producer, 1 = MMA issuer (leader) / stage relay (peer), 2..9 = epilogue (TMEM -> +bias -> Gx).
 // ---------------------------------------------------------------------------------------------
 constexpr int XP_RING = 6;
 constexpr int XP_STAGE_BYTES = 2 * 4 * KCH_BYTES;     // [hl][4 kc][128][8] = 16 KB
-constexpr int XP_THREADS = 192;
+constexpr int XP_THREADS = 320;                        // warps: producer, MMA/relay, 8 epilogue
 
 template <int KC>
 constexpr size_t xproj_smem_bytes() {
@@ -184,7 +184,7 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 8);
+      mbar_init(&acc_empty[i], 16);
     }
     mbar_init(b_full, 1);
     fence_barrier_init();
@@ -268,8 +268,10 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
   } else {
     // ---- epilogue: TMEM -> + bias -> Gx (float4 per hidden unit, 512 B per warp store) ----
     const int quarter = warp & 3;
+    const int colhalf = (warp - 2) >> 2;               // two warps per lane quarter split the 256 columns
     const int r = quarter * 32 + lane;
-    const int dir = nb >> 1, unit0 = (nb & 1) * 64;
+    const int dir = nb >> 1, unit0 = (nb & 1) * 64 + colhalf * 32;
+    const uint32_t leader_acc_empty[2] = {map_to_cta(smem_u32(&acc_empty[0]), 0), map_to_cta(smem_u32(&acc_empty[1]), 0)};
     uint32_t it = 0;
     for (int rp = grp; rp < num_row_pairs; rp += ngrp, ++it) {
       const uint32_t buf = it & 1;
@@ -277,22 +279,25 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
       tc_fence_after();
       float* out = Gx + ((size_t)rp * 2 + rank) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) +
                    (size_t)unit0 * 512 + r * 4;
-      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + colhalf * 128;
+      const float* bs = bias_s + colhalf * 128;
 #pragma unroll 2
-      for (int c = 0; c < 256; c += 16) {
-        float v[16];
+      for (int c = 0; c < 128; c += 32) {
+        float v[32];
         tmem_ld16(taddr + c, v);
+        tmem_ld16(taddr + c + 16, v + 16);
         tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float4 o = make_float4(v[4 * u] + bias_s[c + 4 * u], v[4 * u + 1] + bias_s[c + 4 * u + 1],
-                                 v[4 * u + 2] + bias_s[c + 4 * u + 2], v[4 * u + 3] + bias_s[c + 4 * u + 3]);
+        for (int u = 0; u < 8; ++u) {
+          float4 o = make_float4(v[4 * u] + bs[c + 4 * u], v[4 * u + 1] + bs[c + 4 * u + 1],
+                                 v[4 * u + 2] + bs[c + 4 * u + 2], v[4 * u + 3] + bs[c + 4 * u + 3]);
           *reinterpret_cast<float4*>(out + (size_t)(c / 4 + u) * 512) = o;
         }
       }
+      // the accumulator is drained (tcgen05.ld complete): no need to wait for the Gx stores before handing it back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&acc_empty[buf]), 0));
+      if (lane == 0) mbar_arrive_cluster_relaxed(leader_acc_empty[buf]);
     }
   }
   tc_fence_before();
@@ -530,20 +535,23 @@ lstm_rec(const __half* __restrict__ Wh, const float* __restrict__ Gx, void* __re
 //   Wh   : [dir][q][hl][b 4][kc 16][64 rows][8]  (row r of CTA q, block b = gate column b*128 + q*64 + r)
 //   Wx   : [dir][q][hl][b 4][kc 6][64 rows][8]   (FUSE_X only; k = 32, 33 hold bias hi / lo)
 //   X48  : [(t*NT+tile)][hl][kc 6][128][8]       (FUSE_X only; k = 32, 33 are 1.0)
-// Warps: 0 = MMA issuer (leader CTA), 1..8 = epilogue, 9 = x_t ring (FUSE_X).
+// Warps: 0 = MMA issuer (leader CTA), 1..4G = epilogue (G warps per TMEM lane quarter), 4G+1 = loads (x_t / Gx ring).
 // ---------------------------------------------------------------------------------------------
-constexpr int SEQ_THREADS = 320;
+constexpr int SEQ_G = 2;                                // epilogue warps per TMEM lane quarter (2 or 4)
+constexpr int SEQ_THREADS = 32 * (2 + 4 * SEQ_G);
 constexpr int SEQ_W_BYTES = 2 * 4 * 16 * 1024;          // 131072
 constexpr int SEQ_WX_BYTES = 2 * 4 * 6 * 1024;          // 49152
 constexpr int SEQ_X_STAGE = 2 * 6 * KCH_BYTES;          // 24576
 constexpr int X48_TILE_HALVES = 2 * 6 * KCH;
+constexpr int SEQ_G_STAGE = 16 * 128 * 16;              // Gx of 16 hidden units x 128 rows (float4 each) = 32768
+constexpr int SEQ_G_RING = 3;
 template <bool FUSE_X>
 constexpr size_t seq_smem_bytes() {
-  return (size_t)SEQ_W_BYTES + (FUSE_X ? SEQ_WX_BYTES + 2 * SEQ_X_STAGE : 0) + 256 + 1024;
+  return (size_t)SEQ_W_BYTES + (FUSE_X ? SEQ_WX_BYTES + 2 * SEQ_X_STAGE : SEQ_G_RING * SEQ_G_STAGE) + 256 + 1024;
 }
 
-template <bool FUSE_X, int OUT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SEQ_THREADS, 1)
+template <bool FUSE_X, int OUT, int G>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (2 + 4 * G), 1)
 lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __half* __restrict__ X48,
          const float* __restrict__ Gx, void* __restrict__ Hout, int NT, int64_t np) {
   extern __shared__ uint8_t smem_raw[];
@@ -551,7 +559,8 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
   uint8_t* Ws = smem;                                            // [hl][b][kc 16][64][8]
   uint8_t* Wxs = smem + SEQ_W_BYTES;                             // [hl][b][kc 6][64][8]
   uint8_t* Xs = Wxs + (FUSE_X ? SEQ_WX_BYTES : 0);               // [2 stages][hl][kc 6][128][8]
-  uint64_t* bars = (uint64_t*)(Xs + (FUSE_X ? 2 * SEQ_X_STAGE : 0));
+  uint8_t* Gs = Wxs;                                             // !FUSE_X: [3 stages][16 units][128 rows][4 floats]
+  uint64_t* bars = (uint64_t*)(Xs + (FUSE_X ? 2 * SEQ_X_STAGE : SEQ_G_RING * SEQ_G_STAGE));
   uint64_t* acc_full = bars;           // [2] gate block complete (MMA commit, both CTAs)
   uint64_t* acc_empty = bars + 2;      // [2] (leader) accumulator drained by all 16 epilogue warps of the pair
   uint64_t* h_ready = bars + 4;        // (leader) h_t of both CTAs is in tensor memory
@@ -559,7 +568,9 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
   uint64_t* x_peer = bars + 7;         // [2] (leader) the peer's x_t tile landed
   uint64_t* x_empty = bars + 9;        // [2] x_t tile consumed (MMA commit, both CTAs)
   uint64_t* w_full = bars + 11;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+  uint64_t* g_full = bars + 12;        // [3] Gx half-block landed
+  uint64_t* g_empty = bars + 15;       // [3] Gx half-block consumed by its 4 epilogue warps
+  uint32_t* tmem_slot = (uint32_t*)(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -569,12 +580,16 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 16);
+      mbar_init(&acc_empty[i], 8 * G);
       mbar_init(&x_full[i], 1);
       mbar_init(&x_peer[i], 1);
       mbar_init(&x_empty[i], 1);
     }
-    mbar_init(h_ready, 16);
+    for (int i = 0; i < SEQ_G_RING; ++i) {
+      mbar_init(&g_full[i], 1);
+      mbar_init(&g_empty[i], 4 * G);
+    }
+    mbar_init(h_ready, 8 * G);
     mbar_init(w_full, 1);
     fence_barrier_init();
     const uint8_t* src = (const uint8_t*)Wh + ((size_t)dir * 2 + rank) * SEQ_W_BYTES;
@@ -651,7 +666,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == 1 + 4 * G) {
     if (lane == 0) {
       if (FUSE_X) {
         // ---- x_t ring: each CTA loads its own 128 rows; the peer tells the leader when its tile has landed ----
@@ -665,36 +680,44 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
             mbar_arrive_cluster(map_to_cta(smem_u32(&x_peer[st]), 0));
           }
         }
+      } else {
+        // ---- Gx ring: half-blocks of 16 hidden units (32 KB, contiguous in Gx) in consumption order ----
+        uint32_t q = 0;
+        for (int s = 0; s < T_STEPS; ++s) {
+          const int t = dir ? (T_STEPS - 1 - s) : s;
+          const float* g = Gx + ((size_t)t * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2);
+          for (int hb = 0; hb < 8; ++hb, ++q) {
+            const uint32_t st = q % SEQ_G_RING;
+            mbar_wait(&g_empty[st], ((q / SEQ_G_RING) & 1) ^ 1);
+            mbar_expect_tx(&g_full[st], SEQ_G_STAGE);
+            bulk_g2s(Gs + st * SEQ_G_STAGE, g + (size_t)hb * (SEQ_G_STAGE / 4), SEQ_G_STAGE, &g_full[st]);
+          }
+        }
       }
     }
     __syncwarp();
   } else {
-    // ---- epilogue warps ----
+    // ---- epilogue warps: G warps per TMEM lane quarter; a gate block (32 units) is two half-blocks of 16 units
+    //      (= one Gx ring stage), and every warp takes UPS = 16/G units of EACH half-block, so all warps walk the
+    //      ring stages in the same order ----
+    constexpr int UPS = 16 / G;
     const int ew = warp - 1;
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
-    const int half = ew >> 2;                          // which 16 of the 32 hidden units of a gate block
+    const int sub = ew >> 2;                           // 0..G-1
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     const uint32_t leader_h_ready = map_to_cta(smem_u32(h_ready), 0);
     const uint32_t leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
     const uint32_t leader_acc_empty1 = map_to_cta(smem_u32(&acc_empty[1]), 0);
-    float c[4][16];
+    float c[4][2][UPS];
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) c[b][i] = 0.f;
-
-    auto gx_ptr = [&](int s) {
-      const int t = dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
-      return Gx + ((size_t)t * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) + (size_t)(half * 16) * 512 + r * 4;
-    };
-    const float* gx = FUSE_X ? nullptr : gx_ptr(0);
-    float4 gq[2][4];
-    if (!FUSE_X) {
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) gq[0][k] = ld_stream4(gx + (size_t)k * 512);
-    }
-    uint32_t use0 = 0, use1 = 0;
+        for (int i = 0; i < UPS; ++i) c[b][j][i] = 0.f;
+
+    uint32_t use0 = 0, use1 = 0, gq_idx = 0;
     // Gx tiles (written by xproj_pair, HBM-resident) are pulled into L2 two steps ahead, paced by the step loop
     auto prefetch_gx = [&](int sp) {
       const int tp = dir ? (T_STEPS - 1 - sp) : sp;
@@ -707,8 +730,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
     }
 
     for (int s = 0; s < T_STEPS; ++s) {
-      const int t = dir ? (T_STEPS - 1 - s) : s;
-      const float* gx_next = FUSE_X ? nullptr : gx_ptr(s + 1 < T_STEPS ? s + 1 : s);
+      const int t = dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
       const bool have_acc = FUSE_X || s > 0;
       if (!FUSE_X && ew == 0 && lane == 0 && s + 2 < T_STEPS) prefetch_gx(s + 2);
       const uint32_t h_st = lane_base + 256 + (s & 1) * 128;
@@ -721,64 +743,78 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
           ++use;
           tc_fence_after();
         }
-        float hv[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int j = 0; j < 2; ++j) {
+          const int u0 = b * 32 + j * 16 + sub * UPS;  // first hidden unit of this thread's slice
+          float4 gq[UPS];
           if (!FUSE_X) {
-            // prefetch the next group's pre-activations (next block / next step at the boundaries)
-            const float* nx = g < 3 ? gx + (size_t)(b * 32 + 4 * (g + 1)) * 512
-                                    : (b < 3 ? gx + (size_t)((b + 1) * 32) * 512 : gx_next);
+            const uint32_t gst = gq_idx % SEQ_G_RING;
+            mbar_wait(&g_full[gst], (gq_idx / SEQ_G_RING) & 1);
+            ++gq_idx;
+            const float4* gsm = reinterpret_cast<const float4*>(Gs + gst * SEQ_G_STAGE) + (sub * UPS) * 128 + r;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) gq[(g + 1) & 1][k] = ld_stream4(nx + (size_t)k * 512);
+            for (int k = 0; k < UPS; ++k) gq[k] = gsm[k * 128];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&g_empty[gst]);
           }
-          float v[16];
+          float v[4 * UPS];
           if (have_acc) {
-            tmem_ld16(lane_base + i * 128 + half * 64 + g * 16, v);
+#pragma unroll
+            for (int k = 0; k < UPS / 4; ++k) tmem_ld16(lane_base + i * 128 + (j * 16 + sub * UPS) * 4 + k * 16, v + 16 * k);
             tmem_ld_wait();
-            if (g == 3) {
-              // the accumulator is fully in registers: hand it back to the MMA issuer
+            if (j == 1) {
+              // this warp's part of the accumulator is in registers: hand it back to the MMA issuer
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive_cluster(i ? leader_acc_empty1 : leader_acc_empty0);
+              if (lane == 0) mbar_arrive_cluster_relaxed(i ? leader_acc_empty1 : leader_acc_empty0);
             }
           } else {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = 0.f;
+            for (int k = 0; k < 4 * UPS; ++k) v[k] = 0.f;
           }
+          float hv[UPS];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < UPS; ++k) {
             float pi = v[4 * k], pg = v[4 * k + 1], pf = v[4 * k + 2], po = v[4 * k + 3];
             if (!FUSE_X) {
-              const float4 q = gq[g & 1][k];
-              pi += q.x; pg += q.y; pf += q.z; po += q.w;
+              pi += gq[k].x; pg += gq[k].y; pf += gq[k].z; po += gq[k].w;
             }
-            hv[4 * g + k] = lstm_cell(pi, pg, pf, po, c[b][4 * g + k]);
+            hv[k] = lstm_cell(pi, pg, pf, po, c[b][j][k]);
+          }
+          // h_t of these units: fp16 hi/lo words (two units per word) -> tensor memory (next step's A operand) and
+          // -> the next layer's operand tile in global memory
+          uint32_t whi[UPS / 2], wlo[UPS / 2];
+#pragma unroll
+          for (int k = 0; k < UPS / 2; ++k) {
+            const __half2 h2 = __floats2half2_rn(hv[2 * k], hv[2 * k + 1]);
+            const float2 back = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(hv[2 * k] - back.x, hv[2 * k + 1] - back.y);
+            whi[k] = *reinterpret_cast<const uint32_t*>(&h2);
+            wlo[k] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          if constexpr (UPS == 8) {
+            tmem_st4(h_st + (u0 >> 1), whi);
+            tmem_st4(h_st + 64 + (u0 >> 1), wlo);
+          } else {
+            tmem_st2(h_st + (u0 >> 1), whi);
+            tmem_st2(h_st + 64 + (u0 >> 1), wlo);
+          }
+          if (OUT == 0) {
+            __half* out = (__half*)Hout + ((size_t)t * NT + tile) * (2 * 32 * KCH) + (size_t)(dir * 16 + (u0 >> 3)) * KCH + r * 8 + (u0 & 7);
+            if constexpr (UPS == 8) {
+              *reinterpret_cast<uint4*>(out) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+              *reinterpret_cast<uint4*>(out + 32 * KCH) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+            } else {
+              *reinterpret_cast<uint2*>(out) = make_uint2(whi[0], whi[1]);
+              *reinterpret_cast<uint2*>(out + 32 * KCH) = make_uint2(wlo[0], wlo[1]);
+            }
+          } else {
+            float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + u0) * np + (size_t)tile * 128 + r;
+#pragma unroll
+            for (int k = 0; k < UPS; ++k) out[(size_t)k * np] = hv[k];
           }
         }
-        // h_t of these 16 units: fp16 hi/lo words (two units per word), to tensor memory and to the next layer
-        uint4 hi[2], lo[2];
-        split8(hv, hi[0], lo[0]);
-        split8(hv + 8, hi[1], lo[1]);
-        {
-          const uint32_t col = (uint32_t)(b * 32 + half * 16) >> 1;
-          const uint32_t whi[8] = {hi[0].x, hi[0].y, hi[0].z, hi[0].w, hi[1].x, hi[1].y, hi[1].z, hi[1].w};
-          const uint32_t wlo[8] = {lo[0].x, lo[0].y, lo[0].z, lo[0].w, lo[1].x, lo[1].y, lo[1].z, lo[1].w};
-          tmem_st8(h_st + col, whi);
-          tmem_st8(h_st + 64 + col, wlo);
-        }
-        if (OUT == 0) {
-          __half* out = (__half*)Hout + ((size_t)t * NT + tile) * (2 * 32 * KCH) + (size_t)(dir * 16 + b * 4 + half * 2) * KCH + r * 8;
-          *reinterpret_cast<uint4*>(out) = hi[0];
-          *reinterpret_cast<uint4*>(out + KCH) = hi[1];
-          *reinterpret_cast<uint4*>(out + 32 * KCH) = lo[0];
-          *reinterpret_cast<uint4*>(out + 33 * KCH) = lo[1];
-        } else {
-          float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + b * 32 + half * 16) * np + (size_t)tile * 128 + r;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) out[(size_t)k * np] = hv[k];
-        }
       }
-      gx = gx_next;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -798,8 +834,21 @@ __global__ void __launch_bounds__(128) prep_tiles48(const TIn* __restrict__ x, _
   float v[32];
   if (site < n) {
     const TIn* src = x + site * SITE_ELEMS + t * F_IN;
+    if constexpr (sizeof(TIn) == 4) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (float)src[i];
+      for (int i = 0; i < 8; ++i) {
+        float4 q = *reinterpret_cast<const float4*>(src + 4 * i);
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 q = *reinterpret_cast<const uint4*>(src + 8 * i);
+        const int16_t* e = reinterpret_cast<const int16_t*>(&q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * i + j] = (float)e[j];
+      }
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -1233,9 +1282,9 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
   if ((st = cudaMalloc((void**)&ws.H1, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.X48, (size_t)T_STEPS * NT * X48_TILE_HALVES * 2)) != cudaSuccess) return st;
   if (const char* rk = getenv("CLAIRB_REC")) ws.use_seq = strcmp(rk, "v1") != 0;
-  if ((st = cudaFuncSetAttribute(lstm_seq<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(lstm_seq<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(lstm_seq<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq<true, 0, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq<false, 0, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq<false, 1, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H2, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H2t, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
   cudaDeviceGetAttribute(&ws.sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -1275,14 +1324,14 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
     else prep_tiles48<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X48, n, NT);
     hook(0, false);
     hook(2, true);
-    lstm_seq<true, 0><<<grec, SEQ_THREADS, seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np);
+    lstm_seq<true, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np);
     hook(2, false);
     hook(3, true);
     xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs);
     hook(3, false);
     hook(4, true);
-    if (fuse_tail) lstm_seq<false, 0><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2, NT, np);
-    else lstm_seq<false, 1><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np);
+    if (fuse_tail) lstm_seq<false, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2, NT, np);
+    else lstm_seq<false, 1, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np);
     hook(4, false);
     *launches += 4;
   } else {
