@@ -54,7 +54,7 @@ struct clairb_engine {
   int64_t max_sites = 0;
   int batch = 1000;
   int bp = 1024;
-  int64_t chunk_sites = 0;     // real sites per chunk (multiple of batch)
+  int64_t chunk_sites = 0;     // real sites per chunk
   int64_t chunk_np = 0;        // padded sites per chunk
   EngineKind kind = ENGINE_SIMT;
   bool finalized = false;
@@ -75,6 +75,7 @@ struct clairb_engine {
   tc::Workspace tcws;
   void* d_x[2] = {nullptr, nullptr};
   float* d_out[2] = {nullptr, nullptr};
+  float* h_out[2] = {nullptr, nullptr};     // pinned staging for results (one per output buffer)
 
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -295,6 +296,7 @@ void free_all(clairb_engine* e) {
     cudaFree(e->d_bp[l]);
     cudaFree(e->d_x[l]);
     cudaFree(e->d_out[l]);
+    if (e->h_out[l]) cudaFreeHost(e->h_out[l]);
     if (e->ev_h2d[l]) cudaEventDestroy(e->ev_h2d[l]);
     if (e->ev_comp[l]) cudaEventDestroy(e->ev_comp[l]);
     if (e->ev_d2h[l]) cudaEventDestroy(e->ev_d2h[l]);
@@ -354,13 +356,23 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
     const char* ft = getenv("CLAIRB_FUSED_TAIL");
     e->fuse_tail = !(ft && !strcmp(ft, "0"));
   }
-  int64_t chunk_batches = e->kind == ENGINE_TC ? 37 : 32;   // TC: 145 CTA pairs x 2 directions ~ 3.9 waves of 74 pairs
-  if (const char* cb = getenv("CLAIRB_CHUNK_BATCHES")) chunk_batches = atoll(cb) > 0 ? atoll(cb) : chunk_batches;
-  int64_t nb_max = (max_sites + batch_sites - 1) / batch_sites;
-  if (chunk_batches > nb_max) chunk_batches = nb_max;
-  e->chunk_sites = chunk_batches * batch_sites;
-  e->chunk_np = e->kind == ENGINE_TC ? (e->chunk_sites + TC_PAIR_SITES - 1) / TC_PAIR_SITES * TC_PAIR_SITES
-                                     : chunk_batches * e->bp;
+  if (e->kind == ENGINE_TC) {
+    // Sites are independent, so a chunk need not be whole predict-batches.  Default: 2 waves of CTA pairs per chunk
+    // (sm_count/2 pairs x 256 sites x 2 waves / 2 directions = 18,944 sites on 148 SMs = exactly one wave of
+    // 148 tiles for the per-tile kernels); small enough that the H2D copy of the next chunk hides behind this one.
+    int64_t cs = (int64_t)(prop.multiProcessorCount / 2) * TC_PAIR_SITES;
+    if (const char* c = getenv("CLAIRB_CHUNK_SITES")) cs = atoll(c) > 0 ? atoll(c) : cs;
+    if (cs > max_sites) cs = max_sites;
+    e->chunk_sites = cs;
+    e->chunk_np = (cs + TC_PAIR_SITES - 1) / TC_PAIR_SITES * TC_PAIR_SITES;
+  } else {
+    int64_t chunk_batches = 32;
+    if (const char* cb = getenv("CLAIRB_CHUNK_BATCHES")) chunk_batches = atoll(cb) > 0 ? atoll(cb) : chunk_batches;
+    int64_t nb_max = (max_sites + batch_sites - 1) / batch_sites;
+    if (chunk_batches > nb_max) chunk_batches = nb_max;
+    e->chunk_sites = chunk_batches * batch_sites;
+    e->chunk_np = chunk_batches * e->bp;
+  }
   auto bail = [&](int rc) {
     g_create_error = e->err;
     free_all(e);
@@ -385,6 +397,7 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
     CR_TRY(cudaEventCreateWithFlags(&e->ev_d2h[b], cudaEventDisableTiming));
     CR_TRY(cudaMalloc(&e->d_x[b], (size_t)e->chunk_sites * SITE_ELEMS * sizeof(float)));
     CR_TRY(cudaMalloc((void**)&e->d_out[b], (size_t)e->chunk_sites * N_OUT * sizeof(float)));
+    CR_TRY(cudaHostAlloc((void**)&e->h_out[b], (size_t)e->chunk_sites * N_OUT * sizeof(float), cudaHostAllocDefault));
   }
   CR_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   const size_t np = (size_t)e->chunk_np;
@@ -555,7 +568,16 @@ int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, f
   if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(e, CLAIRB_EINVAL, "unknown dtype %d", dtype);
   CU_TRY(e, cudaSetDevice(e->device));
   const size_t eb = elem_bytes(dtype);
-  int64_t done = 0;
+  // Results go device -> pinned staging (truly asynchronous) -> the caller's array.  A pageable destination would make
+  // every D2H copy synchronous and serialise the chunk pipeline, and the reference contract hands back a fresh numpy
+  // array per call (clair/model.py:963), i.e. pageable memory.  A destination that is itself pinned is written directly.
+  bool out_pinned = false;
+  {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, out_host) == cudaSuccess) out_pinned = at.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  int64_t done = 0, prev_done = 0, prev_cn = 0;
   int c = 0;
   while (done < n) {
     const int b = c & 1;
@@ -572,12 +594,23 @@ int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, f
     if (rc) return rc;
     CU_TRY(e, cudaEventRecord(e->ev_comp[b], e->s_comp));
     CU_TRY(e, cudaStreamWaitEvent(e->s_d2h, e->ev_comp[b], 0));
-    CU_TRY(e, cudaMemcpyAsync(out_host + (size_t)done * N_OUT, e->d_out[b], (size_t)cn * N_OUT * sizeof(float),
-                              cudaMemcpyDeviceToHost, e->s_d2h));
+    float* dst = out_pinned ? out_host + (size_t)done * N_OUT : e->h_out[b];
+    CU_TRY(e, cudaMemcpyAsync(dst, e->d_out[b], (size_t)cn * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
     CU_TRY(e, cudaEventRecord(e->ev_d2h[b], e->s_d2h));
+    if (!out_pinned && c >= 1) {
+      // while this chunk runs, hand the previous chunk's results to the caller
+      CU_TRY(e, cudaEventSynchronize(e->ev_d2h[b ^ 1]));
+      memcpy(out_host + (size_t)prev_done * N_OUT, e->h_out[b ^ 1], (size_t)prev_cn * N_OUT * sizeof(float));
+    }
     e->last_map = sm;
+    prev_done = done;
+    prev_cn = cn;
     done += cn;
     ++c;
+  }
+  if (!out_pinned) {
+    CU_TRY(e, cudaEventSynchronize(e->ev_d2h[(c - 1) & 1]));
+    memcpy(out_host + (size_t)prev_done * N_OUT, e->h_out[(c - 1) & 1], (size_t)prev_cn * N_OUT * sizeof(float));
   }
   e->last_single_chunk = c == 1;
   // the caller reads out_host as soon as we return (call_var.py:1334-1338)

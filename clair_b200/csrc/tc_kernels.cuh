@@ -73,6 +73,9 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
@@ -155,7 +158,7 @@ constexpr size_t xproj_smem_bytes() {
 template <int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XP_THREADS, 1)
 xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const float* __restrict__ bias,
-           float* __restrict__ Gx, int num_row_pairs) {
+           float* __restrict__ Gx, int num_row_pairs, int dbg) {
   constexpr int NST = KC / 4;                          // K=32 stages per row tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -208,10 +211,20 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
       uint32_t use = 0;
       for (int rp = grp; rp < num_row_pairs; rp += ngrp) {
         const __half* at = A + ((size_t)rp * 2 + rank) * (2 * KC * KCH);
+        {
+          // pull the A tile two row-pairs ahead from HBM into L2 so the ring's bulk copies see L2 latency only
+          const int rpn = rp + 2 * ngrp;
+          if (rpn < num_row_pairs) {
+            const uint8_t* an = (const uint8_t*)(A + ((size_t)rpn * 2 + rank) * (2 * KC * KCH));
+            for (int i = 0; i < 2 * KC * KCH_BYTES; i += 32768)
+              bulk_prefetch_l2(an + i, (2 * KC * KCH_BYTES - i) < 32768 ? (2 * KC * KCH_BYTES - i) : 32768);
+          }
+        }
         for (int ks = 0; ks < NST; ++ks, ++use) {
           const int slot = use % XP_RING;
           mbar_wait(&empty[slot], ((use / XP_RING) & 1) ^ 1);
           uint8_t* dst = ring + slot * XP_STAGE_BYTES;
+          if (dbg & 8) { mbar_arrive(&full[slot]); continue; }
           mbar_expect_tx(&full[slot], XP_STAGE_BYTES);
           bulk_g2s(dst, at + (size_t)ks * 4 * KCH, 4 * KCH_BYTES, &full[slot]);
           bulk_g2s(dst + 4 * KCH_BYTES, at + (size_t)KC * KCH + (size_t)ks * 4 * KCH, 4 * KCH_BYTES, &full[slot]);
@@ -244,7 +257,7 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
             const int slot = use % XP_RING;
             const uint32_t par = (use / XP_RING) & 1;
             mbar_wait(&full[slot], par);
-            mbar_wait(&peer_full[slot], par);
+            if (!(dbg & 4)) mbar_wait(&peer_full[slot], par);
             tc_fence_after();
             const uint32_t a_base = smem_u32(ring + slot * XP_STAGE_BYTES);
 #pragma unroll
@@ -255,8 +268,10 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
               const uint64_t b_hi = make_smem_desc(b_base + bo, KCH_BYTES, 128);
               const uint64_t b_lo = make_smem_desc(b_base + KC * KCH_BYTES + bo, KCH_BYTES, 128);
               umma_f16_pair(d, a_hi, b_hi, idesc, (ks | kk) != 0);
-              umma_f16_pair(d, a_lo, b_hi, idesc, 1);
-              umma_f16_pair(d, a_hi, b_lo, idesc, 1);
+              if (!(dbg & 2)) {
+                umma_f16_pair(d, a_lo, b_hi, idesc, 1);
+                umma_f16_pair(d, a_hi, b_lo, idesc, 1);
+              }
             }
             umma_commit_pair(&empty[slot], 0b11);
           }
@@ -291,7 +306,10 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
         for (int u = 0; u < 8; ++u) {
           float4 o = make_float4(v[4 * u] + bs[c + 4 * u], v[4 * u + 1] + bs[c + 4 * u + 1],
                                  v[4 * u + 2] + bs[c + 4 * u + 2], v[4 * u + 3] + bs[c + 4 * u + 3]);
-          *reinterpret_cast<float4*>(out + (size_t)(c / 4 + u) * 512) = o;
+          if (!(dbg & 1)) {
+            if (dbg & 16) st_stream4(out + (size_t)(c / 4 + u) * 512, o);
+            else *reinterpret_cast<float4*>(out + (size_t)(c / 4 + u) * 512) = o;
+          }
         }
       }
       // the accumulator is drained (tcgen05.ld complete): no need to wait for the Gx stores before handing it back
@@ -818,7 +836,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_h_ready);
+      if (lane == 0) mbar_arrive_cluster_relaxed(leader_h_ready);   // payload is tensor memory (tcgen05 fences order it)
     }
   }
   tc_fence_before();
@@ -1315,6 +1333,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   int ncl = (ws.sm_count / 2) / 4 * 4;
   if (ncl > 4 * num_row_pairs) ncl = 4 * num_row_pairs;
   if (ncl < 4) ncl = 4;
+  static const int xp_dbg = getenv("CLAIRB_XP_DBG") ? atoi(getenv("CLAIRB_XP_DBG")) : 0;   // timing experiments only
   dim3 gprep((unsigned)NT, T_STEPS);
   dim3 grec((unsigned)NT, 2);
   if (ws.use_seq) {
@@ -1327,7 +1346,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
     lstm_seq<true, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np);
     hook(2, false);
     hook(3, true);
-    xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs);
+    xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs, xp_dbg);
     hook(3, false);
     hook(4, true);
     if (fuse_tail) lstm_seq<false, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2, NT, np);
@@ -1340,13 +1359,13 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
     else prep_tiles<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X16, n, NT);
     hook(0, false);
     hook(1, true);
-    xproj_pair<4><<<2 * ncl, XP_THREADS, xproj_smem_bytes<4>(), st>>>(ws.X16, w.Wx[0], w.bx[0], ws.Gx, num_row_pairs);
+    xproj_pair<4><<<2 * ncl, XP_THREADS, xproj_smem_bytes<4>(), st>>>(ws.X16, w.Wx[0], w.bx[0], ws.Gx, num_row_pairs, xp_dbg);
     hook(1, false);
     hook(2, true);
     lstm_rec<0><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[0], ws.Gx, ws.H1, NT, np);
     hook(2, false);
     hook(3, true);
-    xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs);
+    xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs, xp_dbg);
     hook(3, false);
     hook(4, true);
     if (fuse_tail) lstm_rec<0><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, ws.H2, NT, np);

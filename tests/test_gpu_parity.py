@@ -110,6 +110,31 @@ def test_multi_chunk_equals_single_calls(gpu_model):
     assert np.isfinite(full).all()
 
 
+def test_chunk_pipeline_pageable_and_pinned_outputs(weights1234, monkeypatch):
+    # small chunks force the copy-overlapped multi-chunk pipeline (3 chunks + a ragged 4th); results must not depend on
+    # chunking nor on whether the destination is pageable (staged through pinned memory) or pinned (written directly)
+    from clair_b200.model import Clair, pinned_empty, pinned_free
+    monkeypatch.setenv("CLAIRB_CHUNK_SITES", "1024")
+    m = Clair(max_sites=4096, batch_sites=1000)
+    monkeypatch.delenv("CLAIRB_CHUNK_SITES")
+    m.set_weights(weights1234)
+    X = synth.synthetic_tensors(3300, seed=77)
+    a = m.predict_packed(X)                                   # pageable destination
+    ref = O.forward_packed(X[::13], weights1234, np.float64)
+    assert np.abs(a[::13] - ref).max() <= TOL
+    out = pinned_empty((3300, 90), np.float32)
+    rc = m._lib.clairb_predict(m._h, X.ctypes.data_as(ctypes.c_void_p), _lib.DTYPE_F32, 3300,
+                               out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    np.testing.assert_array_equal(a, out)
+    one = Clair(max_sites=4096, batch_sites=1000)             # default chunking: a single chunk
+    one.set_weights(weights1234)
+    np.testing.assert_array_equal(a, one.predict_packed(X))
+    pinned_free(out)
+    m.close()
+    one.close()
+
+
 def test_predict_from_worker_thread(gpu_model):
     import threading
     X = synth.synthetic_tensors(100, seed=2)
