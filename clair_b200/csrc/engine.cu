@@ -162,8 +162,8 @@ SiteMap make_map(const clairb_engine* e, int64_t n) {
 
 // ---- per-kernel event timing --------------------------------------------------------------------
 const char* kKernelNames[] = {"prep_input", "lstm_layer1", "lstm_layer2", "l3_slice_dense", "l4_dense",
-                              "tail_heads", "prep_tiles", "xproj1", "lstm_rec1", "xproj2", "lstm_rec2", "l3l4_fused", "transpose_h2"};
-constexpr int kNumKernelNames = 13;
+                              "tail_heads", "prep_tiles", "lstm_seq1", "xproj2", "lstm_seq2", "l3l4_fused"};
+constexpr int kNumKernelNames = 11;
 
 void prof_fold(clairb_engine* e) {
   for (auto& sp : e->prof_open) {

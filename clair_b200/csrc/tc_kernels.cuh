@@ -4,12 +4,13 @@
 // hi*hi + lo*hi + hi*lo accumulated in fp32 in TMEM (kind::f16).  That keeps ~22 mantissa bits per operand, which the
 // <=1e-4 logit gate needs (single fp16/bf16/tf32 operands fail it: SURVEY.md section 7).
 //
-// One bidirectional LSTM layer (reference clair/model.py:265-312) is two kernels:
-//   xproj_pair  Gx[t,site,dir,512] = x_t . W_x + b          one large GEMM over all 33 steps (no time dependence)
-//   lstm_rec    gates = Gx[t] + h_{t-1} . W_h ; (c,h) update  33 dependent steps, W_h resident in shared memory
+// A bidirectional LSTM layer (reference clair/model.py:265-312) is
+//   layer 1: lstm_seq<FUSE_X>     gates = x_t . W_x + b + h_{t-1} . W_h, all inside the recurrent kernel (K_x = 32)
+//   layer 2: xproj_pair           Gx[t,site,dir,512] = x_t . W_x + b   one large GEMM over all 33 steps (K_x = 256)
+//            lstm_seq             gates = Gx[t] + h_{t-1} . W_h ; (c,h) update, 33 dependent steps
 // Both run on CTA pairs (cta_group::2): a pair owns 256 sites, each CTA holds its 128 rows of the A operand and one
 // half of the gate columns of the B operand, so the 256 KB fp16 hi/lo recurrent kernel of one direction is split
-// 128 KB + 128 KB over the two SMs and never re-read from L2.
+// 128 KB + 128 KB over the two SMs, stays resident in shared memory and is never re-read from L2.
 //
 // Operand tiles live in global memory already in the UMMA canonical K-major no-swizzle order
 // [k/8][row][8] (see tc_common.cuh), so they move with plain 1-D bulk copies in both directions.
@@ -34,12 +35,12 @@ constexpr int KCH = 1024;                      // halves per k-chunk of a 128-ro
 constexpr int KCH_BYTES = 2048;
 constexpr int GX_TILE_FLOATS = 2 * 128 * 128 * 4;   // per (t, tile): [dir][unit 128][row 128][gate 4]
 constexpr int L3_TG = 5;                                  // time groups of 8 kept per channel (t = 0..39, 33..39 zero)
-constexpr int L3A_HALVES = 2 * L3_TG * 1024;              // per (tile, channel): [hl][tg][16 site groups][8 t][8 sites]
+constexpr int L3A_HALVES = 2 * L3_TG * 1024;              // per (tile, channel): [hl][t/8][site/64][t%8][64 sites, 128B-swizzled]
 constexpr int L3A_BYTES = L3A_HALVES * 2;                 // 20480
 // per-channel weight blob of l3l4_fused: W3_c hi|lo ([6 kc][32 o][8 t]) , W4_c hi|lo ([4 kc][192 n][8 o]) , b3_c[32]
 constexpr int L3W_BYTES = 6 * 32 * 16;                    // 3072
 constexpr int L4W_BYTES = 4 * 192 * 16;                   // 12288
-constexpr int L3L4_BLOB_BYTES = 2 * L3W_BYTES + 2 * L4W_BYTES + 128;   // 30848
+constexpr int L3L4_BLOB_BYTES = 31 * 1024;                            // 30848 used, padded so ring stages stay 1 KB aligned
 
 constexpr float LOG2E = 1.4426950408889634f;
 // Gate pre-activations reach the epilogue pre-scaled (the scale is folded into W and b on the host):
@@ -63,6 +64,31 @@ __device__ __forceinline__ float lstm_cell(float pi, float pg, float pf, float p
   c = cn;
   const float e = ex2f(fminf(cn * (-2.f * LOG2E), 40.f)), f = ex2f(fminf(po, 40.f));
   return (1.f - e) * rcpf((1.f + e) * (1.f + f));
+}
+// 8x8 transpose of fp16 values across the 8 lanes of a row group: on entry lane i (= lane & 7) holds 8 consecutive hidden
+// units of row i as 4 words (two units per word); on exit it holds unit i for the 8 rows (two rows per word).
+__device__ __forceinline__ void transpose8x8_h(uint32_t* w, int lane) {
+  // 1) 2x2 blocks of halves between lanes i, i^1
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t p = __shfl_xor_sync(0xffffffffu, w[k], 1);
+    w[k] = (lane & 1) ? __byte_perm(w[k], p, 0x3276) : __byte_perm(w[k], p, 0x5410);
+  }
+  // 2) 4x4 transpose of words between lanes (bits 1,2) and registers
+#pragma unroll
+  for (int k1 = 0; k1 < 2; ++k1) {
+    const bool up = lane & 2;
+    const uint32_t send = up ? w[2 * k1] : w[2 * k1 + 1];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+    if (up) w[2 * k1] = recv; else w[2 * k1 + 1] = recv;
+  }
+#pragma unroll
+  for (int k0 = 0; k0 < 2; ++k0) {
+    const bool up = lane & 4;
+    const uint32_t send = up ? w[k0] : w[2 + k0];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 4);
+    if (up) w[k0] = recv; else w[2 + k0] = recv;
+  }
 }
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
@@ -97,42 +123,6 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
                   *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
   lo = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
                   *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
-}
-
-// ---------------------------------------------------------------------------------------------
-// prep: x[n][33][32] (f32 or i16; clair/utils.py:95 order) -> A tiles of the layer-1 input projection
-//   X16[(t*NT + tile)][hl][kc 4][row 128][8] fp16   (model.py:403-418: reshape + time-major transpose)
-// grid = (NT, 33), block 128: thread = one site of the tile.  Padding rows are zero.
-// ---------------------------------------------------------------------------------------------
-template <typename TIn>
-__global__ void __launch_bounds__(128) prep_tiles(const TIn* __restrict__ x, __half* __restrict__ X16, int64_t n, int NT) {
-  const int tile = blockIdx.x, t = blockIdx.y, r = threadIdx.x;
-  const int64_t site = (int64_t)tile * 128 + r;
-  float v[32];
-  if (site < n) {
-    const TIn* src = x + site * SITE_ELEMS + t * F_IN;
-    if constexpr (sizeof(TIn) == 4) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 q = *reinterpret_cast<const float4*>(src + 4 * i);
-        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = (float)src[i];
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-  }
-  __half* base = X16 + ((size_t)t * NT + tile) * (2 * 4 * KCH);
-#pragma unroll
-  for (int kc = 0; kc < 4; ++kc) {
-    uint4 hi, lo;
-    split8(v + 8 * kc, hi, lo);
-    *reinterpret_cast<uint4*>(base + kc * KCH + r * 8) = hi;
-    *reinterpret_cast<uint4*>(base + 4 * KCH + kc * KCH + r * 8) = lo;
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -323,223 +313,10 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
   if (warp == 0) tmem_dealloc_pair<512>(tmem);
 }
 
-// ---------------------------------------------------------------------------------------------
-// lstm_rec<OUT>: the 33 dependent steps of one direction of one BiLSTM layer for a pair of site tiles.
-//   grid = (2 * pairs, 2 directions), cluster (2,1,1); CTA rank q owns tile 2*pair+q (128 sites) and the gate
-//   columns {n*256 + q*128 .. +128 : n = 0,1} of the recurrent kernel.
-//   Wh   : [dir][q][hl][n 2][kc 16][128][8] fp16 (128 KB per CTA, loaded once, resident)
-//   Gx   : see xproj_pair (bias already folded in)
-//   OUT == 0: h_t -> A tiles of the next layer's input projection  Hout[(t*NT+tile)][hl][kc 32][128][8] fp16,
-//             direction d fills kc d*16..+16 (model.py:306-312: out[t] = concat(fw_t, bw_t)), moved by the bulk-copy
-//             engine straight from the shared-memory operand tile
-//   OUT == 1: h_t -> fp32 planes  Hout[(t*256 + dir*128 + unit)][np]  (input of the CUDA-core slice-dense kernel)
-// Per step the leader's control thread issues 2 x 24 pair-MMAs (gate blocks n = 0,1: 8 k-steps x 3 split terms) and
-// commits each block to both CTAs; the 8 epilogue warps of each CTA turn block 0 into (c,h) while block 1 is still in
-// the tensor pipe, then block 1, write h_t (fp16 hi/lo) back into the operand tile and signal the leader.
-// c lives in registers for all 33 steps (64 units per thread).
-// ---------------------------------------------------------------------------------------------
-constexpr int REC_EPI_WARPS = 8;
-constexpr int REC_THREADS = 32 * (1 + REC_EPI_WARPS);
-constexpr int REC_W_BYTES = 2 * 2 * 16 * KCH_BYTES;     // 131072
-constexpr int REC_H_BYTES = 2 * 16 * KCH_BYTES;         // 65536
-constexpr size_t rec_smem_bytes() { return (size_t)REC_W_BYTES + REC_H_BYTES + 256 + 1024; }
-
-template <int OUT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(REC_THREADS, 1)
-lstm_rec(const __half* __restrict__ Wh, const float* __restrict__ Gx, void* __restrict__ Hout, int NT, int64_t np) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* Ws = smem;                                  // [hl][n][kc 16][128][8]
-  uint8_t* Hs = smem + REC_W_BYTES;                    // [hl][kc 16][128][8]
-  uint64_t* bars = (uint64_t*)(Hs + REC_H_BYTES);
-  uint64_t* gates_full = bars;                         // [2] block n complete (MMA commit, both CTAs)
-  uint64_t* h_ready = bars + 2;                        // (leader) h_t of both CTAs written, TMEM drained
-  uint64_t* h_local = bars + 3;                        // h_t of this CTA written
-  uint64_t* hbuf_free = bars + 4;                      // bulk store of h_{t-1} has finished reading Hs
-  uint64_t* w_full = bars + 5;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 6);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int dir = blockIdx.y;
-  const int tile = blockIdx.x;                         // = 2*pair + rank
-
-  if (threadIdx.x == 0) {
-    mbar_init(&gates_full[0], 1);
-    mbar_init(&gates_full[1], 1);
-    mbar_init(h_ready, 2 * REC_EPI_WARPS);
-    mbar_init(h_local, REC_EPI_WARPS);
-    mbar_init(hbuf_free, 1);
-    mbar_init(w_full, 1);
-    fence_barrier_init();
-    const uint8_t* src = (const uint8_t*)(Wh + ((size_t)dir * 2 + rank) * (REC_W_BYTES / 2));
-    mbar_expect_tx(w_full, REC_W_BYTES);
-    for (int i = 0; i < REC_W_BYTES; i += 32768) bulk_g2s(Ws + i, src + i, 32768, w_full);
-  }
-  if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
-  __syncthreads();                                     // barrier inits visible before anyone polls them
-  mbar_wait(w_full, 0);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ---- control thread: MMA issue (leader) and h_t write-out (both CTAs) ----
-      const uint32_t idesc = make_idesc_f16(256, 256);
-      const uint32_t w_base = smem_u32(Ws), h_base = smem_u32(Hs);
-      for (int sp = 0; sp < 2; ++sp) {
-        const int tn = dir ? (T_STEPS - 1 - sp) : sp;
-        const float* g = Gx + ((size_t)tn * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2);
-        for (int i = 0; i < 4; ++i) bulk_prefetch_l2(g + i * 16384, 65536);
-      }
-      for (int s = 1; s <= T_STEPS; ++s) {
-        // h_{s-1} complete?
-        if (rank == 0) mbar_wait(h_ready, (s - 1) & 1);
-        else mbar_wait(h_local, (s - 1) & 1);
-        tc_fence_after();
-        if (s + 1 < T_STEPS) {
-          // pull the Gx tile of step s+1 (256 KB, written by the previous kernel) from HBM into L2
-          const int tn = dir ? (T_STEPS - 2 - s) : (s + 1);
-          const float* g = Gx + ((size_t)tn * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2);
-          for (int i = 0; i < 4; ++i) bulk_prefetch_l2(g + i * 16384, 65536);
-        }
-        if (OUT == 0) {
-          const int tp = dir ? (T_STEPS - s) : (s - 1);          // time index of step s-1
-          __half* dst = (__half*)Hout + ((size_t)tp * NT + tile) * (2 * 32 * KCH) + (size_t)dir * 16 * KCH;
-          bulk_s2g(dst, Hs, 16 * KCH_BYTES);
-          bulk_s2g(dst + 32 * KCH, Hs + 16 * KCH_BYTES, 16 * KCH_BYTES);
-          bulk_commit();
-        }
-        if (rank == 0 && s < T_STEPS) {
-#pragma unroll
-          for (int n = 0; n < 2; ++n) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint64_t a_hi = make_smem_desc(h_base + j * 2 * KCH_BYTES, KCH_BYTES, 128);
-              const uint64_t a_lo = make_smem_desc(h_base + 16 * KCH_BYTES + j * 2 * KCH_BYTES, KCH_BYTES, 128);
-              const uint32_t bo = n * 16 * KCH_BYTES + j * 2 * KCH_BYTES;
-              const uint64_t b_hi = make_smem_desc(w_base + bo, KCH_BYTES, 128);
-              const uint64_t b_lo = make_smem_desc(w_base + 2 * 16 * KCH_BYTES + bo, KCH_BYTES, 128);
-              umma_f16_pair(tmem + n * 256, a_hi, b_hi, idesc, j != 0);
-              umma_f16_pair(tmem + n * 256, a_lo, b_hi, idesc, 1);
-              umma_f16_pair(tmem + n * 256, a_hi, b_lo, idesc, 1);
-            }
-            umma_commit_pair(&gates_full[n], 0b11);
-          }
-        }
-        if (OUT == 0) {
-          bulk_wait_read0();
-          mbar_arrive(hbuf_free);
-        }
-      }
-      if (OUT == 0) bulk_wait0();
-    }
-    __syncwarp();
-  } else {
-    // ---- epilogue warps ----
-    const int ew = warp - 1;
-    const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
-    const int colhalf = ew >> 2;                       // which 128 columns of each 256-column gate block
-    const int r = quarter * 32 + lane;
-    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + colhalf * 128;
-    const uint32_t leader_h_ready = map_to_cta(smem_u32(h_ready), 0);
-    float c[2][32];
-#pragma unroll
-    for (int n = 0; n < 2; ++n)
-#pragma unroll
-      for (int i = 0; i < 32; ++i) c[n][i] = 0.f;
-
-    // Gx of (step s, block n, group g): four float4 (one per hidden unit), prefetched one group ahead
-    auto gx_ptr = [&](int s) {
-      const int t = dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
-      return Gx + ((size_t)t * NT + tile) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) +
-             (size_t)(colhalf * 32) * 512 + r * 4;
-    };
-    const float* gx = gx_ptr(0);
-    float4 gq[2][4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) gq[0][k] = ld_stream4(gx + (size_t)k * 512);
-
-    for (int s = 0; s < T_STEPS; ++s) {
-      const int t = dir ? (T_STEPS - 1 - s) : s;
-      const float* gx_next = gx_ptr(s + 1 < T_STEPS ? s + 1 : s);
-      uint4 keep_hi[4], keep_lo[4];
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        const int unit0 = n * 64 + colhalf * 32;
-        if (s > 0) {
-          mbar_wait(&gates_full[n], (s - 1) & 1);
-          tc_fence_after();
-        }
-        float hv[32];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          // prefetch the next group's pre-activations (next block / next step at the boundaries)
-          {
-            const float* nx = g < 7 ? gx + (size_t)(n * 64 + 4 * (g + 1)) * 512
-                                    : (n == 0 ? gx + (size_t)64 * 512 : gx_next);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) gq[(g + 1) & 1][k] = ld_stream4(nx + (size_t)k * 512);
-          }
-          float v[16];
-          if (s > 0) {
-            tmem_ld16(taddr + n * 256 + g * 16, v);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.f;
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 q = gq[g & 1][k];
-            hv[4 * g + k] = lstm_cell(v[4 * k] + q.x, v[4 * k + 1] + q.y, v[4 * k + 2] + q.z, v[4 * k + 3] + q.w,
-                                      c[n][4 * g + k]);
-          }
-        }
-        if (OUT == 1) {
-          float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + unit0) * np + (size_t)tile * 128 + r;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) out[(size_t)i * np] = hv[i];
-        }
-        if (n == 0) {
-          // block 1 is still reading h_{t-1}: park block 0's h_t in registers
-#pragma unroll
-          for (int q = 0; q < 4; ++q) split8(hv + 8 * q, keep_hi[q], keep_lo[q]);
-        } else {
-          if (OUT == 0 && s > 0) mbar_wait(hbuf_free, (s - 1) & 1);
-          // all MMAs of this step are complete (gates_full[1]): the operand tile may be overwritten
-          uint8_t* h0 = Hs + (size_t)((colhalf * 32) / 8) * KCH_BYTES + r * 16;            // units of block 0
-          uint8_t* h1 = Hs + (size_t)((64 + colhalf * 32) / 8) * KCH_BYTES + r * 16;       // units of block 1
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 hi, lo;
-            split8(hv + 8 * q, hi, lo);
-            *reinterpret_cast<uint4*>(h0 + q * KCH_BYTES) = keep_hi[q];
-            *reinterpret_cast<uint4*>(h0 + 16 * KCH_BYTES + q * KCH_BYTES) = keep_lo[q];
-            *reinterpret_cast<uint4*>(h1 + q * KCH_BYTES) = hi;
-            *reinterpret_cast<uint4*>(h1 + 16 * KCH_BYTES + q * KCH_BYTES) = lo;
-          }
-        }
-      }
-      gx = gx_next;
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(h_local);
-        mbar_arrive_cluster(leader_h_ready);
-      }
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 0) tmem_dealloc_pair<512>(tmem);
-}
 
 // ---------------------------------------------------------------------------------------------
-// lstm_seq<FUSE_X, OUT>: second-generation recurrent kernel.  Differences from lstm_rec:
+// lstm_seq<FUSE_X, OUT, G>: the 33 dependent steps of one direction of one BiLSTM layer for a pair of site tiles
+// (grid = (2 * pairs, 2 directions), cluster (2,1,1); CTA rank q owns tile 2*pair+q).
 //   * h_t never touches shared memory: the epilogue packs it to fp16 hi/lo and writes it with tcgen05.st into
 //     tensor memory, from where the next step's MMAs read it as the A operand (".ts" form).  Two h buffers
 //     (2 x 128 columns) + two 128-column gate accumulators fill the 512 TMEM columns.
@@ -826,10 +603,26 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
               *reinterpret_cast<uint2*>(out) = make_uint2(whi[0], whi[1]);
               *reinterpret_cast<uint2*>(out + 32 * KCH) = make_uint2(wlo[0], wlo[1]);
             }
-          } else {
+          } else if (OUT == 1) {
             float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + u0) * np + (size_t)tile * 128 + r;
 #pragma unroll
             for (int k = 0; k < UPS; ++k) out[(size_t)k * np] = hv[k];
+          } else {
+            // OUT == 2: MN-major SWIZZLE_128B tiles for the slice-dense MMA (K = time, M = site), per channel
+            //   H2t[tile][c][hl][t/8 (5)][site/64 (2)][t%8][16-byte chunk ((site%64)/8) ^ (t%8)][site%8]
+            // an 8x8 register transpose gives every lane one channel x 8 sites = one 16-byte chunk; the four row groups
+            // of a warp land in one 64-byte run
+            static_assert(OUT != 2 || UPS == 8, "the MN-major output needs 8 units per slice");
+            if constexpr (UPS == 8) {
+              transpose8x8_h(whi, lane);
+              transpose8x8_h(wlo, lane);
+              const int c = dir * H + u0 + (lane & 7);
+              const int rg = r >> 3;                                  // site group of 8 within the tile (0..15)
+              uint8_t* out = (uint8_t*)Hout + ((size_t)tile * 2 * H + c) * L3A_BYTES + (size_t)(t >> 3) * 2048 +
+                             (rg >> 3) * 1024 + (t & 7) * 128 + (((rg & 7) ^ (t & 7)) << 4);
+              *reinterpret_cast<uint4*>(out) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+              *reinterpret_cast<uint4*>(out + L3A_BYTES / 2) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+            }
           }
         }
       }
@@ -887,62 +680,12 @@ __global__ void __launch_bounds__(128) prep_tiles48(const TIn* __restrict__ x, _
 }
 
 // ---------------------------------------------------------------------------------------------
-// transpose_h2: K-major operand tiles of LSTM2's output  H2[(t*NT+tile)][hl][kc 32][row 128][8 units]
-//            -> MN-major tiles for the slice-dense MMA     H2t[tile][c][hl][t/8 (5)][row/8 (16)][t%8][row%8]
-// (model.py:461 transposes [33,B,256] -> [B,33,256]; here the contraction axis of L3 -- time -- becomes the K axis.)
-// One CTA per (tile, kc, hl, time group of 8): 16 KB in, 16 KB out, both fully coalesced; the 8x8 fp16 transposes run
-// on ldmatrix.trans.  t = 33..39 are written as zeros.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) transpose_h2(const __half* __restrict__ H2, __half* __restrict__ H2t, int NT) {
-  __shared__ __align__(128) uint8_t in_s[8 * KCH_BYTES];      // [t%8][row 128][8 units]
-  __shared__ __align__(128) uint8_t out_s[8 * 2048];          // [unit 8][row/8 16][t%8][row%8]
-  const int tile = blockIdx.x, kc = blockIdx.y >> 1, hl = blockIdx.y & 1, tg = blockIdx.z;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // load: 8 time steps x 2 KB
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = tid + i * 256;                 // 16-byte chunk index, 128 per time step
-    const int tl = idx >> 7, t = tg * 8 + tl;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (t < T_STEPS)
-      v = *reinterpret_cast<const uint4*>(H2 + (((size_t)t * NT + tile) * 2 + hl) * (32 * KCH) + (size_t)kc * KCH + (idx & 127) * 8);
-    reinterpret_cast<uint4*>(in_s)[idx] = v;
-  }
-  __syncthreads();
-  // warp = time step within the group; 4 x ldmatrix.x4.trans cover the 16 row groups
-  {
-    const int tl = warp;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int mg = j * 4 + (lane >> 3);          // lanes 8m..8m+7 give the row addresses of matrix m
-      const uint32_t addr = smem_u32(in_s + tl * KCH_BYTES + (mg * 8 + (lane & 7)) * 16);
-      uint32_t q[4];
-      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(addr));
-      // lane holds, for unit lane/4, rows 2*(lane%4), +1 of row group j*4+m in q[m]
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-        *reinterpret_cast<uint32_t*>(out_s + (lane >> 2) * 2048 + (j * 4 + m) * 128 + tl * 16 + (lane & 3) * 4) = q[m];
-    }
-  }
-  __syncthreads();
-  // store: unit u -> 2 KB run at H2t[tile][kc*8+u][hl][tg]
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = tid + i * 256;
-    const int u = idx >> 7;
-    __half* dst = H2t + ((size_t)tile * 2 * H + kc * 8 + u) * L3A_HALVES + (size_t)hl * (L3A_HALVES / 2) + (size_t)tg * 1024;
-    reinterpret_cast<uint4*>(dst)[idx & 127] = reinterpret_cast<const uint4*>(out_s)[idx];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // l3l4_fused: slice-dense L3 (model.py:225-244, 464-471) chained into dense L4 (model.py:482-488) per 128-site tile.
 //   for every channel c (256):  S_c[128 x 32] = selu(A_c[128 x t] . W3_c[t x o] + b3_c)      (o padded 30 -> 32)
 //                               D4[128 x 192] += S_c . W4[(o,c), :]                          (L4 rows regrouped by channel)
 //   then l4[128 x 192] = selu(D4 + b4) -> planes l4T[192][np] fp32 for the heads kernel.
 // The [B,30,256] -> [B,7680] flatten (model.py:474-478, index o*256+c) never materialises: S_c goes TMEM -> registers ->
-// fp16 hi/lo operand tile in shared memory -> next MMA.  A_c arrives MN-major (K = time) from transpose_h2; the k-group
+// fp16 hi/lo operand tile in shared memory -> next MMA.  A_c arrives MN-major, 128B-swizzled (K = time) from lstm_seq<.,2>; the k-group
 // t = 40..47 of the third k-step points at a shared zero block through the descriptor's leading-dimension offset.
 // Warp roles: 0 = producer (one A tile + one weight blob per channel, 3-stage ring), 1 = MMA issuer,
 // 2..9 = epilogue: group g = (warp-2)/4 owns channels c = g mod 2 with its own D3 / S_c buffers.
@@ -1037,10 +780,12 @@ l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, co
         const uint32_t d3 = tmem + 192 + g * 32;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          // MN-major A: LBO = distance between the two time groups of this k-step, SBO = site-group stride
+          // MN-major SWIZZLE_128B A: LBO = distance between the two 64-site atoms, SBO = distance between the two
+          // time groups of this k-step (for t = 32..47 the second group is the shared zero block)
           const uint32_t a_hi_addr = a_base + j * 2 * 2048, a_lo_addr = a_base + L3A_BYTES / 2 + j * 2 * 2048;
-          const uint64_t a_hi = j < 2 ? make_smem_desc(a_hi_addr, 2048, 128) : make_smem_desc(a_hi_addr, zero_addr - a_hi_addr, 128);
-          const uint64_t a_lo = j < 2 ? make_smem_desc(a_lo_addr, 2048, 128) : make_smem_desc(a_lo_addr, zero_addr - a_lo_addr, 128);
+          const uint64_t sw128 = (uint64_t)2 << 61;
+          const uint64_t a_hi = sw128 | (j < 2 ? make_smem_desc(a_hi_addr, 1024, 2048) : make_smem_desc(a_hi_addr, 1024, zero_addr - a_hi_addr));
+          const uint64_t a_lo = sw128 | (j < 2 ? make_smem_desc(a_lo_addr, 1024, 2048) : make_smem_desc(a_lo_addr, 1024, zero_addr - a_lo_addr));
           const uint64_t b_hi = make_smem_desc(w_base + j * 2 * 512, 512, 128);
           const uint64_t b_lo = make_smem_desc(w_base + L3W_BYTES + j * 2 * 512, 512, 128);
           umma_f16(d3, a_hi, b_hi, idesc3, j != 0);
@@ -1129,9 +874,8 @@ struct HostModel {
 };
 
 struct Weights {
-  __half* Wx[2] = {nullptr, nullptr};      // per layer: [nb 4][q 2][hl][KC][128][8]
-  float* bx[2] = {nullptr, nullptr};       // per layer: [nb 4][256]
-  __half* Wh[2] = {nullptr, nullptr};      // per layer: [dir][q][hl][n][kc 16][128][8]
+  __half* Wx2 = nullptr;                   // xproj_pair<32>, layer 2: [nb 4][q 2][hl][kc 32][128][8]
+  float* bx2 = nullptr;                    // layer 2: [nb 4][256]
   __half* Whs[2] = {nullptr, nullptr};     // lstm_seq, per layer: [dir][q][hl][b 4][kc 16][64][8]
   __half* Wxf = nullptr;                   // lstm_seq<FUSE_X>, layer 1: [dir][q][hl][b 4][kc 6][64][8] (k 32,33 = bias hi,lo)
   uint8_t* l3l4 = nullptr;                 // [256] per-channel blobs (L3L4_BLOB_BYTES each)
@@ -1140,13 +884,10 @@ struct Weights {
 
 struct Workspace {
   int64_t np_max = 0;
-  __half* X16 = nullptr;     // [33*NT][hl][4][128][8]
-  float* Gx = nullptr;       // [33*NT][dir][unit][row][4]
-  __half* X48 = nullptr;     // [33*NT][hl][6][128][8]      layer-1 input tiles with the bias columns (lstm_seq<FUSE_X>)
-  __half* H1 = nullptr;      // [33*NT][hl][32][128][8]
-  bool use_seq = true;       // second-generation recurrent kernel (h in tensor memory, fused layer-1 projection)
-  __half* H2 = nullptr;      // [33*NT][hl][32][128][8]      LSTM2 output, same tile format as H1
-  __half* H2t = nullptr;     // [NT][256][hl][5][16][8][8]   the same, MN-major per channel (t = 33..39 zero)
+  __half* X48 = nullptr;     // [33*NT][hl][6][128][8]       layer-1 input tiles incl. the two bias columns
+  __half* H1 = nullptr;      // [33*NT][hl][32][128][8]      LSTM1 output = A tiles of the layer-2 input projection
+  float* Gx = nullptr;       // [33*NT][dir][unit][row][4]   layer-2 input projection (+bias, gate-scaled)
+  __half* H2t = nullptr;     // [NT][256][hl][5][2][8][64]   LSTM2 output, MN-major 128B-swizzled per channel (t = 33..39 zero)
   int sm_count = 148;
 };
 
@@ -1160,16 +901,24 @@ inline void split_half(float v, __half& hi, __half& lo) {
 // gate column j (unit*4+gate) of a direction -> TF kernel column (gate*128+unit)
 inline int tf_col(int j) { return (j & 3) * H + (j >> 2); }
 
+template <typename Tp>
+inline cudaError_t upload_vec(Tp** dptr, const std::vector<Tp>& h) {
+  cudaError_t st = cudaMalloc((void**)dptr, h.size() * sizeof(Tp));
+  if (st != cudaSuccess) return st;
+  return cudaMemcpy(*dptr, h.data(), h.size() * sizeof(Tp), cudaMemcpyHostToDevice);
+}
+
 inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
   const int kx[2] = {F_IN, 2 * H};
-  for (int l = 0; l < 2; ++l) {
-    const int KC = kx[l] / 8;
+  cudaError_t st;
+  // ---- layer-2 input projection (xproj_pair<32>): N-blocks of 256 gate columns, 128 rows per CTA ----
+  {
+    const int KC = 32;
     std::vector<__half> wx((size_t)4 * 2 * 2 * KC * KCH);
     std::vector<float> bx((size_t)4 * 256);
-    std::vector<__half> wh((size_t)2 * 2 * 2 * 2 * 16 * KCH);
     for (int dir = 0; dir < 2; ++dir) {
-      const float* K = hm.lstm_kernel[l][dir];
-      const float* B = hm.lstm_bias[l][dir];
+      const float* K = hm.lstm_kernel[1][dir];
+      const float* B = hm.lstm_bias[1][dir];
       for (int half = 0; half < 2; ++half) {
         const int nb = dir * 2 + half;
         for (int c = 0; c < 256; ++c) bx[(size_t)nb * 256 + c] = B[tf_col(half * 256 + c)] * GATE_SCALE[c & 3];
@@ -1177,33 +926,18 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
           for (int row = 0; row < 128; ++row) {
             const int col = tf_col(half * 256 + q * 128 + row);
             const float gs = GATE_SCALE[row & 3];                 // fold the exp2 scaling of this gate into W
-            // input projection rows (x first in the TF kernel)
-            for (int k = 0; k < kx[l]; ++k) {
+            for (int k = 0; k < kx[1]; ++k) {
               __half hi, lo;
               split_half(K[(size_t)k * G4 + col] * gs, hi, lo);
               const size_t base = (((size_t)nb * 2 + q) * 2) * KC * KCH + (size_t)(k / 8) * KCH + row * 8 + k % 8;
               wx[base] = hi;
               wx[base + (size_t)KC * KCH] = lo;
             }
-            // recurrent rows: block n == half
-            for (int k = 0; k < H; ++k) {
-              __half hi, lo;
-              split_half(K[(size_t)(kx[l] + k) * G4 + col] * gs, hi, lo);
-              const size_t cta = ((size_t)dir * 2 + q) * (2 * 2 * 16 * KCH);
-              const size_t off = (size_t)half * 16 * KCH + (size_t)(k / 8) * KCH + row * 8 + k % 8;
-              wh[cta + off] = hi;
-              wh[cta + (size_t)2 * 16 * KCH + off] = lo;
-            }
           }
       }
     }
-    cudaError_t st;
-    if ((st = cudaMalloc((void**)&w.Wx[l], wx.size() * 2)) != cudaSuccess) return st;
-    if ((st = cudaMalloc((void**)&w.bx[l], bx.size() * 4)) != cudaSuccess) return st;
-    if ((st = cudaMalloc((void**)&w.Wh[l], wh.size() * 2)) != cudaSuccess) return st;
-    if ((st = cudaMemcpy(w.Wx[l], wx.data(), wx.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
-    if ((st = cudaMemcpy(w.bx[l], bx.data(), bx.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
-    if ((st = cudaMemcpy(w.Wh[l], wh.data(), wh.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
+    if ((st = upload_vec(&w.Wx2, wx)) != cudaSuccess) return st;
+    if ((st = upload_vec(&w.bx2, bx)) != cudaSuccess) return st;
   }
   // ---- lstm_seq layouts: gate blocks of 128 columns, 64 rows per CTA ----
   for (int l = 0; l < 2; ++l) {
@@ -1244,13 +978,8 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
             }
           }
     }
-    cudaError_t st;
-    if ((st = cudaMalloc((void**)&w.Whs[l], whs.size() * 2)) != cudaSuccess) return st;
-    if ((st = cudaMemcpy(w.Whs[l], whs.data(), whs.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
-    if (l == 0) {
-      if ((st = cudaMalloc((void**)&w.Wxf, wxf.size() * 2)) != cudaSuccess) return st;
-      if ((st = cudaMemcpy(w.Wxf, wxf.data(), wxf.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return st;
-    }
+    if ((st = upload_vec(&w.Whs[l], whs)) != cudaSuccess) return st;
+    if (l == 0 && (st = upload_vec(&w.Wxf, wxf)) != cudaSuccess) return st;
   }
   // ---- slice-dense + L4 blobs ----
   {
@@ -1275,55 +1004,45 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
         }
       }
     }
-    cudaError_t st;
-    if ((st = cudaMalloc((void**)&w.l3l4, blob.size())) != cudaSuccess) return st;
-    if ((st = cudaMemcpy(w.l3l4, blob.data(), blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return st;
+    if ((st = upload_vec(&w.l3l4, blob)) != cudaSuccess) return st;
   }
   return cudaSuccess;
 }
 
 inline void free_weights(Weights& w) {
-  cudaFree(w.l3l4); cudaFree(w.Wxf); cudaFree(w.Whs[0]); cudaFree(w.Whs[1]);
-  w.l3l4 = nullptr; w.Wxf = nullptr; w.Whs[0] = w.Whs[1] = nullptr;
-  for (int l = 0; l < 2; ++l) {
-    cudaFree(w.Wx[l]); cudaFree(w.bx[l]); cudaFree(w.Wh[l]);
-    w.Wx[l] = nullptr; w.bx[l] = nullptr; w.Wh[l] = nullptr;
-  }
+  cudaFree(w.l3l4); cudaFree(w.Wxf); cudaFree(w.Whs[0]); cudaFree(w.Whs[1]); cudaFree(w.Wx2); cudaFree(w.bx2);
+  w.l3l4 = nullptr; w.Wxf = nullptr; w.Whs[0] = w.Whs[1] = nullptr; w.Wx2 = nullptr; w.bx2 = nullptr;
 }
 
 inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
   ws.np_max = np_max;
   const size_t NT = (size_t)np_max / 128;
   cudaError_t st;
-  if ((st = cudaMalloc((void**)&ws.X16, (size_t)T_STEPS * NT * 2 * 4 * KCH * 2)) != cudaSuccess) return st;
-  if ((st = cudaMalloc((void**)&ws.Gx, (size_t)T_STEPS * NT * GX_TILE_FLOATS * 4)) != cudaSuccess) return st;
-  if ((st = cudaMalloc((void**)&ws.H1, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.X48, (size_t)T_STEPS * NT * X48_TILE_HALVES * 2)) != cudaSuccess) return st;
-  if (const char* rk = getenv("CLAIRB_REC")) ws.use_seq = strcmp(rk, "v1") != 0;
-  if ((st = cudaFuncSetAttribute(lstm_seq<true, 0, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(lstm_seq<false, 0, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(lstm_seq<false, 1, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
-  if ((st = cudaMalloc((void**)&ws.H2, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
+  if ((st = cudaMalloc((void**)&ws.H1, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
+  if ((st = cudaMalloc((void**)&ws.Gx, (size_t)T_STEPS * NT * GX_TILE_FLOATS * 4)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H2t, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
+  // time steps 33..39 of the last time group are never written by lstm_seq and must read as zeros
+  if ((st = cudaMemset(ws.H2t, 0, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
   cudaDeviceGetAttribute(&ws.sm_count, cudaDevAttrMultiProcessorCount, device);
-  if ((st = cudaFuncSetAttribute(xproj_pair<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<4>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(xproj_pair<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<32>())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(lstm_rec<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem_bytes())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(lstm_rec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem_bytes())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq<true, 0, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq<false, 1, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq<false, 2, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(l3l4_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3l4_smem_bytes())) != cudaSuccess) return st;
   return cudaSuccess;
 }
 
 inline void free_workspace(Workspace& ws) {
-  cudaFree(ws.X16); cudaFree(ws.Gx); cudaFree(ws.H1); cudaFree(ws.H2); cudaFree(ws.H2t); cudaFree(ws.X48);
-  ws.X16 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr; ws.H2 = nullptr; ws.H2t = nullptr; ws.X48 = nullptr;
+  cudaFree(ws.X48); cudaFree(ws.Gx); cudaFree(ws.H1); cudaFree(ws.H2t);
+  ws.X48 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr; ws.H2t = nullptr;
 }
 
-// Both BiLSTM layers for np padded sites (np % 256 == 0).
-//   fuse_tail = false: x -> h2 planes [33*256][np] fp32 (CUDA-core slice-dense / L4 follow)
-//   fuse_tail = true : x -> l4T planes [192][np] fp32 through transpose_h2 + l3l4_fused
-// `hook(id)` brackets every launch for the per-kernel event timing
-// (id: 0 prep, 1 xproj1, 2 rec1, 3 xproj2, 4 rec2, 5 l3l4_fused, 6 transpose_h2).
+// Both BiLSTM layers (+ slice-dense and L4 when fuse_tail) for np padded sites (np % 256 == 0).
+//   fuse_tail = false: x -> h2 planes [33*256][np] fp32 (the CUDA-core slice-dense / L4 follow; parity cross-check)
+//   fuse_tail = true : x -> l4T planes [192][np] fp32 through lstm_seq<.,2> + l3l4_fused
+// `hook(id, begin)` brackets every launch for the per-kernel event timing
+// (id: 0 prep_tiles, 1 lstm_seq1, 2 xproj2, 3 lstm_seq2, 4 l3l4_fused).
 template <typename Hook>
 inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_dev, int dtype_is_i16, int64_t n, int64_t np,
                                 float* h2_planes, float* l4T, bool fuse_tail, cudaStream_t st, int* launches, Hook&& hook) {
@@ -1336,51 +1055,25 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   static const int xp_dbg = getenv("CLAIRB_XP_DBG") ? atoi(getenv("CLAIRB_XP_DBG")) : 0;   // timing experiments only
   dim3 gprep((unsigned)NT, T_STEPS);
   dim3 grec((unsigned)NT, 2);
-  if (ws.use_seq) {
-    // layer 1: input projection fused into the recurrent kernel (no Gx round trip)
-    hook(0, true);
-    if (dtype_is_i16) prep_tiles48<int16_t><<<gprep, 128, 0, st>>>((const int16_t*)x_dev, ws.X48, n, NT);
-    else prep_tiles48<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X48, n, NT);
-    hook(0, false);
-    hook(2, true);
-    lstm_seq<true, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np);
-    hook(2, false);
-    hook(3, true);
-    xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs, xp_dbg);
-    hook(3, false);
-    hook(4, true);
-    if (fuse_tail) lstm_seq<false, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2, NT, np);
-    else lstm_seq<false, 1, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np);
-    hook(4, false);
-    *launches += 4;
-  } else {
-    hook(0, true);
-    if (dtype_is_i16) prep_tiles<int16_t><<<gprep, 128, 0, st>>>((const int16_t*)x_dev, ws.X16, n, NT);
-    else prep_tiles<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X16, n, NT);
-    hook(0, false);
-    hook(1, true);
-    xproj_pair<4><<<2 * ncl, XP_THREADS, xproj_smem_bytes<4>(), st>>>(ws.X16, w.Wx[0], w.bx[0], ws.Gx, num_row_pairs, xp_dbg);
-    hook(1, false);
-    hook(2, true);
-    lstm_rec<0><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[0], ws.Gx, ws.H1, NT, np);
-    hook(2, false);
-    hook(3, true);
-    xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx[1], w.bx[1], ws.Gx, num_row_pairs, xp_dbg);
-    hook(3, false);
-    hook(4, true);
-    if (fuse_tail) lstm_rec<0><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, ws.H2, NT, np);
-    else lstm_rec<1><<<grec, REC_THREADS, rec_smem_bytes(), st>>>(w.Wh[1], ws.Gx, h2_planes, NT, np);
-    hook(4, false);
-    *launches += 5;
-  }
+  hook(0, true);
+  if (dtype_is_i16) prep_tiles48<int16_t><<<gprep, 128, 0, st>>>((const int16_t*)x_dev, ws.X48, n, NT);
+  else prep_tiles48<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X48, n, NT);
+  hook(0, false);
+  hook(1, true);   // layer 1: input projection fused into the recurrent kernel (no Gx round trip)
+  lstm_seq<true, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np);
+  hook(1, false);
+  hook(2, true);
+  xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx2, w.bx2, ws.Gx, num_row_pairs, xp_dbg);
+  hook(2, false);
+  hook(3, true);
+  if (fuse_tail) lstm_seq<false, 2, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2t, NT, np);
+  else lstm_seq<false, 1, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np);
+  hook(3, false);
+  *launches += 4;
   if (fuse_tail) {
-    hook(6, true);
-    transpose_h2<<<dim3((unsigned)NT, 64, L3_TG), 256, 0, st>>>(ws.H2, ws.H2t, NT);
-    hook(6, false);
-    *launches += 1;
-    hook(5, true);
+    hook(4, true);
     l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, np, nullptr);
-    hook(5, false);
+    hook(4, false);
     *launches += 1;
   }
   return cudaGetLastError();
@@ -1412,7 +1105,7 @@ inline cudaError_t dump_l3(const Weights& w, const Workspace& ws, int64_t np, fl
   return st != cudaSuccess ? st : cudaDeviceSynchronize();
 }
 
-// parity hook: LSTM2 output [33][n][256] fp32 rebuilt from the MN-major hi/lo tiles
+// parity hook: LSTM2 output [33][n][256] fp32 rebuilt from the MN-major swizzled hi/lo tiles
 inline cudaError_t get_lstm2(const Workspace& ws, int64_t n, int64_t np, float* out_host) {
   const size_t NT = (size_t)np / 128;
   std::vector<__half> buf(NT * 2 * H * (size_t)L3A_HALVES);
@@ -1420,10 +1113,10 @@ inline cudaError_t get_lstm2(const Workspace& ws, int64_t n, int64_t np, float* 
   if (st != cudaSuccess) return st;
   for (int t = 0; t < T_STEPS; ++t)
     for (int64_t s = 0; s < n; ++s) {
-      const int r = (int)(s % 128);
+      const int r = (int)(s % 128), rg = r >> 3;
       for (int f = 0; f < 2 * H; ++f) {
         const size_t base = ((size_t)(s / 128) * 2 * H + f) * L3A_HALVES;
-        const size_t off = (size_t)(t >> 3) * 1024 + (r >> 3) * 64 + (t & 7) * 8 + (r & 7);
+        const size_t off = (size_t)(t >> 3) * 1024 + (rg >> 3) * 512 + (t & 7) * 64 + (((rg & 7) ^ (t & 7)) << 3) + (r & 7);
         out_host[((size_t)t * n + s) * 2 * H + f] =
             __half2float(buf[base + off]) + __half2float(buf[base + L3A_HALVES / 2 + off]);
       }
