@@ -5,8 +5,9 @@
 
 Workload (BASELINE.json configs[1]): ONT-shape model, 1M synthetic candidate sites in
 predict-batches of 1000.  A "step" is one pass of the forward over a pool of `--batches-per-step`
-predict-batches (default 64 x 1000 sites = 270 MB of fp32 input, larger than the 126 MB L2, so
-every step re-reads its inputs from HBM); the default 16 steps are 1.024 M sites.
+predict-batches (default 75 x 1000 sites = 317 MB of fp32 input, larger than the 126 MB L2, so
+every step re-reads its inputs from HBM; 75,000 sites = 3 full chunks of 18,944 sites + one of 18,168, i.e. whole
+waves of CTA pairs); the default 14 steps are 1.05 M sites.
   value : device-resident sites/s (inputs already in HBM, CUDA events on the launching stream)
   e2e   : the same through the reference-facing call (Clair.predict_packed -> clairb_predict):
           pinned HOST input, H2D + forward + D2H inside the timed region
@@ -42,10 +43,10 @@ WORKLOAD = "ONT-shape model inference, 1M synthetic candidate sites, batch=1000,
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=14)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batches-per-step", type=int, default=64)
+    ap.add_argument("--batches-per-step", type=int, default=75)
     ap.add_argument("--cpu-baseline-batches", type=int, default=0, help="0 = auto (about 10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -200,7 +200,7 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
       // ---- A producer (each CTA loads its own 128 rows) ----
       uint32_t use = 0;
       for (int rp = grp; rp < num_row_pairs; rp += ngrp) {
-        const __half* at = A + ((size_t)rp * 2 + rank) * (2 * KC * KCH);
+        const __half* at = A + ((size_t)((dbg & 64) ? (rp & 7) : rp) * 2 + rank) * (2 * KC * KCH);
         {
           // pull the A tile two row-pairs ahead from HBM into L2 so the ring's bulk copies see L2 latency only
           const int rpn = rp + 2 * ngrp;
@@ -282,7 +282,7 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
       const uint32_t buf = it & 1;
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      float* out = Gx + ((size_t)rp * 2 + rank) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) +
+      float* out = Gx + ((size_t)((dbg & 32) ? (rp & 7) : rp) * 2 + rank) * GX_TILE_FLOATS + (size_t)dir * (GX_TILE_FLOATS / 2) +
                    (size_t)unit0 * 512 + r * 4;
       const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + colhalf * 128;
       const float* bs = bias_s + colhalf * 128;
@@ -348,7 +348,7 @@ constexpr size_t seq_smem_bytes() {
 template <bool FUSE_X, int OUT, int G>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (2 + 4 * G), 1)
 lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __half* __restrict__ X48,
-         const float* __restrict__ Gx, void* __restrict__ Hout, int NT, int64_t np) {
+         const float* __restrict__ Gx, void* __restrict__ Hout, int NT, int64_t np, int pf_dist) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* Ws = smem;                                            // [hl][b][kc 16][64][8]
@@ -520,14 +520,13 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
       for (int i = 0; i < 4; ++i) bulk_prefetch_l2(g + i * 16384, 65536);
     };
     if (!FUSE_X && ew == 0 && lane == 0) {
-      prefetch_gx(0);
-      prefetch_gx(1);
+      for (int sp = 0; sp < pf_dist; ++sp) prefetch_gx(sp);
     }
 
     for (int s = 0; s < T_STEPS; ++s) {
       const int t = dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
       const bool have_acc = FUSE_X || s > 0;
-      if (!FUSE_X && ew == 0 && lane == 0 && s + 2 < T_STEPS) prefetch_gx(s + 2);
+      if (!FUSE_X && ew == 0 && lane == 0 && pf_dist > 0 && s + pf_dist < T_STEPS) prefetch_gx(s + pf_dist);
       const uint32_t h_st = lane_base + 256 + (s & 1) * 128;
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
@@ -1052,6 +1051,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   int ncl = (ws.sm_count / 2) / 4 * 4;
   if (ncl > 4 * num_row_pairs) ncl = 4 * num_row_pairs;
   if (ncl < 4) ncl = 4;
+  static const int gx_pf = getenv("CLAIRB_GX_PF") ? atoi(getenv("CLAIRB_GX_PF")) : 0;   // Gx L2 prefetch distance (steps)
   static const int xp_dbg = getenv("CLAIRB_XP_DBG") ? atoi(getenv("CLAIRB_XP_DBG")) : 0;   // timing experiments only
   dim3 gprep((unsigned)NT, T_STEPS);
   dim3 grec((unsigned)NT, 2);
@@ -1060,14 +1060,14 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   else prep_tiles48<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X48, n, NT);
   hook(0, false);
   hook(1, true);   // layer 1: input projection fused into the recurrent kernel (no Gx round trip)
-  lstm_seq<true, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np);
+  lstm_seq<true, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np, 0);
   hook(1, false);
   hook(2, true);
   xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx2, w.bx2, ws.Gx, num_row_pairs, xp_dbg);
   hook(2, false);
   hook(3, true);
-  if (fuse_tail) lstm_seq<false, 2, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2t, NT, np);
-  else lstm_seq<false, 1, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np);
+  if (fuse_tail) lstm_seq<false, 2, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2t, NT, np, gx_pf);
+  else lstm_seq<false, 1, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np, gx_pf);
   hook(3, false);
   *launches += 4;
   if (fuse_tail) {
