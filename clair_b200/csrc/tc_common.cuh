@@ -103,6 +103,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)1 << 46;
   return d;
 }
+// advance the start address of a descriptor by `bytes` (the address field holds addr >> 4; shared memory < 256 KB, so
+// the 14-bit field cannot carry) -- one 32-bit add instead of rebuilding the descriptor for every MMA
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // Instruction descriptor for kind::f16 with fp16 A/B (K-major both), fp32 accumulate
 // (InstrDescriptor: [4,6) c_format=1 F32, [7,10) a_format=0 F16, [10,13) b_format=0 F16,
 //  bit15 a_major=0 K, bit16 b_major=0 K, [17,23) N>>3, [24,29) M>>4).

@@ -358,15 +358,18 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
   uint64_t* bars = (uint64_t*)(Xs + (FUSE_X ? 2 * SEQ_X_STAGE : SEQ_G_RING * SEQ_G_STAGE));
   uint64_t* acc_full = bars;           // [2] gate block complete (MMA commit, both CTAs)
   uint64_t* acc_empty = bars + 2;      // [2] (leader) accumulator drained by all 16 epilogue warps of the pair
-  uint64_t* h_ready = bars + 4;        // (leader) h_t of both CTAs is in tensor memory
+  uint64_t* hq = bars + 18;            // [4] (leader) units 32b..32b+31 of h_t of both CTAs are in tensor memory
   uint64_t* x_full = bars + 5;         // [2] this CTA's x_t tile landed
   uint64_t* x_peer = bars + 7;         // [2] (leader) the peer's x_t tile landed
   uint64_t* x_empty = bars + 9;        // [2] x_t tile consumed (MMA commit, both CTAs)
   uint64_t* w_full = bars + 11;
   uint64_t* g_full = bars + 12;        // [3] Gx half-block landed
   uint64_t* g_empty = bars + 15;       // [3] Gx half-block consumed by its 4 epilogue warps
-  uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 22);
 
+  // EARLY: hand h_t to the MMA issuer block by block (helps when the tensor pipe has slack, i.e. layer 2; with the
+  // fused input projection the extra tcgen05.wait::st per block costs more than the shorter step boundary saves)
+  constexpr bool EARLY = !FUSE_X;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int dir = blockIdx.y;
@@ -384,7 +387,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
       mbar_init(&g_full[i], 1);
       mbar_init(&g_empty[i], 4 * G);
     }
-    mbar_init(h_ready, 8 * G);
+    for (int i = 0; i < 4; ++i) mbar_init(&hq[i], 8 * G);
     mbar_init(w_full, 1);
     fence_barrier_init();
     const uint8_t* src = (const uint8_t*)Wh + ((size_t)dir * 2 + rank) * SEQ_W_BYTES;
@@ -406,56 +409,100 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
   if (warp == 0) {
     if (lane == 0 && rank == 0) {
       // ---- MMA issuer ----
+      // Per step: four gate blocks b (accumulator b&1).  The recurrent part of block b contracts over all 128 units of
+      // h_{s-1}, but those arrive block by block from the previous step's epilogue (hq[kq] = units 32kq..32kq+31 are in
+      // tensor memory), so the k-steps of blocks 0 and 1 are issued as their slice of h becomes available; only the
+      // last two k-steps (units 96..127) wait for the end of the previous step.
       const uint32_t idesc = make_idesc_f16(256, 128);
-      const uint32_t w_base = smem_u32(Ws), wx_base = smem_u32(Wxs);
+      const uint64_t wdesc = make_smem_desc(smem_u32(Ws), 1024, 128);        // recurrent kernel: 64-row k-chunks
+      const uint64_t wxdesc = make_smem_desc(smem_u32(Wxs), 1024, 128);      // input kernel (FUSE_X)
+      const uint64_t xdesc = make_smem_desc(smem_u32(Xs), KCH_BYTES, 128);   // x_t tile: 128-row k-chunks
       uint32_t use0 = 0, use1 = 0;
       for (int s = 0; s < T_STEPS; ++s) {
         if (!FUSE_X && s == 0) continue;               // h_{-1} = 0 and no x part: nothing to accumulate
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        const uint32_t h_hi = tmem + 256 + ((s - 1) & 1) * 128, h_lo = h_hi + 64;
+        const uint32_t hpar = (s - 1) & 1;
+        auto acquire_acc = [&](int b) {
           const int i = b & 1;
           uint32_t& use = i ? use1 : use0;
           mbar_wait(&acc_empty[i], (use & 1) ^ 1);
           ++use;
           tc_fence_after();
-          const uint32_t d = tmem + i * 128;
-          if (FUSE_X) {
-            const int st = s & 1;
-            if (b == 0) {
-              mbar_wait(&x_full[st], (s >> 1) & 1);
-              mbar_wait(&x_peer[st], (s >> 1) & 1);
-              tc_fence_after();
-            }
-            const uint32_t x_base = smem_u32(Xs + st * SEQ_X_STAGE);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const uint64_t a_hi = make_smem_desc(x_base + j * 2 * KCH_BYTES, KCH_BYTES, 128);
-              const uint64_t a_lo = make_smem_desc(x_base + 6 * KCH_BYTES + j * 2 * KCH_BYTES, KCH_BYTES, 128);
-              const uint32_t bo = b * 6 * 1024 + j * 2 * 1024;
-              const uint64_t b_hi = make_smem_desc(wx_base + bo, 1024, 128);
-              const uint64_t b_lo = make_smem_desc(wx_base + 4 * 6 * 1024 + bo, 1024, 128);
-              umma_f16_pair(d, a_hi, b_hi, idesc, j != 0);
-              umma_f16_pair(d, a_lo, b_hi, idesc, 1);
-              umma_f16_pair(d, a_hi, b_lo, idesc, 1);
-            }
+        };
+        auto x_part = [&](int b) {                     // x_t . W_x (+ bias through the constant-one columns)
+          if (!FUSE_X) return;
+          const int st = s & 1;
+          if (b == 0) {
+            mbar_wait(&x_full[st], (s >> 1) & 1);
+            mbar_wait(&x_peer[st], (s >> 1) & 1);
+            tc_fence_after();
           }
-          if (s > 0) {
-            if (b == 0) {
-              mbar_wait(h_ready, (s - 1) & 1);
-              tc_fence_after();
-            }
-            const uint32_t h_hi = tmem + 256 + ((s - 1) & 1) * 128, h_lo = h_hi + 64;
+          const uint32_t d = tmem + (b & 1) * 128;
+          const uint64_t a_hi0 = desc_advance(xdesc, st * SEQ_X_STAGE), a_lo0 = desc_advance(a_hi0, 6 * KCH_BYTES);
+          const uint64_t b_hi0 = desc_advance(wxdesc, b * 6 * 1024), b_lo0 = desc_advance(b_hi0, 4 * 6 * 1024);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t bo = b * 16 * 1024 + j * 2 * 1024;
-              const uint64_t b_hi = make_smem_desc(w_base + bo, 1024, 128);
-              const uint64_t b_lo = make_smem_desc(w_base + 4 * 16 * 1024 + bo, 1024, 128);
-              umma_f16_pair_ts(d, h_hi + j * 8, b_hi, idesc, (FUSE_X || j != 0) ? 1u : 0u);
-              umma_f16_pair_ts(d, h_lo + j * 8, b_hi, idesc, 1);
-              umma_f16_pair_ts(d, h_hi + j * 8, b_lo, idesc, 1);
-            }
+          for (int j = 0; j < 3; ++j) {
+            const uint64_t a_hi = desc_advance(a_hi0, j * 2 * KCH_BYTES), a_lo = desc_advance(a_lo0, j * 2 * KCH_BYTES);
+            const uint64_t b_hi = desc_advance(b_hi0, j * 2 * 1024), b_lo = desc_advance(b_lo0, j * 2 * 1024);
+            umma_f16_pair(d, a_hi, b_hi, idesc, j != 0);
+            umma_f16_pair(d, a_lo, b_hi, idesc, 1);
+            umma_f16_pair(d, a_hi, b_lo, idesc, 1);
           }
-          umma_commit_pair(&acc_full[i], 0b11);
+        };
+        auto h_part = [&](int b, int j0, int j1) {     // k-steps j0..j1-1 of h_{s-1} . W_h for block b
+          const uint32_t d = tmem + (b & 1) * 128;
+          const uint64_t b_hi0 = desc_advance(wdesc, b * 16 * 1024), b_lo0 = desc_advance(b_hi0, 4 * 16 * 1024);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < j0 || j >= j1) continue;
+            const uint64_t b_hi = desc_advance(b_hi0, j * 2 * 1024), b_lo = desc_advance(b_lo0, j * 2 * 1024);
+            umma_f16_pair_ts(d, h_hi + j * 8, b_hi, idesc, (FUSE_X || j != 0) ? 1u : 0u);
+            umma_f16_pair_ts(d, h_lo + j * 8, b_hi, idesc, 1);
+            umma_f16_pair_ts(d, h_hi + j * 8, b_lo, idesc, 1);
+          }
+        };
+        auto wait_h = [&](int kq) {
+          mbar_wait(&hq[kq], hpar);
+          tc_fence_after();
+        };
+        if (s == 0) {                                  // FUSE_X only: input projection alone
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            acquire_acc(b);
+            x_part(b);
+            umma_commit_pair(&acc_full[b & 1], 0b11);
+          }
+        } else if (!EARLY) {
+          // whole-step hand-off: every block waits for all of h_{s-1} (signalled once per step on hq[3])
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            acquire_acc(b);
+            x_part(b);
+            if (b == 0) wait_h(3);
+            h_part(b, 0, 8);
+            umma_commit_pair(&acc_full[b & 1], 0b11);
+          }
+        } else {
+          acquire_acc(0);
+          x_part(0);
+          wait_h(0); h_part(0, 0, 2);
+          wait_h(1); h_part(0, 2, 4);
+          wait_h(2); h_part(0, 4, 6);
+          acquire_acc(1);
+          x_part(1);
+          h_part(1, 0, 6);
+          wait_h(3);
+          h_part(0, 6, 8);
+          umma_commit_pair(&acc_full[0], 0b11);
+          h_part(1, 6, 8);
+          umma_commit_pair(&acc_full[1], 0b11);
+#pragma unroll
+          for (int b = 2; b < 4; ++b) {
+            acquire_acc(b);
+            x_part(b);
+            h_part(b, 0, 8);
+            umma_commit_pair(&acc_full[b & 1], 0b11);
+          }
         }
         if (FUSE_X) umma_commit_pair(&x_empty[s & 1], 0b11);
       }
@@ -501,7 +548,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
     const int sub = ew >> 2;                           // 0..G-1
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t leader_h_ready = map_to_cta(smem_u32(h_ready), 0);
+    const uint32_t leader_hq = map_to_cta(smem_u32(hq), 0);
     const uint32_t leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
     const uint32_t leader_acc_empty1 = map_to_cta(smem_u32(&acc_empty[1]), 0);
     float c[4][2][UPS];
@@ -624,11 +671,15 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
             }
           }
         }
+        if (EARLY || b == 3) {
+          // this warp's slice of h_t (block b; with !EARLY: all four blocks) is in tensor memory: the MMA issuer may
+          // start contracting over it.  The payload is tensor memory, ordered by the tcgen05 fences.
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(leader_hq + b * 8);
+        }
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(leader_h_ready);   // payload is tensor memory (tcgen05 fences order it)
     }
   }
   tc_fence_before();
