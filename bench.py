@@ -35,7 +35,7 @@ LSTM1_FLOP_PER_SITE = 2 * 5406720
 KERNEL_FLOP_PER_SITE = {"lstm_layer2": LSTM2_FLOP_PER_SITE, "lstm_layer1": LSTM1_FLOP_PER_SITE,
                         "l4_dense": 2 * 1474560, "l3_slice_dense": 2 * 253440, "tail_heads": 2 * (73728 + 8640),
                         "lstm_seq1": 2 * 5406720, "xproj2": 2 * 8650752, "lstm_seq2": 2 * 4325376,
-                        "l3l4_fused": 2 * (253440 + 1474560), "prep_tiles": 0, "prep_input": 0, "transpose_h2": 0}
+                        "l3l4_fused": 2 * (253440 + 1474560), "prep_tiles": 0, "prep_input": 0, "heads_tc": 2 * (73728 + 8640)}
 BATCH = 1000                        # shared/param.py:16 predictBatchSize
 WORKLOAD = "ONT-shape model inference, 1M synthetic candidate sites, batch=1000, 1xB200"
 

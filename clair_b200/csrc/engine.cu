@@ -162,8 +162,8 @@ SiteMap make_map(const clairb_engine* e, int64_t n) {
 
 // ---- per-kernel event timing --------------------------------------------------------------------
 const char* kKernelNames[] = {"prep_input", "lstm_layer1", "lstm_layer2", "l3_slice_dense", "l4_dense",
-                              "tail_heads", "prep_tiles", "lstm_seq1", "xproj2", "lstm_seq2", "l3l4_fused"};
-constexpr int kNumKernelNames = 11;
+                              "tail_heads", "prep_tiles", "lstm_seq1", "xproj2", "lstm_seq2", "l3l4_fused", "heads_tc"};
+constexpr int kNumKernelNames = 12;
 
 void prof_fold(clairb_engine* e) {
   for (auto& sp : e->prof_open) {
@@ -275,10 +275,10 @@ int forward_chunk(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, fl
       else { delete open; open = nullptr; }
     };
     cudaError_t cst = tc::forward_lstm(e->tcw, e->tcws, x_dev, dtype == CLAIRB_DTYPE_I16, sm.n, sm.np, e->d_h2, e->d_l4T,
-                                       e->fuse_tail, st, &nl, hook);
+                                       out_dev, e->d_logits, e->fuse_tail, st, &nl, hook);
     e->launches += nl;
     if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "tensor-core forward failed: %s", cudaGetErrorString(cst));
-    if (e->fuse_tail) return forward_heads(e, sm, out_dev, st);
+    if (e->fuse_tail) return CLAIRB_OK;
     return forward_tail(e, sm, out_dev, st);
   }
   return forward_simt(e, x_dev, dtype, sm, out_dev, st);
@@ -527,6 +527,17 @@ int clairb_finalize_weights(clairb_engine* e) {
         hm.lstm_bias[l][d] = e->hw[lstm_name(l + 1, d, "bias")].data.data();
       }
     hm.w3 = w3.data(); hm.b3 = b3.data(); hm.W4 = W4->data.data();
+    for (int k = 0; k < 4; ++k) {
+      char nm[96];
+      snprintf(nm, sizeof nm, "L5_%d/kernel", k + 1);
+      hm.W5[k] = e->hw[nm].data.data();
+      snprintf(nm, sizeof nm, "L5_%d/bias", k + 1);
+      hm.b5[k] = e->hw[nm].data.data();
+      snprintf(nm, sizeof nm, "Prediction/%s/kernel", kHeadNames[k]);
+      hm.Whd[k] = e->hw[nm].data.data();
+      snprintf(nm, sizeof nm, "Prediction/%s/bias", kHeadNames[k]);
+      hm.bhd[k] = e->hw[nm].data.data();
+    }
     tc::free_weights(e->tcw);
     e->tcw.b4 = e->d_b4;
     cudaError_t cst = tc::build_weights(e->tcw, hm);

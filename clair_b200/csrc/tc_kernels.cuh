@@ -748,7 +748,7 @@ constexpr size_t l3l4_smem_bytes() { return (size_t)LF_STAGES * LF_STAGE_BYTES +
 
 __global__ void __launch_bounds__(LF_THREADS, 1)
 l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, const float* __restrict__ b4,
-           float* __restrict__ l4T, int64_t np, float* __restrict__ l3_dbg) {
+           float* __restrict__ l4T, __half* __restrict__ L4t, int64_t np, float* __restrict__ l3_dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stages = smem;
@@ -903,7 +903,213 @@ l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, co
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float x = v[i] + __ldg(b4 + col0 + i);
-        out[(size_t)(col0 + i) * np] = x >= 0.f ? SELU_SCALE * x : (SELU_SCALE * SELU_ALPHA) * (__expf(x) - 1.f);
+        v[i] = x >= 0.f ? SELU_SCALE * x : (SELU_SCALE * SELU_ALPHA) * (__expf(x) - 1.f);
+        out[(size_t)(col0 + i) * np] = v[i];           // fp32 planes: parity hook / CUDA-core heads
+      }
+      // the same activations as the K-major fp16 hi/lo operand tile of heads_tc: [tile][hl][kc 24][128][8]
+      __half* lt = L4t + (size_t)tile * (2 * 24 * KCH) + (size_t)(col0 / 8) * KCH + r * 8;
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(lt) = hi;
+      *reinterpret_cast<uint4*>(lt + 24 * KCH) = lo;
+      split8(v + 8, hi, lo);
+      *reinterpret_cast<uint4*>(lt + KCH) = hi;
+      *reinterpret_cast<uint4*>(lt + 25 * KCH) = lo;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// heads_tc: L5_1..4 (192 -> 96, SELU), the four heads (96 -> 21/3/33/33, SELU) and their softmax
+// (model.py:507-622) for one 128-site tile, on tensor cores.
+//   L4t   : [tile][hl][kc 24][128][8] fp16   L4 activations as a K-major operand tile (written by l3l4_fused)
+//   blob  : per head k: W5_k as two 48-column halves [hf][hl][kc 24][48][8], Whd_k [hl][kc 12][48][8] (rows >= n_k
+//           zero), b5_k[96], bh_k[48]        (HEAD_BLOB_BYTES each)
+// Per head: two L5 MMAs groups (N = 48 each) into D5 -> epilogue (+b5, SELU, fp16 hi/lo) -> smem operand -> head MMA
+// (N = 48) into D6 -> epilogue (+bh, SELU = the reference's "logits"; softmax over the n_k real columns).
+// Strictly sequential per tile (each stage is tiny); one CTA per tile, the grid is one wave.
+// Warps: 0 = producer, 1 = MMA issuer, 2..5 = epilogue (one per TMEM lane quarter).
+// ---------------------------------------------------------------------------------------------
+constexpr int HD_A4_BYTES = 2 * 24 * KCH_BYTES;              // 98304
+constexpr int HD_W5_BYTES = 2 * 24 * 48 * 16;                // 36864 (one 48-column half, hi|lo)
+constexpr int HD_A5_BYTES = 2 * 12 * KCH_BYTES;              // 49152
+constexpr int HD_WH_BYTES = 2 * 12 * 48 * 16;                // 18432
+constexpr int HEAD_BLOB_BYTES = 2 * HD_W5_BYTES + HD_WH_BYTES + 96 * 4 + 48 * 4;   // 92736
+constexpr int HD_THREADS = 192;
+constexpr size_t heads_smem_bytes() { return (size_t)HD_A4_BYTES + HD_W5_BYTES + HD_A5_BYTES + HD_WH_BYTES + 1024 + 256 + 1024; }
+
+__global__ void __launch_bounds__(HD_THREADS, 1)
+heads_tc(const __half* __restrict__ L4t, const uint8_t* __restrict__ blobs, float* __restrict__ probs,
+         float* __restrict__ logits, int64_t n) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* A4 = smem;
+  uint8_t* W5 = A4 + HD_A4_BYTES;
+  uint8_t* A5 = W5 + HD_W5_BYTES;
+  uint8_t* WH = A5 + HD_A5_BYTES;
+  float* bias = (float*)(WH + HD_WH_BYTES);            // [4][96 + 48] floats would not fit: per head, reloaded: [96 | 48]
+  uint64_t* bars = (uint64_t*)((uint8_t*)bias + 1024);
+  uint64_t* a4_full = bars;        // L4 tile landed
+  uint64_t* w5_full = bars + 1;    // W5 half landed
+  uint64_t* w5_free = bars + 2;    // W5 half consumed (MMA commit)
+  uint64_t* d5_full = bars + 3;    // both halves of D5 complete
+  uint64_t* d5_free = bars + 4;    // D5 drained (4 epilogue warps)
+  uint64_t* a5_full = bars + 5;    // L5 operand tile written (4 epilogue warps)
+  uint64_t* wh_full = bars + 6;    // head weights + biases landed
+  uint64_t* d6_full = bars + 7;    // head accumulator complete (also: A5 and WH consumed)
+  uint64_t* d6_free = bars + 8;    // D6 drained (4 epilogue warps)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(a4_full, 1); mbar_init(w5_full, 1); mbar_init(w5_free, 1); mbar_init(d5_full, 1);
+    mbar_init(d5_free, 4); mbar_init(a5_full, 4); mbar_init(wh_full, 1); mbar_init(d6_full, 1); mbar_init(d6_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;     // cols 0..95: D5, 96..143: D6
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(a4_full, HD_A4_BYTES);
+      for (int i = 0; i < HD_A4_BYTES; i += 32768)
+        bulk_g2s(A4 + i, (const uint8_t*)L4t + (size_t)tile * HD_A4_BYTES + i, 32768, a4_full);
+      for (int k = 0; k < 4; ++k) {
+        const uint8_t* blob = blobs + (size_t)k * HEAD_BLOB_BYTES;
+        for (int hf = 0; hf < 2; ++hf) {
+          const int u = k * 2 + hf;
+          mbar_wait(w5_free, (u & 1) ^ 1);
+          mbar_expect_tx(w5_full, HD_W5_BYTES);
+          bulk_g2s(W5, blob + (size_t)hf * HD_W5_BYTES, HD_W5_BYTES, w5_full);
+        }
+        // head weights + the two bias vectors (contiguous in the blob); WH / bias are free once the epilogue of
+        // head k-1 has read its accumulator and biases
+        if (k > 0) mbar_wait(d6_free, (k - 1) & 1);
+        mbar_expect_tx(wh_full, HD_WH_BYTES + 576);
+        bulk_g2s(WH, blob + 2 * HD_W5_BYTES, HD_WH_BYTES + 576, wh_full);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 48);
+      const uint64_t a4d = make_smem_desc(smem_u32(A4), KCH_BYTES, 128), a5d = make_smem_desc(smem_u32(A5), KCH_BYTES, 128);
+      const uint64_t w5d = make_smem_desc(smem_u32(W5), 768, 128), whd = make_smem_desc(smem_u32(WH), 768, 128);
+      mbar_wait(a4_full, 0);
+      for (int k = 0; k < 4; ++k) {
+        mbar_wait(d5_free, (k & 1) ^ 1);
+        for (int hf = 0; hf < 2; ++hf) {
+          const int u = k * 2 + hf;
+          mbar_wait(w5_full, u & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < 12; ++j) {
+            const uint64_t a_hi = desc_advance(a4d, j * 2 * KCH_BYTES), a_lo = desc_advance(a_hi, 24 * KCH_BYTES);
+            const uint64_t b_hi = desc_advance(w5d, j * 2 * 768), b_lo = desc_advance(b_hi, 24 * 768);
+            umma_f16(tmem + hf * 48, a_hi, b_hi, idesc, j != 0);
+            umma_f16(tmem + hf * 48, a_lo, b_hi, idesc, 1);
+            umma_f16(tmem + hf * 48, a_hi, b_lo, idesc, 1);
+          }
+          umma_commit(w5_free);
+        }
+        umma_commit(d5_full);
+        mbar_wait(a5_full, k & 1);
+        mbar_wait(wh_full, k & 1);
+        mbar_wait(d6_free, (k & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const uint64_t a_hi = desc_advance(a5d, j * 2 * KCH_BYTES), a_lo = desc_advance(a_hi, 12 * KCH_BYTES);
+          const uint64_t b_hi = desc_advance(whd, j * 2 * 768), b_lo = desc_advance(b_hi, 12 * 768);
+          umma_f16(tmem + 96, a_hi, b_hi, idesc, j != 0);
+          umma_f16(tmem + 96, a_lo, b_hi, idesc, 1);
+          umma_f16(tmem + 96, a_hi, b_lo, idesc, 1);
+        }
+        umma_commit(d6_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int64_t site = (int64_t)tile * 128 + r;
+    for (int k = 0; k < 4; ++k) {
+      // ---- L5_k: D5 -> +b5 -> SELU -> fp16 hi/lo operand tile ----
+      mbar_wait(d5_full, k & 1);
+      tc_fence_after();
+      mbar_wait(wh_full, k & 1);                       // biases of head k ride with the head weights
+      const float* b5 = bias;                          // [96]
+      const float* bh = bias + 96;                     // [48]
+      if (k > 0) mbar_wait(d6_full, (k - 1) & 1);      // head k-1 has finished reading A5
+#pragma unroll
+      for (int cb = 0; cb < 96; cb += 16) {
+        float v[16];
+        tmem_ld16(lane_addr + cb, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x = v[i] + b5[cb + i];
+          v[i] = x >= 0.f ? SELU_SCALE * x : (SELU_SCALE * SELU_ALPHA) * (__expf(x) - 1.f);
+        }
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(A5 + (cb / 8) * KCH_BYTES + r * 16) = hi;
+        *reinterpret_cast<uint4*>(A5 + 12 * KCH_BYTES + (cb / 8) * KCH_BYTES + r * 16) = lo;
+        split8(v + 8, hi, lo);
+        *reinterpret_cast<uint4*>(A5 + (cb / 8 + 1) * KCH_BYTES + r * 16) = hi;
+        *reinterpret_cast<uint4*>(A5 + 12 * KCH_BYTES + (cb / 8 + 1) * KCH_BYTES + r * 16) = lo;
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(d5_free);
+        mbar_arrive(a5_full);
+      }
+      // ---- head k: D6 -> +bh -> SELU (= the reference's *_logits) -> softmax ----
+      mbar_wait(d6_full, k & 1);
+      tc_fence_after();
+      const int off = kHeadOff[k], cnt = kHeadOff[k + 1] - off;
+      float z[48];
+#pragma unroll
+      for (int cb = 0; cb < 48; cb += 16) tmem_ld16(lane_addr + 96 + cb, z + cb);
+      tmem_ld_wait();
+      float m = -3.0e38f;
+#pragma unroll
+      for (int i = 0; i < 48; ++i) {
+        const float x = z[i] + bh[i];
+        z[i] = x >= 0.f ? SELU_SCALE * x : (SELU_SCALE * SELU_ALPHA) * (__expf(x) - 1.f);
+        if (i < cnt) m = fmaxf(m, z[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d6_free);
+      float sum = 0.f;
+      float e[48];
+#pragma unroll
+      for (int i = 0; i < 48; ++i) {
+        e[i] = i < cnt ? __expf(z[i] - m) : 0.f;
+        sum += e[i];
+      }
+      const float inv = 1.f / sum;
+      float* lg = logits + site * N_OUT + off;
+#pragma unroll
+      for (int i = 0; i < 48; ++i)
+        if (i < cnt) lg[i] = z[i];
+      if (site < n) {
+        float* pr = probs + site * N_OUT + off;
+#pragma unroll
+        for (int i = 0; i < 48; ++i)
+          if (i < cnt) pr[i] = e[i] * inv;
       }
     }
   }
@@ -921,6 +1127,10 @@ struct HostModel {
   const float* w3;                  // [256][33][30]  (L3/Unit_c/kernel)
   const float* b3;                  // [256][30]
   const float* W4;                  // [7680][192], row = o*256 + c
+  const float* W5[4];               // L5_k/kernel [192][96]
+  const float* b5[4];               // [96]
+  const float* Whd[4];              // Prediction/*_logits/kernel [96][n_k]
+  const float* bhd[4];              // [n_k]
 };
 
 struct Weights {
@@ -929,6 +1139,7 @@ struct Weights {
   __half* Whs[2] = {nullptr, nullptr};     // lstm_seq, per layer: [dir][q][hl][b 4][kc 16][64][8]
   __half* Wxf = nullptr;                   // lstm_seq<FUSE_X>, layer 1: [dir][q][hl][b 4][kc 6][64][8] (k 32,33 = bias hi,lo)
   uint8_t* l3l4 = nullptr;                 // [256] per-channel blobs (L3L4_BLOB_BYTES each)
+  uint8_t* heads = nullptr;                // [4] per-head blobs (HEAD_BLOB_BYTES each)
   const float* b4 = nullptr;               // [192] (owned by the engine)
 };
 
@@ -938,6 +1149,7 @@ struct Workspace {
   __half* H1 = nullptr;      // [33*NT][hl][32][128][8]      LSTM1 output = A tiles of the layer-2 input projection
   float* Gx = nullptr;       // [33*NT][dir][unit][row][4]   layer-2 input projection (+bias, gate-scaled)
   __half* H2t = nullptr;     // [NT][256][hl][5][2][8][64]   LSTM2 output, MN-major 128B-swizzled per channel (t = 33..39 zero)
+  __half* L4t = nullptr;     // [NT][hl][24][128][8]         L4 activations as the operand tile of heads_tc
   int sm_count = 148;
 };
 
@@ -1056,10 +1268,39 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
     }
     if ((st = upload_vec(&w.l3l4, blob)) != cudaSuccess) return st;
   }
+  // ---- L5 + head blobs ----
+  {
+    const int head_n[4] = {21, 3, 33, 33};
+    std::vector<uint8_t> blob((size_t)4 * HEAD_BLOB_BYTES, 0);
+    for (int k = 0; k < 4; ++k) {
+      uint8_t* b = blob.data() + (size_t)k * HEAD_BLOB_BYTES;
+      for (int hf = 0; hf < 2; ++hf) {
+        __half* hi = (__half*)(b + (size_t)hf * HD_W5_BYTES);
+        __half* lo = hi + 24 * 48 * 8;
+        for (int row = 0; row < 48; ++row)
+          for (int kk = 0; kk < L4_UNITS; ++kk) {
+            const size_t idx = (size_t)(kk / 8) * 48 * 8 + row * 8 + kk % 8;
+            split_half(hm.W5[k][(size_t)kk * L5_UNITS + hf * 48 + row], hi[idx], lo[idx]);
+          }
+      }
+      __half* hi = (__half*)(b + 2 * HD_W5_BYTES);
+      __half* lo = hi + 12 * 48 * 8;
+      for (int o = 0; o < head_n[k]; ++o)
+        for (int j = 0; j < L5_UNITS; ++j) {
+          const size_t idx = (size_t)(j / 8) * 48 * 8 + o * 8 + j % 8;
+          split_half(hm.Whd[k][(size_t)j * head_n[k] + o], hi[idx], lo[idx]);
+        }
+      float* bb = (float*)(b + 2 * HD_W5_BYTES + HD_WH_BYTES);
+      for (int j = 0; j < L5_UNITS; ++j) bb[j] = hm.b5[k][j];
+      for (int o = 0; o < head_n[k]; ++o) bb[96 + o] = hm.bhd[k][o];
+    }
+    if ((st = upload_vec(&w.heads, blob)) != cudaSuccess) return st;
+  }
   return cudaSuccess;
 }
 
 inline void free_weights(Weights& w) {
+  cudaFree(w.heads); w.heads = nullptr;
   cudaFree(w.l3l4); cudaFree(w.Wxf); cudaFree(w.Whs[0]); cudaFree(w.Whs[1]); cudaFree(w.Wx2); cudaFree(w.bx2);
   w.l3l4 = nullptr; w.Wxf = nullptr; w.Whs[0] = w.Whs[1] = nullptr; w.Wx2 = nullptr; w.bx2 = nullptr;
 }
@@ -1074,6 +1315,8 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
   if ((st = cudaMalloc((void**)&ws.H2t, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
   // time steps 33..39 of the last time group are never written by lstm_seq and must read as zeros
   if ((st = cudaMemset(ws.H2t, 0, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
+  if ((st = cudaMalloc((void**)&ws.L4t, NT * (size_t)HD_A4_BYTES)) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(heads_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem_bytes())) != cudaSuccess) return st;
   cudaDeviceGetAttribute(&ws.sm_count, cudaDevAttrMultiProcessorCount, device);
   if ((st = cudaFuncSetAttribute(xproj_pair<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<32>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq<true, 0, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
@@ -1084,18 +1327,19 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
 }
 
 inline void free_workspace(Workspace& ws) {
-  cudaFree(ws.X48); cudaFree(ws.Gx); cudaFree(ws.H1); cudaFree(ws.H2t);
-  ws.X48 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr; ws.H2t = nullptr;
+  cudaFree(ws.X48); cudaFree(ws.Gx); cudaFree(ws.H1); cudaFree(ws.H2t); cudaFree(ws.L4t);
+  ws.L4t = nullptr; ws.X48 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr; ws.H2t = nullptr;
 }
 
 // Both BiLSTM layers (+ slice-dense and L4 when fuse_tail) for np padded sites (np % 256 == 0).
 //   fuse_tail = false: x -> h2 planes [33*256][np] fp32 (the CUDA-core slice-dense / L4 follow; parity cross-check)
-//   fuse_tail = true : x -> l4T planes [192][np] fp32 through lstm_seq<.,2> + l3l4_fused
+//   fuse_tail = true : x -> probabilities [n][90] (+ logits [np][90]) through lstm_seq<.,2> + l3l4_fused + heads_tc
 // `hook(id, begin)` brackets every launch for the per-kernel event timing
-// (id: 0 prep_tiles, 1 lstm_seq1, 2 xproj2, 3 lstm_seq2, 4 l3l4_fused).
+// (id: 0 prep_tiles, 1 lstm_seq1, 2 xproj2, 3 lstm_seq2, 4 l3l4_fused, 5 heads_tc).
 template <typename Hook>
 inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_dev, int dtype_is_i16, int64_t n, int64_t np,
-                                float* h2_planes, float* l4T, bool fuse_tail, cudaStream_t st, int* launches, Hook&& hook) {
+                                float* h2_planes, float* l4T, float* probs, float* logits, bool fuse_tail, cudaStream_t st,
+                                int* launches, Hook&& hook) {
   const int NT = (int)(np / 128);
   const int num_row_pairs = T_STEPS * NT / 2;
   // persistent input-projection grid: whole groups of 4 CTA pairs (one pair per N-block), one pair per 2 SMs
@@ -1123,9 +1367,12 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   *launches += 4;
   if (fuse_tail) {
     hook(4, true);
-    l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, np, nullptr);
+    l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, nullptr);
     hook(4, false);
-    *launches += 1;
+    hook(5, true);
+    heads_tc<<<(unsigned)NT, HD_THREADS, heads_smem_bytes(), st>>>(ws.L4t, w.heads, probs, logits, n);
+    hook(5, false);
+    *launches += 2;
   }
   return cudaGetLastError();
 }
@@ -1151,7 +1398,7 @@ inline cudaError_t get_lstm1(const Workspace& ws, int64_t n, int64_t np, float* 
 
 // parity hook: re-run the fused slice-dense on the retained H2t with the L3 activations written out as planes
 inline cudaError_t dump_l3(const Weights& w, const Workspace& ws, int64_t np, float* l4T, float* l3_planes) {
-  l3l4_fused<<<(unsigned)(np / 128), LF_THREADS, l3l4_smem_bytes(), 0>>>(ws.H2t, w.l3l4, w.b4, l4T, np, l3_planes);
+  l3l4_fused<<<(unsigned)(np / 128), LF_THREADS, l3l4_smem_bytes(), 0>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, l3_planes);
   cudaError_t st = cudaGetLastError();
   return st != cudaSuccess ? st : cudaDeviceSynchronize();
 }
