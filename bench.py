@@ -36,8 +36,11 @@ KERNEL_FLOP_PER_SITE = {"lstm_layer2": LSTM2_FLOP_PER_SITE, "lstm_layer1": LSTM1
                         "l4_dense": 2 * 1474560, "l3_slice_dense": 2 * 253440, "tail_heads": 2 * (73728 + 8640),
                         "lstm_seq1": 2 * 5406720, "xproj2": 2 * 8650752, "lstm_seq2": 2 * 4325376,
                         "l3l4_fused": 2 * (253440 + 1474560), "prep_tiles": 0, "prep_input": 0, "heads_tc": 2 * (73728 + 8640)}
+# algorithmic HBM bytes per site of each kernel (operand tiles in + results out)
+KERNEL_BYTES_PER_SITE = {"prep_tiles": 4224 + 6336, "lstm_seq1": 6336 + 33792, "xproj2": 33792 + 135168,
+                         "lstm_seq2": 135168 + 40960, "l3l4_fused": 40960 + 768 + 768, "heads_tc": 768 + 360 + 360}
 BATCH = 1000                        # shared/param.py:16 predictBatchSize
-WORKLOAD = "ONT-shape model inference, 1M synthetic candidate sites, batch=1000, 1xB200"
+WORKLOAD = "ONT-shape model inference, 1M synthetic candidate sites, batch=1000, %dxB200"
 
 
 def parse_args():
@@ -50,6 +53,18 @@ def parse_args():
     ap.add_argument("--cpu-baseline-batches", type=int, default=0, help="0 = auto (about 10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
+
+
+def measured_traffic(kernel, sites_per_launch):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic.json),
+    scaled to this run's sites per launch; None when no capture covers the kernel."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return t["dram_bytes_per_site"][kernel] * sites_per_launch
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def measured_peaks():
@@ -173,7 +188,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "candidate-sites/sec", "value": value, "unit": "sites/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch": BATCH, "sites_per_step": per_step * BATCH,
+        "config": {"workload": WORKLOAD % 1, "batch": BATCH, "sites_per_step": per_step * BATCH,
                    "note": "reference CPU path = fp32 torch-CPU port of the reference graph (TensorFlow 1.13.2 not installable)"},
         "cpu_baseline": {"value": value, "unit": "sites/s", "cores": fo.threads, "kind": "port", "sample": sample,
                          "cpu_model": model, "host_cores": cores},
@@ -298,11 +313,15 @@ def main():
             achieved = flop / (avg_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": achieved,
                         "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                        "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+                        "traffic": measured_traffic(dom["kernel"], sites_per_launch),
+                        "traffic_source": "ncu dram__bytes_read+write per launch (profiles/r01_traffic.json), scaled by sites",
+                        "algorithmic_bytes": KERNEL_BYTES_PER_SITE.get(dom["kernel"], 0) * sites_per_launch,
+                        "peak_source": peaks["source"] + " (sustained bf16)",
                         "avg_launch_ms": avg_ms, "sites_per_launch": sites_per_launch,
                         "whole_path_frac": value / world * FLOP_PER_SITE / 1e12 / peaks["bf16_sustained"],
                         "kernel_share": {k: v["ms"] / max(1e-9, sum(p["ms"] for p in profile)) for k, v in prof.items()},
-                        "note": "logit tolerance 1e-4 needs the 3-term fp16 split: attainable ceiling is 1/3 of peak"}
+                        "note": "logit tolerance 1e-4 needs the 3-term fp16 split (3 MMAs per algorithmic MAC): attainable "
+                                "ceiling is 1/3 of peak, i.e. frac 0.333 = tensor pipe saturated"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             nb = args.cpu_baseline_batches or 24
@@ -318,7 +337,7 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (fp16 hi/lo split operands, f32 accumulate)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch": BATCH, "batches_per_step": bps, "sites_per_step": sites,
+            "config": {"workload": WORKLOAD % world, "batch": BATCH, "batches_per_step": bps, "sites_per_step": sites,
                        "l2": "inputs larger than L2: %.0f MB of fp32 input re-read per step" % (sites * 4224 / 1e6),
                        "weights": "random-init ONT-shape, seed 1234", "engine": engine,
                        "parallelism": "sites sharded over %d GPU(s), one NCCL gather of [sites,90] per step" % world},

@@ -748,7 +748,7 @@ constexpr size_t l3l4_smem_bytes() { return (size_t)LF_STAGES * LF_STAGE_BYTES +
 
 __global__ void __launch_bounds__(LF_THREADS, 1)
 l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, const float* __restrict__ b4,
-           float* __restrict__ l4T, __half* __restrict__ L4t, int64_t np, float* __restrict__ l3_dbg) {
+           float* __restrict__ l4T, __half* __restrict__ L4t, int64_t np, float* __restrict__ l3_dbg, int pf_dist) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stages = smem;
@@ -786,7 +786,11 @@ l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, co
   if (warp == 0) {
     if (lane == 0) {
       const uint8_t* a_src = (const uint8_t*)(H2t + (size_t)tile * 2 * H * L3A_HALVES);
+      // the ring (3 x 52 KB) is too shallow for HBM latency: pull the LSTM2 tiles of the next channels into L2 ahead of
+      // the bulk copies (the weight blobs are shared by all CTAs and stay L2-resident by themselves)
+      for (int c = 0; c < pf_dist && c < 2 * H; ++c) bulk_prefetch_l2(a_src + (size_t)c * L3A_BYTES, L3A_BYTES);
       for (int c = 0; c < 2 * H; ++c) {
+        if (c + pf_dist < 2 * H && pf_dist > 0) bulk_prefetch_l2(a_src + (size_t)(c + pf_dist) * L3A_BYTES, L3A_BYTES);
         const int st = c % LF_STAGES;
         mbar_wait(&stage_empty[st], ((c / LF_STAGES) & 1) ^ 1);
         uint8_t* dst = stages + st * LF_STAGE_BYTES;
@@ -1347,6 +1351,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   if (ncl > 4 * num_row_pairs) ncl = 4 * num_row_pairs;
   if (ncl < 4) ncl = 4;
   static const int gx_pf = getenv("CLAIRB_GX_PF") ? atoi(getenv("CLAIRB_GX_PF")) : 0;   // Gx L2 prefetch distance (steps)
+  static const int l3_pf = getenv("CLAIRB_L3_PF") ? atoi(getenv("CLAIRB_L3_PF")) : 8;   // l3l4 L2 prefetch distance (channels)
   static const int xp_dbg = getenv("CLAIRB_XP_DBG") ? atoi(getenv("CLAIRB_XP_DBG")) : 0;   // timing experiments only
   dim3 gprep((unsigned)NT, T_STEPS);
   dim3 grec((unsigned)NT, 2);
@@ -1367,7 +1372,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   *launches += 4;
   if (fuse_tail) {
     hook(4, true);
-    l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, nullptr);
+    l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, nullptr, l3_pf);
     hook(4, false);
     hook(5, true);
     heads_tc<<<(unsigned)NT, HD_THREADS, heads_smem_bytes(), st>>>(ws.L4t, w.heads, probs, logits, n);
@@ -1398,7 +1403,7 @@ inline cudaError_t get_lstm1(const Workspace& ws, int64_t n, int64_t np, float* 
 
 // parity hook: re-run the fused slice-dense on the retained H2t with the L3 activations written out as planes
 inline cudaError_t dump_l3(const Weights& w, const Workspace& ws, int64_t np, float* l4T, float* l3_planes) {
-  l3l4_fused<<<(unsigned)(np / 128), LF_THREADS, l3l4_smem_bytes(), 0>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, l3_planes);
+  l3l4_fused<<<(unsigned)(np / 128), LF_THREADS, l3l4_smem_bytes(), 0>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, l3_planes, 0);
   cudaError_t st = cudaGetLastError();
   return st != cudaSuccess ? st : cudaDeviceSynchronize();
 }
