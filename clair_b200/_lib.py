@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libclair_b200.so")
+LIB_PATH = os.environ.get("CLAIRB_LIB") or os.path.join(_HERE, "lib", "libclair_b200.so")   # CLAIRB_LIB: A/B builds
 
 OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, EWEIGHTS = range(6)
 DTYPE_F32, DTYPE_I16 = 0, 1

@@ -59,6 +59,7 @@ struct clairb_engine {
   EngineKind kind = ENGINE_SIMT;
   bool finalized = false;
   bool fuse_tail = false;      // TC engine: slice-dense + L4 on tensor cores (l3l4_fused)
+  bool ramp = false;           // first chunk of a multi-chunk host call is a quarter chunk
   std::string err;
   int64_t launches = 0;
 
@@ -355,6 +356,8 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
   if (e->kind == ENGINE_TC) {
     const char* ft = getenv("CLAIRB_FUSED_TAIL");
     e->fuse_tail = !(ft && !strcmp(ft, "0"));
+    const char* rp = getenv("CLAIRB_RAMP");
+    e->ramp = !(rp && !strcmp(rp, "0"));
   }
   if (e->kind == ENGINE_TC) {
     // Sites are independent, so a chunk need not be whole predict-batches.  Default: 2 waves of CTA pairs per chunk
@@ -593,6 +596,9 @@ int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, f
   while (done < n) {
     const int b = c & 1;
     int64_t cn = n - done < e->chunk_sites ? n - done : e->chunk_sites;
+    // ramp-up: nothing can overlap the very first host->device copy, so the first chunk of a multi-chunk call is a
+    // quarter chunk (one half-wave of CTA pairs) and the forward starts after 20 MB instead of 80 MB
+    if (c == 0 && n > e->chunk_sites && e->ramp) cn = (e->chunk_sites / 4 + TC_PAIR_SITES - 1) / TC_PAIR_SITES * TC_PAIR_SITES;
     SiteMap sm = make_map(e, cn);
     // input buffer b is free once the forward of chunk c-2 has consumed it
     CU_TRY(e, cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));

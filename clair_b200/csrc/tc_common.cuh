@@ -39,12 +39,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or ~`ns` elapse, so a waiting
+// warp does not burn issue slots of the warp it shares a scheduler with
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must not hang the GPU (it traps after ~2 s instead).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+  uint32_t spins = 0;
+#ifndef CLAIRB_WAIT_HINT_NS
+#define CLAIRB_WAIT_HINT_NS 0u   // measured: a suspend-time hint changes nothing (A/B on one box), plain try_wait polling it is
+#endif
+  while (!(CLAIRB_WAIT_HINT_NS ? mbar_try_wait_hint(bar, parity, CLAIRB_WAIT_HINT_NS) : mbar_try_wait(bar, parity))) {
+    if (++spins > (CLAIRB_WAIT_HINT_NS ? 200000u : 400000000u)) {          // ~2 s without progress
       printf("clair_b200: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
              threadIdx.x, smem_u32(bar), parity);
       __trap();

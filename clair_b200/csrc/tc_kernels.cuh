@@ -99,6 +99,11 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
+__device__ __forceinline__ float4 lds4(uint32_t smem_addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem_addr));
+  return r;
+}
 __device__ __forceinline__ void st_stream4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -560,6 +565,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
         for (int i = 0; i < UPS; ++i) c[b][j][i] = 0.f;
 
     uint32_t use0 = 0, use1 = 0, gq_idx = 0;
+    const uint32_t gs_base = smem_u32(Gs);
     // Gx tiles (written by xproj_pair, HBM-resident) are pulled into L2 two steps ahead, paced by the step loop
     auto prefetch_gx = [&](int sp) {
       const int tp = dir ? (T_STEPS - 1 - sp) : sp;
@@ -592,9 +598,9 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
             const uint32_t gst = gq_idx % SEQ_G_RING;
             mbar_wait(&g_full[gst], (gq_idx / SEQ_G_RING) & 1);
             ++gq_idx;
-            const float4* gsm = reinterpret_cast<const float4*>(Gs + gst * SEQ_G_STAGE) + (sub * UPS) * 128 + r;
+            const uint32_t gsm = gs_base + gst * SEQ_G_STAGE + ((sub * UPS) * 128 + r) * 16;
 #pragma unroll
-            for (int k = 0; k < UPS; ++k) gq[k] = gsm[k * 128];
+            for (int k = 0; k < UPS; ++k) gq[k] = lds4(gsm + k * 128 * 16);
             __syncwarp();
             if (lane == 0) mbar_arrive(&g_empty[gst]);
           }

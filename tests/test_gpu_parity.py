@@ -135,6 +135,27 @@ def test_chunk_pipeline_pageable_and_pinned_outputs(weights1234, monkeypatch):
     one.close()
 
 
+@pytest.mark.parametrize("env", [{"CLAIRB_ENGINE": "simt"}, {"CLAIRB_FUSED_TAIL": "0"}])
+def test_cross_check_engines(weights1234, monkeypatch, env):
+    # the CUDA-core fp32 engine and the mixed path (tensor-core LSTMs into the CUDA-core slice-dense / L4 / heads) are the
+    # on-device cross-checks of the production tensor-core path: all three must meet the oracle and each other
+    from clair_b200.model import Clair
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = Clair(max_sites=1024, batch_sites=1000)
+    for k in env:
+        monkeypatch.delenv(k)
+    alt.set_weights(weights1234)
+    X = synth.synthetic_tensors(300, seed=91)
+    assert_parity(alt, X, weights1234, check_layers=True)
+    prod = Clair(max_sites=1024, batch_sites=1000)
+    prod.set_weights(weights1234)
+    a, b = alt.predict_packed(X), prod.predict_packed(X)
+    assert np.abs(a - b).max() <= 2e-5
+    alt.close()
+    prod.close()
+
+
 def test_predict_from_worker_thread(gpu_model):
     import threading
     X = synth.synthetic_tensors(100, seed=2)
