@@ -230,38 +230,42 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
   } else if (warp == 1) {
     if (lane == 0) {
       if (rank == 1) {
-        // ---- relay: tell the leader when this CTA's stage has landed ----
+        // ---- relay: tell the leader when this CTA's stage has landed.  The payload was written by the bulk-copy
+        //      engine and is complete once `full` flips; a release-arrive (ERRBAR + fence, ~700 cycles each) would make
+        //      this thread the pipeline's bottleneck (measured: the leader waited on peer_full 10x more than on anything
+        //      else), so the remote arrive is relaxed ----
         uint32_t use = 0;
+        const uint32_t leader_peer_full = map_to_cta(smem_u32(peer_full), 0);
         for (int rp = grp; rp < num_row_pairs; rp += ngrp)
           for (int ks = 0; ks < NST; ++ks, ++use) {
             const int slot = use % XP_RING;
             mbar_wait(&full[slot], (use / XP_RING) & 1);
-            mbar_arrive_cluster(map_to_cta(smem_u32(&peer_full[slot]), 0));
+            mbar_arrive_cluster_relaxed(leader_peer_full + slot * 8);
           }
       } else {
-        // ---- MMA issuer ----
+        // ---- MMA issuer (one thread feeds the tensor pipe: keep its instruction stream short -- descriptors are
+        //      advanced with one add, ring slot / parity are carried instead of divided) ----
         const uint32_t idesc = make_idesc_f16(256, 256);
-        const uint32_t b_base = smem_u32(Bs);
-        uint32_t use = 0, it = 0;
+        const uint64_t b_hi0 = make_smem_desc(smem_u32(Bs), KCH_BYTES, 128);
+        const uint64_t b_lo0 = desc_advance(b_hi0, KC * KCH_BYTES);
+        const uint64_t a_ring = make_smem_desc(smem_u32(ring), KCH_BYTES, 128);
+        uint32_t slot = 0, par = 0, it = 0;
         for (int rp = grp; rp < num_row_pairs; rp += ngrp, ++it) {
           const uint32_t buf = it & 1;
           mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d = tmem + buf * 256;
-          for (int ks = 0; ks < NST; ++ks, ++use) {
-            const int slot = use % XP_RING;
-            const uint32_t par = (use / XP_RING) & 1;
+#pragma unroll
+          for (int ks = 0; ks < NST; ++ks) {
             mbar_wait(&full[slot], par);
-            if (!(dbg & 4)) mbar_wait(&peer_full[slot], par);
+            mbar_wait(&peer_full[slot], par);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(ring + slot * XP_STAGE_BYTES);
+            const uint64_t a_hi0 = desc_advance(a_ring, slot * XP_STAGE_BYTES), a_lo0 = desc_advance(a_hi0, 4 * KCH_BYTES);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
-              const uint64_t a_hi = make_smem_desc(a_base + kk * 2 * KCH_BYTES, KCH_BYTES, 128);
-              const uint64_t a_lo = make_smem_desc(a_base + 4 * KCH_BYTES + kk * 2 * KCH_BYTES, KCH_BYTES, 128);
-              const uint32_t bo = (ks * 4 + kk * 2) * KCH_BYTES;
-              const uint64_t b_hi = make_smem_desc(b_base + bo, KCH_BYTES, 128);
-              const uint64_t b_lo = make_smem_desc(b_base + KC * KCH_BYTES + bo, KCH_BYTES, 128);
+              const uint64_t a_hi = desc_advance(a_hi0, kk * 2 * KCH_BYTES), a_lo = desc_advance(a_lo0, kk * 2 * KCH_BYTES);
+              const uint64_t b_hi = desc_advance(b_hi0, (ks * 4 + kk * 2) * KCH_BYTES);
+              const uint64_t b_lo = desc_advance(b_lo0, (ks * 4 + kk * 2) * KCH_BYTES);
               umma_f16_pair(d, a_hi, b_hi, idesc, (ks | kk) != 0);
               if (!(dbg & 2)) {
                 umma_f16_pair(d, a_lo, b_hi, idesc, 1);
@@ -269,6 +273,7 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
               }
             }
             umma_commit_pair(&empty[slot], 0b11);
+            if (++slot == XP_RING) { slot = 0; par ^= 1; }
           }
           umma_commit_pair(&acc_full[buf], 0b11);
         }
@@ -293,6 +298,7 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
       const float* bs = bias_s + colhalf * 128;
 #pragma unroll 2
       for (int c = 0; c < 128; c += 32) {
+        if ((dbg & 128) && c) __nanosleep((dbg >> 8) * 100);      // pacing experiment
         float v[32];
         tmem_ld16(taddr + c, v);
         tmem_ld16(taddr + c + 16, v + 16);
@@ -524,7 +530,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
           bulk_g2s(Xs + st * SEQ_X_STAGE, X48 + ((size_t)t * NT + tile) * X48_TILE_HALVES, SEQ_X_STAGE, &x_full[st]);
           if (rank == 1) {
             mbar_wait(&x_full[st], (s >> 1) & 1);
-            mbar_arrive_cluster(map_to_cta(smem_u32(&x_peer[st]), 0));
+            mbar_arrive_cluster_relaxed(map_to_cta(smem_u32(&x_peer[st]), 0));   // payload written by the bulk-copy engine
           }
         }
       } else {
