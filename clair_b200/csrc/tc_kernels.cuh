@@ -137,12 +137,13 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
 //              CTA q of the pair supplies rows q*128..+128 of the block
 //   bias     : [nb 4][256] fp32 in the same column order
 // Persistent CTA pairs: a pair keeps ONE N-block of Wx resident in shared memory (B operand, <=128 KB per CTA) and
-// streams row-pairs (256 rows = two A tiles) through a ring of K=32 stages.  Pairs 4g..4g+3 walk the same row-pairs
+// streams row-pairs (256 rows = two A tiles) through a ring of K=64 stages.  Pairs 4g..4g+3 walk the same row-pairs
 // with the four different N-blocks at the same time, so each A tile is read from HBM once and hit in L2 three times.
 // Warp roles: 0 = A producer, 1 = MMA issuer (leader) / stage relay (peer), 2..9 = epilogue (TMEM -> +bias -> Gx).
 // ---------------------------------------------------------------------------------------------
-constexpr int XP_RING = 6;
-constexpr int XP_STAGE_BYTES = 2 * 4 * KCH_BYTES;     // [hl][4 kc][128][8] = 16 KB
+constexpr int XP_SKC = 8;                              // k-chunks of 8 per ring stage: K = 64 per stage
+constexpr int XP_RING = 3;
+constexpr int XP_STAGE_BYTES = 2 * XP_SKC * KCH_BYTES; // [hl][8 kc][128][8] = 32 KB
 constexpr int XP_THREADS = 320;                        // warps: producer, MMA/relay, 8 epilogue
 
 template <int KC>
@@ -154,7 +155,7 @@ template <int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XP_THREADS, 1)
 xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const float* __restrict__ bias,
            float* __restrict__ Gx, int num_row_pairs, int dbg) {
-  constexpr int NST = KC / 4;                          // K=32 stages per row tile
+  constexpr int NST = KC / XP_SKC;                     // ring stages per row tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* Bs = smem;                                  // [hl][KC][128][8]
@@ -221,8 +222,8 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
           uint8_t* dst = ring + slot * XP_STAGE_BYTES;
           if (dbg & 8) { mbar_arrive(&full[slot]); continue; }
           mbar_expect_tx(&full[slot], XP_STAGE_BYTES);
-          bulk_g2s(dst, at + (size_t)ks * 4 * KCH, 4 * KCH_BYTES, &full[slot]);
-          bulk_g2s(dst + 4 * KCH_BYTES, at + (size_t)KC * KCH + (size_t)ks * 4 * KCH, 4 * KCH_BYTES, &full[slot]);
+          bulk_g2s(dst, at + (size_t)ks * XP_SKC * KCH, XP_SKC * KCH_BYTES, &full[slot]);
+          bulk_g2s(dst + XP_SKC * KCH_BYTES, at + (size_t)KC * KCH + (size_t)ks * XP_SKC * KCH, XP_SKC * KCH_BYTES, &full[slot]);
         }
       }
     }
@@ -230,17 +231,18 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
   } else if (warp == 1) {
     if (lane == 0) {
       if (rank == 1) {
-        // ---- relay: tell the leader when this CTA's stage has landed.  The payload was written by the bulk-copy
-        //      engine and is complete once `full` flips; a release-arrive (ERRBAR + fence, ~700 cycles each) would make
-        //      this thread the pipeline's bottleneck (measured: the leader waited on peer_full 10x more than on anything
-        //      else), so the remote arrive is relaxed ----
+        // ---- relay: tell the leader when this CTA's stage has landed.  The arrive MUST be a release at cluster scope:
+        //      with a relaxed arrive the pair-MMA occasionally read this CTA's stage before the bulk copy's data was
+        //      visible to it (rare, size-dependent logit errors ~3e-3; tools/parity_loop.py).  The release costs ~700
+        //      cycles (ERRBAR + cluster fence), so stages are K = 64 (4 relays per unit, not 8) to keep this thread off
+        //      the critical path. ----
         uint32_t use = 0;
         const uint32_t leader_peer_full = map_to_cta(smem_u32(peer_full), 0);
         for (int rp = grp; rp < num_row_pairs; rp += ngrp)
           for (int ks = 0; ks < NST; ++ks, ++use) {
             const int slot = use % XP_RING;
             mbar_wait(&full[slot], (use / XP_RING) & 1);
-            mbar_arrive_cluster_relaxed(leader_peer_full + slot * 8);
+            mbar_arrive_cluster(leader_peer_full + slot * 8);
           }
       } else {
         // ---- MMA issuer (one thread feeds the tensor pipe: keep its instruction stream short -- descriptors are
@@ -260,12 +262,12 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
             mbar_wait(&full[slot], par);
             mbar_wait(&peer_full[slot], par);
             tc_fence_after();
-            const uint64_t a_hi0 = desc_advance(a_ring, slot * XP_STAGE_BYTES), a_lo0 = desc_advance(a_hi0, 4 * KCH_BYTES);
+            const uint64_t a_hi0 = desc_advance(a_ring, slot * XP_STAGE_BYTES), a_lo0 = desc_advance(a_hi0, XP_SKC * KCH_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
+            for (int kk = 0; kk < XP_SKC / 2; ++kk) {
               const uint64_t a_hi = desc_advance(a_hi0, kk * 2 * KCH_BYTES), a_lo = desc_advance(a_lo0, kk * 2 * KCH_BYTES);
-              const uint64_t b_hi = desc_advance(b_hi0, (ks * 4 + kk * 2) * KCH_BYTES);
-              const uint64_t b_lo = desc_advance(b_lo0, (ks * 4 + kk * 2) * KCH_BYTES);
+              const uint64_t b_hi = desc_advance(b_hi0, (ks * XP_SKC + kk * 2) * KCH_BYTES);
+              const uint64_t b_lo = desc_advance(b_lo0, (ks * XP_SKC + kk * 2) * KCH_BYTES);
               umma_f16_pair(d, a_hi, b_hi, idesc, (ks | kk) != 0);
               if (!(dbg & 2)) {
                 umma_f16_pair(d, a_lo, b_hi, idesc, 1);
