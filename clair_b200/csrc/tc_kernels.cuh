@@ -144,7 +144,7 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
 constexpr int XP_SKC = 8;                              // k-chunks of 8 per ring stage: K = 64 per stage
 constexpr int XP_RING = 3;
 constexpr int XP_STAGE_BYTES = 2 * XP_SKC * KCH_BYTES; // [hl][8 kc][128][8] = 32 KB
-constexpr int XP_THREADS = 320;                        // warps: producer, MMA/relay, 8 epilogue
+constexpr int XP_THREADS = 352;                        // warps: producer, MMA / relay, 8 epilogue, second relay
 
 template <int KC>
 constexpr size_t xproj_smem_bytes() {
@@ -200,6 +200,19 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // relay (peer CTA): forwards "stage landed" for every second stage (two relay threads alternate, so each release-arrive
+  // -- ~700 cycles -- has two stage times to complete)
+  auto relay_stages = [&](int which) {
+    uint32_t use = 0;
+    const uint32_t leader_peer_full = map_to_cta(smem_u32(peer_full), 0);
+    for (int rp = grp; rp < num_row_pairs; rp += ngrp)
+      for (int ks = 0; ks < NST; ++ks, ++use) {
+        if ((int)(use & 1) != which) continue;
+        const int slot = use % XP_RING;
+        mbar_wait(&full[slot], (use / XP_RING) & 1);
+        mbar_arrive_cluster(leader_peer_full + slot * 8);
+      }
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -236,14 +249,7 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
         //      visible to it (rare, size-dependent logit errors ~3e-3; tools/parity_loop.py).  The release costs ~700
         //      cycles (ERRBAR + cluster fence), so stages are K = 64 (4 relays per unit, not 8) to keep this thread off
         //      the critical path. ----
-        uint32_t use = 0;
-        const uint32_t leader_peer_full = map_to_cta(smem_u32(peer_full), 0);
-        for (int rp = grp; rp < num_row_pairs; rp += ngrp)
-          for (int ks = 0; ks < NST; ++ks, ++use) {
-            const int slot = use % XP_RING;
-            mbar_wait(&full[slot], (use / XP_RING) & 1);
-            mbar_arrive_cluster(leader_peer_full + slot * 8);
-          }
+        relay_stages(0);
       } else {
         // ---- MMA issuer (one thread feeds the tensor pipe: keep its instruction stream short -- descriptors are
         //      advanced with one add, ring slot / parity are carried instead of divided) ----
@@ -281,6 +287,9 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
         }
       }
     }
+    __syncwarp();
+  } else if (warp == 10) {
+    if (lane == 0 && rank == 1) relay_stages(1);
     __syncwarp();
   } else {
     // ---- epilogue: TMEM -> + bias -> Gx (float4 per hidden unit, 512 B per warp store) ----
@@ -532,7 +541,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
           bulk_g2s(Xs + st * SEQ_X_STAGE, X48 + ((size_t)t * NT + tile) * X48_TILE_HALVES, SEQ_X_STAGE, &x_full[st]);
           if (rank == 1) {
             mbar_wait(&x_full[st], (s >> 1) & 1);
-            mbar_arrive_cluster_relaxed(map_to_cta(smem_u32(&x_peer[st]), 0));   // payload written by the bulk-copy engine
+            mbar_arrive_cluster(map_to_cta(smem_u32(&x_peer[st]), 0));   // release: see the relay note in xproj_pair
           }
         }
       } else {

@@ -156,6 +156,26 @@ def test_cross_check_engines(weights1234, monkeypatch, env):
     prod.close()
 
 
+def test_full_machine_stress_is_exact_and_repeatable(weights1234):
+    # 40,000 sites fill every SM for several waves, which is where inter-CTA ordering bugs show (a relaxed mbarrier
+    # arrive between the two CTAs of a pair once produced rare ~3e-3 errors that no small test saw): results must be
+    # bit-identical between calls, identical to the same sites predicted alone, and meet the oracle on a sample
+    from clair_b200.model import Clair
+    m = Clair(max_sites=75000, batch_sites=1000)
+    m.set_weights(weights1234)
+    X = synth.synthetic_tensors(40000, seed=20240608)
+    a = m.predict_packed(X)
+    for _ in range(2):
+        np.testing.assert_array_equal(a, m.predict_packed(X))
+    idx = np.arange(0, 40000, 211)
+    ref = O.forward_packed(X[idx], weights1234, np.float64)
+    assert np.abs(a[idx] - ref).max() <= TOL
+    for h, (lo, hi) in enumerate(((0, 21), (21, 24), (24, 57), (57, 90))):
+        np.testing.assert_array_equal(a[idx, lo:hi].argmax(1), ref[:, lo:hi].argmax(1))
+    np.testing.assert_array_equal(a[idx], m.predict_packed(X[idx]))     # position / chunk independence at scale
+    m.close()
+
+
 def test_predict_from_worker_thread(gpu_model):
     import threading
     X = synth.synthetic_tensors(100, seed=2)
