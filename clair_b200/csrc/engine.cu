@@ -59,6 +59,7 @@ struct clairb_engine {
   EngineKind kind = ENGINE_SIMT;
   bool finalized = false;
   bool fuse_tail = false;      // TC engine: slice-dense + L4 on tensor cores (l3l4_fused)
+  bool l2_stream = true;       // TC engine: layer-2 input projection streamed through the recurrent kernel (lstm_seq_x2)
   bool ramp = false;           // first chunk of a multi-chunk host call is a quarter chunk
   std::string err;
   int64_t launches = 0;
@@ -163,8 +164,9 @@ SiteMap make_map(const clairb_engine* e, int64_t n) {
 
 // ---- per-kernel event timing --------------------------------------------------------------------
 const char* kKernelNames[] = {"prep_input", "lstm_layer1", "lstm_layer2", "l3_slice_dense", "l4_dense",
-                              "tail_heads", "prep_tiles", "lstm_seq1", "xproj2", "lstm_seq2", "l3l4_fused", "heads_tc"};
-constexpr int kNumKernelNames = 12;
+                              "tail_heads", "prep_tiles", "lstm_seq1", "xproj2", "lstm_seq2", "l3l4_fused", "heads_tc",
+                              "lstm_seq_x2"};
+constexpr int kNumKernelNames = 13;
 
 void prof_fold(clairb_engine* e) {
   for (auto& sp : e->prof_open) {
@@ -276,7 +278,7 @@ int forward_chunk(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, fl
       else { delete open; open = nullptr; }
     };
     cudaError_t cst = tc::forward_lstm(e->tcw, e->tcws, x_dev, dtype == CLAIRB_DTYPE_I16, sm.n, sm.np, e->d_h2, e->d_l4T,
-                                       out_dev, e->d_logits, e->fuse_tail, st, &nl, hook);
+                                       out_dev, e->d_logits, e->fuse_tail, e->l2_stream, st, &nl, hook);
     e->launches += nl;
     if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "tensor-core forward failed: %s", cudaGetErrorString(cst));
     if (e->fuse_tail) return CLAIRB_OK;
@@ -356,6 +358,8 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
   if (e->kind == ENGINE_TC) {
     const char* ft = getenv("CLAIRB_FUSED_TAIL");
     e->fuse_tail = !(ft && !strcmp(ft, "0"));
+    const char* ls = getenv("CLAIRB_L2_STREAM");
+    e->l2_stream = !(ls && !strcmp(ls, "0"));
     const char* rp = getenv("CLAIRB_RAMP");
     e->ramp = !(rp && !strcmp(rp, "0"));
   }

@@ -710,6 +710,295 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
   if (warp == 0) tmem_dealloc_pair<512>(tmem);
 }
 
+// ---------------------------------------------------------------------------------------------
+// lstm_seq_x2<OUT, G>: layer 2 with its input projection streamed through the recurrent kernel (no Gx in HBM).
+//   gates(t) = h1_t . W_x + b + h_{t-1} . W_h        K_x = 256: W_x hi/lo of one direction is 512 KB, i.e. 256 KB per
+// CTA of the pair - it cannot be resident next to W_h (128 KB), so both operands of the x part stream through a ring:
+//   stage (32 KB, K = 32) = [A hi 8K | A lo 8K | B hi 8K | B lo 8K]
+//     A = this CTA's 128 rows of the h1_t tile (written by lstm_seq<FUSE_X>, K-major [hl][32 kc][128][8])
+//     B = this CTA's 128 gate columns of TWO gate blocks: the x part is issued as M=256, N=256 pair-MMAs that fill both
+//         ping-pong accumulators at once, so every A stage is used for 256 columns and h1_t streams twice per step
+//         (block pairs (0,1) and (2,3)); 16 stages = 512 KB per CTA-step, all L2 hits except the first pass over h1_t.
+// Per step the issuer runs   x(0,1) | h(0) h(1) | x(2,3) | h(2) h(3)   : x(0,1) of step s does not depend on the
+// recurrence and fills the tensor pipe while the epilogue is still turning blocks 2, 3 of step s-1 into h_{s-1}.
+// Accumulator column c of block b is gate column b*128 + c in both parts (x part: CTA q, row r -> block 2bp+q, c = r).
+//   Wx   : [dir][q][bp 2][st 8][hl][kc 4][128 rows][8]   bias: [dir][512] (unit*4+gate order, gate-scaled)
+// Warps: 0 = MMA issuer (leader) / relay 0 (peer), 1..4G = epilogue, 4G+1 = ring producer, 4G+2 = relay 1 (peer).
+// ---------------------------------------------------------------------------------------------
+constexpr int SX_STAGE = 32768;
+constexpr int SX_RING = 3;
+constexpr int SX_NST = 8;                               // stages per block pair: K = 256 / 32
+constexpr int SX_THREADS = 32 * (3 + 4 * SEQ_G);
+constexpr size_t seqx_smem_bytes() { return (size_t)SEQ_W_BYTES + SX_RING * SX_STAGE + 2048 + 256 + 128; }
+
+template <int OUT, int G>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (3 + 4 * G), 1)
+lstm_seq_x2(const __half* __restrict__ Wh, const uint8_t* __restrict__ Wx, const float* __restrict__ bias,
+            const __half* __restrict__ H1, void* __restrict__ Hout, int NT, int64_t np) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  uint8_t* Ws = smem;                                            // [hl][b][kc 16][64][8]
+  uint8_t* ring = smem + SEQ_W_BYTES;                            // [3 stages][A hi | A lo | B hi | B lo]
+  float* bias_s = (float*)(ring + SX_RING * SX_STAGE);           // [128 units][4 gates]
+  uint64_t* bars = (uint64_t*)(bias_s + 512);
+  uint64_t* acc_full = bars;           // [2] gate block complete (MMA commit, both CTAs)
+  uint64_t* acc_empty = bars + 2;      // [2] (leader) accumulator drained by all 16 epilogue warps of the pair
+  uint64_t* hq = bars + 4;             // [4] (leader) units 32b..32b+31 of h_t of both CTAs are in tensor memory
+  uint64_t* full = bars + 8;           // [3] this CTA's stage landed
+  uint64_t* peer_full = bars + 11;     // [3] (leader) the peer's stage landed
+  uint64_t* empty = bars + 14;         // [3] stage consumed (MMA commit, both CTAs)
+  uint64_t* w_full = bars + 17;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int dir = blockIdx.y;
+  const int tile = blockIdx.x;                                   // = 2*pair + rank
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8 * G);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&hq[i], 8 * G);
+    for (int i = 0; i < SX_RING; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&peer_full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+    const uint8_t* src = (const uint8_t*)Wh + ((size_t)dir * 2 + rank) * SEQ_W_BYTES;
+    mbar_expect_tx(w_full, SEQ_W_BYTES);
+    for (int i = 0; i < SEQ_W_BYTES; i += 32768) bulk_g2s(Ws + i, src + i, 32768, w_full);
+  }
+  if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
+  for (int i = threadIdx.x; i < 512; i += 32 * (3 + 4 * G)) bias_s[i] = bias[dir * 512 + i];
+  __syncthreads();                                     // barrier inits visible before anyone polls them
+  mbar_wait(w_full, 0);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;    // cols 0..127 acc0, 128..255 acc1, 256..383 h buffer 0 (hi 64 | lo 64), 384..511 h buffer 1
+
+  // relay (peer CTA): "my stage landed" -> the leader, release at cluster scope (see xproj_pair); two threads alternate
+  auto relay_stages = [&](int which) {
+    const uint32_t leader_peer_full = map_to_cta(smem_u32(peer_full), 0);
+    uint32_t slot = 0, par = 0;
+    for (int use = 0; use < T_STEPS * 2 * SX_NST; ++use) {
+      if ((use & 1) == which) {
+        mbar_wait(&full[slot], par);
+        mbar_arrive_cluster(leader_peer_full + slot * 8);
+      }
+      if (++slot == SX_RING) { slot = 0; par ^= 1; }
+    }
+  };
+
+  if (warp == 0) {
+    if (lane == 0 && rank == 1) relay_stages(0);
+    if (lane == 0 && rank == 0) {
+      // ---- MMA issuer ----
+      const uint32_t idesc_x = make_idesc_f16(256, 256), idesc_h = make_idesc_f16(256, 128);
+      const uint64_t wdesc = make_smem_desc(smem_u32(Ws), 1024, 128);        // recurrent kernel: 64-row k-chunks
+      const uint64_t rdesc = make_smem_desc(smem_u32(ring), KCH_BYTES, 128); // ring operands: 128-row k-chunks
+      uint32_t slot = 0, par = 0, use0 = 0, use1 = 0;
+      for (int s = 0; s < T_STEPS; ++s) {
+        const uint32_t h_hi = tmem + 256 + ((s - 1) & 1) * 128, h_lo = h_hi + 64;
+        const uint32_t hpar = (s - 1) & 1;
+        auto h_part = [&](int b, int j0, int j1) {     // k-steps j0..j1-1 of h_{s-1} . W_h for block b
+          const uint32_t d = tmem + (b & 1) * 128;
+          const uint64_t b_hi0 = desc_advance(wdesc, b * 16 * 1024), b_lo0 = desc_advance(b_hi0, 4 * 16 * 1024);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < j0 || j >= j1) continue;
+            const uint64_t b_hi = desc_advance(b_hi0, j * 2 * 1024), b_lo = desc_advance(b_lo0, j * 2 * 1024);
+            umma_f16_pair_ts(d, h_hi + j * 8, b_hi, idesc_h, 1);
+            umma_f16_pair_ts(d, h_lo + j * 8, b_hi, idesc_h, 1);
+            umma_f16_pair_ts(d, h_hi + j * 8, b_lo, idesc_h, 1);
+          }
+        };
+        auto wait_h = [&](int kq) {
+          mbar_wait(&hq[kq], hpar);
+          tc_fence_after();
+        };
+#pragma unroll
+        for (int bp = 0; bp < 2; ++bp) {
+          // both accumulators drained (blocks 2,3 of the previous step / blocks 0,1 of this one)
+          mbar_wait(&acc_empty[0], (use0 & 1) ^ 1); ++use0;
+          mbar_wait(&acc_empty[1], (use1 & 1) ^ 1); ++use1;
+          tc_fence_after();
+          // ---- x part of blocks 2bp, 2bp+1: N = 256 into acc0|acc1 ----
+#pragma unroll 1
+          for (int st = 0; st < SX_NST; ++st) {
+            mbar_wait(&full[slot], par);
+            mbar_wait(&peer_full[slot], par);
+            tc_fence_after();
+            const uint64_t a_hi0 = desc_advance(rdesc, slot * SX_STAGE), a_lo0 = desc_advance(a_hi0, 8192);
+            const uint64_t b_hi0 = desc_advance(a_hi0, 16384), b_lo0 = desc_advance(a_hi0, 24576);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t a_hi = desc_advance(a_hi0, kk * 2 * KCH_BYTES), a_lo = desc_advance(a_lo0, kk * 2 * KCH_BYTES);
+              const uint64_t b_hi = desc_advance(b_hi0, kk * 2 * KCH_BYTES), b_lo = desc_advance(b_lo0, kk * 2 * KCH_BYTES);
+              umma_f16_pair(tmem, a_hi, b_hi, idesc_x, (st | kk) != 0);
+              umma_f16_pair(tmem, a_lo, b_hi, idesc_x, 1);
+              umma_f16_pair(tmem, a_hi, b_lo, idesc_x, 1);
+            }
+            umma_commit_pair(&empty[slot], 0b11);
+            if (++slot == SX_RING) { slot = 0; par ^= 1; }
+          }
+          // ---- h part ----
+          if (s == 0) {                                // h_{-1} = 0
+            umma_commit_pair(&acc_full[0], 0b11);
+            umma_commit_pair(&acc_full[1], 0b11);
+          } else if (bp == 0) {
+            // h_{s-1} arrives block by block from the epilogue of the previous step
+            wait_h(0); h_part(0, 0, 2); h_part(1, 0, 2);
+            wait_h(1); h_part(0, 2, 4); h_part(1, 2, 4);
+            wait_h(2); h_part(0, 4, 6); h_part(1, 4, 6);
+            wait_h(3); h_part(0, 6, 8);
+            umma_commit_pair(&acc_full[0], 0b11);
+            h_part(1, 6, 8);
+            umma_commit_pair(&acc_full[1], 0b11);
+          } else {
+            h_part(2, 0, 8);
+            umma_commit_pair(&acc_full[0], 0b11);
+            h_part(3, 0, 8);
+            umma_commit_pair(&acc_full[1], 0b11);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 + 4 * G) {
+    if (lane == 0) {
+      // ---- ring producer: each CTA loads its own rows of h1_t and its own gate columns of W_x ----
+      const uint8_t* wx = Wx + ((size_t)dir * 2 + rank) * (2 * SX_NST * 16384);
+      uint32_t slot = 0, par = 1;
+      for (int s = 0; s < T_STEPS; ++s) {
+        const int t = dir ? (T_STEPS - 1 - s) : s;
+        const uint8_t* a = (const uint8_t*)(H1 + ((size_t)t * NT + tile) * (2 * 32 * KCH));
+        if (s + 1 < T_STEPS) {
+          // the next step's h1 tile: HBM -> L2 while this step streams
+          const int tn = dir ? (T_STEPS - 2 - s) : s + 1;
+          const uint8_t* an = (const uint8_t*)(H1 + ((size_t)tn * NT + tile) * (2 * 32 * KCH));
+          for (int i = 0; i < 4; ++i) bulk_prefetch_l2(an + i * 32768, 32768);
+        }
+        for (int bp = 0; bp < 2; ++bp)
+          for (int st = 0; st < SX_NST; ++st) {
+            mbar_wait(&empty[slot], par);
+            uint8_t* dst = ring + slot * SX_STAGE;
+            mbar_expect_tx(&full[slot], SX_STAGE);
+            bulk_g2s(dst, a + (size_t)st * 4 * KCH_BYTES, 8192, &full[slot]);
+            bulk_g2s(dst + 8192, a + (size_t)(32 + st * 4) * KCH_BYTES, 8192, &full[slot]);
+            bulk_g2s(dst + 16384, wx + (size_t)(bp * SX_NST + st) * 16384, 16384, &full[slot]);
+            if (++slot == SX_RING) { slot = 0; par ^= 1; }
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2 + 4 * G) {
+    if (lane == 0 && rank == 1) relay_stages(1);
+    __syncwarp();
+  } else {
+    // ---- epilogue warps (as lstm_seq): G warps per TMEM lane quarter, UPS units of each half-block per warp ----
+    constexpr int UPS = 16 / G;
+    const int ew = warp - 1;
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+    const int sub = ew >> 2;                           // 0..G-1
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t leader_hq = map_to_cta(smem_u32(hq), 0);
+    const uint32_t leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
+    const uint32_t leader_acc_empty1 = map_to_cta(smem_u32(&acc_empty[1]), 0);
+    const uint32_t bias_base = smem_u32(bias_s);
+    float c[4][2][UPS];
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < UPS; ++i) c[b][j][i] = 0.f;
+
+    uint32_t use0 = 0, use1 = 0;
+    for (int s = 0; s < T_STEPS; ++s) {
+      const int t = dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
+      const uint32_t h_st = lane_base + 256 + (s & 1) * 128;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = b & 1;
+        {
+          uint32_t& use = i ? use1 : use0;
+          mbar_wait(&acc_full[i], use & 1);
+          ++use;
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int u0 = b * 32 + j * 16 + sub * UPS;  // first hidden unit of this thread's slice
+          float v[4 * UPS];
+#pragma unroll
+          for (int k = 0; k < UPS / 4; ++k) tmem_ld16(lane_base + i * 128 + (j * 16 + sub * UPS) * 4 + k * 16, v + 16 * k);
+          tmem_ld_wait();
+          if (j == 1) {
+            // this warp's part of the accumulator is in registers: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(i ? leader_acc_empty1 : leader_acc_empty0);
+          }
+          float hv[UPS];
+#pragma unroll
+          for (int k = 0; k < UPS; ++k) {
+            const float4 bq = lds4(bias_base + (u0 + k) * 16);
+            hv[k] = lstm_cell(v[4 * k] + bq.x, v[4 * k + 1] + bq.y, v[4 * k + 2] + bq.z, v[4 * k + 3] + bq.w, c[b][j][k]);
+          }
+          uint32_t whi[UPS / 2], wlo[UPS / 2];
+#pragma unroll
+          for (int k = 0; k < UPS / 2; ++k) {
+            const __half2 h2 = __floats2half2_rn(hv[2 * k], hv[2 * k + 1]);
+            const float2 back = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(hv[2 * k] - back.x, hv[2 * k + 1] - back.y);
+            whi[k] = *reinterpret_cast<const uint32_t*>(&h2);
+            wlo[k] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          if constexpr (UPS == 8) {
+            tmem_st4(h_st + (u0 >> 1), whi);
+            tmem_st4(h_st + 64 + (u0 >> 1), wlo);
+          } else {
+            tmem_st2(h_st + (u0 >> 1), whi);
+            tmem_st2(h_st + 64 + (u0 >> 1), wlo);
+          }
+          if (OUT == 1) {
+            float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + u0) * np + (size_t)tile * 128 + r;
+#pragma unroll
+            for (int k = 0; k < UPS; ++k) out[(size_t)k * np] = hv[k];
+          } else {
+            // OUT == 2: MN-major SWIZZLE_128B tiles for the slice-dense MMA (see lstm_seq)
+            static_assert(OUT != 2 || UPS == 8, "the MN-major output needs 8 units per slice");
+            if constexpr (UPS == 8) {
+              transpose8x8_h(whi, lane);
+              transpose8x8_h(wlo, lane);
+              const int ch = dir * H + u0 + (lane & 7);
+              const int rg = r >> 3;                                  // site group of 8 within the tile (0..15)
+              uint8_t* out = (uint8_t*)Hout + ((size_t)tile * 2 * H + ch) * L3A_BYTES + (size_t)(t >> 3) * 2048 +
+                             (rg >> 3) * 1024 + (t & 7) * 128 + (((rg & 7) ^ (t & 7)) << 4);
+              *reinterpret_cast<uint4*>(out) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+              *reinterpret_cast<uint4*>(out + L3A_BYTES / 2) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+            }
+          }
+        }
+        // this warp's slice of block b of h_t is in tensor memory: the MMA issuer may start contracting over it
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(leader_hq + b * 8);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
 // prep for the fused layer-1 kernel: like prep_tiles but K = 48 (k = 32, 33 are the constant-one bias columns)
 template <typename TIn>
 __global__ void __launch_bounds__(128) prep_tiles48(const TIn* __restrict__ x, __half* __restrict__ X48, int64_t n, int NT) {
@@ -1163,6 +1452,8 @@ struct HostModel {
 struct Weights {
   __half* Wx2 = nullptr;                   // xproj_pair<32>, layer 2: [nb 4][q 2][hl][kc 32][128][8]
   float* bx2 = nullptr;                    // layer 2: [nb 4][256]
+  uint8_t* Wx2s = nullptr;                 // lstm_seq_x2, layer 2: [dir][q][bp 2][st 8][hl][kc 4][128][8] fp16
+  float* bx2s = nullptr;                   // layer 2: [dir][512] (unit*4+gate order, gate-scaled)
   __half* Whs[2] = {nullptr, nullptr};     // lstm_seq, per layer: [dir][q][hl][b 4][kc 16][64][8]
   __half* Wxf = nullptr;                   // lstm_seq<FUSE_X>, layer 1: [dir][q][hl][b 4][kc 6][64][8] (k 32,33 = bias hi,lo)
   uint8_t* l3l4 = nullptr;                 // [256] per-channel blobs (L3L4_BLOB_BYTES each)
@@ -1227,6 +1518,34 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
     }
     if ((st = upload_vec(&w.Wx2, wx)) != cudaSuccess) return st;
     if ((st = upload_vec(&w.bx2, bx)) != cudaSuccess) return st;
+  }
+  // ---- layer-2 input projection streamed through lstm_seq_x2: per CTA q and block pair bp, row r = gate column
+  //      (2bp+q)*128 + r; ring stages of K = 32 ----
+  {
+    std::vector<__half> wx((size_t)2 * 2 * 2 * SX_NST * 8192);
+    std::vector<float> bx((size_t)2 * 512);
+    for (int dir = 0; dir < 2; ++dir) {
+      const float* K = hm.lstm_kernel[1][dir];
+      const float* B = hm.lstm_bias[1][dir];
+      for (int j = 0; j < 512; ++j) bx[(size_t)dir * 512 + j] = B[tf_col(j)] * GATE_SCALE[j & 3];
+      for (int q = 0; q < 2; ++q)
+        for (int bp = 0; bp < 2; ++bp)
+          for (int row = 0; row < 128; ++row) {
+            const int col = tf_col((2 * bp + q) * 128 + row);
+            const float gs = GATE_SCALE[row & 3];
+            for (int k = 0; k < kx[1]; ++k) {
+              __half hi, lo;
+              split_half(K[(size_t)k * G4 + col] * gs, hi, lo);
+              const int st = k / 32, kc = (k % 32) / 8;
+              const size_t base = ((((size_t)dir * 2 + q) * 2 + bp) * SX_NST + st) * 8192 + (size_t)kc * KCH + row * 8 + k % 8;
+              wx[base] = hi;
+              wx[base + 4 * KCH] = lo;
+            }
+          }
+    }
+    std::vector<uint8_t> raw((const uint8_t*)wx.data(), (const uint8_t*)wx.data() + wx.size() * 2);
+    if ((st = upload_vec(&w.Wx2s, raw)) != cudaSuccess) return st;
+    if ((st = upload_vec(&w.bx2s, bx)) != cudaSuccess) return st;
   }
   // ---- lstm_seq layouts: gate blocks of 128 columns, 64 rows per CTA ----
   for (int l = 0; l < 2; ++l) {
@@ -1329,6 +1648,7 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
 inline void free_weights(Weights& w) {
   cudaFree(w.heads); w.heads = nullptr;
   cudaFree(w.l3l4); cudaFree(w.Wxf); cudaFree(w.Whs[0]); cudaFree(w.Whs[1]); cudaFree(w.Wx2); cudaFree(w.bx2);
+  cudaFree(w.Wx2s); cudaFree(w.bx2s); w.Wx2s = nullptr; w.bx2s = nullptr;
   w.l3l4 = nullptr; w.Wxf = nullptr; w.Whs[0] = w.Whs[1] = nullptr; w.Wx2 = nullptr; w.bx2 = nullptr;
 }
 
@@ -1350,6 +1670,8 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
   if ((st = cudaFuncSetAttribute(lstm_seq<false, 1, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq<false, 2, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(l3l4_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3l4_smem_bytes())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq_x2<1, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seqx_smem_bytes())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq_x2<2, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seqx_smem_bytes())) != cudaSuccess) return st;
   return cudaSuccess;
 }
 
@@ -1362,11 +1684,11 @@ inline void free_workspace(Workspace& ws) {
 //   fuse_tail = false: x -> h2 planes [33*256][np] fp32 (the CUDA-core slice-dense / L4 follow; parity cross-check)
 //   fuse_tail = true : x -> probabilities [n][90] (+ logits [np][90]) through lstm_seq<.,2> + l3l4_fused + heads_tc
 // `hook(id, begin)` brackets every launch for the per-kernel event timing
-// (id: 0 prep_tiles, 1 lstm_seq1, 2 xproj2, 3 lstm_seq2, 4 l3l4_fused, 5 heads_tc).
+// (id: 0 prep_tiles, 1 lstm_seq1, 2 xproj2, 3 lstm_seq2, 4 l3l4_fused, 5 heads_tc, 6 lstm_seq_x2).
 template <typename Hook>
 inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_dev, int dtype_is_i16, int64_t n, int64_t np,
-                                float* h2_planes, float* l4T, float* probs, float* logits, bool fuse_tail, cudaStream_t st,
-                                int* launches, Hook&& hook) {
+                                float* h2_planes, float* l4T, float* probs, float* logits, bool fuse_tail, bool l2_stream,
+                                cudaStream_t st, int* launches, Hook&& hook) {
   const int NT = (int)(np / 128);
   const int num_row_pairs = T_STEPS * NT / 2;
   // persistent input-projection grid: whole groups of 4 CTA pairs (one pair per N-block), one pair per 2 SMs
@@ -1385,14 +1707,24 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   hook(1, true);   // layer 1: input projection fused into the recurrent kernel (no Gx round trip)
   lstm_seq<true, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np, 0);
   hook(1, false);
-  hook(2, true);
-  xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx2, w.bx2, ws.Gx, num_row_pairs, xp_dbg);
-  hook(2, false);
-  hook(3, true);
-  if (fuse_tail) lstm_seq<false, 2, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2t, NT, np, gx_pf);
-  else lstm_seq<false, 1, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np, gx_pf);
-  hook(3, false);
-  *launches += 4;
+  // layer 2: input projection streamed through the recurrent kernel (default), or the two-kernel path
+  // xproj_pair -> Gx -> lstm_seq (CLAIRB_L2_STREAM=0: on-device cross-check)
+  if (l2_stream) {
+    hook(6, true);
+    if (fuse_tail) lstm_seq_x2<2, SEQ_G><<<grec, SX_THREADS, seqx_smem_bytes(), st>>>(w.Whs[1], w.Wx2s, w.bx2s, ws.H1, ws.H2t, NT, np);
+    else lstm_seq_x2<1, SEQ_G><<<grec, SX_THREADS, seqx_smem_bytes(), st>>>(w.Whs[1], w.Wx2s, w.bx2s, ws.H1, h2_planes, NT, np);
+    hook(6, false);
+    *launches += 3;
+  } else {
+    hook(2, true);
+    xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx2, w.bx2, ws.Gx, num_row_pairs, xp_dbg);
+    hook(2, false);
+    hook(3, true);
+    if (fuse_tail) lstm_seq<false, 2, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2t, NT, np, gx_pf);
+    else lstm_seq<false, 1, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np, gx_pf);
+    hook(3, false);
+    *launches += 4;
+  }
   if (fuse_tail) {
     hook(4, true);
     l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, nullptr, l3_pf);

@@ -135,7 +135,8 @@ def test_chunk_pipeline_pageable_and_pinned_outputs(weights1234, monkeypatch):
     one.close()
 
 
-@pytest.mark.parametrize("env", [{"CLAIRB_ENGINE": "simt"}, {"CLAIRB_FUSED_TAIL": "0"}])
+@pytest.mark.parametrize("env", [{"CLAIRB_ENGINE": "simt"}, {"CLAIRB_FUSED_TAIL": "0"}, {"CLAIRB_L2_STREAM": "0"},
+                                 {"CLAIRB_L2_STREAM": "0", "CLAIRB_FUSED_TAIL": "0"}])
 def test_cross_check_engines(weights1234, monkeypatch, env):
     # the CUDA-core fp32 engine and the mixed path (tensor-core LSTMs into the CUDA-core slice-dense / L4 / heads) are the
     # on-device cross-checks of the production tensor-core path: all three must meet the oracle and each other
