@@ -18,6 +18,7 @@
 // Gate column order inside a direction: j = unit*4 + gate, gate in TF LSTMBlockCell order (i, c, f, o), so the four
 // pre-activations of one hidden unit are one float4 of Gx and four adjacent TMEM columns.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -714,27 +715,54 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
 // lstm_seq_x2<OUT, G>: layer 2 with its input projection streamed through the recurrent kernel (no Gx in HBM).
 //   gates(t) = h1_t . W_x + b + h_{t-1} . W_h        K_x = 256: W_x hi/lo of one direction is 512 KB, i.e. 256 KB per
 // CTA of the pair - it cannot be resident next to W_h (128 KB), so both operands of the x part stream through a ring:
-//   stage (32 KB, K = 32) = [A hi 8K | A lo 8K | B hi 8K | B lo 8K]
+//   stage (32 KB, K = 32) = [A hi 8K | A lo 8K | B hi 8K | B lo 8K]     (K = 16 stages were measured slower: 1.15 vs 1.09 ms)
 //     A = this CTA's 128 rows of the h1_t tile (written by lstm_seq<FUSE_X>, K-major [hl][32 kc][128][8])
 //     B = this CTA's 128 gate columns of TWO gate blocks: the x part is issued as M=256, N=256 pair-MMAs that fill both
 //         ping-pong accumulators at once, so every A stage is used for 256 columns and h1_t streams twice per step
 //         (block pairs (0,1) and (2,3)); 16 stages = 512 KB per CTA-step, all L2 hits except the first pass over h1_t.
-// Per step the issuer runs   x(0,1) | h(0) h(1) | x(2,3) | h(2) h(3)   : x(0,1) of step s does not depend on the
-// recurrence and fills the tensor pipe while the epilogue is still turning blocks 2, 3 of step s-1 into h_{s-1}.
+//   Stages are loaded by BOTH CTAs with tensor-map TMA in the cta_group::2 form, whose completion bytes are signalled on
+//   the LEADER's mbarrier (the plain bulk copy can only signal its own CTA, which needed a relay thread and a
+//   cluster-scope release per stage: ~700 cycles on the ring's round trip).  The maps view H1 / W_x as [rows][1 KB].
+// Issue order per step:  x(0,1) | h(0) h(1) || h(2) | h(3) | x(2,3)
+//   x(0,1) of step s does not depend on the recurrence and fills the tensor pipe while the epilogue is still turning
+//   blocks 2, 3 of step s-1 into h_{s-1}; in the second half the recurrent parts go first because each needs only ITS
+//   accumulator drained, while the N=256 x part needs both.
+// Epilogue warps read their whole share of an accumulator into registers and hand it back before doing any math.
 // Accumulator column c of block b is gate column b*128 + c in both parts (x part: CTA q, row r -> block 2bp+q, c = r).
-//   Wx   : [dir][q][bp 2][st 8][hl][kc 4][128 rows][8]   bias: [dir][512] (unit*4+gate order, gate-scaled)
-// Warps: 0 = MMA issuer (leader) / relay 0 (peer), 1..4G = epilogue, 4G+1 = ring producer, 4G+2 = relay 1 (peer).
+//   Wx   : [dir][q][bp 2][st 8][hl][kc 4][128 rows][8]    bias: [dir][512] (unit*4+gate order, gate-scaled)
+// Warps: 0 = MMA issuer (leader), 1..4G = epilogue, 4G+1 = ring producer.
 // ---------------------------------------------------------------------------------------------
-constexpr int SX_STAGE = 32768;
-constexpr int SX_RING = 3;
-constexpr int SX_NST = 8;                               // stages per block pair: K = 256 / 32
-constexpr int SX_THREADS = 32 * (3 + 4 * SEQ_G);
+#ifndef CLAIRB_SX_KC
+#define CLAIRB_SX_KC 4
+#endif
+constexpr int SX_KC = CLAIRB_SX_KC;                     // k-chunks of 8 per ring stage (2: K = 16 per stage, 4: K = 32)
+constexpr int SX_STAGE = 4 * SX_KC * KCH_BYTES;         // A hi | A lo | B hi | B lo
+constexpr int SX_RING = 98304 / SX_STAGE;
+constexpr int SX_NST = 32 / SX_KC;                      // stages per block pair (K = 256)
+constexpr int SX_G = 2;                                 // epilogue warps per TMEM lane quarter (2 or 4)
+constexpr int SX_THREADS = 32 * (2 + 4 * SX_G);
 constexpr size_t seqx_smem_bytes() { return (size_t)SEQ_W_BYTES + SX_RING * SX_STAGE + 2048 + 256 + 128; }
 
+// 2-D tiled tensor-map load, issued by each CTA of a pair for its own shared memory; completion bytes go to the
+// mbarrier at the same offset in the LEADER CTA (cluster address `leader_bar`)
+__device__ __forceinline__ void tma2_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+// arrive + expect_tx on an mbarrier of another CTA of the cluster (no payload of this thread to publish: relaxed)
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+               : "memory");
+}
+
 template <int OUT, int G>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (3 + 4 * G), 1)
-lstm_seq_x2(const __half* __restrict__ Wh, const uint8_t* __restrict__ Wx, const float* __restrict__ bias,
-            const __half* __restrict__ H1, void* __restrict__ Hout, int NT, int64_t np) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (2 + 4 * G), 1)
+lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const float* __restrict__ bias, const __half* __restrict__ H1, void* __restrict__ Hout, int NT, int64_t np,
+            int dbg, long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   uint8_t* Ws = smem;                                            // [hl][b][kc 16][64][8]
@@ -742,18 +770,20 @@ lstm_seq_x2(const __half* __restrict__ Wh, const uint8_t* __restrict__ Wx, const
   float* bias_s = (float*)(ring + SX_RING * SX_STAGE);           // [128 units][4 gates]
   uint64_t* bars = (uint64_t*)(bias_s + 512);
   uint64_t* acc_full = bars;           // [2] gate block complete (MMA commit, both CTAs)
-  uint64_t* acc_empty = bars + 2;      // [2] (leader) accumulator drained by all 16 epilogue warps of the pair
+  uint64_t* acc_empty = bars + 2;      // [2] (leader) accumulator drained by all epilogue warps of the pair
   uint64_t* hq = bars + 4;             // [4] (leader) units 32b..32b+31 of h_t of both CTAs are in tensor memory
-  uint64_t* full = bars + 8;           // [3] this CTA's stage landed
-  uint64_t* peer_full = bars + 11;     // [3] (leader) the peer's stage landed
-  uint64_t* empty = bars + 14;         // [3] stage consumed (MMA commit, both CTAs)
-  uint64_t* w_full = bars + 17;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+  uint64_t* full = bars + 8;           // [<=6] (leader) the stage of BOTH CTAs landed (2 arrivals + 2 x stage bytes)
+  uint64_t* empty = bars + 14;         // [<=6] stage consumed (MMA commit, both CTAs)
+  uint64_t* w_full = bars + 20;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int dir = blockIdx.y;
   const int tile = blockIdx.x;                                   // = 2*pair + rank
+  // timeline probe (CLAIRB_SX_TRACE): clock64 stamps of the leader CTA of pair 0, direction 0: [step][64 events]
+  const bool tr_on = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  auto stamp = [&](int s, int ev) { if (tr_on) trace[s * 64 + ev] = clock64(); };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -762,8 +792,7 @@ lstm_seq_x2(const __half* __restrict__ Wh, const uint8_t* __restrict__ Wx, const
     }
     for (int i = 0; i < 4; ++i) mbar_init(&hq[i], 8 * G);
     for (int i = 0; i < SX_RING; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&peer_full[i], 1);
+      mbar_init(&full[i], 2);
       mbar_init(&empty[i], 1);
     }
     mbar_init(w_full, 1);
@@ -773,7 +802,7 @@ lstm_seq_x2(const __half* __restrict__ Wh, const uint8_t* __restrict__ Wx, const
     for (int i = 0; i < SEQ_W_BYTES; i += 32768) bulk_g2s(Ws + i, src + i, 32768, w_full);
   }
   if (warp == 0) tmem_alloc_pair<512>(tmem_slot);
-  for (int i = threadIdx.x; i < 512; i += 32 * (3 + 4 * G)) bias_s[i] = bias[dir * 512 + i];
+  for (int i = threadIdx.x; i < 512; i += 32 * (2 + 4 * G)) bias_s[i] = bias[dir * 512 + i];
   __syncthreads();                                     // barrier inits visible before anyone polls them
   mbar_wait(w_full, 0);
   tc_fence_before();
@@ -781,21 +810,7 @@ lstm_seq_x2(const __half* __restrict__ Wh, const uint8_t* __restrict__ Wx, const
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;    // cols 0..127 acc0, 128..255 acc1, 256..383 h buffer 0 (hi 64 | lo 64), 384..511 h buffer 1
 
-  // relay (peer CTA): "my stage landed" -> the leader, release at cluster scope (see xproj_pair); two threads alternate
-  auto relay_stages = [&](int which) {
-    const uint32_t leader_peer_full = map_to_cta(smem_u32(peer_full), 0);
-    uint32_t slot = 0, par = 0;
-    for (int use = 0; use < T_STEPS * 2 * SX_NST; ++use) {
-      if ((use & 1) == which) {
-        mbar_wait(&full[slot], par);
-        mbar_arrive_cluster(leader_peer_full + slot * 8);
-      }
-      if (++slot == SX_RING) { slot = 0; par ^= 1; }
-    }
-  };
-
   if (warp == 0) {
-    if (lane == 0 && rank == 1) relay_stages(0);
     if (lane == 0 && rank == 0) {
       // ---- MMA issuer ----
       const uint32_t idesc_x = make_idesc_f16(256, 256), idesc_h = make_idesc_f16(256, 128);
@@ -805,78 +820,89 @@ lstm_seq_x2(const __half* __restrict__ Wh, const uint8_t* __restrict__ Wx, const
       for (int s = 0; s < T_STEPS; ++s) {
         const uint32_t h_hi = tmem + 256 + ((s - 1) & 1) * 128, h_lo = h_hi + 64;
         const uint32_t hpar = (s - 1) & 1;
-        auto h_part = [&](int b, int j0, int j1) {     // k-steps j0..j1-1 of h_{s-1} . W_h for block b
+        auto h_part = [&](int b, int j0, int j1, bool fresh) {   // k-steps j0..j1-1 of h_{s-1} . W_h for block b
           const uint32_t d = tmem + (b & 1) * 128;
           const uint64_t b_hi0 = desc_advance(wdesc, b * 16 * 1024), b_lo0 = desc_advance(b_hi0, 4 * 16 * 1024);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (j < j0 || j >= j1) continue;
             const uint64_t b_hi = desc_advance(b_hi0, j * 2 * 1024), b_lo = desc_advance(b_lo0, j * 2 * 1024);
-            umma_f16_pair_ts(d, h_hi + j * 8, b_hi, idesc_h, 1);
+            umma_f16_pair_ts(d, h_hi + j * 8, b_hi, idesc_h, (fresh && j == 0) ? 0u : 1u);
             umma_f16_pair_ts(d, h_lo + j * 8, b_hi, idesc_h, 1);
             umma_f16_pair_ts(d, h_hi + j * 8, b_lo, idesc_h, 1);
           }
         };
-        auto wait_h = [&](int kq) {
-          mbar_wait(&hq[kq], hpar);
-          tc_fence_after();
-        };
-#pragma unroll
-        for (int bp = 0; bp < 2; ++bp) {
-          // both accumulators drained (blocks 2,3 of the previous step / blocks 0,1 of this one)
-          mbar_wait(&acc_empty[0], (use0 & 1) ^ 1); ++use0;
-          mbar_wait(&acc_empty[1], (use1 & 1) ^ 1); ++use1;
-          tc_fence_after();
-          // ---- x part of blocks 2bp, 2bp+1: N = 256 into acc0|acc1 ----
+        auto x_part = [&](bool fresh) {                // x part of one block pair: N = 256 into acc0|acc1
 #pragma unroll 1
           for (int st = 0; st < SX_NST; ++st) {
             mbar_wait(&full[slot], par);
-            mbar_wait(&peer_full[slot], par);
             tc_fence_after();
-            const uint64_t a_hi0 = desc_advance(rdesc, slot * SX_STAGE), a_lo0 = desc_advance(a_hi0, 8192);
-            const uint64_t b_hi0 = desc_advance(a_hi0, 16384), b_lo0 = desc_advance(a_hi0, 24576);
+            const uint64_t a_hi0 = desc_advance(rdesc, slot * SX_STAGE), a_lo0 = desc_advance(a_hi0, SX_STAGE / 4);
+            const uint64_t b_hi0 = desc_advance(a_hi0, SX_STAGE / 2), b_lo0 = desc_advance(a_hi0, 3 * (SX_STAGE / 4));
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
+            for (int kk = 0; kk < SX_KC / 2; ++kk) {
               const uint64_t a_hi = desc_advance(a_hi0, kk * 2 * KCH_BYTES), a_lo = desc_advance(a_lo0, kk * 2 * KCH_BYTES);
               const uint64_t b_hi = desc_advance(b_hi0, kk * 2 * KCH_BYTES), b_lo = desc_advance(b_lo0, kk * 2 * KCH_BYTES);
-              umma_f16_pair(tmem, a_hi, b_hi, idesc_x, (st | kk) != 0);
+              umma_f16_pair(tmem, a_hi, b_hi, idesc_x, (fresh && st == 0 && kk == 0) ? 0u : 1u);
               umma_f16_pair(tmem, a_lo, b_hi, idesc_x, 1);
               umma_f16_pair(tmem, a_hi, b_lo, idesc_x, 1);
             }
             umma_commit_pair(&empty[slot], 0b11);
             if (++slot == SX_RING) { slot = 0; par ^= 1; }
           }
-          // ---- h part ----
-          if (s == 0) {                                // h_{-1} = 0
-            umma_commit_pair(&acc_full[0], 0b11);
-            umma_commit_pair(&acc_full[1], 0b11);
-          } else if (bp == 0) {
-            // h_{s-1} arrives block by block from the epilogue of the previous step
-            wait_h(0); h_part(0, 0, 2); h_part(1, 0, 2);
-            wait_h(1); h_part(0, 2, 4); h_part(1, 2, 4);
-            wait_h(2); h_part(0, 4, 6); h_part(1, 4, 6);
-            wait_h(3); h_part(0, 6, 8);
-            umma_commit_pair(&acc_full[0], 0b11);
-            h_part(1, 6, 8);
-            umma_commit_pair(&acc_full[1], 0b11);
-          } else {
-            h_part(2, 0, 8);
-            umma_commit_pair(&acc_full[0], 0b11);
-            h_part(3, 0, 8);
-            umma_commit_pair(&acc_full[1], 0b11);
-          }
+        };
+        auto acquire = [&](int i) {
+          uint32_t& use = i ? use1 : use0;
+          mbar_wait(&acc_empty[i], (use & 1) ^ 1);
+          ++use;
+          tc_fence_after();
+        };
+        auto wait_h = [&](int kq) {
+          mbar_wait(&hq[kq], hpar);
+          tc_fence_after();
+        };
+        // ---- blocks 0, 1: x part first (independent of the recurrence), then h_{s-1} as it arrives ----
+        acquire(0);
+        acquire(1);
+        stamp(s, 0);
+        x_part(true);
+        stamp(s, 1);
+        if (s > 0) {
+          wait_h(0); stamp(s, 2); h_part(0, 0, 2, false); h_part(1, 0, 2, false);
+          wait_h(1); h_part(0, 2, 4, false); h_part(1, 2, 4, false);
+          wait_h(2); h_part(0, 4, 6, false); h_part(1, 4, 6, false);
+          wait_h(3); stamp(s, 3); h_part(0, 6, 8, false);
+          umma_commit_pair(&acc_full[0], 0b11);
+          h_part(1, 6, 8, false);
+          umma_commit_pair(&acc_full[1], 0b11);
+        } else {
+          umma_commit_pair(&acc_full[0], 0b11);
+          umma_commit_pair(&acc_full[1], 0b11);
         }
+        stamp(s, 4);
+        // ---- blocks 2, 3: each recurrent part needs only its own accumulator; the x part needs both ----
+        acquire(0);
+        stamp(s, 8);
+        if (s > 0) h_part(2, 0, 8, true);
+        acquire(1);
+        stamp(s, 9);
+        if (s > 0) h_part(3, 0, 8, true);
+        x_part(s == 0);
+        umma_commit_pair(&acc_full[0], 0b11);
+        umma_commit_pair(&acc_full[1], 0b11);
+        stamp(s, 12);
       }
     }
     __syncwarp();
   } else if (warp == 1 + 4 * G) {
     if (lane == 0) {
-      // ---- ring producer: each CTA loads its own rows of h1_t and its own gate columns of W_x ----
-      const uint8_t* wx = Wx + ((size_t)dir * 2 + rank) * (2 * SX_NST * 16384);
+      // ---- ring producer: each CTA loads its own rows of h1_t and its own gate columns of W_x; both signal the leader ----
+      const uint32_t leader_full = map_to_cta(smem_u32(full), 0);
+      const int wrow0 = (dir * 2 + (int)rank) * (2 * SX_NST * 4 * SX_KC);   // 1 KB rows of W_x: 4*SX_KC per stage
       uint32_t slot = 0, par = 1;
       for (int s = 0; s < T_STEPS; ++s) {
         const int t = dir ? (T_STEPS - 1 - s) : s;
-        const uint8_t* a = (const uint8_t*)(H1 + ((size_t)t * NT + tile) * (2 * 32 * KCH));
+        const int arow0 = (t * NT + tile) * 128;                          // 1 KB rows of H1: 128 per tile (hi 64 | lo 64)
         if (s + 1 < T_STEPS) {
           // the next step's h1 tile: HBM -> L2 while this step streams
           const int tn = dir ? (T_STEPS - 2 - s) : s + 1;
@@ -887,21 +913,24 @@ lstm_seq_x2(const __half* __restrict__ Wh, const uint8_t* __restrict__ Wx, const
           for (int st = 0; st < SX_NST; ++st) {
             mbar_wait(&empty[slot], par);
             uint8_t* dst = ring + slot * SX_STAGE;
-            mbar_expect_tx(&full[slot], SX_STAGE);
-            bulk_g2s(dst, a + (size_t)st * 4 * KCH_BYTES, 8192, &full[slot]);
-            bulk_g2s(dst + 8192, a + (size_t)(32 + st * 4) * KCH_BYTES, 8192, &full[slot]);
-            bulk_g2s(dst + 16384, wx + (size_t)(bp * SX_NST + st) * 16384, 16384, &full[slot]);
+            const uint32_t bar = leader_full + slot * 8;
+            if (dbg & 1) {                             // timing experiment: no operand traffic
+              if (rank == 0) mbar_arrive(&full[slot]); else mbar_arrive_cluster_relaxed(bar);
+            } else {
+              if (rank == 0) mbar_expect_tx(&full[slot], SX_STAGE); else mbar_expect_tx_cluster(bar, SX_STAGE);
+              tma2_pair(dst, &tmA, 0, arow0 + st * 2 * SX_KC, bar);
+              tma2_pair(dst + SX_STAGE / 4, &tmA, 0, arow0 + 64 + st * 2 * SX_KC, bar);
+              tma2_pair(dst + SX_STAGE / 2, &tmB, 0, wrow0 + (bp * SX_NST + st) * 4 * SX_KC, bar);
+            }
             if (++slot == SX_RING) { slot = 0; par ^= 1; }
           }
       }
     }
     __syncwarp();
-  } else if (warp == 2 + 4 * G) {
-    if (lane == 0 && rank == 1) relay_stages(1);
-    __syncwarp();
   } else {
-    // ---- epilogue warps (as lstm_seq): G warps per TMEM lane quarter, UPS units of each half-block per warp ----
-    constexpr int UPS = 16 / G;
+    // ---- epilogue warps: G warps per TMEM lane quarter; warp `sub` of a quarter owns units sub*UW..+UW of every gate
+    //      block (UW = 32/G) and handles them in slices of 8 ----
+    constexpr int UW = 32 / G, NSL = UW / 8;
     const int ew = warp - 1;
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
     const int sub = ew >> 2;                           // 0..G-1
@@ -911,13 +940,11 @@ lstm_seq_x2(const __half* __restrict__ Wh, const uint8_t* __restrict__ Wx, const
     const uint32_t leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
     const uint32_t leader_acc_empty1 = map_to_cta(smem_u32(&acc_empty[1]), 0);
     const uint32_t bias_base = smem_u32(bias_s);
-    float c[4][2][UPS];
+    float c[4][UW];
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < UPS; ++i) c[b][j][i] = 0.f;
+      for (int i = 0; i < UW; ++i) c[b][i] = 0.f;
 
     uint32_t use0 = 0, use1 = 0;
     for (int s = 0; s < T_STEPS; ++s) {
@@ -932,65 +959,61 @@ lstm_seq_x2(const __half* __restrict__ Wh, const uint8_t* __restrict__ Wx, const
           ++use;
           tc_fence_after();
         }
+        if (threadIdx.x == 32) stamp(s, 16 + b * 8);
+        // this warp's whole share of the accumulator -> registers, then hand the accumulator back at once
+        float v[4 * UW];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int u0 = b * 32 + j * 16 + sub * UPS;  // first hidden unit of this thread's slice
-          float v[4 * UPS];
+        for (int k = 0; k < UW / 4; ++k) tmem_ld16(lane_base + i * 128 + sub * UW * 4 + k * 16, v + 16 * k);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(i ? leader_acc_empty1 : leader_acc_empty0);
+        if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 1);
 #pragma unroll
-          for (int k = 0; k < UPS / 4; ++k) tmem_ld16(lane_base + i * 128 + (j * 16 + sub * UPS) * 4 + k * 16, v + 16 * k);
-          tmem_ld_wait();
-          if (j == 1) {
-            // this warp's part of the accumulator is in registers: hand it back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(i ? leader_acc_empty1 : leader_acc_empty0);
-          }
-          float hv[UPS];
+        for (int sl = 0; sl < NSL; ++sl) {
+          const int u0 = b * 32 + sub * UW + sl * 8;   // first hidden unit of this slice
+          float hv[8];
 #pragma unroll
-          for (int k = 0; k < UPS; ++k) {
+          for (int k = 0; k < 8; ++k) {
             const float4 bq = lds4(bias_base + (u0 + k) * 16);
-            hv[k] = lstm_cell(v[4 * k] + bq.x, v[4 * k + 1] + bq.y, v[4 * k + 2] + bq.z, v[4 * k + 3] + bq.w, c[b][j][k]);
+            const float* vv = v + (sl * 8 + k) * 4;
+            hv[k] = lstm_cell(vv[0] + bq.x, vv[1] + bq.y, vv[2] + bq.z, vv[3] + bq.w, c[b][sl * 8 + k]);
           }
-          uint32_t whi[UPS / 2], wlo[UPS / 2];
+          if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 2 + sl * 2);
+          uint32_t whi[4], wlo[4];
 #pragma unroll
-          for (int k = 0; k < UPS / 2; ++k) {
+          for (int k = 0; k < 4; ++k) {
             const __half2 h2 = __floats2half2_rn(hv[2 * k], hv[2 * k + 1]);
             const float2 back = __half22float2(h2);
             const __half2 l2 = __floats2half2_rn(hv[2 * k] - back.x, hv[2 * k + 1] - back.y);
             whi[k] = *reinterpret_cast<const uint32_t*>(&h2);
             wlo[k] = *reinterpret_cast<const uint32_t*>(&l2);
           }
-          if constexpr (UPS == 8) {
-            tmem_st4(h_st + (u0 >> 1), whi);
-            tmem_st4(h_st + 64 + (u0 >> 1), wlo);
-          } else {
-            tmem_st2(h_st + (u0 >> 1), whi);
-            tmem_st2(h_st + 64 + (u0 >> 1), wlo);
-          }
+          tmem_st4(h_st + (u0 >> 1), whi);
+          tmem_st4(h_st + 64 + (u0 >> 1), wlo);
           if (OUT == 1) {
             float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + u0) * np + (size_t)tile * 128 + r;
 #pragma unroll
-            for (int k = 0; k < UPS; ++k) out[(size_t)k * np] = hv[k];
+            for (int k = 0; k < 8; ++k) out[(size_t)k * np] = hv[k];
           } else {
             // OUT == 2: MN-major SWIZZLE_128B tiles for the slice-dense MMA (see lstm_seq)
-            static_assert(OUT != 2 || UPS == 8, "the MN-major output needs 8 units per slice");
-            if constexpr (UPS == 8) {
-              transpose8x8_h(whi, lane);
-              transpose8x8_h(wlo, lane);
-              const int ch = dir * H + u0 + (lane & 7);
-              const int rg = r >> 3;                                  // site group of 8 within the tile (0..15)
-              uint8_t* out = (uint8_t*)Hout + ((size_t)tile * 2 * H + ch) * L3A_BYTES + (size_t)(t >> 3) * 2048 +
-                             (rg >> 3) * 1024 + (t & 7) * 128 + (((rg & 7) ^ (t & 7)) << 4);
-              *reinterpret_cast<uint4*>(out) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
-              *reinterpret_cast<uint4*>(out + L3A_BYTES / 2) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
-            }
+            transpose8x8_h(whi, lane);
+            transpose8x8_h(wlo, lane);
+            const int ch = dir * H + u0 + (lane & 7);
+            const int rg = r >> 3;                                  // site group of 8 within the tile (0..15)
+            uint8_t* out = (uint8_t*)Hout + ((size_t)tile * 2 * H + ch) * L3A_BYTES + (size_t)(t >> 3) * 2048 +
+                           (rg >> 3) * 1024 + (t & 7) * 128 + (((rg & 7) ^ (t & 7)) << 4);
+            *reinterpret_cast<uint4*>(out) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+            *reinterpret_cast<uint4*>(out + L3A_BYTES / 2) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
           }
+          if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 3 + sl * 2);
         }
         // this warp's slice of block b of h_t is in tensor memory: the MMA issuer may start contracting over it
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(leader_hq + b * 8);
+        if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 7);
       }
     }
   }
@@ -1437,6 +1460,31 @@ heads_tc(const __half* __restrict__ L4t, const uint8_t* __restrict__ blobs, floa
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// A flat byte range viewed as a 2-D tensor [bytes/1024][256 x u32] for tensor-map TMA: a box of `box_rows` rows is
+// box_rows KB of contiguous memory, landing contiguously in shared memory.  cuTensorMapEncodeTiled is fetched through
+// the runtime (no link-time dependency on libcuda).
+inline cudaError_t make_flat_map(CUtensorMap* tm, void* base, size_t bytes, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t st = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (st != cudaSuccess) return st;
+    if (q != cudaDriverEntryPointSuccess || !p) return cudaErrorNotSupported;
+    fn = (EncodeFn)p;
+  }
+  const cuuint64_t dims[2] = {256, (cuuint64_t)(bytes / 1024)};
+  const cuuint64_t strides[1] = {1024};
+  const cuuint32_t box[2] = {256, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 struct HostModel {
   const float* lstm_kernel[2][2];   // [layer][dir] TF layout [(Kx+128)][512], rows x first, columns gate-major i,c,f,o
   const float* lstm_bias[2][2];     // [512]
@@ -1454,6 +1502,7 @@ struct Weights {
   float* bx2 = nullptr;                    // layer 2: [nb 4][256]
   uint8_t* Wx2s = nullptr;                 // lstm_seq_x2, layer 2: [dir][q][bp 2][st 8][hl][kc 4][128][8] fp16
   float* bx2s = nullptr;                   // layer 2: [dir][512] (unit*4+gate order, gate-scaled)
+  CUtensorMap tmWx;                        // Wx2s as [rows][1 KB], box = 8 rows (one ring stage of B)
   __half* Whs[2] = {nullptr, nullptr};     // lstm_seq, per layer: [dir][q][hl][b 4][kc 16][64][8]
   __half* Wxf = nullptr;                   // lstm_seq<FUSE_X>, layer 1: [dir][q][hl][b 4][kc 6][64][8] (k 32,33 = bias hi,lo)
   uint8_t* l3l4 = nullptr;                 // [256] per-channel blobs (L3L4_BLOB_BYTES each)
@@ -1469,6 +1518,8 @@ struct Workspace {
   __half* H2t = nullptr;     // [NT][256][hl][5][2][8][64]   LSTM2 output, MN-major 128B-swizzled per channel (t = 33..39 zero)
   __half* L4t = nullptr;     // [NT][hl][24][128][8]         L4 activations as the operand tile of heads_tc
   int sm_count = 148;
+  CUtensorMap tmH1;          // H1 as [rows][1 KB], box = 4 rows (hi or lo half of one ring stage of A)
+  long long* trace = nullptr; // CLAIRB_SX_TRACE=<file>: [33][64] clock64 stamps of one CTA pair of lstm_seq_x2 (dumped at destroy)
 };
 
 inline bool available() { return true; }
@@ -1520,9 +1571,9 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
     if ((st = upload_vec(&w.bx2, bx)) != cudaSuccess) return st;
   }
   // ---- layer-2 input projection streamed through lstm_seq_x2: per CTA q and block pair bp, row r = gate column
-  //      (2bp+q)*128 + r; ring stages of K = 32 ----
+  //      (2bp+q)*128 + r; ring stages of K = 8*SX_KC: [hl][kc][128][8] ----
   {
-    std::vector<__half> wx((size_t)2 * 2 * 2 * SX_NST * 8192);
+    std::vector<__half> wx((size_t)2 * 2 * 2 * SX_NST * 2 * SX_KC * KCH);
     std::vector<float> bx((size_t)2 * 512);
     for (int dir = 0; dir < 2; ++dir) {
       const float* K = hm.lstm_kernel[1][dir];
@@ -1536,16 +1587,17 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
             for (int k = 0; k < kx[1]; ++k) {
               __half hi, lo;
               split_half(K[(size_t)k * G4 + col] * gs, hi, lo);
-              const int st = k / 32, kc = (k % 32) / 8;
-              const size_t base = ((((size_t)dir * 2 + q) * 2 + bp) * SX_NST + st) * 8192 + (size_t)kc * KCH + row * 8 + k % 8;
+              const int st = k / (8 * SX_KC), kc = (k % (8 * SX_KC)) / 8;
+              const size_t base = ((((size_t)dir * 2 + q) * 2 + bp) * SX_NST + st) * (2 * SX_KC * KCH) + (size_t)kc * KCH + row * 8 + k % 8;
               wx[base] = hi;
-              wx[base + 4 * KCH] = lo;
+              wx[base + SX_KC * KCH] = lo;
             }
           }
     }
     std::vector<uint8_t> raw((const uint8_t*)wx.data(), (const uint8_t*)wx.data() + wx.size() * 2);
     if ((st = upload_vec(&w.Wx2s, raw)) != cudaSuccess) return st;
     if ((st = upload_vec(&w.bx2s, bx)) != cudaSuccess) return st;
+    if ((st = make_flat_map(&w.tmWx, w.Wx2s, raw.size(), 4 * SX_KC)) != cudaSuccess) return st;
   }
   // ---- lstm_seq layouts: gate blocks of 128 columns, 64 rows per CTA ----
   for (int l = 0; l < 2; ++l) {
@@ -1658,6 +1710,7 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
   cudaError_t st;
   if ((st = cudaMalloc((void**)&ws.X48, (size_t)T_STEPS * NT * X48_TILE_HALVES * 2)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H1, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
+  if ((st = make_flat_map(&ws.tmH1, ws.H1, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2, 2 * SX_KC)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.Gx, (size_t)T_STEPS * NT * GX_TILE_FLOATS * 4)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H2t, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
   // time steps 33..39 of the last time group are never written by lstm_seq and must read as zeros
@@ -1665,17 +1718,34 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
   if ((st = cudaMalloc((void**)&ws.L4t, NT * (size_t)HD_A4_BYTES)) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(heads_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem_bytes())) != cudaSuccess) return st;
   cudaDeviceGetAttribute(&ws.sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (getenv("CLAIRB_SX_TRACE")) {
+    if ((st = cudaMalloc((void**)&ws.trace, T_STEPS * 64 * sizeof(long long))) != cudaSuccess) return st;
+    cudaMemset(ws.trace, 0, T_STEPS * 64 * sizeof(long long));
+  }
   if ((st = cudaFuncSetAttribute(xproj_pair<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<32>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq<true, 0, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq<false, 1, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq<false, 2, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(l3l4_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3l4_smem_bytes())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(lstm_seq_x2<1, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seqx_smem_bytes())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(lstm_seq_x2<2, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seqx_smem_bytes())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq_x2<1, SX_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seqx_smem_bytes())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq_x2<2, SX_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seqx_smem_bytes())) != cudaSuccess) return st;
   return cudaSuccess;
 }
 
 inline void free_workspace(Workspace& ws) {
+  if (ws.trace) {
+    std::vector<long long> h(T_STEPS * 64);
+    if (cudaMemcpy(h.data(), ws.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      if (FILE* f = fopen(getenv("CLAIRB_SX_TRACE") ? getenv("CLAIRB_SX_TRACE") : "/dev/null", "w")) {
+        for (int s = 0; s < T_STEPS; ++s) {
+          for (int e = 0; e < 64; ++e) fprintf(f, "%lld%c", h[s * 64 + e], e == 63 ? '\n' : ' ');
+        }
+        fclose(f);
+      }
+    }
+    cudaFree(ws.trace);
+    ws.trace = nullptr;
+  }
   cudaFree(ws.X48); cudaFree(ws.Gx); cudaFree(ws.H1); cudaFree(ws.H2t); cudaFree(ws.L4t);
   ws.L4t = nullptr; ws.X48 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr; ws.H2t = nullptr;
 }
@@ -1698,6 +1768,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   static const int gx_pf = getenv("CLAIRB_GX_PF") ? atoi(getenv("CLAIRB_GX_PF")) : 0;   // Gx L2 prefetch distance (steps)
   static const int l3_pf = getenv("CLAIRB_L3_PF") ? atoi(getenv("CLAIRB_L3_PF")) : 8;   // l3l4 L2 prefetch distance (channels)
   static const int xp_dbg = getenv("CLAIRB_XP_DBG") ? atoi(getenv("CLAIRB_XP_DBG")) : 0;   // timing experiments only
+  static const int sx_dbg = getenv("CLAIRB_SX_DBG") ? atoi(getenv("CLAIRB_SX_DBG")) : 0;   // timing experiments only
   dim3 gprep((unsigned)NT, T_STEPS);
   dim3 grec((unsigned)NT, 2);
   hook(0, true);
@@ -1711,8 +1782,8 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   // xproj_pair -> Gx -> lstm_seq (CLAIRB_L2_STREAM=0: on-device cross-check)
   if (l2_stream) {
     hook(6, true);
-    if (fuse_tail) lstm_seq_x2<2, SEQ_G><<<grec, SX_THREADS, seqx_smem_bytes(), st>>>(w.Whs[1], w.Wx2s, w.bx2s, ws.H1, ws.H2t, NT, np);
-    else lstm_seq_x2<1, SEQ_G><<<grec, SX_THREADS, seqx_smem_bytes(), st>>>(w.Whs[1], w.Wx2s, w.bx2s, ws.H1, h2_planes, NT, np);
+    if (fuse_tail) lstm_seq_x2<2, SX_G><<<grec, SX_THREADS, seqx_smem_bytes(), st>>>(w.Whs[1], ws.tmH1, w.tmWx, w.bx2s, ws.H1, ws.H2t, NT, np, sx_dbg, ws.trace);
+    else lstm_seq_x2<1, SX_G><<<grec, SX_THREADS, seqx_smem_bytes(), st>>>(w.Whs[1], ws.tmH1, w.tmWx, w.bx2s, ws.H1, h2_planes, NT, np, sx_dbg, ws.trace);
     hook(6, false);
     *launches += 3;
   } else {

@@ -26,3 +26,4 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / R
 print("sites %d  %.3f ms  %.2f M sites/s  (%.1f ns/site)" % (n, ms, n / ms / 1e3, ms * 1e6 / n), " ".join(
     "%s=%.3f" % (p["kernel"], p["ms"] / p["launches"]) for p in m.read_profile()), flush=True)
+m.close()
