@@ -35,10 +35,12 @@ LSTM1_FLOP_PER_SITE = 2 * 5406720
 KERNEL_FLOP_PER_SITE = {"lstm_layer2": LSTM2_FLOP_PER_SITE, "lstm_layer1": LSTM1_FLOP_PER_SITE,
                         "l4_dense": 2 * 1474560, "l3_slice_dense": 2 * 253440, "tail_heads": 2 * (73728 + 8640),
                         "lstm_seq1": 2 * 5406720, "xproj2": 2 * 8650752, "lstm_seq2": 2 * 4325376,
-                        "l3l4_fused": 2 * (253440 + 1474560), "prep_tiles": 0, "prep_input": 0, "heads_tc": 2 * (73728 + 8640)}
+                        "l3l4_fused": 2 * (253440 + 1474560), "prep_tiles": 0, "prep_input": 0, "heads_tc": 2 * (73728 + 8640),
+                        "lstm_seq_x2": LSTM2_FLOP_PER_SITE}
 # algorithmic HBM bytes per site of each kernel (operand tiles in + results out)
 KERNEL_BYTES_PER_SITE = {"prep_tiles": 4224 + 6336, "lstm_seq1": 6336 + 33792, "xproj2": 33792 + 135168,
-                         "lstm_seq2": 135168 + 40960, "l3l4_fused": 40960 + 768 + 768, "heads_tc": 768 + 360 + 360}
+                         "lstm_seq2": 135168 + 40960, "l3l4_fused": 40960 + 768 + 768, "heads_tc": 768 + 360 + 360,
+                         "lstm_seq_x2": 2 * 33792 + 40960}      # h1 read once per direction, h2 tiles written
 BATCH = 1000                        # shared/param.py:16 predictBatchSize
 WORKLOAD = "ONT-shape model inference, 1M synthetic candidate sites, batch=1000, %dxB200"
 
@@ -56,9 +58,9 @@ def parse_args():
 
 
 def measured_traffic(kernel, sites_per_launch):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic.json),
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic_s4.json),
     scaled to this run's sites per launch; None when no capture covers the kernel."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r01_traffic_s4.json")
     try:
         with open(path) as f:
             t = json.load(f)
@@ -314,7 +316,7 @@ def main():
             roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": achieved,
                         "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                         "traffic": measured_traffic(dom["kernel"], sites_per_launch),
-                        "traffic_source": "ncu dram__bytes_read+write per launch (profiles/r01_traffic.json), scaled by sites",
+                        "traffic_source": "ncu dram__bytes_read+write per launch (profiles/r01_traffic_s4.json), scaled by sites",
                         "algorithmic_bytes": KERNEL_BYTES_PER_SITE.get(dom["kernel"], 0) * sites_per_launch,
                         "peak_source": peaks["source"] + " (sustained bf16)",
                         "avg_launch_ms": avg_ms, "sites_per_launch": sites_per_launch,
