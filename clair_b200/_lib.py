@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("CLAIRB_LIB") or os.path.join(_HERE, "lib", "libclair_
 OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, EWEIGHTS = range(6)
 DTYPE_F32, DTYPE_I16 = 0, 1
 N_OUT = 90
+DECISION_WORDS = 6
 SITE_ELEMS = 1056
 LAYER_LSTM1, LAYER_LSTM2, LAYER_L3, LAYER_L4, LAYER_LOGITS = 1, 2, 3, 4, 5
 
@@ -23,6 +24,8 @@ SYMBOLS = {
     "clairb_finalize_weights": (_c.c_int, [_c.c_void_p]),
     "clairb_predict": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p]),
     "clairb_predict_device": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p]),
+    "clairb_predict_decide": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "clairb_decide": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p]),
     "clairb_get_layer": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int64]),
     "clairb_host_alloc": (_c.c_int, [_c.POINTER(_c.c_void_p), _c.c_int64]),
     "clairb_host_free": (_c.c_int, [_c.c_void_p]),

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "decide_kernels.cuh"
 
 using namespace clairb;
 
@@ -78,6 +79,10 @@ struct clairb_engine {
   void* d_x[2] = {nullptr, nullptr};
   float* d_out[2] = {nullptr, nullptr};
   float* h_out[2] = {nullptr, nullptr};     // pinned staging for results (one per output buffer)
+  // first-choice decision stage (clairb_predict_decide / clairb_decide): reference bases in, 6-word records out
+  uint8_t* d_ref[2] = {nullptr, nullptr};
+  int32_t* d_dec[2] = {nullptr, nullptr};
+  int32_t* h_dec[2] = {nullptr, nullptr};   // pinned staging
 
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -165,8 +170,8 @@ SiteMap make_map(const clairb_engine* e, int64_t n) {
 // ---- per-kernel event timing --------------------------------------------------------------------
 const char* kKernelNames[] = {"prep_input", "lstm_layer1", "lstm_layer2", "l3_slice_dense", "l4_dense",
                               "tail_heads", "prep_tiles", "lstm_seq1", "xproj2", "lstm_seq2", "l3l4_fused", "heads_tc",
-                              "lstm_seq_x2"};
-constexpr int kNumKernelNames = 13;
+                              "lstm_seq_x2", "decide_sites"};
+constexpr int kNumKernelNames = 14;
 
 void prof_fold(clairb_engine* e) {
   for (auto& sp : e->prof_open) {
@@ -300,6 +305,9 @@ void free_all(clairb_engine* e) {
     cudaFree(e->d_x[l]);
     cudaFree(e->d_out[l]);
     if (e->h_out[l]) cudaFreeHost(e->h_out[l]);
+    cudaFree(e->d_ref[l]);
+    cudaFree(e->d_dec[l]);
+    if (e->h_dec[l]) cudaFreeHost(e->h_dec[l]);
     if (e->ev_h2d[l]) cudaEventDestroy(e->ev_h2d[l]);
     if (e->ev_comp[l]) cudaEventDestroy(e->ev_comp[l]);
     if (e->ev_d2h[l]) cudaEventDestroy(e->ev_d2h[l]);
@@ -405,6 +413,9 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
     CR_TRY(cudaMalloc(&e->d_x[b], (size_t)e->chunk_sites * SITE_ELEMS * sizeof(float)));
     CR_TRY(cudaMalloc((void**)&e->d_out[b], (size_t)e->chunk_sites * N_OUT * sizeof(float)));
     CR_TRY(cudaHostAlloc((void**)&e->h_out[b], (size_t)e->chunk_sites * N_OUT * sizeof(float), cudaHostAllocDefault));
+    CR_TRY(cudaMalloc((void**)&e->d_ref[b], (size_t)e->chunk_sites));
+    CR_TRY(cudaMalloc((void**)&e->d_dec[b], (size_t)e->chunk_sites * decide::REC_WORDS * sizeof(int32_t)));
+    CR_TRY(cudaHostAlloc((void**)&e->h_dec[b], (size_t)e->chunk_sites * decide::REC_WORDS * sizeof(int32_t), cudaHostAllocDefault));
   }
   CR_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   const size_t np = (size_t)e->chunk_np;
@@ -579,7 +590,11 @@ int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_
   return CLAIRB_OK;
 }
 
-int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_host) {
+// Shared body of clairb_predict / clairb_predict_decide: chunked, copy-overlapped forward; when `ref_host` / `dec_host`
+// are given the decision kernel runs on each chunk right behind the heads, on the probabilities and the input tensor
+// that are still resident, and its 24-byte records travel back with the probabilities.
+static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_host, const uint8_t* ref_host,
+                        int32_t* dec_host) {
   if (!e) return CLAIRB_EINVAL;
   if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
   if (!x_host || !out_host || n <= 0 || n > e->max_sites) return fail(e, CLAIRB_EINVAL, "predict: bad n or buffers");
@@ -608,20 +623,36 @@ int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, f
     CU_TRY(e, cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));
     CU_TRY(e, cudaMemcpyAsync(e->d_x[b], (const char*)x_host + (size_t)done * SITE_ELEMS * eb,
                               (size_t)cn * SITE_ELEMS * eb, cudaMemcpyHostToDevice, e->s_h2d));
+    if (dec_host) CU_TRY(e, cudaMemcpyAsync(e->d_ref[b], ref_host + done, (size_t)cn, cudaMemcpyHostToDevice, e->s_h2d));
     CU_TRY(e, cudaEventRecord(e->ev_h2d[b], e->s_h2d));
     CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_h2d[b], 0));
     CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_d2h[b], 0));   // output buffer b drained
     int rc = forward_chunk(e, e->d_x[b], dtype, sm, e->d_out[b], e->s_comp);
     if (rc) return rc;
+    if (dec_host) {
+      ProfScope ps(e, 13, e->s_comp);
+      cudaError_t dst_ = dtype == CLAIRB_DTYPE_I16
+                             ? decide::launch<int16_t>(e->d_out[b], e->d_ref[b], (const int16_t*)e->d_x[b], e->d_dec[b], cn, e->s_comp)
+                             : decide::launch<float>(e->d_out[b], e->d_ref[b], (const float*)e->d_x[b], e->d_dec[b], cn, e->s_comp);
+      if (dst_ != cudaSuccess) return fail(e, CLAIRB_ECUDA, "decide_sites launch failed: %s", cudaGetErrorString(dst_));
+      e->launches += 1;
+    }
     CU_TRY(e, cudaEventRecord(e->ev_comp[b], e->s_comp));
     CU_TRY(e, cudaStreamWaitEvent(e->s_d2h, e->ev_comp[b], 0));
     float* dst = out_pinned ? out_host + (size_t)done * N_OUT : e->h_out[b];
     CU_TRY(e, cudaMemcpyAsync(dst, e->d_out[b], (size_t)cn * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+    if (dec_host)
+      CU_TRY(e, cudaMemcpyAsync(e->h_dec[b], e->d_dec[b], (size_t)cn * decide::REC_WORDS * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, e->s_d2h));
     CU_TRY(e, cudaEventRecord(e->ev_d2h[b], e->s_d2h));
     if (!out_pinned && c >= 1) {
       // while this chunk runs, hand the previous chunk's results to the caller
       CU_TRY(e, cudaEventSynchronize(e->ev_d2h[b ^ 1]));
       memcpy(out_host + (size_t)prev_done * N_OUT, e->h_out[b ^ 1], (size_t)prev_cn * N_OUT * sizeof(float));
+    }
+    if (dec_host && c >= 1) {
+      CU_TRY(e, cudaEventSynchronize(e->ev_d2h[b ^ 1]));
+      memcpy(dec_host + (size_t)prev_done * decide::REC_WORDS, e->h_dec[b ^ 1], (size_t)prev_cn * decide::REC_WORDS * sizeof(int32_t));
     }
     e->last_map = sm;
     prev_done = done;
@@ -633,10 +664,56 @@ int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, f
     CU_TRY(e, cudaEventSynchronize(e->ev_d2h[(c - 1) & 1]));
     memcpy(out_host + (size_t)prev_done * N_OUT, e->h_out[(c - 1) & 1], (size_t)prev_cn * N_OUT * sizeof(float));
   }
+  if (dec_host) {
+    CU_TRY(e, cudaEventSynchronize(e->ev_d2h[(c - 1) & 1]));
+    memcpy(dec_host + (size_t)prev_done * decide::REC_WORDS, e->h_dec[(c - 1) & 1], (size_t)prev_cn * decide::REC_WORDS * sizeof(int32_t));
+  }
   e->last_single_chunk = c == 1;
   // the caller reads out_host as soon as we return (call_var.py:1334-1338)
   CU_TRY(e, cudaStreamSynchronize(e->s_d2h));
   CU_TRY(e, cudaStreamSynchronize(e->s_comp));
+  return CLAIRB_OK;
+}
+
+int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_host) {
+  return predict_impl(e, x_host, dtype, n, out_host, nullptr, nullptr);
+}
+
+int clairb_predict_decide(clairb_engine* e, const void* x_host, int dtype, int64_t n, const uint8_t* ref_base, float* out_host,
+                          int32_t* decision) {
+  if (!e) return CLAIRB_EINVAL;
+  if (!ref_base || !decision) return fail(e, CLAIRB_EINVAL, "predict_decide: ref_base and decision are required");
+  return predict_impl(e, x_host, dtype, n, out_host, ref_base, decision);
+}
+
+int clairb_decide(clairb_engine* e, const float* probs_host, const uint8_t* ref_base, const void* x_host, int dtype, int64_t n,
+                  int32_t* decision) {
+  if (!e) return CLAIRB_EINVAL;
+  if (!probs_host || !ref_base || !decision || n <= 0) return fail(e, CLAIRB_EINVAL, "decide: bad n or buffers");
+  if (x_host && dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(e, CLAIRB_EINVAL, "unknown dtype %d", dtype);
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t eb = elem_bytes(dtype);
+  for (int64_t done = 0; done < n; done += e->chunk_sites) {
+    const int64_t cn = n - done < e->chunk_sites ? n - done : e->chunk_sites;
+    CU_TRY(e, cudaMemcpyAsync(e->d_out[0], probs_host + (size_t)done * N_OUT, (size_t)cn * N_OUT * sizeof(float),
+                              cudaMemcpyHostToDevice, e->s_comp));
+    CU_TRY(e, cudaMemcpyAsync(e->d_ref[0], ref_base + done, (size_t)cn, cudaMemcpyHostToDevice, e->s_comp));
+    if (x_host)
+      CU_TRY(e, cudaMemcpyAsync(e->d_x[0], (const char*)x_host + (size_t)done * SITE_ELEMS * eb, (size_t)cn * SITE_ELEMS * eb,
+                                cudaMemcpyHostToDevice, e->s_comp));
+    cudaError_t st;
+    {
+      ProfScope ps(e, 13, e->s_comp);
+      st = (x_host && dtype == CLAIRB_DTYPE_I16)
+               ? decide::launch<int16_t>(e->d_out[0], e->d_ref[0], (const int16_t*)e->d_x[0], e->d_dec[0], cn, e->s_comp)
+               : decide::launch<float>(e->d_out[0], e->d_ref[0], x_host ? (const float*)e->d_x[0] : nullptr, e->d_dec[0], cn, e->s_comp);
+    }
+    if (st != cudaSuccess) return fail(e, CLAIRB_ECUDA, "decide_sites launch failed: %s", cudaGetErrorString(st));
+    e->launches += 1;
+    CU_TRY(e, cudaMemcpyAsync(decision + (size_t)done * decide::REC_WORDS, e->d_dec[0],
+                              (size_t)cn * decide::REC_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_comp));
+    CU_TRY(e, cudaStreamSynchronize(e->s_comp));
+  }
   return CLAIRB_OK;
 }
 

@@ -127,6 +127,59 @@ class Clair(object):
         self.prediction = prediction
         return prediction
 
+    def predict_and_decide(self, batchX, ref_bases):
+        """predict() plus the first-choice variant decision of every site in the same device pass.
+
+        ref_bases: [n] uint8 codes 0..3 (clair_b200.decision.ref_base_codes).  Returns (prediction, Decision): the
+        list of four arrays predict() returns (also stored in .prediction) and a clair_b200.decision.Decision of
+        arrays - what possible_outcome_probabilites_from + the first pass of output_from's loop would select
+        (clair/call_var.py:589-690, 732-760)."""
+        from . import decision as _decision
+        if not self._has_weights:
+            raise RuntimeError("predict() before init()/restore_parameters()")
+        X, _ = self.tensor_transform_function(batchX, None, "predict")
+        X, dtype = self._as_input(X)
+        n = X.shape[0]
+        ref = np.ascontiguousarray(ref_bases, dtype=np.uint8).reshape(-1)
+        if ref.shape[0] != n or (ref > 3).any():
+            raise ValueError("ref_bases must be %d codes in 0..3" % n)
+        out = np.empty((n, _lib.N_OUT), dtype=np.float32)
+        rec = np.empty((n, _lib.DECISION_WORDS), dtype=np.int32)
+        with self._lock:
+            for s in range(0, n, self.max_sites):
+                m = min(self.max_sites, n - s)
+                rc = self._lib.clairb_predict_decide(
+                    self._h, X[s:s + m].ctypes.data_as(ctypes.c_void_p), dtype, m,
+                    ref[s:s + m].ctypes.data_as(ctypes.c_void_p), out[s:s + m].ctypes.data_as(ctypes.c_void_p),
+                    rec[s:s + m].ctypes.data_as(ctypes.c_void_p))
+                _lib.check(rc, self._h, "clairb_predict_decide")
+        split = np.cumsum(self.output_label_split)[:-1]
+        self.prediction = [np.ascontiguousarray(a) for a in np.split(out, split, axis=1)]
+        return self.prediction, _decision.unpack(rec)
+
+    def decide(self, probs, ref_bases, batchX=None):
+        """Decision alone from [n,90] probabilities the caller holds (e.g. an ensemble average)."""
+        from . import decision as _decision
+        P = np.ascontiguousarray(probs, dtype=np.float32)
+        if P.ndim != 2 or P.shape[1] != _lib.N_OUT or P.shape[0] < 1:
+            raise ValueError("probs must be [n,90]")
+        n = P.shape[0]
+        ref = np.ascontiguousarray(ref_bases, dtype=np.uint8).reshape(-1)
+        if ref.shape[0] != n or (ref > 3).any():
+            raise ValueError("ref_bases must be %d codes in 0..3" % n)
+        xp, dtype = None, _lib.DTYPE_F32
+        if batchX is not None:
+            X, dtype = self._as_input(batchX)
+            if X.shape[0] != n:
+                raise ValueError("batchX and probs disagree on n")
+            xp = X.ctypes.data_as(ctypes.c_void_p)
+        rec = np.empty((n, _lib.DECISION_WORDS), dtype=np.int32)
+        with self._lock:
+            rc = self._lib.clairb_decide(self._h, P.ctypes.data_as(ctypes.c_void_p), ref.ctypes.data_as(ctypes.c_void_p),
+                                         xp, dtype, n, rec.ctypes.data_as(ctypes.c_void_p))
+            _lib.check(rc, self._h, "clairb_decide")
+        return _decision.unpack(rec)
+
     def get_layer(self, layer, n):
         """Parity hook: activations of the last (single-chunk) predict at one graph stage."""
         shapes = {_lib.LAYER_LSTM1: (33, n, 256), _lib.LAYER_LSTM2: (33, n, 256), _lib.LAYER_L3: (n, 30, 256),

@@ -83,6 +83,37 @@ int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, f
 int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_t n,
                           float* out_dev, void* stream);
 
+/* ---- first-choice variant decision (the head of the reference's VCF stage) --------------
+ * Replaces, per site, possible_outcome_probabilites_from (clair/call_var.py:589-690) plus the first pass of
+ * output_from's selection loop (clair/call_var.py:732-760): which of the ~1.2 k outcome products is the
+ * maximum, in the reference's float32 arithmetic and with its tie order (first category in elif order, then
+ * list.index).  The string assembly of REF/ALT, the indel-base lookups and the rare retry iterations stay with
+ * the caller (clair/call_var.py:762-929).
+ *   ref_base : [n] uint8, 0..3 = A C G T: BASE2ACGT[reference_sequence[16]] (clair/call_var.py:718)
+ *   decision : [n][CLAIRB_DECISION_WORDS] int32 records
+ *              [0] category 0..9 in the order of output_from's flags tuple (clair/call_var.py:931-937):
+ *                  reference, homo SNP, hetero SNP, homo Ins, hetero ACGT+Ins, hetero InsIns, homo Del,
+ *                  hetero ACGT+Del, hetero DelDel, Ins+Del
+ *              [1],[2] variant lengths: homo Ins/Del and ACGT+Ins/Del: (length, 0); InsIns / DelDel: the
+ *                  (shorter, longer) tuple; Ins+Del: (deletion length, insertion length) as
+ *                  hetero_InsDel_tuples_from stores it (clair/call_var.py:411-424)
+ *              [3] aux: reference / SNP: the gt21 index of the label (clair/task/gt21.py:27-48);
+ *                  ACGT+Ins/Del: the hetero base 0..3
+ *              [4] maximum probability, float32 bits     [5] read depth
+ *                  sum(x[16,:,delete] + x[16,:,reference]) (clair/call_var.py:1021-1024), float32 bits
+ */
+#define CLAIRB_DECISION_WORDS 6
+
+/* Forward + decision in one pass: as clairb_predict, and the decision kernel runs on every chunk while its
+ * probabilities and input tensor are still in device memory. */
+int clairb_predict_decide(clairb_engine* e, const void* x_host, int dtype, int64_t n,
+                          const uint8_t* ref_base, float* out_host, int32_t* decision);
+
+/* Decision alone, from probabilities the caller already holds (e.g. an ensemble average,
+ * clair/post_processing/ensemble.py).  x_host may be NULL (read depth is then reported as 0). */
+int clairb_decide(clairb_engine* e, const float* probs_host, const uint8_t* ref_base, const void* x_host,
+                  int dtype, int64_t n, int32_t* decision);
+
 /* Parity hook: activations of the most recent clairb_predict* call at one stage of the graph,
  * copied to host as float32 in the reference's own axis order (see CLAIRB_LAYER_*).
  * out_host must hold layer_elems(layer) * n floats. */

@@ -1,0 +1,123 @@
+"""First-choice variant decision.
+
+CPU: the oracle restatement against the golden outcomes the REFERENCE's own output_from produced
+(tests/golden/decision_cases.npz, oracle/gen_golden_decision.py) - parity pinned.
+GPU (-m gpu): the decide_sites kernel through the C-ABI against the same goldens (bit-exact), against the oracle on
+the model's real outputs, and the fused clairb_predict_decide path against the two-call path.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from clair_b200 import _lib, decision, synth
+from oracle import decision_oracle as D
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decision_cases.npz")
+
+
+@pytest.fixture(scope="module")
+def cases():
+    with np.load(GOLD) as z:
+        return {k: z[k] for k in z.files}
+
+
+def golden_X(cases):
+    X = np.zeros((len(cases["probs"]), 33, 8, 4), np.float32)
+    X[:, 16] = cases["X16"]
+    return X
+
+
+def test_oracle_matches_the_reference_outcomes(cases):
+    dec, maxp, depth = D.decide(cases["probs"], cases["ref_bases"], golden_X(cases))
+    np.testing.assert_array_equal(dec, cases["decision"])
+    np.testing.assert_array_equal(maxp, cases["max_probability"])          # float32, bit-exact
+    np.testing.assert_array_equal(depth, cases["read_depth"])
+    assert set(cases["decision"][:, 0]) == set(range(10))                  # every category is covered
+
+
+def test_golden_cases_cover_ties_and_degenerate_heads(cases):
+    P = cases["probs"]
+    assert (P.sum(1) == 0).any()                                           # all-zero probabilities -> "reference"
+    zero = np.where(P.sum(1) == 0)[0][0]
+    assert cases["decision"][zero, 0] == 0
+    onehot = (P.max(1) == 1.0) & ((P == 0).sum(1) >= 80)
+    assert onehot.sum() >= 21
+
+
+def test_outcome_list_sizes_follow_the_reference():
+    p = np.full(90, 0.1, np.float32)
+    lists = D.outcome_lists(p[:21], p[21:24], p[24:57], p[57:], 2)
+    # Ref, homoSNP, heteroSNP, homoIns, ACGT+Ins, InsIns, homoDel, ACGT+Del, DelDel, InsDel (call_var.py:344-424)
+    assert [len(x) for x in lists] == [1, 4, 6, 16, 64, 256, 16, 64, 240, 512]
+
+
+def test_host_helpers():
+    infos = [["chr1", "10", "A" * 16 + b + "C" * 16] for b in "ACGTURYSWKMBDHVN"]
+    codes = decision.ref_base_codes(infos)
+    assert codes.tolist() == ["ACGT".index(c) for c in "ACGTTACCAGACAAAA"]          # shared/utils.py:19-29
+    assert decision.flags_tuple(4) == (False,) * 4 + (True,) + (False,) * 5
+    assert decision.snp_bases(6) == ("C", "T")
+    rec = np.zeros((2, 6), np.int32)
+    rec[0, :4] = (5, 2, 7, 0)
+    rec.view(np.float32)[0, 4:] = (0.25, 31.0)
+    d = decision.unpack(rec)
+    assert (d.category[0], d.len1[0], d.len2[0], d.max_probability[0], d.read_depth[0]) == (5, 2, 7, 0.25, 31.0)
+
+
+# ---- GPU ----------------------------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+def test_kernel_matches_the_reference_outcomes(gpu_model, cases):
+    d = gpu_model.decide(cases["probs"], cases["ref_bases"], golden_X(cases))
+    got = np.stack([d.category, d.len1, d.len2, d.aux], axis=1)
+    np.testing.assert_array_equal(got, cases["decision"])
+    np.testing.assert_array_equal(d.max_probability, cases["max_probability"])
+    np.testing.assert_array_equal(d.read_depth, cases["read_depth"])
+    d2 = gpu_model.decide(cases["probs"], cases["ref_bases"])             # no tensor: depth reported as 0
+    np.testing.assert_array_equal(d2.category, d.category)
+    assert (d2.read_depth == 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,dtype", [(1, np.float32), (777, np.float32), (2500, np.int16)])
+def test_fused_predict_decide_equals_two_calls_and_oracle(gpu_model, n, dtype):
+    counts = synth.synthetic_counts(n, seed=400 + n).astype(np.int32)
+    counts[..., 1:] -= counts[..., 0:1]
+    X = counts.astype(dtype)
+    ref = np.random.default_rng(n).integers(0, 4, n).astype(np.uint8)
+    probs = gpu_model.predict_packed(X)
+    pred, d = gpu_model.predict_and_decide(X, ref)
+    np.testing.assert_array_equal(np.concatenate(pred, axis=1), probs)     # same forward, bit for bit
+    assert gpu_model.prediction is pred
+    two = gpu_model.decide(probs, ref, X)
+    for a, b in zip(d, two):
+        np.testing.assert_array_equal(a, b)
+    sel = np.arange(0, n, max(1, n // 300))
+    dec, maxp, depth = D.decide(probs[sel], ref[sel], X[sel].astype(np.float32))
+    np.testing.assert_array_equal(np.stack([d.category, d.len1, d.len2, d.aux], axis=1)[sel], dec)
+    np.testing.assert_array_equal(d.max_probability[sel], maxp)
+    np.testing.assert_array_equal(d.read_depth[sel], depth)
+
+
+@pytest.mark.gpu
+def test_decision_multi_chunk_pipeline(weights1234, monkeypatch):
+    from clair_b200.model import Clair
+    monkeypatch.setenv("CLAIRB_CHUNK_SITES", "1024")
+    m = Clair(max_sites=4096, batch_sites=1000)
+    monkeypatch.delenv("CLAIRB_CHUNK_SITES")
+    m.set_weights(weights1234)
+    X = synth.synthetic_tensors(3300, seed=5)
+    ref = (np.arange(3300) % 4).astype(np.uint8)
+    pred, d = m.predict_and_decide(X, ref)
+    probs = np.concatenate(pred, axis=1)
+    np.testing.assert_array_equal(probs, m.predict_packed(X))
+    dec, maxp, depth = D.decide(probs[::11], ref[::11], X[::11])
+    np.testing.assert_array_equal(np.stack([d.category, d.len1, d.len2, d.aux], axis=1)[::11], dec)
+    np.testing.assert_array_equal(d.max_probability[::11], maxp)
+    np.testing.assert_array_equal(d.read_depth[::11], depth)
+    with pytest.raises(ValueError):
+        m.predict_and_decide(X, ref[:10])
+    with pytest.raises(ValueError):
+        m.decide(probs, np.full(3300, 7, np.uint8))
+    m.close()
