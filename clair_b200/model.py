@@ -75,9 +75,14 @@ class Clair(object):
         self.set_weights(_weights.random_weights(seed=self._seed, bias_std=0.0))
 
     def restore_parameters(self, file_name):
-        """Reference: tf.train.Saver.restore (clair/model.py:1016-1020).  Here: the .npz weight
-        blob keyed by TF variable name (clair_b200/weights.py)."""
-        self.set_weights(_weights.load_blob(file_name))
+        """Reference: tf.train.Saver.restore (clair/model.py:1016-1020).  `file_name` is either the prefix of a
+        TensorFlow V2 checkpoint bundle (<prefix>.index + <prefix>.data-*, read without TensorFlow by
+        clair_b200/checkpoint.py) or the .npz weight blob keyed by TF variable name (clair_b200/weights.py)."""
+        from . import checkpoint as _checkpoint
+        if _checkpoint.is_checkpoint_prefix(file_name):
+            self.set_weights(_checkpoint.load_checkpoint(file_name))
+        else:
+            self.set_weights(_weights.load_blob(file_name))
 
     def set_weights(self, weights):
         _weights.check_weights(weights)
