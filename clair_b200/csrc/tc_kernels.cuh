@@ -739,7 +739,10 @@ constexpr int SX_KC = CLAIRB_SX_KC;                     // k-chunks of 8 per rin
 constexpr int SX_STAGE = 4 * SX_KC * KCH_BYTES;         // A hi | A lo | B hi | B lo
 constexpr int SX_RING = 98304 / SX_STAGE;
 constexpr int SX_NST = 32 / SX_KC;                      // stages per block pair (K = 256)
-constexpr int SX_G = 2;                                 // epilogue warps per TMEM lane quarter (2 or 4)
+#ifndef CLAIRB_SX_G
+#define CLAIRB_SX_G 2
+#endif
+constexpr int SX_G = CLAIRB_SX_G;                                 // epilogue warps per TMEM lane quarter (2 or 4)
 constexpr int SX_THREADS = 32 * (2 + 4 * SX_G);
 constexpr size_t seqx_smem_bytes() { return (size_t)SEQ_W_BYTES + SX_RING * SX_STAGE + 2048 + 256 + 128; }
 
