@@ -38,7 +38,7 @@ constexpr int GX_TILE_FLOATS = 2 * 128 * 128 * 4;   // per (t, tile): [dir][unit
 constexpr int L3_TG = 5;                                  // time groups of 8 kept per channel (t = 0..39, 33..39 zero)
 constexpr int L3A_HALVES = 2 * L3_TG * 1024;              // per (tile, channel): [hl][t/8][site/64][t%8][64 sites, 128B-swizzled]
 constexpr int L3A_BYTES = L3A_HALVES * 2;                 // 20480
-// per-channel weight blob of l3l4_fused: W3_c hi|lo ([6 kc][32 o][8 t]) , W4_c hi|lo ([4 kc][192 n][8 o]) , b3_c[32]
+// per-channel weight blob of l3l4_fused: W3_c ([6 kc][hi 32 o | lo 32 o][8 t]) , W4_c hi|lo ([4 kc][192 n][8 o]) , b3_c[32]
 constexpr int L3W_BYTES = 6 * 32 * 16;                    // 3072
 constexpr int L4W_BYTES = 4 * 192 * 16;                   // 12288
 constexpr int L3L4_BLOB_BYTES = 31 * 1024;                            // 30848 used, padded so ring stages stay 1 KB aligned
@@ -1073,37 +1073,50 @@ __global__ void __launch_bounds__(128) prep_tiles48(const TIn* __restrict__ x, _
 //                               D4[128 x 192] += S_c . W4[(o,c), :]                          (L4 rows regrouped by channel)
 //   then l4[128 x 192] = selu(D4 + b4) -> planes l4T[192][np] fp32 for the heads kernel.
 // The [B,30,256] -> [B,7680] flatten (model.py:474-478, index o*256+c) never materialises: S_c goes TMEM -> registers ->
-// fp16 hi/lo operand tile in shared memory -> next MMA.  A_c arrives MN-major, 128B-swizzled (K = time) from lstm_seq<.,2>; the k-group
-// t = 40..47 of the third k-step points at a shared zero block through the descriptor's leading-dimension offset.
-// Warp roles: 0 = producer (one A tile + one weight blob per channel, 3-stage ring), 1 = MMA issuer,
-// 2..9 = epilogue: group g = (warp-2)/4 owns channels c = g mod 2 with its own D3 / S_c buffers.
+// fp16 hi/lo pairs back into TENSOR MEMORY, from where the L4 MMAs read it as their A operand.  A_c arrives MN-major,
+// 128B-swizzled (K = time) from lstm_seq_x2; the k-group t = 40..47 of the third k-step points at a shared zero block
+// through the descriptor's leading-dimension offset.
+// What bounds it (timeline probe CLAIRB_LF_TRACE, tools/lf_trace.py): the time a channel keeps its ring stage - load
+// ~1.0-1.5 k cycles, L3 ~0.9 k, epilogue ~1.9 k, L4 ~0.9 k - divided by the ring depth.  Hence
+//   * 4 ring stages of (A tile + weight blob) = 205 KB: possible because S_c lives in tensor memory, not in smem;
+//   * the MMAs of a tile are issued by TWO threads (warp 1: L3, warp 10: L4): one issuing thread needed ~100 cycles per
+//     MMA plus ~400 cycles between bursts (it shares a scheduler with two epilogue warps) and capped the kernel at
+//     2 x (400 + 640) = 2.05 k cycles per channel;
+//   * L3 of a channel is two independent accumulation chains instead of one chain of 9 (links that accumulate into the
+//     same columns are ~90 cycles apart however small N is):
+//         D3[ 0..63] += A_hi . [W_hi ; W_lo]^T   (N = 64: hi.hi | hi.lo)      D3[64..95] += A_lo . W_hi^T   (N = 32)
+//     interleaved over the 3 k-steps; the epilogue adds the three 32-column groups;
+//   * every shared-memory descriptor is precomputed per ring stage and the loops are unrolled over the 4 stages.
+// Warp roles: 0 = producer (one A tile + one weight blob per channel), 1 = L3 MMA issuer, 2..9 = epilogue: group
+// g = (warp-2)/4 owns channels c = g mod 2 with its own D3 / S_c buffers, 10 = L4 MMA issuer.
 // ---------------------------------------------------------------------------------------------
-constexpr int LF_STAGES = 3;
+constexpr int LF_STAGES = 4;
 constexpr int LF_STAGE_BYTES = L3A_BYTES + L3L4_BLOB_BYTES;          // 51328
-constexpr int LF_A4_BYTES = 2 * 4 * KCH_BYTES;                       // [hl][4 kc][128][8] = 16384
-constexpr int LF_THREADS = 320;
-constexpr size_t l3l4_smem_bytes() { return (size_t)LF_STAGES * LF_STAGE_BYTES + 2 * LF_A4_BYTES + 2048 + 256 + 1024; }
+constexpr int LF_THREADS = 352;
+constexpr size_t l3l4_smem_bytes() { return (size_t)LF_STAGES * LF_STAGE_BYTES + 2048 + 256 + 1024; }
 
 __global__ void __launch_bounds__(LF_THREADS, 1)
 l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, const float* __restrict__ b4,
-           float* __restrict__ l4T, __half* __restrict__ L4t, int64_t np, float* __restrict__ l3_dbg, int pf_dist) {
+           float* __restrict__ l4T, __half* __restrict__ L4t, int64_t np, float* __restrict__ l3_dbg, int pf_dist,
+           long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stages = smem;
-  uint8_t* A4 = stages + LF_STAGES * LF_STAGE_BYTES;   // [g 2][hl][4 kc][128][8]
-  uint8_t* zero = A4 + 2 * LF_A4_BYTES;                // 2 KB of zeros (k-group t = 40..47)
+  uint8_t* zero = stages + LF_STAGES * LF_STAGE_BYTES; // 2 KB of zeros (k-group t = 40..47)
   uint64_t* bars = (uint64_t*)(zero + 2048);
-  uint64_t* stage_full = bars;          // [3]
-  uint64_t* stage_empty = bars + 3;     // [3]
-  uint64_t* d3_full = bars + 6;         // [2]
-  uint64_t* d3_empty = bars + 8;        // [2]
-  uint64_t* a4_full = bars + 10;        // [2]
-  uint64_t* a4_empty = bars + 12;       // [2]
-  uint64_t* d4_full = bars + 14;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 15);
+  uint64_t* stage_full = bars;          // [4]
+  uint64_t* stage_empty = bars + 4;     // [4]
+  uint64_t* d3_full = bars + 8;         // [2]
+  uint64_t* d3_empty = bars + 10;       // [2]
+  uint64_t* a4_full = bars + 12;        // [2] S_c of group g is in tensor memory (4 epilogue warps)
+  uint64_t* a4_empty = bars + 14;       // [2] S_c consumed (L4 MMA commit)
+  uint64_t* d4_full = bars + 16;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
+  const bool tr_on = trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](int c, int ev) { if (tr_on) trace[c * 16 + ev] = clock64(); };
   if (threadIdx.x == 0) {
     for (int i = 0; i < LF_STAGES; ++i) { mbar_init(&stage_full[i], 1); mbar_init(&stage_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
@@ -1115,22 +1128,24 @@ l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, co
   }
   for (int i = threadIdx.x; i < 2048 / 16; i += LF_THREADS) reinterpret_cast<uint4*>(zero)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;     // cols 0..191: D4, 192..223: D3[0], 224..255: D3[1]
+  const uint32_t tmem = *tmem_slot;     // cols 0..191: D4, 192..287: D3[0] (hi.hi | hi.lo | lo.hi), 288..383: D3[1],
+                                        // 384..415: S[0] (fp16 pairs: hi 16 cols | lo 16 cols), 416..447: S[1]
 
   if (warp == 0) {
     if (lane == 0) {
       const uint8_t* a_src = (const uint8_t*)(H2t + (size_t)tile * 2 * H * L3A_HALVES);
-      // the ring (3 x 52 KB) is too shallow for HBM latency: pull the LSTM2 tiles of the next channels into L2 ahead of
-      // the bulk copies (the weight blobs are shared by all CTAs and stay L2-resident by themselves)
+      // pull the LSTM2 tiles of the next channels into L2 ahead of the bulk copies (the weight blobs are shared by all
+      // CTAs and stay L2-resident by themselves)
       for (int c = 0; c < pf_dist && c < 2 * H; ++c) bulk_prefetch_l2(a_src + (size_t)c * L3A_BYTES, L3A_BYTES);
       for (int c = 0; c < 2 * H; ++c) {
         if (c + pf_dist < 2 * H && pf_dist > 0) bulk_prefetch_l2(a_src + (size_t)(c + pf_dist) * L3A_BYTES, L3A_BYTES);
         const int st = c % LF_STAGES;
         mbar_wait(&stage_empty[st], ((c / LF_STAGES) & 1) ^ 1);
+        stamp(c, 0);
         uint8_t* dst = stages + st * LF_STAGE_BYTES;
         mbar_expect_tx(&stage_full[st], LF_STAGE_BYTES);
         bulk_g2s(dst, a_src + (size_t)c * L3A_BYTES, L3A_BYTES, &stage_full[st]);
@@ -1140,54 +1155,80 @@ l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, co
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc3 = make_idesc_f16_amn(128, 32);
-      const uint32_t idesc4 = make_idesc_f16(128, 192);
+      // ---- L3 issuer ----
+      const uint32_t idesc3a = make_idesc_f16_amn(128, 64), idesc3b = make_idesc_f16_amn(128, 32);
       const uint32_t zero_addr = smem_u32(zero);
-      auto issue_l4 = [&](int cc) {
-        const int g = cc & 1, use = cc >> 1, st = cc % LF_STAGES;
-        mbar_wait(&a4_full[g], use & 1);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(A4 + g * LF_A4_BYTES);
-        const uint32_t w_base = smem_u32(stages + st * LF_STAGE_BYTES + L3A_BYTES + 2 * L3W_BYTES);
+      const uint64_t sw128 = (uint64_t)2 << 61;
+      uint64_t a3[LF_STAGES][2][3], b3[LF_STAGES][3];
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const uint64_t a_hi = make_smem_desc(a_base + kk * 2 * KCH_BYTES, KCH_BYTES, 128);
-          const uint64_t a_lo = make_smem_desc(a_base + 4 * KCH_BYTES + kk * 2 * KCH_BYTES, KCH_BYTES, 128);
-          const uint64_t b_hi = make_smem_desc(w_base + kk * 2 * (192 * 16), 192 * 16, 128);
-          const uint64_t b_lo = make_smem_desc(w_base + L4W_BYTES + kk * 2 * (192 * 16), 192 * 16, 128);
-          umma_f16(tmem, a_hi, b_hi, idesc4, (cc | kk) != 0);
-          umma_f16(tmem, a_lo, b_hi, idesc4, 1);
-          umma_f16(tmem, a_hi, b_lo, idesc4, 1);
-        }
-        umma_commit(&a4_empty[g]);
-        umma_commit(&stage_empty[st]);
-      };
-      for (int c = 0; c < 2 * H; ++c) {
-        const int g = c & 1, use = c >> 1, st = c % LF_STAGES;
-        mbar_wait(&stage_full[st], (c / LF_STAGES) & 1);
-        mbar_wait(&d3_empty[g], (use & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(stages + st * LF_STAGE_BYTES);
-        const uint32_t w_base = a_base + L3A_BYTES;
-        const uint32_t d3 = tmem + 192 + g * 32;
+      for (int st = 0; st < LF_STAGES; ++st) {
+        const uint32_t a_base = smem_u32(stages + st * LF_STAGE_BYTES), w_base = a_base + L3A_BYTES;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          // MN-major SWIZZLE_128B A: LBO = distance between the two 64-site atoms, SBO = distance between the two
-          // time groups of this k-step (for t = 32..47 the second group is the shared zero block)
-          const uint32_t a_hi_addr = a_base + j * 2 * 2048, a_lo_addr = a_base + L3A_BYTES / 2 + j * 2 * 2048;
-          const uint64_t sw128 = (uint64_t)2 << 61;
-          const uint64_t a_hi = sw128 | (j < 2 ? make_smem_desc(a_hi_addr, 1024, 2048) : make_smem_desc(a_hi_addr, 1024, zero_addr - a_hi_addr));
-          const uint64_t a_lo = sw128 | (j < 2 ? make_smem_desc(a_lo_addr, 1024, 2048) : make_smem_desc(a_lo_addr, 1024, zero_addr - a_lo_addr));
-          const uint64_t b_hi = make_smem_desc(w_base + j * 2 * 512, 512, 128);
-          const uint64_t b_lo = make_smem_desc(w_base + L3W_BYTES + j * 2 * 512, 512, 128);
-          umma_f16(d3, a_hi, b_hi, idesc3, j != 0);
-          umma_f16(d3, a_lo, b_hi, idesc3, 1);
-          umma_f16(d3, a_hi, b_lo, idesc3, 1);
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl) {
+            // MN-major SWIZZLE_128B A: LBO = distance between the two 64-site atoms, SBO = distance between the two
+            // time groups of this k-step (for t = 32..47 the second group is the shared zero block)
+            const uint32_t addr = a_base + hl * (L3A_BYTES / 2) + j * 2 * 2048;
+            a3[st][hl][j] = sw128 | (j < 2 ? make_smem_desc(addr, 1024, 2048) : make_smem_desc(addr, 1024, zero_addr - addr));
+          }
+          b3[st][j] = make_smem_desc(w_base + j * 2 * 1024, 1024, 128);      // [kc][hi 32 rows | lo 32 rows][8]
         }
-        umma_commit(&d3_full[g]);
-        if (c >= 1) issue_l4(c - 1);
       }
-      issue_l4(2 * H - 1);
+      for (int c0 = 0; c0 < 2 * H; c0 += LF_STAGES) {
+#pragma unroll
+        for (int u = 0; u < LF_STAGES; ++u) {
+          const int c = c0 + u, st = u, g = u & 1;
+          mbar_wait(&stage_full[st], (c / LF_STAGES) & 1);
+          mbar_wait(&d3_empty[g], ((c >> 1) & 1) ^ 1);
+          tc_fence_after();
+          stamp(c, 2);
+          const uint32_t d3 = tmem + 192 + g * 96;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            umma_f16(d3, a3[st][0][j], b3[st][j], idesc3a, j != 0);
+            umma_f16(d3 + 64, a3[st][1][j], b3[st][j], idesc3b, j != 0);
+          }
+          umma_commit(&d3_full[g]);
+          stamp(c, 3);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    if (lane == 0) {
+      // ---- L4 issuer: D4[128 x 192] += S_c . W4_c as soon as the epilogue has written S_c; frees the S_c buffer and
+      //      the ring stage of channel c ----
+      const uint32_t idesc4 = make_idesc_f16(128, 192);
+      uint64_t b4d[LF_STAGES][2][2];
+#pragma unroll
+      for (int st = 0; st < LF_STAGES; ++st) {
+        const uint32_t w_base = smem_u32(stages + st * LF_STAGE_BYTES) + L3A_BYTES + 2 * L3W_BYTES;
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            b4d[st][hl][kk] = make_smem_desc(w_base + hl * L4W_BYTES + kk * 2 * (192 * 16), 192 * 16, 128);
+      }
+      for (int c0 = 0; c0 < 2 * H; c0 += LF_STAGES) {
+#pragma unroll
+        for (int u = 0; u < LF_STAGES; ++u) {
+          const int c = c0 + u, st = u, g = u & 1;
+          mbar_wait(&a4_full[g], (c >> 1) & 1);
+          tc_fence_after();
+          stamp(c, 4);
+          const uint32_t s_hi = tmem + 384 + g * 32, s_lo = s_hi + 16;     // A operand from tensor memory
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            umma_f16_ts(tmem, s_hi + kk * 8, b4d[st][0][kk], idesc4, (c | kk) != 0);
+            umma_f16_ts(tmem, s_lo + kk * 8, b4d[st][0][kk], idesc4, 1);
+            umma_f16_ts(tmem, s_hi + kk * 8, b4d[st][1][kk], idesc4, 1);
+          }
+          umma_commit(&a4_empty[g]);
+          umma_commit(&stage_empty[st]);
+          stamp(c, 5);
+        }
+      }
       umma_commit(d4_full);
     }
     __syncwarp();
@@ -1196,18 +1237,29 @@ l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, co
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* a4 = A4 + g * LF_A4_BYTES + r * 16;
     for (int c = g; c < 2 * H; c += 2) {
       const int use = c >> 1, st = c % LF_STAGES;
       mbar_wait(&d3_full[g], use & 1);
       tc_fence_after();
+      if (lane == 0 && quarter == 0) stamp(c, 8);
       float v[32];
-      tmem_ld16(lane_addr + 192 + g * 32, v);
-      tmem_ld16(lane_addr + 192 + g * 32 + 16, v + 16);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&d3_empty[g]);
+      {
+        // the three partial products of the hi/lo split sit in three 32-column groups: add them up
+        float p1[32], p2[32];
+        const uint32_t d3 = lane_addr + 192 + g * 96;
+        tmem_ld16(d3, v);
+        tmem_ld16(d3 + 16, v + 16);
+        tmem_ld16(d3 + 32, p1);
+        tmem_ld16(d3 + 48, p1 + 16);
+        tmem_ld16(d3 + 64, p2);
+        tmem_ld16(d3 + 80, p2 + 16);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d3_empty[g]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += p1[i] + p2[i];
+      }
       const float* b3 = reinterpret_cast<const float*>(stages + st * LF_STAGE_BYTES + L3A_BYTES + 2 * L3W_BYTES + 2 * L4W_BYTES);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -1219,18 +1271,27 @@ l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, co
 #pragma unroll
         for (int i = 0; i < L3_UNITS; ++i) l3_dbg[((size_t)i * 2 * H + c) * np + (size_t)tile * 128 + r] = v[i];
       }
-      uint4 hi[4], lo[4];
+      // S_c as fp16 hi/lo pairs -> tensor memory (the A operand of the L4 MMAs)
+      uint32_t whi[16], wlo[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) split8(v + 8 * q, hi[q], lo[q]);
-      mbar_wait(&a4_empty[g], (use & 1) ^ 1);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        *reinterpret_cast<uint4*>(a4 + q * KCH_BYTES) = hi[q];
-        *reinterpret_cast<uint4*>(a4 + 4 * KCH_BYTES + q * KCH_BYTES) = lo[q];
+      for (int q = 0; q < 16; ++q) {
+        const __half2 h2 = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+        const float2 back = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(v[2 * q] - back.x, v[2 * q + 1] - back.y);
+        whi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+        wlo[q] = *reinterpret_cast<const uint32_t*>(&l2);
       }
-      fence_proxy_async();
+      if (lane == 0 && quarter == 0) stamp(c, 9);
+      mbar_wait(&a4_empty[g], (use & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0 && quarter == 0) stamp(c, 10);
+      tmem_st16(lane_addr + 384 + g * 32, whi);
+      tmem_st16(lane_addr + 384 + g * 32 + 16, wlo);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a4_full[g]);
+      if (lane == 0) stamp(c, 11 + quarter);
     }
     // ---- L4 epilogue: group g takes columns g*96..+96 ----
     mbar_wait(d4_full, 0);
@@ -1261,7 +1322,7 @@ l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
+  if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 
@@ -1522,6 +1583,7 @@ struct Workspace {
   __half* L4t = nullptr;     // [NT][hl][24][128][8]         L4 activations as the operand tile of heads_tc
   int sm_count = 148;
   CUtensorMap tmH1;          // H1 as [rows][1 KB], box = 4 rows (hi or lo half of one ring stage of A)
+  long long* lf_trace = nullptr;   // CLAIRB_LF_TRACE=<file>: [256 channels][16] clock64 stamps of tile 0 of l3l4_fused
   long long* trace = nullptr; // CLAIRB_SX_TRACE=<file>: [33][64] clock64 stamps of one CTA pair of lstm_seq_x2 (dumped at destroy)
 };
 
@@ -1649,15 +1711,15 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
     std::vector<uint8_t> blob((size_t)2 * H * L3L4_BLOB_BYTES, 0);
     for (int c = 0; c < 2 * H; ++c) {
       uint8_t* b = blob.data() + (size_t)c * L3L4_BLOB_BYTES;
-      __half* w3hi = (__half*)b;
-      __half* w3lo = (__half*)(b + L3W_BYTES);
+      __half* w3 = (__half*)b;
       __half* w4hi = (__half*)(b + 2 * L3W_BYTES);
       __half* w4lo = (__half*)(b + 2 * L3W_BYTES + L4W_BYTES);
       float* bb = (float*)(b + 2 * L3W_BYTES + 2 * L4W_BYTES);
+      // W3 as ONE K-major B tile of 64 rows per k-chunk: rows 0..31 = hi[o], rows 32..63 = lo[o]
       for (int t = 0; t < T_STEPS; ++t)
         for (int o = 0; o < L3_UNITS; ++o) {
-          const size_t idx = (size_t)(t / 8) * 32 * 8 + o * 8 + t % 8;
-          split_half(hm.w3[((size_t)c * T_STEPS + t) * L3_UNITS + o], w3hi[idx], w3lo[idx]);
+          const size_t idx = (size_t)(t / 8) * 64 * 8 + o * 8 + t % 8;
+          split_half(hm.w3[((size_t)c * T_STEPS + t) * L3_UNITS + o], w3[idx], w3[idx + 32 * 8]);
         }
       for (int o = 0; o < L3_UNITS; ++o) {
         bb[o] = hm.b3[(size_t)c * L3_UNITS + o];
@@ -1721,6 +1783,10 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
   if ((st = cudaMalloc((void**)&ws.L4t, NT * (size_t)HD_A4_BYTES)) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(heads_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem_bytes())) != cudaSuccess) return st;
   cudaDeviceGetAttribute(&ws.sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (getenv("CLAIRB_LF_TRACE")) {
+    if ((st = cudaMalloc((void**)&ws.lf_trace, 256 * 16 * sizeof(long long))) != cudaSuccess) return st;
+    cudaMemset(ws.lf_trace, 0, 256 * 16 * sizeof(long long));
+  }
   if (getenv("CLAIRB_SX_TRACE")) {
     if ((st = cudaMalloc((void**)&ws.trace, T_STEPS * 64 * sizeof(long long))) != cudaSuccess) return st;
     cudaMemset(ws.trace, 0, T_STEPS * 64 * sizeof(long long));
@@ -1736,6 +1802,18 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
 }
 
 inline void free_workspace(Workspace& ws) {
+  if (ws.lf_trace) {
+    std::vector<long long> h(256 * 16);
+    if (cudaMemcpy(h.data(), ws.lf_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      if (FILE* f = fopen(getenv("CLAIRB_LF_TRACE") ? getenv("CLAIRB_LF_TRACE") : "/dev/null", "w")) {
+        for (int c = 0; c < 256; ++c)
+          for (int e = 0; e < 16; ++e) fprintf(f, "%lld%c", h[c * 16 + e], e == 15 ? '\n' : ' ');
+        fclose(f);
+      }
+    }
+    cudaFree(ws.lf_trace);
+    ws.lf_trace = nullptr;
+  }
   if (ws.trace) {
     std::vector<long long> h(T_STEPS * 64);
     if (cudaMemcpy(h.data(), ws.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
@@ -1801,7 +1879,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   }
   if (fuse_tail) {
     hook(4, true);
-    l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, nullptr, l3_pf);
+    l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, nullptr, l3_pf, ws.lf_trace);
     hook(4, false);
     hook(5, true);
     heads_tc<<<(unsigned)NT, HD_THREADS, heads_smem_bytes(), st>>>(ws.L4t, w.heads, probs, logits, n);
@@ -1832,7 +1910,7 @@ inline cudaError_t get_lstm1(const Workspace& ws, int64_t n, int64_t np, float* 
 
 // parity hook: re-run the fused slice-dense on the retained H2t with the L3 activations written out as planes
 inline cudaError_t dump_l3(const Weights& w, const Workspace& ws, int64_t np, float* l4T, float* l3_planes) {
-  l3l4_fused<<<(unsigned)(np / 128), LF_THREADS, l3l4_smem_bytes(), 0>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, l3_planes, 0);
+  l3l4_fused<<<(unsigned)(np / 128), LF_THREADS, l3l4_smem_bytes(), 0>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, l3_planes, 0, nullptr);
   cudaError_t st = cudaGetLastError();
   return st != cudaSuccess ? st : cudaDeviceSynchronize();
 }
