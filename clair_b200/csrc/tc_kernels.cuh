@@ -949,10 +949,53 @@ lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap t
 #pragma unroll
       for (int i = 0; i < UW; ++i) c[b][i] = 0.f;
 
+    // With G = 4 the two warp pairs of a scheduler run half a block out of phase: warps sub >= 2 ("lagging") defer the
+    // non-MUFU tail of block b (pack, tcgen05.st, transposes, global stores) until they have drained block b+1, so it
+    // overlaps the other pair's cell math instead of leaving the MUFU pipe idle while all warps pack in lockstep.
+    constexpr bool SKEW = (G == 4);
+    const bool lag = SKEW && sub >= 2;
     uint32_t use0 = 0, use1 = 0;
     for (int s = 0; s < T_STEPS; ++s) {
       const int t = dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
       const uint32_t h_st = lane_base + 256 + (s & 1) * 128;
+      // tail of one slice: h_t -> fp16 hi/lo -> tensor memory (next step's A operand) and -> the next layer's tiles
+      auto post = [&](int b, int sl, const float* hv) {
+        const int u0 = b * 32 + sub * UW + sl * 8;     // first hidden unit of this slice
+        uint32_t whi[4], wlo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __half2 h2 = __floats2half2_rn(hv[2 * k], hv[2 * k + 1]);
+          const float2 back = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(hv[2 * k] - back.x, hv[2 * k + 1] - back.y);
+          whi[k] = *reinterpret_cast<const uint32_t*>(&h2);
+          wlo[k] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        tmem_st4(h_st + (u0 >> 1), whi);
+        tmem_st4(h_st + 64 + (u0 >> 1), wlo);
+        if (OUT == 1) {
+          float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + u0) * np + (size_t)tile * 128 + r;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) out[(size_t)k * np] = hv[k];
+        } else {
+          // OUT == 2: MN-major SWIZZLE_128B tiles for the slice-dense MMA (see lstm_seq)
+          transpose8x8_h(whi, lane);
+          transpose8x8_h(wlo, lane);
+          const int ch = dir * H + u0 + (lane & 7);
+          const int rg = r >> 3;                                  // site group of 8 within the tile (0..15)
+          uint8_t* out = (uint8_t*)Hout + ((size_t)tile * 2 * H + ch) * L3A_BYTES + (size_t)(t >> 3) * 2048 +
+                         (rg >> 3) * 1024 + (t & 7) * 128 + (((rg & 7) ^ (t & 7)) << 4);
+          *reinterpret_cast<uint4*>(out) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+          *reinterpret_cast<uint4*>(out + L3A_BYTES / 2) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+        }
+      };
+      // this warp's slice of block b of h_t is in tensor memory: the MMA issuer may start contracting over it
+      auto publish = [&](int b) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(leader_hq + b * 8);
+      };
+      float hv_prev[8];                                // lagging warps: h_t of the previous block, tail still to do
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int i = b & 1;
@@ -972,9 +1015,13 @@ lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap t
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(i ? leader_acc_empty1 : leader_acc_empty0);
         if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 1);
+        if (SKEW && b > 0 && lag) {
+          post(b - 1, 0, hv_prev);
+          publish(b - 1);
+        }
 #pragma unroll
         for (int sl = 0; sl < NSL; ++sl) {
-          const int u0 = b * 32 + sub * UW + sl * 8;   // first hidden unit of this slice
+          const int u0 = b * 32 + sub * UW + sl * 8;
           float hv[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -983,39 +1030,15 @@ lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap t
             hv[k] = lstm_cell(vv[0] + bq.x, vv[1] + bq.y, vv[2] + bq.z, vv[3] + bq.w, c[b][sl * 8 + k]);
           }
           if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 2 + sl * 2);
-          uint32_t whi[4], wlo[4];
+          if (SKEW && b < 3 && lag) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const __half2 h2 = __floats2half2_rn(hv[2 * k], hv[2 * k + 1]);
-            const float2 back = __half22float2(h2);
-            const __half2 l2 = __floats2half2_rn(hv[2 * k] - back.x, hv[2 * k + 1] - back.y);
-            whi[k] = *reinterpret_cast<const uint32_t*>(&h2);
-            wlo[k] = *reinterpret_cast<const uint32_t*>(&l2);
-          }
-          tmem_st4(h_st + (u0 >> 1), whi);
-          tmem_st4(h_st + 64 + (u0 >> 1), wlo);
-          if (OUT == 1) {
-            float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + u0) * np + (size_t)tile * 128 + r;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) out[(size_t)k * np] = hv[k];
+            for (int k = 0; k < 8; ++k) hv_prev[k] = hv[k];
           } else {
-            // OUT == 2: MN-major SWIZZLE_128B tiles for the slice-dense MMA (see lstm_seq)
-            transpose8x8_h(whi, lane);
-            transpose8x8_h(wlo, lane);
-            const int ch = dir * H + u0 + (lane & 7);
-            const int rg = r >> 3;                                  // site group of 8 within the tile (0..15)
-            uint8_t* out = (uint8_t*)Hout + ((size_t)tile * 2 * H + ch) * L3A_BYTES + (size_t)(t >> 3) * 2048 +
-                           (rg >> 3) * 1024 + (t & 7) * 128 + (((rg & 7) ^ (t & 7)) << 4);
-            *reinterpret_cast<uint4*>(out) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
-            *reinterpret_cast<uint4*>(out + L3A_BYTES / 2) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+            post(b, sl, hv);
           }
           if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 3 + sl * 2);
         }
-        // this warp's slice of block b of h_t is in tensor memory: the MMA issuer may start contracting over it
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(leader_hq + b * 8);
+        if (!(SKEW && b < 3 && lag)) publish(b);
         if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 7);
       }
     }
