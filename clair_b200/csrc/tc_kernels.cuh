@@ -58,13 +58,17 @@ __device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f3
 //   h  = (1-e) / [(1+e)(1+f)],  e=e^-2c', f=e^-zo                 2 ex2 + 1 rcp
 // Exponent arguments are clamped at 2^40 so the denominators stay finite (sigmoid(-27.7) ~ 1e-12).
 __device__ __forceinline__ float lstm_cell(float pi, float pg, float pf, float po, float& c) {
+  // The epilogue that calls this sits on its issue-slot bound, so the products are folded into FFMAs:
+  //   (1+a)(1+b) = B + a*B,   (1+a)(1+b)(1+d) = AB + d*AB,   (1-b)(1+d) = nb + d*nb,   (1-e)*r = r - e*r
   const float a = ex2f(fminf(pi, 40.f)), b = ex2f(fminf(pg, 40.f)), d = ex2f(fminf(pf, 40.f));
-  const float A = 1.f + a, B = 1.f + b, D = 1.f + d;
-  const float AB = A * B;
-  const float cn = fmaf(c, AB, (1.f - b) * D) * rcpf(AB * D);
+  const float B = 1.f + b, nb = 1.f - b;
+  const float AB = fmaf(a, B, B);
+  const float cn = fmaf(c, AB, fmaf(d, nb, nb)) * rcpf(fmaf(AB, d, AB));
   c = cn;
   const float e = ex2f(fminf(cn * (-2.f * LOG2E), 40.f)), f = ex2f(fminf(po, 40.f));
-  return (1.f - e) * rcpf((1.f + e) * (1.f + f));
+  const float E = 1.f + e;
+  const float r = rcpf(fmaf(E, f, E));
+  return fmaf(-e, r, r);
 }
 // 8x8 transpose of fp16 values across the 8 lanes of a row group: on entry lane i (= lane & 7) holds 8 consecutive hidden
 // units of row i as 4 words (two units per word); on exit it holds unit i for the 8 rows (two rows per word).
@@ -785,8 +789,12 @@ lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap t
   const int dir = blockIdx.y;
   const int tile = blockIdx.x;                                   // = 2*pair + rank
   // timeline probe (CLAIRB_SX_TRACE): clock64 stamps of the leader CTA of pair 0, direction 0: [step][64 events]
+#ifdef CLAIRB_TRACE
   const bool tr_on = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   auto stamp = [&](int s, int ev) { if (tr_on) trace[s * 64 + ev] = clock64(); };
+#else
+  auto stamp = [&](int, int) {};                       // probes compiled out (build with -DCLAIRB_TRACE to enable)
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -1138,8 +1146,12 @@ l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
+#ifdef CLAIRB_TRACE
   const bool tr_on = trace != nullptr && blockIdx.x == 0;
   auto stamp = [&](int c, int ev) { if (tr_on) trace[c * 16 + ev] = clock64(); };
+#else
+  auto stamp = [&](int, int) {};                       // probes compiled out (build with -DCLAIRB_TRACE to enable)
+#endif
   if (threadIdx.x == 0) {
     for (int i = 0; i < LF_STAGES; ++i) { mbar_init(&stage_full[i], 1); mbar_init(&stage_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
