@@ -338,6 +338,37 @@ def main():
     assert np.array_equal(out_i, out), "int16 transport must give bit-identical results"
     assert np.isfinite(out).all()
 
+    # ---- the same end-to-end call with the first-choice variant decision fused behind the heads
+    #      (clairb_predict_decide), and the reference-equivalent Python restatement timed on a small sample ----
+    ref_bases = (np.arange(sites) % 4).astype(np.uint8)
+    for _ in range(2):
+        _, dec = m.predict_and_decide(X, ref_bases)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, dec = m.predict_and_decide(X, ref_bases)
+    torch.cuda.synchronize()
+    e2e_dec_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dec_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dec_s = float(t.item())
+    decision_info = None
+    if rank == 0:
+        from oracle import decision_oracle as DO
+        ns = 300
+        t0 = time.perf_counter()
+        want, want_p, _ = DO.decide(out[:ns], ref_bases[:ns])
+        cpu_dec = ns / (time.perf_counter() - t0)
+        got = np.stack([dec.category, dec.len1, dec.len2, dec.aux], axis=1)[:ns]
+        assert np.array_equal(got, want) and np.array_equal(dec.max_probability[:ns], want_p), "decision parity failed"
+        decision_info = {"e2e_with_decision": world * sites * args.steps / e2e_dec_s, "unit": "sites/s",
+                         "extra_d2h_bytes_per_step": sites * 24, "extra_h2d_bytes_per_step": sites,
+                         "cpu_python_restatement_sites_per_s": cpu_dec, "cpu_sample": "%d sites, 1 core" % ns,
+                         "categories_seen": np.bincount(dec.category, minlength=10).tolist(),
+                         "note": "forward + decide_sites kernel per chunk (call_var.py:589-690, 732-760), bit-exact vs oracle on the sample"}
+
     if rank == 0:
         peaks = measured_peaks()
         prof = {p["kernel"]: p for p in profile}
@@ -386,6 +417,7 @@ def main():
                     "d2h_bytes_per_step": sites * 360, "h2d_gbs_measured": h2d_gbs,
                     "h2d_ceiling_sites_per_s": world * h2d_gbs * 1e9 / 4224,
                     "note": "float32 input (the reference generator's dtype): bounded by the pinned host->device copy"},
+            "decision_stage": decision_info,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,

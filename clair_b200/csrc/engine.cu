@@ -84,7 +84,9 @@ struct clairb_engine {
   int32_t* d_dec[2] = {nullptr, nullptr};
   int32_t* h_dec[2] = {nullptr, nullptr};   // pinned staging
 
-  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaStream_t s_h2d = nullptr, s_h2d2 = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d2[2] = {nullptr, nullptr};
+  int h2d_split = 1;           // CLAIRB_H2D_SPLIT=2: the input copy of a chunk goes out as two halves on two streams
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
 
@@ -320,6 +322,8 @@ void free_all(clairb_engine* e) {
   tc::free_weights(e->tcw);
   tc::free_workspace(e->tcws);
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+  if (e->s_h2d2) cudaStreamDestroy(e->s_h2d2);
+  for (int l = 0; l < 2; ++l) if (e->ev_h2d2[l]) cudaEventDestroy(e->ev_h2d2[l]);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
   if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
 }
@@ -404,6 +408,9 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
   } while (0)
   CR_TRY(cudaSetDevice(device));
   CR_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+  CR_TRY(cudaStreamCreateWithFlags(&e->s_h2d2, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) CR_TRY(cudaEventCreateWithFlags(&e->ev_h2d2[b], cudaEventDisableTiming));
+  if (const char* hs = getenv("CLAIRB_H2D_SPLIT")) e->h2d_split = atoi(hs) == 2 ? 2 : 1;
   CR_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
   CR_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
   for (int b = 0; b < 2; ++b) {
@@ -622,8 +629,19 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
     SiteMap sm = make_map(e, cn);
     // input buffer b is free once the forward of chunk c-2 has consumed it
     CU_TRY(e, cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));
-    CU_TRY(e, cudaMemcpyAsync(e->d_x[b], (const char*)x_host + (size_t)done * SITE_ELEMS * eb,
-                              (size_t)cn * SITE_ELEMS * eb, cudaMemcpyHostToDevice, e->s_h2d));
+    {
+      const size_t bytes = (size_t)cn * SITE_ELEMS * eb;
+      const char* src = (const char*)x_host + (size_t)done * SITE_ELEMS * eb;
+      size_t first = bytes;
+      if (e->h2d_split == 2 && bytes >= (8u << 20)) {
+        first = (bytes / 2) & ~(size_t)4095;
+        CU_TRY(e, cudaStreamWaitEvent(e->s_h2d2, e->ev_comp[b], 0));
+        CU_TRY(e, cudaMemcpyAsync((char*)e->d_x[b] + first, src + first, bytes - first, cudaMemcpyHostToDevice, e->s_h2d2));
+        CU_TRY(e, cudaEventRecord(e->ev_h2d2[b], e->s_h2d2));
+        CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_h2d2[b], 0));
+      }
+      CU_TRY(e, cudaMemcpyAsync(e->d_x[b], src, first, cudaMemcpyHostToDevice, e->s_h2d));
+    }
     if (dec_host) CU_TRY(e, cudaMemcpyAsync(e->d_ref[b], ref_host + done, (size_t)cn, cudaMemcpyHostToDevice, e->s_h2d));
     CU_TRY(e, cudaEventRecord(e->ev_h2d[b], e->s_h2d));
     CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_h2d[b], 0));

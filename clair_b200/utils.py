@@ -86,3 +86,84 @@ def format_tensor_row(ctg, pos, seq, counts):
     """Inverse of the decode: the text row CreateTensor prints (CreateTensor.py:60-65)."""
     flat = np.asarray(counts).reshape(-1)
     return "%s %d %s %s" % (ctg, pos, seq, " ".join("%d" % v for v in flat))
+
+
+# ---- binary tensor transport (SURVEY.md 8f row 3) --------------------------------------------------------------------
+# The text wire format costs ~2.5 KB and a str.split + float parse per site (7 k rows/s/thread in the reference).  The
+# binary framing carries exactly the same fields - contig, position, the 33-base sequence and the 1056 raw integer
+# counts of CreateTensor.py:60-65 - as fixed-size little-endian records, so a batch is one read() and one numpy view:
+#     file  = MAGIC (8 bytes) | record*
+#     record = ctg[32] (NUL padded) | pos int64 | seq[33] | 7 pad bytes | counts int16[33][8][4]      = 2192 bytes
+# Decoding applies what tensor_generator_from applies to text rows: the IUPAC filter on seq[16] (utils.py:90) and
+# X[..., 1:] -= X[..., 0:1] (utils.py:96-98), here in int16 (exact: the counts are small non-negative integers), and
+# yields X as int16 - the CLAIRB_DTYPE_I16 transport predict() accepts, half the host->device bytes of float32.
+BINARY_MAGIC = b"CLRBT\x01\x00\n"
+BINARY_RECORD = np.dtype([("ctg", "S32"), ("pos", "<i8"), ("seq", "S33"), ("pad", "V7"),
+                          ("counts", "<i2", (no_of_positions, matrix_row, matrix_num))])
+assert BINARY_RECORD.itemsize == 2192
+
+
+def write_binary_tensors(fo, sites):
+    """Write (ctg, pos, seq, counts[33,8,4]) tuples to the binary file object `fo` (MAGIC first)."""
+    fo.write(BINARY_MAGIC)
+    rec = np.zeros(1, dtype=BINARY_RECORD)
+    for ctg, pos, seq, counts in sites:
+        ctg_b, seq_b = str(ctg).encode(), str(seq).encode()
+        if len(ctg_b) > 32 or len(seq_b) != 2 * param.flankingBaseNum + 1:
+            raise ValueError("contig name longer than 32 bytes or sequence not %d bases" % (2 * param.flankingBaseNum + 1))
+        c = np.asarray(counts).reshape(no_of_positions, matrix_row, matrix_num)
+        if c.min() < -32768 or c.max() > 32767:
+            raise ValueError("count outside the int16 range")
+        rec["ctg"], rec["pos"], rec["seq"], rec["counts"] = ctg_b, int(pos), seq_b, c
+        fo.write(rec.tobytes())
+
+
+def text_to_binary(text_rows, fo):
+    """Convert CreateTensor text rows (an iterable of str) to the binary framing."""
+    def sites():
+        for row in text_rows:
+            columns = row.split()
+            if not columns:
+                continue
+            ctg, pos, seq = columns[:-input_tensor_size]
+            yield ctg, int(pos), seq, np.array(columns[-input_tensor_size:], dtype=np.int64)
+    write_binary_tensors(fo, sites())
+
+
+def binary_tensor_generator_from(tensor_file_path, batch_size, alloc=None, as_float32=False):
+    """Binary counterpart of tensor_generator_from: yields (X, non_tensor_infos) per batch with the same filtering,
+    transform, progress lines and info triples ([ctg, str(pos), seq]).  X is int16 (or float32 when asked);
+    `alloc(shape, dtype)` lets the caller hand out pinned buffers."""
+    fo = sys.stdin.buffer if tensor_file_path == "PIPE" else open(tensor_file_path, "rb")
+    try:
+        if fo.read(len(BINARY_MAGIC)) != BINARY_MAGIC:
+            raise ValueError("%s: not a clair_b200 binary tensor stream" % tensor_file_path)
+        processed_tensors = 0
+        out_dtype = np.float32 if as_float32 else np.int16
+        while True:
+            raw = fo.read(batch_size * BINARY_RECORD.itemsize)
+            if len(raw) % BINARY_RECORD.itemsize:
+                raise ValueError("truncated binary tensor record")
+            if not raw:
+                break
+            recs = np.frombuffer(raw, dtype=BINARY_RECORD)
+            centre = np.frombuffer(raw, dtype=np.uint8).reshape(len(recs), BINARY_RECORD.itemsize)[
+                :, BINARY_RECORD.fields["seq"][1] + param.flankingBaseNum]
+            keep = np.isin(centre, np.frombuffer("".join(sorted(IUPAC_BASES)).encode(), dtype=np.uint8))
+            recs = recs[keep]
+            n = len(recs)
+            processed_tensors += n
+            print("Processed %d tensors" % processed_tensors, file=sys.stderr)
+            if n == 0:
+                continue
+            shape = (batch_size, no_of_positions, matrix_row, matrix_num)
+            X = alloc(shape, out_dtype) if alloc is not None else np.empty(shape, dtype=out_dtype)
+            X[:n] = recs["counts"]
+            subtract_reference_channel(X[:n])
+            infos = [[r["ctg"].decode(), str(int(r["pos"])), r["seq"].decode()] for r in recs]
+            yield X[:n], infos
+            if len(raw) < batch_size * BINARY_RECORD.itemsize:
+                break
+    finally:
+        if fo is not sys.stdin.buffer:
+            fo.close()

@@ -51,3 +51,57 @@ def test_empty_input_yields_nothing(tmp_path):
     with gzip.open(p, "wt") as f:
         f.write("")
     assert list(utils.tensor_generator_from(str(p), 4)) == []
+
+
+def test_binary_transport_equals_the_reference_text_decode(tmp_path, capsys):
+    # the same 11 golden rows through the binary framing: identical batches, infos and progress lines as the text path
+    # (whose expectations were produced by the reference's own generator)
+    with np.load(os.path.join(GOLDEN, "decode_expected.npz")) as z:
+        exp = {k: z[k] for k in z.files}
+    with gzip.open(os.path.join(GOLDEN, "decode_rows.txt.gz"), "rt") as f:
+        rows = f.read().splitlines()
+    p = tmp_path / "t.bin"
+    with open(p, "wb") as fo:
+        utils.text_to_binary(rows, fo)
+    assert os.path.getsize(p) == 8 + 11 * 2192
+    got = list(utils.binary_tensor_generator_from(str(p), 4))
+    assert len(got) == 3
+    for bi, (X, infos) in enumerate(got):
+        assert X.dtype == np.int16
+        np.testing.assert_array_equal(X.astype(np.float32), exp["X%d" % bi])
+        assert [" ".join(i) for i in infos] == list(exp["info%d" % bi])
+    assert capsys.readouterr().err == str(exp["stderr"])
+    f32 = list(utils.binary_tensor_generator_from(str(p), 100, as_float32=True))
+    assert len(f32) == 1 and f32[0][0].dtype == np.float32 and len(f32[0][1]) == 10
+
+
+def test_binary_transport_errors_and_edges(tmp_path):
+    counts = synth.synthetic_counts(3, seed=4)
+    p = tmp_path / "x.bin"
+    with open(p, "wb") as fo:
+        utils.write_binary_tensors(fo, [("chr1", 5 + i, "A" * 16 + "*" + "A" * 16, counts[i]) for i in range(3)])
+    assert list(utils.binary_tensor_generator_from(str(p), 2)) == []          # every centre base filtered
+    with open(p, "wb") as fo:
+        fo.write(utils.BINARY_MAGIC)
+    assert list(utils.binary_tensor_generator_from(str(p), 2)) == []          # header only
+    with open(p, "wb") as fo:
+        utils.write_binary_tensors(fo, [("chr1", 5, "A" * 33, counts[0])])
+        fo.write(b"\x00" * 100)
+    import pytest
+    with pytest.raises(ValueError, match="truncated"):
+        list(utils.binary_tensor_generator_from(str(p), 2))
+    with open(p, "wb") as fo:
+        fo.write(b"chr1 5 AAAA 1 2 3\n")
+    with pytest.raises(ValueError, match="not a clair_b200"):
+        list(utils.binary_tensor_generator_from(str(p), 2))
+    with pytest.raises(ValueError):
+        utils.write_binary_tensors(open(p, "wb"), [("c" * 40, 1, "A" * 33, counts[0])])
+    pinned = []
+    with open(p, "wb") as fo:
+        utils.write_binary_tensors(fo, [("chrX", 7 + i, "ACGT" * 8 + "N", counts[i]) for i in range(3)])
+    def alloc(shape, dtype):
+        pinned.append(np.empty(shape, dtype))
+        return pinned[-1]
+    got = list(utils.binary_tensor_generator_from(str(p), 2, alloc=alloc))
+    assert len(got) == 2 and np.shares_memory(got[0][0], pinned[0])
+    np.testing.assert_array_equal(np.concatenate([x for x, _ in got]).astype(np.float32), synth.synthetic_tensors(3, seed=4))

@@ -257,3 +257,47 @@ def test_drop_in_batch_loop(gpu_model, weights1234):
         ref = O.forward(Xref, weights1234, np.float32)
         for k in range(4):
             np.testing.assert_array_equal(Y[k].argmax(1), ref[k].argmax(1))
+
+
+@pytest.mark.parametrize("batch,n", [(4096, 2 * 4096 + 896), (8192, 8192 + 117)])
+def test_configs_3_and_4_batch_sizes(weights1234, batch, n):
+    # BASELINE.json configs[2] / [3]: predict-batches of 4096 (PacBio-CCS-scale run, ragged last batch of 896 as in
+    # 30,000,000 = 7324 x 4096 + 896) and 8192 (Illumina-scale run); same architecture, only the batching differs
+    from clair_b200.model import Clair
+    m = Clair(max_sites=4 * batch, batch_sites=batch)
+    m.set_weights(weights1234)
+    X = synth.synthetic_tensors(n, seed=batch)
+    out = m.predict_packed(X)
+    idx = np.arange(0, n, 37)
+    ref = O.forward_packed(X[idx], weights1234, np.float64)
+    assert np.abs(out[idx] - ref).max() <= TOL
+    for lo, hi in ((0, 21), (21, 24), (24, 57), (57, 90)):
+        np.testing.assert_array_equal(out[idx, lo:hi].argmax(1), ref[:, lo:hi].argmax(1))
+    # the same sites through single-batch calls give the same bits (tiles run through batch boundaries)
+    np.testing.assert_array_equal(out[batch - 5:batch + 5], m.predict_packed(X[batch - 5:batch + 5]))
+    m.close()
+
+
+def test_full_size_one_million_sites_property(weights1234):
+    # BASELINE.json configs[1] at full size: 1,000,000 sites in one call.  The sites are 20 shuffled copies of 50,000
+    # distinct ones, so every distinct site is computed 20 times at unrelated positions (different chunks, waves, CTA
+    # pairs, TMEM lanes): all copies must agree bit for bit, and a sample must meet the oracle.
+    from clair_b200.model import Clair
+    distinct, copies = 50000, 20
+    base = synth.synthetic_tensors(distinct, seed=20240609)
+    rng = np.random.default_rng(7)
+    order = np.concatenate([rng.permutation(distinct) for _ in range(copies)])
+    m = Clair(max_sites=distinct * copies, batch_sites=1000)
+    m.set_weights(weights1234)
+    out = m.predict_packed(base[order])
+    assert out.shape == (distinct * copies, 90) and np.isfinite(out).all()
+    first = np.empty((distinct, 90), np.float32)
+    first[order[:distinct]] = out[:distinct]
+    for k in range(1, copies):
+        sl = slice(k * distinct, (k + 1) * distinct)
+        np.testing.assert_array_equal(out[sl], first[order[sl]])
+    idx = np.arange(0, distinct, 499)
+    ref = O.forward_packed(base[idx], weights1234, np.float64)
+    assert np.abs(first[idx] - ref).max() <= TOL
+    np.testing.assert_allclose(out[:, :21].sum(1), 1.0, atol=1e-5)
+    m.close()
