@@ -342,12 +342,12 @@ def main():
     #      (clairb_predict_decide), and the reference-equivalent Python restatement timed on a small sample ----
     ref_bases = (np.arange(sites) % 4).astype(np.uint8)
     for _ in range(2):
-        _, dec = m.predict_and_decide(X, ref_bases)
+        _, dec = m.predict_and_decide_packed(X, ref_bases)
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, dec = m.predict_and_decide(X, ref_bases)
+        _, dec = m.predict_and_decide_packed(X, ref_bases)
     torch.cuda.synchronize()
     e2e_dec_s = time.perf_counter() - t0
     if world > 1:

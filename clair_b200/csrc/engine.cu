@@ -83,6 +83,7 @@ struct clairb_engine {
   uint8_t* d_ref[2] = {nullptr, nullptr};
   int32_t* d_dec[2] = {nullptr, nullptr};
   int32_t* h_dec[2] = {nullptr, nullptr};   // pinned staging
+  uint8_t* h_ref[2] = {nullptr, nullptr};   // pinned staging (a pageable source would make the copy synchronous and stall the chunk pipeline)
 
   cudaStream_t s_h2d = nullptr, s_h2d2 = nullptr, s_comp = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d2[2] = {nullptr, nullptr};
@@ -310,6 +311,7 @@ void free_all(clairb_engine* e) {
     cudaFree(e->d_ref[l]);
     cudaFree(e->d_dec[l]);
     if (e->h_dec[l]) cudaFreeHost(e->h_dec[l]);
+    if (e->h_ref[l]) cudaFreeHost(e->h_ref[l]);
     if (e->ev_h2d[l]) cudaEventDestroy(e->ev_h2d[l]);
     if (e->ev_comp[l]) cudaEventDestroy(e->ev_comp[l]);
     if (e->ev_d2h[l]) cudaEventDestroy(e->ev_d2h[l]);
@@ -423,6 +425,7 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
     CR_TRY(cudaMalloc((void**)&e->d_ref[b], (size_t)e->chunk_sites));
     CR_TRY(cudaMalloc((void**)&e->d_dec[b], (size_t)e->chunk_sites * decide::REC_WORDS * sizeof(int32_t)));
     CR_TRY(cudaHostAlloc((void**)&e->h_dec[b], (size_t)e->chunk_sites * decide::REC_WORDS * sizeof(int32_t), cudaHostAllocDefault));
+    CR_TRY(cudaHostAlloc((void**)&e->h_ref[b], (size_t)e->chunk_sites, cudaHostAllocDefault));
   }
   CR_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   const size_t np = (size_t)e->chunk_np;
@@ -642,7 +645,12 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
       }
       CU_TRY(e, cudaMemcpyAsync(e->d_x[b], src, first, cudaMemcpyHostToDevice, e->s_h2d));
     }
-    if (dec_host) CU_TRY(e, cudaMemcpyAsync(e->d_ref[b], ref_host + done, (size_t)cn, cudaMemcpyHostToDevice, e->s_h2d));
+    if (dec_host) {
+      // the staging buffer was last read by the copy of chunk c-2, which ev_h2d[b] covers
+      if (c >= 2) CU_TRY(e, cudaEventSynchronize(e->ev_h2d[b]));
+      memcpy(e->h_ref[b], ref_host + done, (size_t)cn);
+      CU_TRY(e, cudaMemcpyAsync(e->d_ref[b], e->h_ref[b], (size_t)cn, cudaMemcpyHostToDevice, e->s_h2d));
+    }
     CU_TRY(e, cudaEventRecord(e->ev_h2d[b], e->s_h2d));
     CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_h2d[b], 0));
     CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_d2h[b], 0));   // output buffer b drained

@@ -133,12 +133,20 @@ class Clair(object):
         return prediction
 
     def predict_and_decide(self, batchX, ref_bases):
-        """predict() plus the first-choice variant decision of every site in the same device pass.
+        """predict() plus the first-choice variant decision of every site in the same device pass: returns
+        (prediction, Decision) with `prediction` the list of four arrays predict() returns (also stored in
+        .prediction).  See predict_and_decide_packed."""
+        out, dec = self.predict_and_decide_packed(batchX, ref_bases)
+        split = np.cumsum(self.output_label_split)[:-1]
+        self.prediction = [np.ascontiguousarray(a) for a in np.split(out, split, axis=1)]
+        return self.prediction, dec
 
-        ref_bases: [n] uint8 codes 0..3 (clair_b200.decision.ref_base_codes).  Returns (prediction, Decision): the
-        list of four arrays predict() returns (also stored in .prediction) and a clair_b200.decision.Decision of
-        arrays - what possible_outcome_probabilites_from + the first pass of output_from's loop would select
-        (clair/call_var.py:589-690, 732-760)."""
+    def predict_and_decide_packed(self, batchX, ref_bases):
+        """predict_packed() plus the first-choice variant decision of every site in the same device pass.
+
+        ref_bases: [n] uint8 codes 0..3 (clair_b200.decision.ref_base_codes).  Returns ([n,90] probabilities,
+        clair_b200.decision.Decision of arrays) - what possible_outcome_probabilites_from + the first pass of
+        output_from's loop would select (clair/call_var.py:589-690, 732-760)."""
         from . import decision as _decision
         if not self._has_weights:
             raise RuntimeError("predict() before init()/restore_parameters()")
@@ -158,9 +166,7 @@ class Clair(object):
                     ref[s:s + m].ctypes.data_as(ctypes.c_void_p), out[s:s + m].ctypes.data_as(ctypes.c_void_p),
                     rec[s:s + m].ctypes.data_as(ctypes.c_void_p))
                 _lib.check(rc, self._h, "clairb_predict_decide")
-        split = np.cumsum(self.output_label_split)[:-1]
-        self.prediction = [np.ascontiguousarray(a) for a in np.split(out, split, axis=1)]
-        return self.prediction, _decision.unpack(rec)
+        return out, _decision.unpack(rec)
 
     def decide(self, probs, ref_bases, batchX=None):
         """Decision alone from [n,90] probabilities the caller holds (e.g. an ensemble average)."""
