@@ -359,6 +359,9 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
 //   X48  : [(t*NT+tile)][hl][kc 6][128][8]       (FUSE_X only; k = 32, 33 are 1.0)
 // Warps: 0 = MMA issuer (leader CTA), 1..4G = epilogue (G warps per TMEM lane quarter), 4G+1 = loads (x_t / Gx ring).
 // ---------------------------------------------------------------------------------------------
+#ifndef CLAIRB_SEQ1_EARLY
+#define CLAIRB_SEQ1_EARLY 1   // block-wise hand-off of h_t to the MMA issuer in layer 1 as well (0.483 -> 0.468 ms per chunk)
+#endif
 constexpr int SEQ_G = 2;                                // epilogue warps per TMEM lane quarter (2 or 4)
 constexpr int SEQ_THREADS = 32 * (2 + 4 * SEQ_G);
 constexpr int SEQ_W_BYTES = 2 * 4 * 16 * 1024;          // 131072
@@ -396,7 +399,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
 
   // EARLY: hand h_t to the MMA issuer block by block (helps when the tensor pipe has slack, i.e. layer 2; with the
   // fused input projection the extra tcgen05.wait::st per block costs more than the shorter step boundary saves)
-  constexpr bool EARLY = !FUSE_X;
+  constexpr bool EARLY = CLAIRB_SEQ1_EARLY ? true : !FUSE_X;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int dir = blockIdx.y;
