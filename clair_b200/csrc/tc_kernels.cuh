@@ -397,8 +397,9 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
   uint64_t* g_empty = bars + 15;       // [3] Gx half-block consumed by its 4 epilogue warps
   uint32_t* tmem_slot = (uint32_t*)(bars + 22);
 
-  // EARLY: hand h_t to the MMA issuer block by block (helps when the tensor pipe has slack, i.e. layer 2; with the
-  // fused input projection the extra tcgen05.wait::st per block costs more than the shorter step boundary saves)
+  // EARLY: hand h_t to the MMA issuer block by block, so that only the last two k-steps of a step's first gate block
+  // wait for the end of the previous step (an early A/B had this slower for the fused-x kernel; with the current
+  // epilogue it is 3 % faster there too, CLAIRB_SEQ1_EARLY)
   constexpr bool EARLY = CLAIRB_SEQ1_EARLY ? true : !FUSE_X;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
