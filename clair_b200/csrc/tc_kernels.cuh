@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -1133,7 +1134,7 @@ constexpr size_t l3l4_smem_bytes() { return (size_t)LF_STAGES * LF_STAGE_BYTES +
 __global__ void __launch_bounds__(LF_THREADS, 1)
 l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, const float* __restrict__ b4,
            float* __restrict__ l4T, __half* __restrict__ L4t, int64_t np, float* __restrict__ l3_dbg, int pf_dist,
-           long long* __restrict__ trace) {
+           long long* __restrict__ trace, float w4_unscale) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stages = smem;
@@ -1344,7 +1345,7 @@ l3l4_fused(const __half* __restrict__ H2t, const uint8_t* __restrict__ blobs, co
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float x = v[i] + __ldg(b4 + col0 + i);
+        const float x = fmaf(v[i], w4_unscale, __ldg(b4 + col0 + i));      // W4 was uploaded scaled by a power of two
         v[i] = x >= 0.f ? SELU_SCALE * x : (SELU_SCALE * SELU_ALPHA) * (__expf(x) - 1.f);
         out[(size_t)(col0 + i) * np] = v[i];           // fp32 planes: parity hook / CUDA-core heads
       }
@@ -1611,6 +1612,7 @@ struct Weights {
   uint8_t* l3l4 = nullptr;                 // [256] per-channel blobs (L3L4_BLOB_BYTES each)
   uint8_t* heads = nullptr;                // [4] per-head blobs (HEAD_BLOB_BYTES each)
   const float* b4 = nullptr;               // [192] (owned by the engine)
+  float w4_unscale = 1.f;                  // 1 / (power-of-two scale folded into the W4 operand tiles)
 };
 
 struct Workspace {
@@ -1747,6 +1749,17 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
   }
   // ---- slice-dense + L4 blobs ----
   {
+    // W4's entries are small (fan-in 7680: std ~0.013), so the low halves of an unscaled hi/lo split land in the fp16
+    // subnormals (steps of 6e-8, i.e. ~18 bits of the weight instead of 22).  Scale by a power of two (exact) so that
+    // the largest |w| sits near 2^10; the L4 epilogue multiplies the accumulator by the inverse.  (Not what limits L4
+    // today: its 2e-5 comes from the tensor core's fp32 accumulation over 1536 chained MMAs per tile - summing 64-channel
+    // segments in fp32 registers brought it to 5.7e-6 but cost 0.05-0.12 ms per chunk, tools/patches/.)
+    float w4_max = 0.f;
+    for (size_t i = 0; i < (size_t)L3_K * L4_UNITS; ++i) w4_max = fmaxf(w4_max, fabsf(hm.W4[i]));
+    int e4 = 0;
+    if (w4_max > 0.f) frexpf(w4_max, &e4);
+    const float w4_scale = ldexpf(1.f, 10 - e4);
+    w.w4_unscale = ldexpf(1.f, e4 - 10);
     std::vector<uint8_t> blob((size_t)2 * H * L3L4_BLOB_BYTES, 0);
     for (int c = 0; c < 2 * H; ++c) {
       uint8_t* b = blob.data() + (size_t)c * L3L4_BLOB_BYTES;
@@ -1764,7 +1777,7 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
         bb[o] = hm.b3[(size_t)c * L3_UNITS + o];
         for (int n = 0; n < L4_UNITS; ++n) {
           const size_t idx = (size_t)(o / 8) * 192 * 8 + n * 8 + o % 8;
-          split_half(hm.W4[((size_t)o * 2 * H + c) * L4_UNITS + n], w4hi[idx], w4lo[idx]);
+          split_half(hm.W4[((size_t)o * 2 * H + c) * L4_UNITS + n] * w4_scale, w4hi[idx], w4lo[idx]);
         }
       }
     }
@@ -1918,7 +1931,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   }
   if (fuse_tail) {
     hook(4, true);
-    l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, nullptr, l3_pf, ws.lf_trace);
+    l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, nullptr, l3_pf, ws.lf_trace, w.w4_unscale);
     hook(4, false);
     hook(5, true);
     heads_tc<<<(unsigned)NT, HD_THREADS, heads_smem_bytes(), st>>>(ws.L4t, w.heads, probs, logits, n);
@@ -1949,7 +1962,7 @@ inline cudaError_t get_lstm1(const Workspace& ws, int64_t n, int64_t np, float* 
 
 // parity hook: re-run the fused slice-dense on the retained H2t with the L3 activations written out as planes
 inline cudaError_t dump_l3(const Weights& w, const Workspace& ws, int64_t np, float* l4T, float* l3_planes) {
-  l3l4_fused<<<(unsigned)(np / 128), LF_THREADS, l3l4_smem_bytes(), 0>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, l3_planes, 0, nullptr);
+  l3l4_fused<<<(unsigned)(np / 128), LF_THREADS, l3l4_smem_bytes(), 0>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, l3_planes, 0, nullptr, w.w4_unscale);
   cudaError_t st = cudaGetLastError();
   return st != cudaSuccess ? st : cudaDeviceSynchronize();
 }
