@@ -20,6 +20,7 @@
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "decide_kernels.cuh"
+#include "decode_host.cuh"
 
 using namespace clairb;
 
@@ -741,6 +742,22 @@ int clairb_decide(clairb_engine* e, const float* probs_host, const uint8_t* ref_
                               (size_t)cn * decide::REC_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_comp));
     CU_TRY(e, cudaStreamSynchronize(e->s_comp));
   }
+  return CLAIRB_OK;
+}
+
+int clairb_decode_rows(const char* text, int64_t text_len, int64_t max_rows, int dtype, void* x_out, int32_t* info_off,
+                       int64_t* rows_read, int64_t* rows_kept, int64_t* consumed) {
+  if (!text || text_len < 0 || max_rows <= 0 || !x_out || !info_off || !rows_read || !rows_kept || !consumed)
+    return fail(nullptr, CLAIRB_EINVAL, "decode_rows: bad arguments");
+  if (text_len >= ((int64_t)1 << 31)) return fail(nullptr, CLAIRB_EINVAL, "decode_rows: text block must be < 2 GiB");
+  if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(nullptr, CLAIRB_EINVAL, "unknown dtype %d", dtype);
+  int64_t bad = -1;
+  static const int threads = getenv("CLAIRB_DECODE_THREADS") ? atoi(getenv("CLAIRB_DECODE_THREADS")) : 4;
+  const int rc = dtype == CLAIRB_DTYPE_I16
+                     ? decode::rows<int16_t>(text, text_len, max_rows, (int16_t*)x_out, info_off, rows_read, rows_kept, consumed, &bad, threads)
+                     : decode::rows<float>(text, text_len, max_rows, (float*)x_out, info_off, rows_read, rows_kept, consumed, &bad, threads);
+  if (rc == 1) return fail(nullptr, CLAIRB_EINVAL, "decode_rows: row %lld is malformed (needs ctg pos seq + 1056 values, seq of >= 17 bases)", (long long)bad);
+  if (rc == 2) return fail(nullptr, CLAIRB_EINVAL, "decode_rows: row %lld holds a value that is not an int16 integer", (long long)bad);
   return CLAIRB_OK;
 }
 

@@ -114,6 +114,17 @@ int clairb_predict_decide(clairb_engine* e, const void* x_host, int dtype, int64
 int clairb_decide(clairb_engine* e, const float* probs_host, const uint8_t* ref_base, const void* x_host,
                   int dtype, int64_t n, int32_t* decision);
 
+/* Host-only (no device): replaces the per-row `row.split()` + `np.array(columns, float32)` of
+ * tensor_generator_from (clair/utils.py:81-98) for one predict-batch of text rows (CreateTensor.py:60-65).
+ * Parses complete '\n'-terminated lines of `text` until max_rows lines are read; rows whose centre base
+ * seq[16] is not an IUPAC code are dropped (clair/utils.py:90), kept rows are written to x_out
+ * ([kept][1056], CLAIRB_DTYPE_F32 or _I16) with channel 0 subtracted from channels 1..3
+ * (clair/utils.py:96-98).  info_off: [max_rows][6] byte offsets into `text` (start, end of ctg, pos, seq) of
+ * every kept row.  rows_read / rows_kept / consumed (bytes) report progress.  A malformed row is
+ * CLAIRB_EINVAL (the reference raises on it); message via clairb_last_error(NULL). */
+int clairb_decode_rows(const char* text, int64_t text_len, int64_t max_rows, int dtype, void* x_out,
+                       int32_t* info_off, int64_t* rows_read, int64_t* rows_kept, int64_t* consumed);
+
 /* Parity hook: activations of the most recent clairb_predict* call at one stage of the graph,
  * copied to host as float32 in the reference's own axis order (see CLAIRB_LAYER_*).
  * out_host must hold layer_elems(layer) * n floats. */

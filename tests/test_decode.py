@@ -12,10 +12,14 @@ from clair_b200 import synth, utils
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def test_generator_matches_reference_fixture(capsys):
+import pytest
+
+
+@pytest.mark.parametrize("decoder", ["native", "python"])
+def test_generator_matches_reference_fixture(capsys, decoder):
     with np.load(os.path.join(GOLDEN, "decode_expected.npz")) as z:
         exp = {k: z[k] for k in z.files}
-    got = list(utils.tensor_generator_from(os.path.join(GOLDEN, "decode_rows.txt.gz"), 4))
+    got = list(utils.tensor_generator_from(os.path.join(GOLDEN, "decode_rows.txt.gz"), 4, decoder=decoder))
     assert len(got) == 3
     total = 0
     for bi, (X, infos) in enumerate(got):
@@ -27,11 +31,12 @@ def test_generator_matches_reference_fixture(capsys):
     assert capsys.readouterr().err == str(exp["stderr"])           # same progress lines
 
 
-def test_generator_reads_stdin_pipe(monkeypatch):
+@pytest.mark.parametrize("decoder", ["native", "python"])
+def test_generator_reads_stdin_pipe(monkeypatch, decoder):
     counts = synth.synthetic_counts(5, seed=1)
     rows = [utils.format_tensor_row("chr1", 100 + i, "A" * 33, counts[i]) for i in range(5)]
     monkeypatch.setattr(sys, "stdin", io.StringIO("\n".join(rows) + "\n"))
-    got = list(utils.tensor_generator_from("PIPE", 2))
+    got = list(utils.tensor_generator_from("PIPE", 2, decoder=decoder))
     assert [len(i) for _, i in got] == [2, 2, 1]                   # ragged last batch
     X = np.concatenate([x for x, _ in got])
     np.testing.assert_array_equal(X, synth.synthetic_tensors(5, seed=1))
@@ -105,3 +110,55 @@ def test_binary_transport_errors_and_edges(tmp_path):
     got = list(utils.binary_tensor_generator_from(str(p), 2, alloc=alloc))
     assert len(got) == 2 and np.shares_memory(got[0][0], pinned[0])
     np.testing.assert_array_equal(np.concatenate([x for x, _ in got]).astype(np.float32), synth.synthetic_tensors(3, seed=4))
+
+
+def test_native_decoder_equals_python_decoder_on_awkward_rows(tmp_path):
+    # tabs, runs of blanks, CRLF, negative and float-formatted values, a last line without newline, int16 output
+    rng = np.random.default_rng(5)
+    rows = []
+    for i in range(9):
+        vals = rng.integers(-40, 300, 1056)
+        toks = ["%d" % v for v in vals]
+        if i == 2:
+            toks[7] = "12.0"
+            toks[9] = "1e1"
+            toks[11] = "+5"
+        sep = "\t" if i % 3 == 0 else ("  " if i % 3 == 1 else " ")
+        seq = "ACGTN" * 6 + "ACG"
+        if i == 4:
+            seq = seq[:16] + "-" + seq[17:]                        # dropped by the IUPAC filter
+        rows.append(sep.join(["ctg_%d" % i, str(1000 + i), seq] + toks) + ("\r" if i == 5 else ""))
+    p = tmp_path / "rows.gz"
+    with gzip.open(p, "wt", newline="") as f:
+        f.write("\n".join(rows))                                   # no trailing newline
+    a = list(utils.tensor_generator_from(str(p), 4, decoder="native"))
+    b = list(utils.tensor_generator_from(str(p), 4, decoder="python"))
+    assert len(a) == len(b) == 3
+    for (Xa, ia), (Xb, ib) in zip(a, b):
+        np.testing.assert_array_equal(Xa, Xb)
+        assert ia == ib and Xa.dtype == np.float32
+    rows_i = [r for k, r in enumerate(rows) if k != 2]              # int16 transport: integers only
+    with gzip.open(p, "wt", newline="") as f:
+        f.write("\n".join(rows_i) + "\n")
+    c = list(utils.tensor_generator_from(str(p), 100, decoder="native", dtype=np.int16))
+    d = list(utils.tensor_generator_from(str(p), 100, decoder="python"))
+    assert c[0][0].dtype == np.int16 and c[0][1] == d[0][1]
+    np.testing.assert_array_equal(c[0][0].astype(np.float32), d[0][0])
+
+
+def test_native_decoder_rejects_malformed_rows(tmp_path):
+    counts = synth.synthetic_counts(2, seed=3)
+    good = utils.format_tensor_row("c", 1, "A" * 33, counts[0])
+    for bad in (good.rsplit(" ", 1)[0], good + " 7", "c 1 " + "A" * 10 + good[good.index("A" * 33) + 33:], "",
+                good.replace(" 1 ", " x1y ", 1) if False else "c 1"):
+        p = tmp_path / "bad.gz"
+        with gzip.open(p, "wt") as f:
+            f.write(good + "\n" + bad + "\n")
+        with pytest.raises(ValueError):
+            list(utils.tensor_generator_from(str(p), 4, decoder="native"))
+    with gzip.open(p, "wt") as f:
+        f.write(good.replace(" %d " % counts[0].reshape(-1)[5], " 40000 ", 1) + "\n")
+    with pytest.raises(ValueError, match="int16"):
+        list(utils.tensor_generator_from(str(p), 4, decoder="native", dtype=np.int16))
+    with pytest.raises(ValueError):
+        list(utils.tensor_generator_from(str(p), 4, decoder="python", dtype=np.int16))
