@@ -11,8 +11,8 @@ every step re-reads its inputs from HBM; 142,000 sites = 14.99 waves of 74 CTA p
 leg, so the per-call cost of the host pipeline (first host->device copy, last device->host copy: about 1.3 ms) is
 paid once per 142 predict-batches.
   value : device-resident sites/s (inputs already in HBM, CUDA events on the launching stream)
-  e2e   : the same through the reference-facing call (Clair.predict_packed -> clairb_predict):
-          pinned HOST input, H2D + forward + D2H inside the timed region
+  e2e   : the same through the reference-facing call (Clair.predict -> clairb_predict_split: four fresh float32
+          arrays per call like clair/model.py:946-966): pinned HOST input, H2D + forward + D2H inside the timed region
   roofline / cpu_baseline : see DESIGN.md section "Measurement"
 N>1 (launched by torchrun, one rank per GPU): every rank runs the same per-GPU workload on its own
 sites (weak scaling) and the packed [sites,90] probabilities are gathered to rank 0 with one NCCL
@@ -295,9 +295,10 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = m.predict_packed(X)          # allocates the fresh result array like the reference
+        out4 = m.predict(X)                # the reference's own call: four fresh float32 arrays (clair/model.py:946-966)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    out = np.concatenate(out4, axis=1)
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -323,14 +324,15 @@ def main():
     Xi[...] = X
     assert np.array_equal(Xi.astype(np.float32), X), "synthetic counts must be exact in int16"
     for _ in range(2):
-        out_i = m.predict_packed(Xi)
+        out_i = m.predict(Xi)
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out_i = m.predict_packed(Xi)
+        out_i = m.predict(Xi)
     torch.cuda.synchronize()
     e2e_i16_s = time.perf_counter() - t0
+    out_i = np.concatenate(out_i, axis=1)
     if world > 1:
         t = torch.tensor([e2e_i16_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -278,7 +278,8 @@ int forward_heads(clairb_engine* e, SiteMap sm, float* out_dev, cudaStream_t st)
   return CLAIRB_OK;
 }
 
-int forward_chunk(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, float* out_dev, cudaStream_t st) {
+int forward_chunk(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, float* out_dev, cudaStream_t st,
+                  int64_t split_rows = 0) {
   if (e->kind == ENGINE_TC) {
     int nl = 0;
     ProfScope* open = nullptr;
@@ -287,7 +288,7 @@ int forward_chunk(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, fl
       else { delete open; open = nullptr; }
     };
     cudaError_t cst = tc::forward_lstm(e->tcw, e->tcws, x_dev, dtype == CLAIRB_DTYPE_I16, sm.n, sm.np, e->d_h2, e->d_l4T,
-                                       out_dev, e->d_logits, e->fuse_tail, e->l2_stream, st, &nl, hook);
+                                       out_dev, e->d_logits, e->fuse_tail, e->l2_stream, st, &nl, hook, split_rows);
     e->launches += nl;
     if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "tensor-core forward failed: %s", cudaGetErrorString(cst));
     if (e->fuse_tail) return CLAIRB_OK;
@@ -604,11 +605,30 @@ int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_
 // Shared body of clairb_predict / clairb_predict_decide: chunked, copy-overlapped forward; when `ref_host` / `dec_host`
 // are given the decision kernel runs on each chunk right behind the heads, on the probabilities and the input tensor
 // that are still resident, and its 24-byte records travel back with the probabilities.
+// `outs` (optional, instead of out_host): four head arrays [n][21], [n][3], [n][33], [n][33] as Clair.predict returns
+// them; the heads kernel then writes head-major chunk buffers and the host only copies contiguous blocks.
 static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_host, const uint8_t* ref_host,
-                        int32_t* dec_host) {
+                        int32_t* dec_host, float* const* outs = nullptr) {
   if (!e) return CLAIRB_EINVAL;
   if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
+  if (outs && (dec_host || !outs[0] || !outs[1] || !outs[2] || !outs[3])) return fail(e, CLAIRB_EINVAL, "predict_split: bad buffers");
+  if (outs) out_host = outs[0];
   if (!x_host || !out_host || n <= 0 || n > e->max_sites) return fail(e, CLAIRB_EINVAL, "predict: bad n or buffers");
+  // head-major chunk buffers need the kernel that can write them (tensor-core heads); the cross-check engines produce
+  // packed rows and the host scatters them
+  const bool dev_split = outs && e->kind == ENGINE_TC && e->fuse_tail;
+  auto deliver = [&](const float* staged, int64_t at, int64_t cnt) {      // staged chunk -> the caller's array(s)
+    if (!outs) {
+      memcpy(out_host + (size_t)at * N_OUT, staged, (size_t)cnt * N_OUT * sizeof(float));
+    } else if (dev_split) {
+      for (int k = 0; k < 4; ++k)
+        memcpy(outs[k] + (size_t)at * kHeadSize[k], staged + (size_t)cnt * kHeadOffH[k], (size_t)cnt * kHeadSize[k] * sizeof(float));
+    } else {
+      for (int64_t r = 0; r < cnt; ++r)
+        for (int k = 0; k < 4; ++k)
+          memcpy(outs[k] + (size_t)(at + r) * kHeadSize[k], staged + (size_t)r * N_OUT + kHeadOffH[k], kHeadSize[k] * sizeof(float));
+    }
+  };
   if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(e, CLAIRB_EINVAL, "unknown dtype %d", dtype);
   CU_TRY(e, cudaSetDevice(e->device));
   const size_t eb = elem_bytes(dtype);
@@ -616,7 +636,7 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
   // every D2H copy synchronous and serialise the chunk pipeline, and the reference contract hands back a fresh numpy
   // array per call (clair/model.py:963), i.e. pageable memory.  A destination that is itself pinned is written directly.
   bool out_pinned = false;
-  {
+  if (!outs) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, out_host) == cudaSuccess) out_pinned = at.type == cudaMemoryTypeHost;
     else cudaGetLastError();
@@ -655,7 +675,7 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
     CU_TRY(e, cudaEventRecord(e->ev_h2d[b], e->s_h2d));
     CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_h2d[b], 0));
     CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_d2h[b], 0));   // output buffer b drained
-    int rc = forward_chunk(e, e->d_x[b], dtype, sm, e->d_out[b], e->s_comp);
+    int rc = forward_chunk(e, e->d_x[b], dtype, sm, e->d_out[b], e->s_comp, dev_split ? cn : 0);
     if (rc) return rc;
     if (dec_host) {
       ProfScope ps(e, 13, e->s_comp);
@@ -676,7 +696,7 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
     if (!out_pinned && c >= 1) {
       // while this chunk runs, hand the previous chunk's results to the caller
       CU_TRY(e, cudaEventSynchronize(e->ev_d2h[b ^ 1]));
-      memcpy(out_host + (size_t)prev_done * N_OUT, e->h_out[b ^ 1], (size_t)prev_cn * N_OUT * sizeof(float));
+      deliver(e->h_out[b ^ 1], prev_done, prev_cn);
     }
     if (dec_host && c >= 1) {
       CU_TRY(e, cudaEventSynchronize(e->ev_d2h[b ^ 1]));
@@ -690,7 +710,7 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
   }
   if (!out_pinned) {
     CU_TRY(e, cudaEventSynchronize(e->ev_d2h[(c - 1) & 1]));
-    memcpy(out_host + (size_t)prev_done * N_OUT, e->h_out[(c - 1) & 1], (size_t)prev_cn * N_OUT * sizeof(float));
+    deliver(e->h_out[(c - 1) & 1], prev_done, prev_cn);
   }
   if (dec_host) {
     CU_TRY(e, cudaEventSynchronize(e->ev_d2h[(c - 1) & 1]));
@@ -705,6 +725,12 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
 
 int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_host) {
   return predict_impl(e, x_host, dtype, n, out_host, nullptr, nullptr);
+}
+
+int clairb_predict_split(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_gt21, float* out_genotype,
+                         float* out_indel_1, float* out_indel_2) {
+  float* outs[4] = {out_gt21, out_genotype, out_indel_1, out_indel_2};
+  return predict_impl(e, x_host, dtype, n, nullptr, nullptr, nullptr, outs);
 }
 
 int clairb_predict_decide(clairb_engine* e, const void* x_host, int dtype, int64_t n, const uint8_t* ref_base, float* out_host,

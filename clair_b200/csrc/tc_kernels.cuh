@@ -1387,7 +1387,7 @@ constexpr size_t heads_smem_bytes() { return (size_t)HD_A4_BYTES + HD_W5_BYTES +
 
 __global__ void __launch_bounds__(HD_THREADS, 1)
 heads_tc(const __half* __restrict__ L4t, const uint8_t* __restrict__ blobs, float* __restrict__ probs,
-         float* __restrict__ logits, int64_t n) {
+         float* __restrict__ logits, int64_t n, int64_t split_rows) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* A4 = smem;
@@ -1549,7 +1549,9 @@ heads_tc(const __half* __restrict__ L4t, const uint8_t* __restrict__ blobs, floa
       for (int i = 0; i < 48; ++i)
         if (i < cnt) lg[i] = z[i];
       if (site < n) {
-        float* pr = probs + site * N_OUT + off;
+        // packed [n][90] rows, or (split_rows > 0) four head-major arrays [split_rows][n_k] laid end to end - the layout
+        // predict() hands back (clair/model.py:963), so the host never has to split rows
+        float* pr = split_rows > 0 ? probs + (size_t)split_rows * off + site * cnt : probs + site * N_OUT + off;
 #pragma unroll
         for (int i = 0; i < 48; ++i)
           if (i < cnt) pr[i] = e[i] * inv;
@@ -1891,7 +1893,7 @@ inline void free_workspace(Workspace& ws) {
 template <typename Hook>
 inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_dev, int dtype_is_i16, int64_t n, int64_t np,
                                 float* h2_planes, float* l4T, float* probs, float* logits, bool fuse_tail, bool l2_stream,
-                                cudaStream_t st, int* launches, Hook&& hook) {
+                                cudaStream_t st, int* launches, Hook&& hook, int64_t split_rows = 0) {
   const int NT = (int)(np / 128);
   const int num_row_pairs = T_STEPS * NT / 2;
   // persistent input-projection grid: whole groups of 4 CTA pairs (one pair per N-block), one pair per 2 SMs
@@ -1934,7 +1936,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
     l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, nullptr, l3_pf, ws.lf_trace, w.w4_unscale);
     hook(4, false);
     hook(5, true);
-    heads_tc<<<(unsigned)NT, HD_THREADS, heads_smem_bytes(), st>>>(ws.L4t, w.heads, probs, logits, n);
+    heads_tc<<<(unsigned)NT, HD_THREADS, heads_smem_bytes(), st>>>(ws.L4t, w.heads, probs, logits, n, split_rows);
     hook(5, false);
     *launches += 2;
   }

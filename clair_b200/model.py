@@ -126,9 +126,19 @@ class Clair(object):
 
     def predict(self, batchX):
         """Reference clair/model.py:946-966: list of 4 float32 arrays, also stored in .prediction."""
-        out = self.predict_packed(batchX)
-        split = np.cumsum(self.output_label_split)[:-1]
-        prediction = [np.ascontiguousarray(a) for a in np.split(out, split, axis=1)]
+        if not self._has_weights:
+            raise RuntimeError("predict() before init()/restore_parameters()")
+        X, _ = self.tensor_transform_function(batchX, None, "predict")      # clair/model.py:953
+        X, dtype = self._as_input(X)
+        n = X.shape[0]
+        prediction = [np.empty((n, k), dtype=np.float32) for k in self.output_label_split]    # fresh every call
+        with self._lock:
+            for s in range(0, n, self.max_sites):
+                m = min(self.max_sites, n - s)
+                rc = self._lib.clairb_predict_split(
+                    self._h, X[s:s + m].ctypes.data_as(ctypes.c_void_p), dtype, m,
+                    *[a[s:s + m].ctypes.data_as(ctypes.c_void_p) for a in prediction])
+                _lib.check(rc, self._h, "clairb_predict_split")
         self.prediction = prediction
         return prediction
 

@@ -77,6 +77,12 @@ int clairb_finalize_weights(clairb_engine* e);
  * The library does not retain x_host or out_host. */
 int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_host);
 
+/* The same call with the reference's own return layout: four arrays [n,21] [n,3] [n,33] [n,33]
+ * (clair/model.py:963, clair/task/main.py:10-29).  The heads kernel writes head-major chunk buffers, so the
+ * host side only copies contiguous blocks (splitting packed rows on the host costs as much as half the forward). */
+int clairb_predict_split(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_gt21,
+                         float* out_genotype, float* out_indel_1, float* out_indel_2);
+
 /* Same forward with both buffers already resident in device memory, enqueued on `stream`
  * (a cudaStream_t; NULL = legacy default stream) without synchronising the host.  Used by
  * bench.py for the device-resident number and by the multi-GPU shard path. */

@@ -301,3 +301,25 @@ def test_full_size_one_million_sites_property(weights1234):
     assert np.abs(first[idx] - ref).max() <= TOL
     np.testing.assert_allclose(out[:, :21].sum(1), 1.0, atol=1e-5)
     m.close()
+
+
+def test_predict_split_layout_equals_packed(weights1234, monkeypatch):
+    # predict() (four arrays, written head-major by the heads kernel) and predict_packed() ([n,90] rows) are the same
+    # numbers, across several chunks, for a ragged size, and on the cross-check engines (host-side scatter)
+    from clair_b200.model import Clair
+    monkeypatch.setenv("CLAIRB_CHUNK_SITES", "1024")
+    m = Clair(max_sites=4096, batch_sites=1000)
+    monkeypatch.setenv("CLAIRB_FUSED_TAIL", "0")
+    alt = Clair(max_sites=4096, batch_sites=1000)
+    monkeypatch.delenv("CLAIRB_FUSED_TAIL")
+    monkeypatch.delenv("CLAIRB_CHUNK_SITES")
+    for eng in (m, alt):
+        eng.set_weights(weights1234)
+        for n in (1, 777, 3300):
+            X = synth.synthetic_tensors(n, seed=600 + n)
+            packed = eng.predict_packed(X)
+            four = eng.predict(X)
+            assert [a.shape for a in four] == [(n, 21), (n, 3), (n, 33), (n, 33)]
+            assert all(a.flags["C_CONTIGUOUS"] and a.dtype == np.float32 for a in four)
+            np.testing.assert_array_equal(np.concatenate(four, axis=1), packed)
+        eng.close()
