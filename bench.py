@@ -82,18 +82,21 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The sampler is started
+    early (nvidia-smi needs a few hundred ms to come up, the timed region is ~130 ms) and every sample carries a
+    timestamp; stop() keeps the samples that fall between mark_begin() and mark_end()."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -102,37 +105,59 @@ class ClockSampler(object):
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    @staticmethod
+    def _stamp(text, fallback):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return fallback
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        rows = []
+        for seen, line in self.lines:
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-                pw.append(float(parts[3]))
+                rows.append((self._stamp(parts[0], seen), float(parts[2]), float(parts[3]), float(parts[4]), parts[6:10]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[5:9]):
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        lo, hi = self.t_begin or 0.0, self.t_end or float("inf")
+        inside = [r for r in rows if lo - 0.005 <= r[0] <= hi + 0.005]
+        window = "timed region"
+        if not inside:
+            # no sample landed inside: take the samples closest to it (the run before / after is the same workload)
+            mid = 0.5 * (lo + hi)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            window = "nearest to the timed region"
+        sm = sorted(r[1] for r in inside)
+        reasons = set()
+        for r in inside:
+            for name, val in zip(names, r[4]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in inside), "power_w_max": max(r[3] for r in inside),
+                "samples": len(inside), "window": window, "reasons": sorted(reasons)}
 
 
 def cpu_info():
@@ -250,6 +275,10 @@ def main():
         if world > 1:
             dist.gather(od, gather_list=gather_bufs, dst=0)     # the path's one exchange
 
+    sampler = ClockSampler(local_rank)       # started well before the timed region: nvidia-smi takes a while to come up
+    if rank == 0:
+        sampler.start()
+
     # ---- parity spot check before any timing counts ----
     if rank == 0:
         from oracle import clair_oracle as O
@@ -264,18 +293,17 @@ def main():
         device_step()
     torch.cuda.synchronize()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     m.set_profiling(True)
     launches0 = m.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    sampler.mark_begin()
     ev0.record(stream)
     for _ in range(args.steps):
         device_step()
     ev1.record(stream)
     torch.cuda.synchronize()
+    sampler.mark_end()
     barrier()
     launches = m.kernel_launches() - launches0
     ms = ev0.elapsed_time(ev1)
