@@ -34,13 +34,19 @@ __device__ __forceinline__ void consider(Best& b, float v, uint32_t key) {
 template <typename TIn>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 decide_sites(const float* __restrict__ probs, const uint8_t* __restrict__ ref_base, const TIn* __restrict__ x,
-             int32_t* __restrict__ rec, int64_t n) {
+             int32_t* __restrict__ rec, int64_t n, int64_t split_rows) {
   __shared__ float sp[WARPS_PER_BLOCK][96];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t site = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
   if (site >= n) return;
   float* p = sp[warp];
-  for (int i = lane; i < N_OUT; i += 32) p[i] = probs[site * N_OUT + i];
+  // packed [n][90] rows, or (split_rows > 0) the four head-major arrays [split_rows][n_k] the heads kernel writes for
+  // Clair.predict
+  for (int i = lane; i < N_OUT; i += 32) {
+    const int k = i < 21 ? 0 : i < 24 ? 1 : i < 57 ? 2 : 3;
+    const int off = kHeadOff[k], cnt = kHeadOff[k + 1] - off;
+    p[i] = split_rows > 0 ? probs[(size_t)split_rows * off + site * cnt + (i - off)] : probs[site * N_OUT + i];
+  }
   __syncwarp();
   const float* gt21 = p;
   const float* vl1 = p + 24 + 16;     // index by signed length -16..16 (VariantLength.index_offset = 16)
@@ -145,10 +151,11 @@ decide_sites(const float* __restrict__ probs, const uint8_t* __restrict__ ref_ba
 }
 
 template <typename TIn>
-inline cudaError_t launch(const float* probs, const uint8_t* ref_base, const TIn* x, int32_t* rec, int64_t n, cudaStream_t st) {
+inline cudaError_t launch(const float* probs, const uint8_t* ref_base, const TIn* x, int32_t* rec, int64_t n, cudaStream_t st,
+                          int64_t split_rows = 0) {
   if (n <= 0) return cudaSuccess;
   const unsigned grid = (unsigned)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-  decide_sites<TIn><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(probs, ref_base, x, rec, n);
+  decide_sites<TIn><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(probs, ref_base, x, rec, n, split_rows);
   return cudaGetLastError();
 }
 

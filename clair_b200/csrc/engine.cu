@@ -611,7 +611,7 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
                         int32_t* dec_host, float* const* outs = nullptr) {
   if (!e) return CLAIRB_EINVAL;
   if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
-  if (outs && (dec_host || !outs[0] || !outs[1] || !outs[2] || !outs[3])) return fail(e, CLAIRB_EINVAL, "predict_split: bad buffers");
+  if (outs && (!outs[0] || !outs[1] || !outs[2] || !outs[3])) return fail(e, CLAIRB_EINVAL, "predict_split: bad buffers");
   if (outs) out_host = outs[0];
   if (!x_host || !out_host || n <= 0 || n > e->max_sites) return fail(e, CLAIRB_EINVAL, "predict: bad n or buffers");
   // head-major chunk buffers need the kernel that can write them (tensor-core heads); the cross-check engines produce
@@ -680,8 +680,8 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
     if (dec_host) {
       ProfScope ps(e, 13, e->s_comp);
       cudaError_t dst_ = dtype == CLAIRB_DTYPE_I16
-                             ? decide::launch<int16_t>(e->d_out[b], e->d_ref[b], (const int16_t*)e->d_x[b], e->d_dec[b], cn, e->s_comp)
-                             : decide::launch<float>(e->d_out[b], e->d_ref[b], (const float*)e->d_x[b], e->d_dec[b], cn, e->s_comp);
+                             ? decide::launch<int16_t>(e->d_out[b], e->d_ref[b], (const int16_t*)e->d_x[b], e->d_dec[b], cn, e->s_comp, dev_split ? cn : 0)
+                             : decide::launch<float>(e->d_out[b], e->d_ref[b], (const float*)e->d_x[b], e->d_dec[b], cn, e->s_comp, dev_split ? cn : 0);
       if (dst_ != cudaSuccess) return fail(e, CLAIRB_ECUDA, "decide_sites launch failed: %s", cudaGetErrorString(dst_));
       e->launches += 1;
     }
@@ -731,6 +731,14 @@ int clairb_predict_split(clairb_engine* e, const void* x_host, int dtype, int64_
                          float* out_indel_1, float* out_indel_2) {
   float* outs[4] = {out_gt21, out_genotype, out_indel_1, out_indel_2};
   return predict_impl(e, x_host, dtype, n, nullptr, nullptr, nullptr, outs);
+}
+
+int clairb_predict_split_decide(clairb_engine* e, const void* x_host, int dtype, int64_t n, const uint8_t* ref_base,
+                                float* out_gt21, float* out_genotype, float* out_indel_1, float* out_indel_2, int32_t* decision) {
+  if (!e) return CLAIRB_EINVAL;
+  if (!ref_base || !decision) return fail(e, CLAIRB_EINVAL, "predict_split_decide: ref_base and decision are required");
+  float* outs[4] = {out_gt21, out_genotype, out_indel_1, out_indel_2};
+  return predict_impl(e, x_host, dtype, n, nullptr, ref_base, decision, outs);
 }
 
 int clairb_predict_decide(clairb_engine* e, const void* x_host, int dtype, int64_t n, const uint8_t* ref_base, float* out_host,

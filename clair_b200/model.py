@@ -146,10 +146,26 @@ class Clair(object):
         """predict() plus the first-choice variant decision of every site in the same device pass: returns
         (prediction, Decision) with `prediction` the list of four arrays predict() returns (also stored in
         .prediction).  See predict_and_decide_packed."""
-        out, dec = self.predict_and_decide_packed(batchX, ref_bases)
-        split = np.cumsum(self.output_label_split)[:-1]
-        self.prediction = [np.ascontiguousarray(a) for a in np.split(out, split, axis=1)]
-        return self.prediction, dec
+        from . import decision as _decision
+        if not self._has_weights:
+            raise RuntimeError("predict() before init()/restore_parameters()")
+        X, _ = self.tensor_transform_function(batchX, None, "predict")
+        X, dtype = self._as_input(X)
+        n = X.shape[0]
+        ref = np.ascontiguousarray(ref_bases, dtype=np.uint8).reshape(-1)
+        if ref.shape[0] != n or (ref > 3).any():
+            raise ValueError("ref_bases must be %d codes in 0..3" % n)
+        prediction = [np.empty((n, k), dtype=np.float32) for k in self.output_label_split]
+        rec = np.empty((n, _lib.DECISION_WORDS), dtype=np.int32)
+        with self._lock:
+            for s in range(0, n, self.max_sites):
+                m = min(self.max_sites, n - s)
+                rc = self._lib.clairb_predict_split_decide(
+                    self._h, X[s:s + m].ctypes.data_as(ctypes.c_void_p), dtype, m, ref[s:s + m].ctypes.data_as(ctypes.c_void_p),
+                    *([a[s:s + m].ctypes.data_as(ctypes.c_void_p) for a in prediction] + [rec[s:s + m].ctypes.data_as(ctypes.c_void_p)]))
+                _lib.check(rc, self._h, "clairb_predict_split_decide")
+        self.prediction = prediction
+        return prediction, _decision.unpack(rec)
 
     def predict_and_decide_packed(self, batchX, ref_bases):
         """predict_packed() plus the first-choice variant decision of every site in the same device pass.

@@ -115,6 +115,11 @@ int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_
 int clairb_predict_decide(clairb_engine* e, const void* x_host, int dtype, int64_t n,
                           const uint8_t* ref_base, float* out_host, int32_t* decision);
 
+/* The same with the four-array return layout of Clair.predict (see clairb_predict_split). */
+int clairb_predict_split_decide(clairb_engine* e, const void* x_host, int dtype, int64_t n,
+                                const uint8_t* ref_base, float* out_gt21, float* out_genotype,
+                                float* out_indel_1, float* out_indel_2, int32_t* decision);
+
 /* Decision alone, from probabilities the caller already holds (e.g. an ensemble average,
  * clair/post_processing/ensemble.py).  x_host may be NULL (read depth is then reported as 0). */
 int clairb_decide(clairb_engine* e, const float* probs_host, const uint8_t* ref_base, const void* x_host,
