@@ -732,10 +732,11 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
 //   Stages are loaded by BOTH CTAs with tensor-map TMA in the cta_group::2 form, whose completion bytes are signalled on
 //   the LEADER's mbarrier (the plain bulk copy can only signal its own CTA, which needed a relay thread and a
 //   cluster-scope release per stage: ~700 cycles on the ring's round trip).  The maps view H1 / W_x as [rows][1 KB].
-// Issue order per step:  x(0,1) | h(0) h(1) || h(2) | h(3) | x(2,3)
+// Issue order per step:  x(0,1) | h(0) | h(1) || h(2) | h(3)[k0] | x(2,3) | h(3)[k1..7]
 //   x(0,1) of step s does not depend on the recurrence and fills the tensor pipe while the epilogue is still turning
-//   blocks 2, 3 of step s-1 into h_{s-1}; in the second half the recurrent parts go first because each needs only ITS
-//   accumulator drained, while the N=256 x part needs both.
+//   blocks 2, 3 of step s-1 into h_{s-1}; in the second half h(2) goes first because it needs only ITS accumulator
+//   drained, while the N=256 x part needs both; the two blocks of a pair complete 1.3-1.5 k cycles apart on purpose
+//   (the epilogue handles them one after the other and hands the second accumulator back that much earlier).
 // Epilogue warps read their whole share of an accumulator into registers and hand it back before doing any math.
 // Accumulator column c of block b is gate column b*128 + c in both parts (x part: CTA q, row r -> block 2bp+q, c = r).
 //   Wx   : [dir][q][bp 2][st 8][hl][kc 4][128 rows][8]    bias: [dir][512] (unit*4+gate order, gate-scaled)
@@ -877,34 +878,39 @@ lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap t
           mbar_wait(&hq[kq], hpar);
           tc_fence_after();
         };
-        // ---- blocks 0, 1: x part first (independent of the recurrence), then h_{s-1} as it arrives ----
+        // ---- blocks 0, 1: x part first (independent of the recurrence), then the recurrent parts one block after the
+        //      other: block 0 completes a whole h part (1.5 k cycles) before block 1, so the epilogue - which handles
+        //      the two blocks back to back - starts that much earlier and hands accumulator 1 back that much earlier ----
         acquire(0);
         acquire(1);
         stamp(s, 0);
         x_part(true);
         stamp(s, 1);
         if (s > 0) {
-          wait_h(0); stamp(s, 2); h_part(0, 0, 2, false); h_part(1, 0, 2, false);
-          wait_h(1); h_part(0, 2, 4, false); h_part(1, 2, 4, false);
-          wait_h(2); h_part(0, 4, 6, false); h_part(1, 4, 6, false);
+          wait_h(0); stamp(s, 2); h_part(0, 0, 2, false);
+          wait_h(1); h_part(0, 2, 4, false);
+          wait_h(2); h_part(0, 4, 6, false);
           wait_h(3); stamp(s, 3); h_part(0, 6, 8, false);
           umma_commit_pair(&acc_full[0], 0b11);
-          h_part(1, 6, 8, false);
+          h_part(1, 0, 8, false);
           umma_commit_pair(&acc_full[1], 0b11);
         } else {
           umma_commit_pair(&acc_full[0], 0b11);
           umma_commit_pair(&acc_full[1], 0b11);
         }
         stamp(s, 4);
-        // ---- blocks 2, 3: each recurrent part needs only its own accumulator; the x part needs both ----
+        // ---- blocks 2, 3: h(2) needs only accumulator 0 (handed back early) and fills the wait for accumulator 1; the
+        //      first k-step of h(3) initialises accumulator 1, the N=256 x part accumulates into both, block 2 is
+        //      complete, and the rest of h(3) staggers block 3 behind it ----
         acquire(0);
         stamp(s, 8);
         if (s > 0) h_part(2, 0, 8, true);
         acquire(1);
         stamp(s, 9);
-        if (s > 0) h_part(3, 0, 8, true);
+        if (s > 0) h_part(3, 0, 1, true);
         x_part(s == 0);
         umma_commit_pair(&acc_full[0], 0b11);
+        if (s > 0) h_part(3, 1, 8, false);
         umma_commit_pair(&acc_full[1], 0b11);
         stamp(s, 12);
       }
