@@ -60,9 +60,9 @@ def parse_args():
 
 
 def measured_traffic(kernel, sites_per_launch):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic_s8.json),
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic_s11.json),
     scaled to this run's sites per launch; None when no capture covers the kernel."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic_s8.json")
+    path = os.path.join(ROOT, "profiles", "r01_traffic_s11.json")
     try:
         with open(path) as f:
             t = json.load(f)
@@ -412,7 +412,7 @@ def main():
             roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": achieved,
                         "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                         "traffic": measured_traffic(dom["kernel"], sites_per_launch),
-                        "traffic_source": "ncu dram__bytes_read+write per launch (profiles/r01_traffic_s8.json), scaled by sites",
+                        "traffic_source": "ncu dram__bytes_read+write per launch (profiles/r01_traffic_s11.json), scaled by sites",
                         "algorithmic_bytes": KERNEL_BYTES_PER_SITE.get(dom["kernel"], 0) * sites_per_launch,
                         "peak_source": peaks["source"] + " (sustained bf16)",
                         "avg_launch_ms": avg_ms, "sites_per_launch": sites_per_launch,
