@@ -15,19 +15,34 @@ from time import time
 from . import param, utils
 
 
-def run_batches(m, tensor_generator, output_stage, *output_args):
-    """Drive ``m.predict`` over every (X, infos) batch of ``tensor_generator``."""
+def run_batches(m, tensor_generator, output_stage, *output_args, with_decision=False):
+    """Drive ``m.predict`` over every (X, infos) batch of ``tensor_generator``.
+
+    with_decision=True drives ``m.predict_and_decide`` instead (reference bases from the info triples,
+    clair_b200.decision.ref_base_codes) and leaves the decision records of the batch in ``m.decision`` next to
+    ``m.prediction``; the output stage is then called as ``output_stage(batch, prediction, decision, *output_args)``
+    with the records of exactly that batch (the same one-iteration hand-over as the prediction)."""
     to_predict = None      # batch loaded in the previous iteration
     to_output = None       # batch predicted in the previous iteration
     source_open = True
+    if with_decision:
+        from . import decision as _decision
+
+        def predict_stage(batch):
+            _, dec = m.predict_and_decide(batch[0], _decision.ref_base_codes(batch[1]))
+            m.decision = dec
 
     while True:
         stages = []
         if to_output is not None:
-            stages.append(Thread(target=output_stage, args=(to_output, m.prediction) + output_args))
+            handed = (to_output, m.prediction, m.decision) if with_decision else (to_output, m.prediction)
+            stages.append(Thread(target=output_stage, args=handed + output_args))
         predicted = None
         if to_predict is not None:
-            stages.append(Thread(target=m.predict, kwargs={"batchX": to_predict[0]}))
+            if with_decision:
+                stages.append(Thread(target=predict_stage, args=(to_predict,)))
+            else:
+                stages.append(Thread(target=m.predict, kwargs={"batchX": to_predict[0]}))
             predicted = to_predict
         fetched = []
         if source_open:

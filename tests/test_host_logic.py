@@ -126,3 +126,36 @@ def test_sharded_predict_two_ranks_gloo(n):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(results)
+
+
+def test_run_batches_with_decision_hands_over_matching_records():
+    from clair_b200 import decision
+
+    class FakeDecider(FakeModel):
+        decision = None
+
+        def predict_and_decide(self, batchX, ref_bases):
+            self.predict(batchX)
+            n = batchX.shape[0]
+            first = int(batchX.reshape(n, -1).sum(1)[0])
+            return self.prediction, decision.Decision(np.full(n, first), np.asarray(ref_bases), None, None, None, None)
+
+    m = FakeDecider()
+    seen = []
+
+    def output(mini_batch, batch_Y, dec, tag):
+        X, infos = mini_batch
+        assert dec.category[0] == int(X.reshape(X.shape[0], -1).sum(1)[0])      # records of exactly this batch
+        assert dec.len1.tolist() == ["ACGT".index(i[2][16]) for i in infos]       # reference bases came from the infos
+        seen.append((len(infos), tag))
+
+    def gen():
+        off = 0
+        for s in (3, 3, 2):
+            X = synth.synthetic_tensors(s, seed=300 + off)
+            yield X, [["chr1", str(off + i), "A" * 16 + "ACGT"[(off + i) % 4] + "A" * 16] for i in range(s)]
+            off += s
+
+    call_var.run_batches(m, gen(), output, "cfg", with_decision=True)
+    assert seen == [(3, "cfg"), (3, "cfg"), (2, "cfg")]
+    assert m.max_in_flight == 1
