@@ -363,6 +363,10 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
 #ifndef CLAIRB_SEQ1_EARLY
 #define CLAIRB_SEQ1_EARLY 1   // block-wise hand-off of h_t to the MMA issuer in layer 1 as well (0.483 -> 0.468 ms per chunk)
 #endif
+#ifndef CLAIRB_SEQ1_G
+#define CLAIRB_SEQ1_G 2
+#endif
+constexpr int SEQ1_G = CLAIRB_SEQ1_G;                              // ... of the layer-1 launch (A/B switch)
 constexpr int SEQ_G = 2;                                // epilogue warps per TMEM lane quarter (2 or 4)
 constexpr int SEQ_THREADS = 32 * (2 + 4 * SEQ_G);
 constexpr int SEQ_W_BYTES = 2 * 4 * 16 * 1024;          // 131072
@@ -1852,7 +1856,7 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
     cudaMemset(ws.trace, 0, T_STEPS * 64 * sizeof(long long));
   }
   if ((st = cudaFuncSetAttribute(xproj_pair<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<32>())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(lstm_seq<true, 0, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(lstm_seq<true, 0, SEQ1_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq<false, 1, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq<false, 2, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(l3l4_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3l4_smem_bytes())) != cudaSuccess) return st;
@@ -1917,7 +1921,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   else prep_tiles48<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X48, n, NT);
   hook(0, false);
   hook(1, true);   // layer 1: input projection fused into the recurrent kernel (no Gx round trip)
-  lstm_seq<true, 0, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np, 0);
+  lstm_seq<true, 0, SEQ1_G><<<grec, 32 * (2 + 4 * SEQ1_G), seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np, 0);
   hook(1, false);
   // layer 2: input projection streamed through the recurrent kernel (default), or the two-kernel path
   // xproj_pair -> Gx -> lstm_seq (CLAIRB_L2_STREAM=0: on-device cross-check)
