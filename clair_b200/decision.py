@@ -35,10 +35,11 @@ def ref_base_codes(non_tensor_infos, centre=16):
 
 
 def unpack(records):
-    """[n,6] int32 device records -> Decision of arrays (the two float fields are bit-cast back)."""
+    """[n,6] int32 device records -> Decision of column views into them (the two float fields are bit-cast back;
+    no copies: splitting 142,000 records into six contiguous arrays costs as much as 10 % of their forward pass)."""
     r = np.ascontiguousarray(records, dtype=np.int32).reshape(-1, _lib.DECISION_WORDS)
     f = r.view(np.float32)
-    return Decision(r[:, 0].copy(), r[:, 1].copy(), r[:, 2].copy(), r[:, 3].copy(), f[:, 4].copy(), f[:, 5].copy())
+    return Decision(r[:, 0], r[:, 1], r[:, 2], r[:, 3], f[:, 4], f[:, 5])
 
 
 def flags_tuple(category):
