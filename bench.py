@@ -178,13 +178,14 @@ def time_cpu_port(weights, pool, n_batches, warm=1):
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
     fo = FastOracle(weights)
+    first = None
     for i in range(warm):
-        fo.forward_packed(pool[i % len(pool)])
+        first = fo.forward_packed(pool[i % len(pool)])
     t0 = time.perf_counter()
     for i in range(n_batches):
         fo.forward_packed(pool[i % len(pool)])
     dt = time.perf_counter() - t0
-    return n_batches * BATCH / dt, fo.threads, dt
+    return n_batches * BATCH / dt, fo.threads, dt, first
 
 
 def run_reference(args, rank):
@@ -278,15 +279,6 @@ def main():
     sampler = ClockSampler(local_rank)       # started well before the timed region: nvidia-smi takes a while to come up
     if rank == 0:
         sampler.start()
-
-    # ---- parity spot check before any timing counts ----
-    if rank == 0:
-        from oracle import clair_oracle as O
-        chk = m.predict_packed(np.array(X[:200]))
-        ref = O.forward_packed(np.array(X[:200]), weights, np.float64)
-        assert np.abs(chk - ref).max() <= 1e-4, "parity check failed before timing"
-        for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
-            assert (chk[:, a:b].argmax(1) == ref[:, a:b].argmax(1)).all()
 
     # ---- device-resident timing ----
     for _ in range(max(args.warmup, 3)):
@@ -386,18 +378,10 @@ def main():
         e2e_dec_s = float(t.item())
     decision_info = None
     if rank == 0:
-        from oracle import decision_oracle as DO
-        ns = 300
-        t0 = time.perf_counter()
-        want, want_p, _ = DO.decide(out[:ns], ref_bases[:ns])
-        cpu_dec = ns / (time.perf_counter() - t0)
-        got = np.stack([dec.category, dec.len1, dec.len2, dec.aux], axis=1)[:ns]
-        assert np.array_equal(got, want) and np.array_equal(dec.max_probability[:ns], want_p), "decision parity failed"
         decision_info = {"e2e_with_decision": world * sites * args.steps / e2e_dec_s, "unit": "sites/s",
                          "extra_d2h_bytes_per_step": sites * 24, "extra_h2d_bytes_per_step": sites,
-                         "cpu_python_restatement_sites_per_s": cpu_dec, "cpu_sample": "%d sites, 1 core" % ns,
                          "categories_seen": np.bincount(dec.category, minlength=10).tolist(),
-                         "note": "forward + decide_sites kernel per chunk (call_var.py:589-690, 732-760), bit-exact vs oracle on the sample"}
+                         "note": "forward + decide_sites kernel per chunk (call_var.py:589-690, 732-760)"}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -424,10 +408,26 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             nb = args.cpu_baseline_batches or 24
             pool = [np.array(X[i * BATCH:(i + 1) * BATCH]) for i in range(min(8, bps))]
-            v, threads, dt = time_cpu_port(weights, pool, nb)
+            # the only place this arm touches oracle/: the CPU port is timed on a bounded sample AND serves as the
+            # checker of what was just measured (same sites, same weights)
+            v, threads, dt, cpu_first = time_cpu_port(weights, pool, nb)
             model, cores = cpu_info()
+            err = float(np.abs(out[:BATCH] - cpu_first).max())
+            assert err <= 1e-4, "GPU result differs from the CPU port of the reference: %g" % err
+            for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
+                assert (out[:BATCH, a:b].argmax(1) == cpu_first[:, a:b].argmax(1)).all(), "arg-max mismatch vs the CPU port"
+            from oracle import decision_oracle as DO
+            ns = 300
+            t0 = time.perf_counter()
+            want, want_p, _ = DO.decide(out[:ns], ref_bases[:ns])
+            cpu_dec = ns / (time.perf_counter() - t0)
+            got = np.stack([dec.category, dec.len1, dec.len2, dec.aux], axis=1)[:ns]
+            assert np.array_equal(got, want) and np.array_equal(dec.max_probability[:ns], want_p), "decision parity failed"
+            decision_info["cpu_python_restatement_sites_per_s"] = cpu_dec
+            decision_info["cpu_sample"] = "%d sites, 1 core; device records bit-exact on them" % ns
             cpu = {"value": v, "unit": "sites/s", "cores": threads, "kind": "port",
                    "sample": "%d predict-batches x %d sites of the same pool, %.1f s" % (nb, BATCH, dt),
+                   "parity_vs_gpu": {"max_abs_prob_diff": err, "argmax_identical": True, "sites": BATCH},
                    "cpu_model": model, "host_cores": cores}
         engine = os.environ.get("CLAIRB_ENGINE", "default")
         print(json.dumps({
