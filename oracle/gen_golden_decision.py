@@ -78,6 +78,16 @@ def make_cases(rng):
         i, j = rng.integers(0, 21, 2)
         p[j] = p[i]
         cases.append(p)
+    # 4) probabilities restricted to a few powers of two: thousands of exactly equal products per site, the winner is
+    #    decided by the reference's tie order alone
+    levels = np.array([0.0, 0.125, 0.25, 0.5], np.float32)
+    for k in range(150):
+        p = levels[rng.integers(0, 4, size=90)]
+        if k < 15:
+            p[24:90] = 0.25
+        elif k < 30:
+            p[0:21] = 0.5
+        cases.append(p)
     cases.append(np.zeros(90, np.float32))             # everything zero: the reference answers "reference"
     P = np.stack(cases).astype(np.float32)
     ref_bases = rng.integers(0, 4, len(P)).astype(np.uint8)

@@ -121,3 +121,22 @@ def test_decision_multi_chunk_pipeline(weights1234, monkeypatch):
     with pytest.raises(ValueError):
         m.decide(probs, np.full(3300, 7, np.uint8))
     m.close()
+
+
+@pytest.mark.gpu
+def test_kernel_tie_breaking_on_quantised_probabilities(gpu_model):
+    # probabilities restricted to a few powers of two make thousands of outcome products exactly equal: the winner is then
+    # decided purely by the reference's tie order (category chain, then list.index), which the oracle reproduces from the
+    # reference-pinned goldens and the kernel must reproduce from the oracle
+    rng = np.random.default_rng(99)
+    n = 600
+    levels = np.array([0.0, 0.125, 0.25, 0.5], np.float32)
+    P = levels[rng.integers(0, 4, size=(n, 90))]
+    P[:50, 24:90] = 0.25                                         # whole length heads equal
+    P[50:100, 0:21] = 0.5                                        # whole gt21 head equal
+    ref = rng.integers(0, 4, n).astype(np.uint8)
+    d = gpu_model.decide(P, ref)
+    dec, maxp, _ = D.decide(P, ref)
+    np.testing.assert_array_equal(np.stack([d.category, d.len1, d.len2, d.aux], axis=1), dec)
+    np.testing.assert_array_equal(d.max_probability, maxp)
+    assert len(set(dec[:, 0])) >= 6

@@ -162,3 +162,29 @@ def test_native_decoder_rejects_malformed_rows(tmp_path):
         list(utils.tensor_generator_from(str(p), 4, decoder="native", dtype=np.int16))
     with pytest.raises(ValueError):
         list(utils.tensor_generator_from(str(p), 4, decoder="python", dtype=np.int16))
+
+
+def test_native_decoder_randomised_rows_match_python(tmp_path):
+    # randomised separators / signs / widths / IUPAC centres, several batches, both decoders must agree exactly
+    rng = np.random.default_rng(11)
+    seps = [" ", "\t", "  ", " \t "]
+    rows = []
+    for i in range(57):
+        vals = rng.integers(-999, 30000, 1056) if i % 7 == 0 else rng.integers(0, 60, 1056)
+        toks = ["%d" % v for v in vals]
+        for k in rng.integers(0, 1056, 3):
+            toks[k] = "+" + toks[k] if not toks[k].startswith("-") else toks[k]
+        centre = "ACGTURYSWKMBDHVNacgtn*-."[int(rng.integers(0, 24))]
+        seq = "".join(rng.choice(list("ACGT"), 16)) + centre + "".join(rng.choice(list("ACGT"), 16))
+        sep = seps[int(rng.integers(0, len(seps)))]
+        lead = " " if i % 5 == 0 else ""
+        rows.append(lead + sep.join(["chr%d" % (i % 4), str(10 ** (i % 9) + i), seq] + toks) + (" " if i % 6 == 0 else ""))
+    p = tmp_path / "r.gz"
+    with gzip.open(p, "wt") as f:
+        f.write("\n".join(rows) + "\n")
+    a = list(utils.tensor_generator_from(str(p), 10, decoder="native"))
+    b = list(utils.tensor_generator_from(str(p), 10, decoder="python"))
+    assert len(a) == len(b) > 0
+    for (Xa, ia), (Xb, ib) in zip(a, b):
+        np.testing.assert_array_equal(Xa, Xb)
+        assert ia == ib
