@@ -433,8 +433,12 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
   const size_t np = (size_t)e->chunk_np;
   CR_TRY(cudaMalloc((void**)&e->d_logits, np * N_OUT * sizeof(float)));
   CR_TRY(cudaMemset(e->d_logits, 0, np * N_OUT * sizeof(float)));
-  CR_TRY(cudaMalloc((void**)&e->d_h2, np * T_STEPS * 2 * H * sizeof(float)));
-  CR_TRY(cudaMalloc((void**)&e->d_l3T, np * L3_K * sizeof(float)));
+  // fp32 planes of the LSTM2 / L3 activations: only the CUDA-core tail reads them (the fused tensor-core path keeps both
+  // on chip; the L3 parity hook allocates its sink on first use)
+  if (e->kind == ENGINE_SIMT || !e->fuse_tail) {
+    CR_TRY(cudaMalloc((void**)&e->d_h2, np * T_STEPS * 2 * H * sizeof(float)));
+    CR_TRY(cudaMalloc((void**)&e->d_l3T, np * L3_K * sizeof(float)));
+  }
   CR_TRY(cudaMalloc((void**)&e->d_l4T, np * L4_UNITS * sizeof(float)));
   CR_TRY(cudaFuncSetAttribute(simt::l4_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt::l4_smem_bytes()));
   CR_TRY(cudaFuncSetAttribute(simt::tail_heads, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -447,7 +451,7 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
     CR_TRY(cudaFuncSetAttribute(simt::lstm_layer<2 * H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)simt::lstm_smem_bytes<2 * H>()));
   } else {
-    CR_TRY(tc::alloc_workspace(e->tcws, e->chunk_np, device));
+    CR_TRY(tc::alloc_workspace(e->tcws, e->chunk_np, device, !e->l2_stream));
   }
 #undef CR_TRY
   *out = e;
@@ -811,6 +815,7 @@ int clairb_get_layer(clairb_engine* e, int layer, float* out_host, int64_t n) {
     return CLAIRB_OK;
   }
   if (e->kind == ENGINE_TC && e->fuse_tail && layer == CLAIRB_LAYER_L3) {
+    if (!e->d_l3T) CU_TRY(e, cudaMalloc((void**)&e->d_l3T, (size_t)e->chunk_np * L3_K * sizeof(float)));
     // the fused path keeps L3 on chip: replay the fused kernel on the retained LSTM2 tiles with the debug sink set
     cudaError_t cst = tc::dump_l3(e->tcw, e->tcws, sm.np, e->d_l4T, e->d_l3T);
     if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "get_layer(L3) replay failed: %s", cudaGetErrorString(cst));

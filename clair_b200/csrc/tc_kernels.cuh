@@ -1833,14 +1833,15 @@ inline void free_weights(Weights& w) {
   w.l3l4 = nullptr; w.Wxf = nullptr; w.Whs[0] = w.Whs[1] = nullptr; w.Wx2 = nullptr; w.bx2 = nullptr;
 }
 
-inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device) {
+inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device, bool need_gx) {
   ws.np_max = np_max;
   const size_t NT = (size_t)np_max / 128;
   cudaError_t st;
   if ((st = cudaMalloc((void**)&ws.X48, (size_t)T_STEPS * NT * X48_TILE_HALVES * 2)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H1, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2)) != cudaSuccess) return st;
   if ((st = make_flat_map(&ws.tmH1, ws.H1, (size_t)T_STEPS * NT * 2 * 32 * KCH * 2, 2 * SX_KC)) != cudaSuccess) return st;
-  if ((st = cudaMalloc((void**)&ws.Gx, (size_t)T_STEPS * NT * GX_TILE_FLOATS * 4)) != cudaSuccess) return st;
+  // Gx (135 KB per site: 2.6 GB for a chunk) only exists on the two-kernel cross-check path of layer 2
+  if (need_gx && (st = cudaMalloc((void**)&ws.Gx, (size_t)T_STEPS * NT * GX_TILE_FLOATS * 4)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.H2t, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
   // time steps 33..39 of the last time group are never written by lstm_seq and must read as zeros
   if ((st = cudaMemset(ws.H2t, 0, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
