@@ -1,0 +1,223 @@
+// CreateTensor on the device: alignments -> 33x8x4 pileup counts, one thread block per
+// candidate site.  Replaces the record lists + generate_tensor of the reference
+// (dataPrepScripts/CreateTensor.py:29-65 and the CIGAR walk :283-366).
+//
+// The reference walks every read once and appends a record to every candidate window the read is currently inside
+// ("active set", :298-320), then folds each candidate's records into counts.  Seen from one candidate c (1-based centre;
+// its window is the 33 zero-based reference positions c-17 .. c+15) and one read, that bookkeeping reduces to:
+//   q = the first reference position at which the read opens the window
+//       = max(POS, c-17) when the read covers a position in [c-17, c+16]      (left edge considered, the default, :88-94)
+//       = c-17           when the read covers c-17, otherwise the read is ignored   (--stop_consider_left_edge, :96)
+//   aligned base (M,=,X) at p in the window: counted                           (a window is opened before the append, :298-314)
+//   deleted base (D) at p:                   counted iff p > q                 (opened after the append, :336-357)
+//   inserted bases (I) before reference position p: counted iff p > q          (no open on an insertion, :322-334)
+// Integer work, no reuse across sites: every block reads the ops / bases of the reads that overlap its window (a few KB,
+// L2-resident for neighbouring candidates), accumulates the 1056 counters in shared memory and writes one coalesced
+// 2,112-byte int16 row, optionally with channel 0 already subtracted from channels 1..3 (the transform
+// utils.tensor_generator_from applies before the network: clair/utils.py:96-98).  HBM-bound by construction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace clairb {
+namespace ct {
+
+constexpr int FLANK = 16;                 // shared/param.py:9
+constexpr int N_POS = 2 * FLANK + 1;      // 33
+constexpr int CELLS = N_POS * 8;          // (position, row) cells of 4 channels
+constexpr int ELEMS = CELLS * 4;          // 1056
+constexpr int OP_M = 0, OP_I = 1, OP_D = 2;   // ops kept by the host encoder; S only advances the query offset,
+                                              // N / H / P advance nothing in the reference (:283-366) and are dropped
+constexpr int THREADS = 128;
+
+// shared/utils.py:24-27 (IUPAC code -> A,C,G,T row), lower case folded as SEQ.upper() / sequence.upper() do
+// (CreateTensor.py:149,261); 255 = not a base, the record is skipped (:37-38)
+__host__ __device__ __forceinline__ int base_row(uint8_t ch) {
+  if (ch >= 'a' && ch <= 'z') ch -= 32;
+  switch (ch) {
+    case 'A': case 'R': case 'W': case 'M': case 'D': case 'H': case 'V': case 'N': return 0;
+    case 'C': case 'Y': case 'S': case 'B': return 1;
+    case 'G': case 'K': return 2;
+    case 'T': case 'U': return 3;
+    default: return 255;
+  }
+}
+
+struct Alignments {
+  // reads that passed the mapping-quality filter and the depth cap (CreateTensor.py:264,274-281), ascending POS
+  const int32_t* read_pos;       // [R]   0-based POS
+  const int32_t* read_end;       // [R]   one past the last reference position an M/=/X/D op covers
+  const int32_t* read_maxend;    // [R]   running maximum of read_end (binary-search key for the first overlapping read)
+  const int32_t* read_op0;       // [R+1] first op of each read
+  const uint8_t* read_strand;    // [R]   FLAG & 16 != 0
+  const int32_t* op_ref;         // [O]   reference position at the start of the op
+  const int32_t* op_qry;         // [O]   offset of the op's first query base in `seq`
+  const int32_t* op_len;         // [O]   length << 2 | OP_*
+  const uint8_t* seq;            // query bases of all reads, back to back
+  const uint8_t* ref;            // reference_sequence
+  int32_t ref_start0;            // reference_start_0_based (:223)
+  int32_t ref_len;
+  int32_t n_reads;
+};
+
+// One read folded into one candidate's counters.  `Add` supplies add(int element): an atomic on shared memory in the
+// kernel, a plain increment when this header is compiled for the host by tests/harness.
+template <typename Add>
+__host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, int center, bool left_edge, Add& add) {
+  const int w0 = center - (FLANK + 1);                 // first window position (0-based)
+  const int pos = a.read_pos[r], end = a.read_end[r];
+  int q;
+  if (left_edge) {
+    if (pos > w0 + 2 * FLANK + 1 || end <= w0) return false;      // no aligned/deleted base in [c-17, c+16]
+    q = pos > w0 ? pos : w0;
+  } else {
+    if (pos > w0 || end <= w0) return false;
+    q = w0;
+  }
+  if (q >= end) return false;
+  const int wend = w0 + N_POS;                         // one past the last counted position
+  const int strand = a.read_strand[r] ? 4 : 0;
+  int lo = a.read_op0[r], hi = a.read_op0[r + 1];
+  const int op_end = hi;
+  // first op whose reference end lies beyond q (an insertion ends where it starts, so this is an M or D op)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int lc = a.op_len[mid];
+    const int e = a.op_ref[mid] + (((lc & 3) == OP_I) ? 0 : (lc >> 2));
+    if (e > q) hi = mid; else lo = mid + 1;
+  }
+  for (int k = lo; k < op_end; ++k) {
+    const int p0 = a.op_ref[k];
+    if (p0 >= wend) break;
+    const int lc = a.op_len[k], len = lc >> 2, code = lc & 3;
+    const int qo = a.op_qry[k];
+    if (code == OP_M) {
+      const int s = p0 > q ? p0 : q, t = p0 + len < wend ? p0 + len : wend;
+      for (int p = s; p < t; ++p) {
+        const int ri = p - a.ref_start0;
+        const int rb = (ri >= 0 && ri < a.ref_len) ? base_row(a.ref[ri]) : 255;
+        const int qb = base_row(a.seq[qo + (p - p0)]);
+        if (rb == 255 || qb == 255) continue;
+        const int cell = (p - w0) * 32 + strand * 4;
+        add.add(cell + rb * 4 + 0);
+        add.add(cell + qb * 4 + 1);
+        add.add(cell + rb * 4 + 2);
+        add.add(cell + qb * 4 + 3);
+      }
+    } else if (code == OP_D) {
+      const int s = p0 > q + 1 ? p0 : q + 1, t = p0 + len < wend ? p0 + len : wend;
+      for (int p = s; p < t; ++p) {
+        const int ri = p - a.ref_start0;
+        const int rb = (ri >= 0 && ri < a.ref_len) ? base_row(a.ref[ri]) : 255;
+        if (rb == 255) continue;
+        add.add((p - w0) * 32 + strand * 4 + rb * 4 + 2);
+      }
+    } else if (p0 > q) {                               // insertion before reference position p0
+      const int i0 = p0 - w0;
+      for (int t = 0; t < len; ++t) {
+        const int qb = base_row(a.seq[qo + t]);
+        if (qb == 255) continue;
+        const int idx = i0 + t < N_POS - 1 ? i0 + t : N_POS - 1;     // min(position_index + queryAdv, 32), :46
+        add.add(idx * 32 + strand * 4 + qb * 4 + 1);
+      }
+    }
+  }
+  return true;
+}
+
+// Reads that can open the window of `center`: [first, last) with first = the first read whose running maximum end reaches
+// into the window and last = the first read that starts beyond the last position that opens it (reads in between that end
+// before the window are rejected by fold_read).
+__host__ __device__ __forceinline__ void read_range(const Alignments& a, int center, bool left_edge, int& first, int& last) {
+  const int w0 = center - (FLANK + 1);
+  int lo = 0, hi = a.n_reads;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a.read_maxend[mid] > w0) hi = mid; else lo = mid + 1;
+  }
+  first = lo;
+  const int last_open = left_edge ? w0 + 2 * FLANK + 1 : w0;
+  lo = 0, hi = a.n_reads;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a.read_pos[mid] > last_open) hi = mid; else lo = mid + 1;
+  }
+  last = lo;
+}
+
+struct SharedAdd {
+  int* cnt;
+  __device__ __forceinline__ void add(int i) { atomicAdd(cnt + i, 1); }
+};
+
+// flags
+constexpr int F_LEFT_EDGE = 1;      // default of the reference (absence of --stop_consider_left_edge)
+constexpr int F_SUBTRACT = 2;       // write channels 1..3 minus channel 0 (clair/utils.py:96-98) instead of raw counts
+
+// x_out: [n_centers][1056] int16; meta: [n_centers][2] = reads that opened the window (0: the reference prints no row),
+// depth at the centre position (depth[flanking_base_num], compared with --minCoverage at :55); overflow: set when a
+// count does not fit int16
+__global__ void __launch_bounds__(THREADS) create_tensors(Alignments a, const int32_t* __restrict__ centers, int n_centers,
+                                                          int flags, int16_t* __restrict__ x_out, int32_t* __restrict__ meta,
+                                                          int* __restrict__ overflow) {
+  __shared__ int cnt[ELEMS];
+  __shared__ int range[2];
+  __shared__ int opened;
+  const bool left_edge = flags & F_LEFT_EDGE;
+  for (int ci = blockIdx.x; ci < n_centers; ci += gridDim.x) {
+    const int center = centers[ci];
+    for (int i = threadIdx.x; i < ELEMS; i += THREADS) cnt[i] = 0;
+    if (threadIdx.x == 0) {
+      opened = 0;
+      read_range(a, center, left_edge, range[0], range[1]);
+    }
+    __syncthreads();
+    SharedAdd add{cnt};
+    int mine = 0;
+    for (int r = range[0] + threadIdx.x; r < range[1]; r += THREADS) mine += fold_read(a, r, center, left_edge, add) ? 1 : 0;
+    if (mine) atomicAdd(&opened, mine);
+    __syncthreads();
+    // one row out: 528 words of two int16 = channels (0,1) or (2,3) of a cell
+    uint32_t* out = reinterpret_cast<uint32_t*>(x_out + (size_t)ci * ELEMS);
+    bool ovf = false;
+    for (int w = threadIdx.x; w < ELEMS / 2; w += THREADS) {
+      const int cell = (w >> 1) * 4;
+      const int c0 = cnt[cell];
+      int v0, v1;
+      if (w & 1) { v0 = cnt[cell + 2]; v1 = cnt[cell + 3]; } else { v0 = c0; v1 = cnt[cell + 1]; }
+      if (flags & F_SUBTRACT) {
+        if (w & 1) v0 -= c0;
+        v1 -= c0;
+      }
+      ovf |= v0 > 32767 || v1 > 32767 || v0 < -32768 || v1 < -32768;
+      out[w] = (uint32_t)(uint16_t)(int16_t)v0 | ((uint32_t)(uint16_t)(int16_t)v1 << 16);
+    }
+    if (ovf) *overflow = 1;
+    if (threadIdx.x < 8) {
+      // depth at the centre = aligned bases at position index 16 = sum over rows of channel 0
+      int d = cnt[FLANK * 32 + threadIdx.x * 4];
+      d += __shfl_down_sync(0xff, d, 4, 8);
+      d += __shfl_down_sync(0xff, d, 2, 8);
+      d += __shfl_down_sync(0xff, d, 1, 8);
+      if (threadIdx.x == 0) {
+        meta[2 * ci] = opened;
+        meta[2 * ci + 1] = d;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// rows[i] of the resident tensor block -> a dense block the forward reads (the candidates the reference would have printed
+// and tensor_generator_from would have kept)
+__global__ void gather_rows(const int16_t* __restrict__ x_all, const int64_t* __restrict__ rows, int64_t n,
+                            int16_t* __restrict__ x_out) {
+  const int64_t i = blockIdx.x;
+  if (i >= n) return;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(x_all + (size_t)rows[i] * ELEMS);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(x_out + (size_t)i * ELEMS);
+  for (int w = threadIdx.x; w < ELEMS / 2; w += blockDim.x) dst[w] = src[w];
+}
+
+}  // namespace ct
+}  // namespace clairb

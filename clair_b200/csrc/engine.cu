@@ -21,6 +21,7 @@
 #include "tc_kernels.cuh"
 #include "decide_kernels.cuh"
 #include "decode_host.cuh"
+#include "create_tensor_kernels.cuh"
 
 using namespace clairb;
 
@@ -95,6 +96,13 @@ struct clairb_engine {
   SiteMap last_map{0, 1000, 1024, 0};
   bool last_single_chunk = false;
 
+  // CreateTensor on the device (clairb_create_tensors / clairb_predict_created): growable device buffers.  ct_x holds the
+  // tensor block of the most recent clairb_create_tensors call ([ct_rows][1056] int16), the rest is upload scratch.
+  struct DevBuf { void* p = nullptr; size_t cap = 0; };
+  DevBuf ct_in[12], ct_x, ct_meta, ct_gather, ct_rows_idx, ct_out;
+  int* ct_overflow = nullptr;
+  int64_t ct_rows = 0;
+
   // optional per-kernel CUDA-event timing (bench.py's roofline leg)
   bool profiling = false;
   struct ProfSpan { cudaEvent_t a, b; int id; };
@@ -130,6 +138,18 @@ int fail(clairb_engine* e, int code, const char* fmt, ...) {
 template <typename Tp>
 int dev_alloc(clairb_engine* e, Tp** p, size_t count) {
   CU_TRY(e, cudaMalloc((void**)p, count * sizeof(Tp)));
+  return CLAIRB_OK;
+}
+
+// device buffer that only ever grows (with 25 % slack), for inputs whose size changes from call to call
+int grow(clairb_engine* e, clairb_engine::DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return CLAIRB_OK;
+  if (b.p) CU_TRY(e, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = bytes + bytes / 4 + 256;
+  CU_TRY(e, cudaMalloc(&b.p, want));
+  b.cap = want;
   return CLAIRB_OK;
 }
 
@@ -174,8 +194,8 @@ SiteMap make_map(const clairb_engine* e, int64_t n) {
 // ---- per-kernel event timing --------------------------------------------------------------------
 const char* kKernelNames[] = {"prep_input", "lstm_layer1", "lstm_layer2", "l3_slice_dense", "l4_dense",
                               "tail_heads", "prep_tiles", "lstm_seq1", "xproj2", "lstm_seq2", "l3l4_fused", "heads_tc",
-                              "lstm_seq_x2", "decide_sites"};
-constexpr int kNumKernelNames = 14;
+                              "lstm_seq_x2", "decide_sites", "create_tensors", "gather_rows"};
+constexpr int kNumKernelNames = 16;
 
 void prof_fold(clairb_engine* e) {
   for (auto& sp : e->prof_open) {
@@ -325,6 +345,9 @@ void free_all(clairb_engine* e) {
   cudaFree(e->d_logits);
   tc::free_weights(e->tcw);
   tc::free_workspace(e->tcws);
+  for (auto& b : e->ct_in) cudaFree(b.p);
+  cudaFree(e->ct_x.p); cudaFree(e->ct_meta.p); cudaFree(e->ct_gather.p); cudaFree(e->ct_rows_idx.p); cudaFree(e->ct_out.p);
+  cudaFree(e->ct_overflow);
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
   if (e->s_h2d2) cudaStreamDestroy(e->s_h2d2);
   for (int l = 0; l < 2; ++l) if (e->ev_h2d2[l]) cudaEventDestroy(e->ev_h2d2[l]);
@@ -780,6 +803,110 @@ int clairb_decide(clairb_engine* e, const float* probs_host, const uint8_t* ref_
                               (size_t)cn * decide::REC_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_comp));
     CU_TRY(e, cudaStreamSynchronize(e->s_comp));
   }
+  return CLAIRB_OK;
+}
+
+// ---- CreateTensor on the device -------------------------------------------------------------
+int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const int32_t* centers, int64_t n_centers, int flags,
+                          int16_t* x_host, int32_t* meta_host) {
+  if (!e) return CLAIRB_EINVAL;
+  if (!a || !centers || n_centers <= 0 || n_centers > 0x7fffffff || !meta_host)
+    return fail(e, CLAIRB_EINVAL, "create_tensors: bad arguments");
+  if (a->n_reads < 0 || a->n_ops < 0 || a->seq_len < 0 || a->ref_len < 0 || a->n_reads > 0x7ffffff0 || a->n_ops > 0x7ffffff0 ||
+      a->seq_len > 0x7ffffff0 || a->ref_len > 0x7ffffff0)
+    return fail(e, CLAIRB_EINVAL, "create_tensors: a block holds at most 2^31 reads / ops / bases");
+  if (a->n_reads && (!a->read_pos || !a->read_end || !a->read_op0 || !a->read_strand))
+    return fail(e, CLAIRB_EINVAL, "create_tensors: read arrays missing");
+  if (a->n_ops && (!a->op_ref || !a->op_qry || !a->op_len || !a->seq)) return fail(e, CLAIRB_EINVAL, "create_tensors: op arrays missing");
+  if (!a->ref || a->ref_len == 0) return fail(e, CLAIRB_EINVAL, "create_tensors: empty reference sequence");
+  const int64_t R = a->n_reads, O = a->n_ops;
+  // the kernel finds the reads of a window by binary search: POS ascending (a sorted BAM), centres ascending
+  std::vector<int32_t> maxend((size_t)R);
+  for (int64_t r = 0; r < R; ++r) {
+    if (r && a->read_pos[r] < a->read_pos[r - 1]) return fail(e, CLAIRB_EINVAL, "create_tensors: reads must be sorted by POS (read %lld)", (long long)r);
+    if (a->read_op0[r] < 0 || a->read_op0[r + 1] < a->read_op0[r] || a->read_op0[r + 1] > O)
+      return fail(e, CLAIRB_EINVAL, "create_tensors: read_op0 is not a prefix array (read %lld)", (long long)r);
+    maxend[r] = r && maxend[r - 1] > a->read_end[r] ? maxend[r - 1] : a->read_end[r];
+  }
+  for (int64_t i = 1; i < n_centers; ++i)
+    if (centers[i] <= centers[i - 1]) return fail(e, CLAIRB_EINVAL, "create_tensors: candidate positions must be strictly ascending");
+  for (int64_t k = 0; k < O; ++k) {
+    const int len = a->op_len[k] >> 2, code = a->op_len[k] & 3;
+    if (code != ct::OP_D && code != ct::OP_M && code != ct::OP_I) return fail(e, CLAIRB_EINVAL, "create_tensors: op %lld has an unknown code", (long long)k);
+    if (code != ct::OP_D && (a->op_qry[k] < 0 || (int64_t)a->op_qry[k] + len > a->seq_len))
+      return fail(e, CLAIRB_EINVAL, "create_tensors: op %lld reads past the end of its SEQ (the reference raises IndexError)", (long long)k);
+  }
+  CU_TRY(e, cudaSetDevice(e->device));
+  cudaStream_t st = e->s_comp;
+  const void* src[9] = {a->read_pos, a->read_end, maxend.data(), a->read_op0, a->read_strand, a->op_ref, a->op_qry, a->op_len, a->seq};
+  const size_t bytes[9] = {(size_t)R * 4, (size_t)R * 4, (size_t)R * 4, (size_t)(R + 1) * 4, (size_t)R, (size_t)O * 4, (size_t)O * 4, (size_t)O * 4,
+                           (size_t)a->seq_len};
+  for (int i = 0; i < 9; ++i) {
+    if (int rc = grow(e, e->ct_in[i], bytes[i] ? bytes[i] : 4)) return rc;
+    if (bytes[i] && src[i]) CU_TRY(e, cudaMemcpyAsync(e->ct_in[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, st));
+  }
+  if (int rc = grow(e, e->ct_in[9], (size_t)a->ref_len)) return rc;
+  CU_TRY(e, cudaMemcpyAsync(e->ct_in[9].p, a->ref, (size_t)a->ref_len, cudaMemcpyHostToDevice, st));
+  if (int rc = grow(e, e->ct_in[10], (size_t)n_centers * 4)) return rc;
+  CU_TRY(e, cudaMemcpyAsync(e->ct_in[10].p, centers, (size_t)n_centers * 4, cudaMemcpyHostToDevice, st));
+  if (int rc = grow(e, e->ct_x, (size_t)n_centers * ct::ELEMS * sizeof(int16_t))) return rc;
+  if (int rc = grow(e, e->ct_meta, (size_t)n_centers * 2 * sizeof(int32_t))) return rc;
+  if (!e->ct_overflow) CU_TRY(e, cudaMalloc((void**)&e->ct_overflow, sizeof(int)));
+  CU_TRY(e, cudaMemsetAsync(e->ct_overflow, 0, sizeof(int), st));
+  e->ct_rows = 0;
+  ct::Alignments da;
+  da.read_pos = (const int32_t*)e->ct_in[0].p;  da.read_end = (const int32_t*)e->ct_in[1].p;
+  da.read_maxend = (const int32_t*)e->ct_in[2].p;  da.read_op0 = (const int32_t*)e->ct_in[3].p;
+  da.read_strand = (const uint8_t*)e->ct_in[4].p;  da.op_ref = (const int32_t*)e->ct_in[5].p;
+  da.op_qry = (const int32_t*)e->ct_in[6].p;  da.op_len = (const int32_t*)e->ct_in[7].p;
+  da.seq = (const uint8_t*)e->ct_in[8].p;  da.ref = (const uint8_t*)e->ct_in[9].p;
+  da.ref_start0 = a->ref_start0;  da.ref_len = (int32_t)a->ref_len;  da.n_reads = (int32_t)R;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+  const int64_t resident = (int64_t)sms * 16;        // 16 blocks of 128 threads per SM: a persistent grid, one wave
+  const unsigned grid = (unsigned)(n_centers < resident ? n_centers : resident);
+  {
+    ProfScope ps(e, 14, st);
+    ct::create_tensors<<<grid, ct::THREADS, 0, st>>>(da, (const int32_t*)e->ct_in[10].p, (int)n_centers, flags,
+                                                     (int16_t*)e->ct_x.p, (int32_t*)e->ct_meta.p, e->ct_overflow);
+  }
+  cudaError_t lst = cudaGetLastError();
+  if (lst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "create_tensors launch failed: %s", cudaGetErrorString(lst));
+  e->launches += 1;
+  int overflow = 0;
+  CU_TRY(e, cudaMemcpyAsync(meta_host, e->ct_meta.p, (size_t)n_centers * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(e, cudaMemcpyAsync(&overflow, e->ct_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (x_host)
+    CU_TRY(e, cudaMemcpyAsync(x_host, e->ct_x.p, (size_t)n_centers * ct::ELEMS * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(e, cudaStreamSynchronize(st));
+  if (overflow) return fail(e, CLAIRB_EINVAL, "create_tensors: a count does not fit int16 (depth above 32767)");
+  e->ct_rows = n_centers;
+  return CLAIRB_OK;
+}
+
+int clairb_predict_created(clairb_engine* e, const int64_t* rows, int64_t n, float* out_host) {
+  if (!e) return CLAIRB_EINVAL;
+  if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
+  if (!rows || !out_host || n <= 0 || n > e->max_sites) return fail(e, CLAIRB_EINVAL, "predict_created: bad n or buffers");
+  if (e->ct_rows <= 0) return fail(e, CLAIRB_EINVAL, "predict_created: no tensor block resident (call clairb_create_tensors first)");
+  for (int64_t i = 0; i < n; ++i)
+    if (rows[i] < 0 || rows[i] >= e->ct_rows) return fail(e, CLAIRB_EINVAL, "predict_created: row %lld is outside the resident block", (long long)rows[i]);
+  CU_TRY(e, cudaSetDevice(e->device));
+  cudaStream_t st = e->s_comp;
+  if (int rc = grow(e, e->ct_rows_idx, (size_t)n * sizeof(int64_t))) return rc;
+  if (int rc = grow(e, e->ct_gather, (size_t)n * ct::ELEMS * sizeof(int16_t))) return rc;
+  if (int rc = grow(e, e->ct_out, (size_t)n * N_OUT * sizeof(float))) return rc;
+  CU_TRY(e, cudaMemcpyAsync(e->ct_rows_idx.p, rows, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  {
+    ProfScope ps(e, 15, st);
+    ct::gather_rows<<<(unsigned)n, 128, 0, st>>>((const int16_t*)e->ct_x.p, (const int64_t*)e->ct_rows_idx.p, n, (int16_t*)e->ct_gather.p);
+  }
+  cudaError_t lst = cudaGetLastError();
+  if (lst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "gather_rows launch failed: %s", cudaGetErrorString(lst));
+  e->launches += 1;
+  if (int rc = clairb_predict_device(e, e->ct_gather.p, CLAIRB_DTYPE_I16, n, (float*)e->ct_out.p, st)) return rc;
+  CU_TRY(e, cudaMemcpyAsync(out_host, e->ct_out.p, (size_t)n * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_TRY(e, cudaStreamSynchronize(st));
   return CLAIRB_OK;
 }
 

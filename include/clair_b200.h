@@ -125,6 +125,62 @@ int clairb_predict_split_decide(clairb_engine* e, const void* x_host, int dtype,
 int clairb_decide(clairb_engine* e, const float* probs_host, const uint8_t* ref_base, const void* x_host,
                   int dtype, int64_t n, int32_t* decision);
 
+/* ---- CreateTensor on the device ------------------------------------------------------------
+ * Replaces the CIGAR walk and generate_tensor of dataPrepScripts/CreateTensor.py (:283-366 and :29-65): alignments in,
+ * one [33,8,4] block of int16 counts per candidate site out, the counts the reference prints as text (:57-62).
+ * The host side (clair_b200/create_tensor.py) keeps what the reference does per SAM row before the walk - the
+ * mapping-quality filter (:264) and the per-POS depth cap (:274-281) - and encodes the surviving reads:
+ *   read_pos    [n_reads]    0-based POS, ascending (a coordinate-sorted BAM)
+ *   read_end    [n_reads]    one past the last reference position covered by an M / = / X / D op
+ *   read_op0    [n_reads+1]  index of each read's first op (prefix array)
+ *   read_strand [n_reads]    (FLAG & 16) != 0                                   (:262)
+ *   op_ref/op_qry/op_len [n_ops]  per kept CIGAR op: reference position at its start, offset of its first base in
+ *               `seq` (soft clips already skipped, :290-291), and length << 2 | code with code CLAIRB_OP_M (M,=,X),
+ *               CLAIRB_OP_I, CLAIRB_OP_D.  N / H / P ops advance nothing in the reference and are not encoded.
+ *   seq         query bases of all reads back to back (any case, :261)
+ *   ref         reference_sequence as `samtools faidx` returned it (any case, :149), its first base being the 0-based
+ *               contig position ref_start0 (reference_start_0_based, :223)
+ * centers: [n_centers] 1-based candidate positions, strictly ascending, already restricted to ctgStart..ctgEnd (:83) and
+ *   to positions whose window starts inside `ref` (:55).
+ * flags: CLAIRB_CT_LEFT_EDGE (the reference's default; clear it for --stop_consider_left_edge) |
+ *        CLAIRB_CT_SUBTRACT (write channels 1..3 minus channel 0, what tensor_generator_from feeds the network,
+ *        clair/utils.py:96-98, instead of the raw counts).
+ * x_host: [n_centers][1056] int16 or NULL (the block then only stays resident on the device for
+ *   clairb_predict_created).  meta_host: [n_centers][2] int32 = number of reads that opened the site's window (0: the
+ *   reference prints no row for it) and the depth at the centre position (what --minCoverage is compared with, :55).
+ * Not modelled: the 5,000,000-record memory guard (available_slots, :180,285-286). */
+#define CLAIRB_OP_M 0
+#define CLAIRB_OP_I 1
+#define CLAIRB_OP_D 2
+#define CLAIRB_CT_LEFT_EDGE 1
+#define CLAIRB_CT_SUBTRACT  2
+
+typedef struct clairb_alignments {
+  const int32_t* read_pos;
+  const int32_t* read_end;
+  const int32_t* read_op0;
+  const uint8_t* read_strand;
+  int64_t n_reads;
+  const int32_t* op_ref;
+  const int32_t* op_qry;
+  const int32_t* op_len;
+  int64_t n_ops;
+  const uint8_t* seq;
+  int64_t seq_len;
+  const uint8_t* ref;
+  int64_t ref_len;
+  int32_t ref_start0;
+} clairb_alignments;
+
+int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const int32_t* centers, int64_t n_centers,
+                          int flags, int16_t* x_host, int32_t* meta_host);
+
+/* Forward over rows of the tensor block the last clairb_create_tensors call (with CLAIRB_CT_SUBTRACT) left on the
+ * device: rows[i] indexes that call's centers.  The tensors never exist in host memory - the text hop between
+ * CreateTensor.py and call_var.py (clair/callVarBam.py:191-200) and the host->device copy are gone.
+ * out_host: [n,90] float32 as clairb_predict. */
+int clairb_predict_created(clairb_engine* e, const int64_t* rows, int64_t n, float* out_host);
+
 /* Host-only (no device): replaces the per-row `row.split()` + `np.array(columns, float32)` of
  * tensor_generator_from (clair/utils.py:81-98) for one predict-batch of text rows (CreateTensor.py:60-65).
  * Parses complete '\n'-terminated lines of `text` until max_rows lines are read; rows whose centre base

@@ -1,0 +1,32 @@
+// TEST INFRASTRUCTURE.  Compiles the __host__ __device__ halves of csrc/create_tensor_kernels.cuh (read_range, fold_read,
+// base_row) for the CPU so that the per-site rule the kernel applies can be checked against the reference-generated golden
+// rows on a machine without a GPU (tests/test_create_tensor.py, -m "not gpu").  Never linked into libclair_b200.so.
+#include "../../clair_b200/csrc/create_tensor_kernels.cuh"
+
+namespace {
+struct PlainAdd {
+  int* cnt;
+  __host__ __device__ void add(int i) { cnt[i] += 1; }
+};
+}  // namespace
+
+extern "C" int ct_host_sites(const int32_t* read_pos, const int32_t* read_end, const int32_t* read_maxend, const int32_t* read_op0,
+                             const uint8_t* read_strand, int32_t n_reads, const int32_t* op_ref, const int32_t* op_qry,
+                             const int32_t* op_len, const uint8_t* seq, const uint8_t* ref, int32_t ref_start0, int32_t ref_len,
+                             const int32_t* centers, int32_t n_centers, int left_edge, int32_t* counts, int32_t* opened) {
+  clairb::ct::Alignments a{read_pos, read_end, read_maxend, read_op0, read_strand, op_ref, op_qry, op_len,
+                           seq,      ref,      ref_start0,  ref_len,  n_reads};
+  for (int ci = 0; ci < n_centers; ++ci) {
+    PlainAdd add{counts + (size_t)ci * clairb::ct::ELEMS};
+    int first, last, n = 0;
+    clairb::ct::read_range(a, centers[ci], left_edge != 0, first, last);
+    for (int r = first; r < last; ++r) n += clairb::ct::fold_read(a, r, centers[ci], left_edge != 0, add) ? 1 : 0;
+    // every read outside [first, last) must be rejected by the rule itself
+    static int scratch[clairb::ct::ELEMS];
+    PlainAdd sink{scratch};
+    for (int r = 0; r < n_reads; ++r)
+      if ((r < first || r >= last) && clairb::ct::fold_read(a, r, centers[ci], left_edge != 0, sink)) return 1 + ci;
+    opened[ci] = n;
+  }
+  return 0;
+}

@@ -1,0 +1,215 @@
+"""CreateTensor on the device.
+
+not gpu: the oracle restatement and the kernel's per-site rule (its __host__ __device__ half compiled for the CPU by
+         tests/harness) against rows printed by the reference's own OutputAlnTensor (tests/golden/create_tensor_cases.json.gz,
+         made by oracle/gen_golden_create_tensor.py); the host encoder.
+gpu:     the CUDA kernel through the C-ABI against the same golden rows and, on larger random regions, against the oracle;
+         tensors born on the device fed to the forward pass against the host-fed forward (bit-identical).
+"""
+import ctypes
+import gzip
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from clair_b200 import create_tensor as CT                      # noqa: E402
+from oracle import create_tensor_oracle as O                    # noqa: E402
+from oracle import gen_golden_create_tensor as G                # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "create_tensor_cases.json.gz")
+
+
+def golden_cases():
+    with gzip.open(GOLDEN) as f:
+        return json.loads(f.read())
+
+
+def reference_window(case):
+    """What `samtools faidx` would have handed the reference for this case (CreateTensor.py:115-159)."""
+    a = case["args"]
+    if a["ctgStart"] is None:
+        return case["contig"].upper(), 0
+    lo = max(1, a["ctgStart"] - a["expandReferenceRegion"])
+    hi = a["ctgEnd"] + a["expandReferenceRegion"]
+    return case["contig"][lo - 1:hi].upper(), lo - 1
+
+
+def candidates_of(case):
+    return [int(l.split()[1]) for l in case["candidates"]]
+
+
+def oracle_rows(case):
+    a = case["args"]
+    seq, start0 = reference_window(case)
+    return O.create_tensors(case["sam"], candidates_of(case), seq, start0, a["ctgName"], a["minMQ"], a["dcov"],
+                            a["minCoverage"], not a["stop_consider_left_edge"], a["ctgStart"], a["ctgEnd"])
+
+
+CASES = golden_cases()
+CASE_IDS = [c["name"] for c in CASES]
+
+
+@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+def test_oracle_reproduces_reference_rows(case):
+    assert [O.format_row(r) for r in oracle_rows(case)] == case["expected"]
+
+
+# ---- the kernel's rule, compiled for the host ------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def host_rule(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("ct_harness") / "ct_host.so")
+    src = os.path.join(ROOT, "tests", "harness", "create_tensor_host.cu")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-shared", "-Xcompiler", "-fPIC", "-o", out, src],
+                   check=True)
+    lib = ctypes.CDLL(out)
+    lib.ct_host_sites.restype = ctypes.c_int
+    return lib
+
+
+def host_rule_rows(lib, case):
+    """Same host-side steps as clair_b200.create_tensor.create_tensors, the device call replaced by the host-compiled rule."""
+    a = case["args"]
+    seq, start0 = reference_window(case)
+    aln = CT.encode_alignments(case["sam"], a["minMQ"], a["dcov"])
+    cand = np.unique(np.asarray(candidates_of(case), np.int64))
+    if a["ctgStart"] is not None:
+        cand = cand[(cand >= a["ctgStart"]) & (cand <= a["ctgEnd"])]
+    cand = cand[cand - start0 - 17 >= 0]
+    centers = cand.astype(np.int32)
+    n = centers.shape[0]
+    counts = np.zeros((n, 1056), np.int32)
+    opened = np.zeros(n, np.int32)
+    ref = np.frombuffer(seq.encode(), np.uint8)
+    maxend = np.maximum.accumulate(aln.read_end) if aln.n_reads else np.zeros(0, np.int32)
+
+    def p(arr):
+        return arr.ctypes.data_as(ctypes.c_void_p)
+
+    rc = lib.ct_host_sites(p(aln.read_pos), p(aln.read_end), p(maxend), p(aln.read_op0), p(aln.read_strand),
+                           ctypes.c_int32(aln.n_reads), p(aln.op_ref), p(aln.op_qry), p(aln.op_len), p(aln.seq), p(ref),
+                           ctypes.c_int32(start0), ctypes.c_int32(ref.shape[0]), p(centers), ctypes.c_int32(n),
+                           ctypes.c_int(0 if a["stop_consider_left_edge"] else 1), p(counts), p(opened))
+    assert rc == 0, "a read outside the searched range opens site %d" % (rc - 1)
+    rows = []
+    for i in range(n):
+        depth = counts[i].reshape(33, 8, 4)[16, :, 0].sum()
+        if opened[i] > 0 and depth >= a["minCoverage"]:
+            s = int(cand[i]) - start0 - 17
+            rows.append((a["ctgName"], int(cand[i]), seq[s:s + 33], counts[i]))
+    return rows
+
+
+@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+def test_kernel_rule_on_host_reproduces_reference_rows(host_rule, case):
+    assert [O.format_row(r) for r in host_rule_rows(host_rule, case)] == case["expected"]
+
+
+def test_kernel_rule_on_host_random_regions(host_rule):
+    rng = np.random.default_rng(77)
+    for k in range(6):
+        case = G.make_case(rng, "rnd%d" % k, 4000, 900, 400, style=["mixed", "dense", "leading"][k % 3],
+                           stop_left=(k == 4), dup_rate=0.2, dcov=5)
+        want = oracle_rows(case)
+        got = host_rule_rows(host_rule, case)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g[:3] == w[:3] and np.array_equal(g[3], w[3].reshape(-1))
+
+
+# ---- host encoder ----------------------------------------------------------------------------------------------------
+def test_encoder_filters_and_offsets():
+    sam = ["@HD\tVN:1.6",
+           "r0\t0\tc\t11\t60\t2S3M1I2M2D1M3H\t*\t0\t0\tNNACGTTTA\t*",      # S skips 2 query bases, H skips nothing
+           "r1\t16\tc\t11\t5\t4M\t*\t0\t0\tACGT\t*",                         # below minMQ
+           "r2\t16\tc\t11\t60\t2M5N2M\t*\t0\t0\tacgt\t*",                    # N advances nothing (CreateTensor.py:283-366)
+           "r3\t0\tc\t11\t60\t4M\t*\t0\t0\tACGT\t*",                         # third read at POS 10 -> depth cap 2 drops it
+           "r4\t0\tc\t15\t60\t*\t*\t0\t0\tAC\t*"]
+    a = CT.encode_alignments(sam, min_mq=10, dcov=2)
+    assert a.read_pos.tolist() == [10, 10, 14] and a.read_strand.tolist() == [0, 1, 0]
+    assert a.read_end.tolist() == [18, 14, 14]
+    assert a.read_op0.tolist() == [0, 5, 7, 7]
+    assert (a.op_len & 3).tolist() == [0, 1, 0, 2, 0, 0, 0] and (a.op_len >> 2).tolist() == [3, 1, 2, 2, 1, 2, 2]
+    assert a.op_ref.tolist() == [10, 13, 13, 15, 17, 10, 12]
+    assert a.op_qry.tolist() == [2, 5, 6, 8, 8, 9, 11]
+    assert bytes(a.seq) == b"NNACGTTTAacgtAC"
+    with pytest.raises(ValueError):
+        CT.encode_alignments(["r\t0\tc\t5\t60\t10M\t*\t0\t0\tACGT\t*"])
+    with pytest.raises(ValueError):
+        CT.encode_alignments(["a\t0\tc\t9\t60\t1M\t*\t0\t0\tA\t*", "b\t0\tc\t5\t60\t1M\t*\t0\t0\tA\t*"])
+    empty = CT.encode_alignments(["@SQ\tSN:c"])
+    assert empty.n_reads == 0 and empty.n_ops == 0 and empty.read_op0.tolist() == [0]
+
+
+# ---- GPU -------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def model():
+    from clair_b200 import weights as W
+    from clair_b200.model import Clair
+    m = Clair(max_sites=4096, batch_sites=1000)
+    m.set_weights(W.random_weights(seed=1234))
+    yield m
+    m.close()
+
+
+def device_block(model, case, **kw):
+    a = case["args"]
+    seq, start0 = reference_window(case)
+    aln = CT.encode_alignments(case["sam"], a["minMQ"], a["dcov"])
+    return CT.create_tensors(model, aln, candidates_of(case), seq, start0, a["ctgName"], a["minCoverage"],
+                             not a["stop_consider_left_edge"], a["ctgStart"], a["ctgEnd"], **kw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+def test_device_rows_equal_reference_rows(model, case):
+    assert device_block(model, case).text_rows() == case["expected"]
+
+
+@pytest.mark.gpu
+def test_device_random_regions_equal_oracle(model):
+    rng = np.random.default_rng(78)
+    for k in range(4):
+        case = G.make_case(rng, "big%d" % k, 6000, 1500, 700, style=["mixed", "dense", "leading", "short"][k],
+                           stop_left=(k == 2), dup_rate=0.2, dcov=5)
+        want = oracle_rows(case)
+        block = device_block(model, case)
+        assert block.positions.tolist() == [r[1] for r in want] and block.sequences == [r[2] for r in want]
+        assert np.array_equal(block.x, np.stack([r[3] for r in want]).astype(np.int16))
+        # the subtracted form is what tensor_generator_from hands the network (clair/utils.py:96-98)
+        sub = device_block(model, case, subtract=True)
+        expect = block.x.copy()
+        expect[..., 1:] -= expect[..., 0:1]
+        assert np.array_equal(sub.x, expect)
+
+
+@pytest.mark.gpu
+def test_device_born_tensors_through_forward(model):
+    rng = np.random.default_rng(79)
+    case = G.make_case(rng, "fwd", 5000, 2500, 600)
+    block = device_block(model, case, subtract=True)
+    keep = block.callable_sites()
+    assert 0 < keep.shape[0] <= len(block)
+    got = block.predict(keep)
+    want = model.predict_packed(block.x[keep])
+    assert np.array_equal(got, want)
+    batches = list(CT.created_tensor_generator_from(block, 250))
+    assert sum(len(info) for _, info in batches) == keep.shape[0]
+    assert np.array_equal(np.concatenate([p for p, _ in batches]), want)
+    assert batches[0][1][0] == [block.ctg_name, str(int(block.positions[keep[0]])), block.sequences[keep[0]]]
+
+
+@pytest.mark.gpu
+def test_device_argument_errors(model):
+    case = CASES[0]
+    seq, start0 = reference_window(case)
+    aln = CT.encode_alignments(case["sam"])
+    aln.read_pos = aln.read_pos[::-1].copy()
+    with pytest.raises(ValueError):
+        CT.create_tensors(model, aln, candidates_of(case), seq, start0)
