@@ -159,7 +159,7 @@ class TensorBlock(object):
         """The rows CreateTensor.py prints (:57-62); needs raw counts fetched to the host."""
         if self.x is None or self.subtracted:
             raise ValueError("text rows need create_tensors(..., fetch=True, subtract=False)")
-        flat = self.x.reshape(len(self), -1)
+        flat = self.x.reshape(len(self), N_POS * 8 * 4)
         return ["%s %d %s %s" % (self.ctg_name, p, s, " ".join(map(str, r.tolist())))
                 for p, s, r in zip(self.positions.tolist(), self.sequences, flat)]
 

@@ -156,31 +156,33 @@ constexpr int F_SUBTRACT = 2;       // write channels 1..3 minus channel 0 (clai
 
 // x_out: [n_centers][1056] int16; meta: [n_centers][2] = reads that opened the window (0: the reference prints no row),
 // depth at the centre position (depth[flanking_base_num], compared with --minCoverage at :55); overflow: set when a
-// count does not fit int16
+// count does not fit int16.
+// One WARP per candidate site (a window is reached by a few dozen reads: one or two rounds of 32 lanes, one read per lane),
+// SITES_PER_BLOCK sites per block, each with its own 4.2 KB of counters; only warp-level synchronisation.
+constexpr int SITES_PER_BLOCK = THREADS / 32;
+
 __global__ void __launch_bounds__(THREADS) create_tensors(Alignments a, const int32_t* __restrict__ centers, int n_centers,
                                                           int flags, int16_t* __restrict__ x_out, int32_t* __restrict__ meta,
                                                           int* __restrict__ overflow) {
-  __shared__ int cnt[ELEMS];
-  __shared__ int range[2];
-  __shared__ int opened;
+  __shared__ int cnt_all[SITES_PER_BLOCK][ELEMS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* cnt = cnt_all[warp];
   const bool left_edge = flags & F_LEFT_EDGE;
-  for (int ci = blockIdx.x; ci < n_centers; ci += gridDim.x) {
+  for (int ci = blockIdx.x * SITES_PER_BLOCK + warp; ci < n_centers; ci += gridDim.x * SITES_PER_BLOCK) {
     const int center = centers[ci];
-    for (int i = threadIdx.x; i < ELEMS; i += THREADS) cnt[i] = 0;
-    if (threadIdx.x == 0) {
-      opened = 0;
-      read_range(a, center, left_edge, range[0], range[1]);
-    }
-    __syncthreads();
+    for (int i = lane; i < ELEMS; i += 32) cnt[i] = 0;
+    int first, last;
+    read_range(a, center, left_edge, first, last);       // warp-uniform: every lane walks the same two searches
+    __syncwarp();
     SharedAdd add{cnt};
-    int mine = 0;
-    for (int r = range[0] + threadIdx.x; r < range[1]; r += THREADS) mine += fold_read(a, r, center, left_edge, add) ? 1 : 0;
-    if (mine) atomicAdd(&opened, mine);
-    __syncthreads();
+    int opened = 0;
+    for (int r = first + lane; r < last; r += 32) opened += fold_read(a, r, center, left_edge, add) ? 1 : 0;
+    opened = __reduce_add_sync(0xffffffffu, opened);
+    __syncwarp();
     // one row out: 528 words of two int16 = channels (0,1) or (2,3) of a cell
     uint32_t* out = reinterpret_cast<uint32_t*>(x_out + (size_t)ci * ELEMS);
     bool ovf = false;
-    for (int w = threadIdx.x; w < ELEMS / 2; w += THREADS) {
+    for (int w = lane; w < ELEMS / 2; w += 32) {
       const int cell = (w >> 1) * 4;
       const int c0 = cnt[cell];
       int v0, v1;
@@ -193,18 +195,14 @@ __global__ void __launch_bounds__(THREADS) create_tensors(Alignments a, const in
       out[w] = (uint32_t)(uint16_t)(int16_t)v0 | ((uint32_t)(uint16_t)(int16_t)v1 << 16);
     }
     if (ovf) *overflow = 1;
-    if (threadIdx.x < 8) {
-      // depth at the centre = aligned bases at position index 16 = sum over rows of channel 0
-      int d = cnt[FLANK * 32 + threadIdx.x * 4];
-      d += __shfl_down_sync(0xff, d, 4, 8);
-      d += __shfl_down_sync(0xff, d, 2, 8);
-      d += __shfl_down_sync(0xff, d, 1, 8);
-      if (threadIdx.x == 0) {
-        meta[2 * ci] = opened;
-        meta[2 * ci + 1] = d;
-      }
+    // depth at the centre = aligned bases at position index 16 = sum over the 8 rows of channel 0
+    int d = lane < 8 ? cnt[FLANK * 32 + lane * 4] : 0;
+    d = __reduce_add_sync(0xffffffffu, d);
+    if (lane == 0) {
+      meta[2 * ci] = opened;
+      meta[2 * ci + 1] = d;
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 

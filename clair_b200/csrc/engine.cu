@@ -863,8 +863,9 @@ int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const in
   da.ref_start0 = a->ref_start0;  da.ref_len = (int32_t)a->ref_len;  da.n_reads = (int32_t)R;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
-  const int64_t resident = (int64_t)sms * 16;        // 16 blocks of 128 threads per SM: a persistent grid, one wave
-  const unsigned grid = (unsigned)(n_centers < resident ? n_centers : resident);
+  // persistent grid: 13 blocks of 4 warps (4 sites, 16.9 KB of counters) fit an SM's shared memory
+  const int64_t resident = (int64_t)sms * 13, blocks = (n_centers + ct::SITES_PER_BLOCK - 1) / ct::SITES_PER_BLOCK;
+  const unsigned grid = (unsigned)(blocks < resident ? blocks : resident);
   {
     ProfScope ps(e, 14, st);
     ct::create_tensors<<<grid, ct::THREADS, 0, st>>>(da, (const int32_t*)e->ct_in[10].p, (int)n_centers, flags,

@@ -66,7 +66,7 @@ def host_rule(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("ct_harness") / "ct_host.so")
     src = os.path.join(ROOT, "tests", "harness", "create_tensor_host.cu")
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-shared", "-Xcompiler", "-fPIC", "-o", out, src],
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", out, src],
                    check=True)
     lib = ctypes.CDLL(out)
     lib.ct_host_sites.restype = ctypes.c_int
