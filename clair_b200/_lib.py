@@ -31,6 +31,9 @@ SYMBOLS = {
     "clairb_decide": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p]),
     "clairb_create_tensors": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "clairb_predict_created": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p]),
+    "clairb_encode_sam": (_c.c_int, [_c.c_char_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int64,
+                                     _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                     _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
     "clairb_decode_rows": (_c.c_int, [_c.c_char_p, _c.c_int64, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p,
                                       _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
     "clairb_get_layer": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int64]),

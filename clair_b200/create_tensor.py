@@ -54,9 +54,64 @@ class Alignments(object):
         return int(self.op_ref.shape[0])
 
 
-def encode_alignments(sam_lines, min_mq=0, dcov=250):
-    """`samtools view` rows -> Alignments.  The row filters are the reference's (CreateTensor.py:253-281); the CIGAR strings
-    of all kept reads are parsed in one vectorised pass."""
+def _pinned_empty(n, dtype):
+    """numpy array over page-locked host memory (clairb_host_alloc): uploads from it run at full PCIe rate and
+    asynchronously; freed when the array is collected."""
+    import weakref
+    lib = _lib.load()
+    nbytes = max(1, int(n)) * np.dtype(dtype).itemsize
+    ptr = ctypes.c_void_p()
+    _lib.check(lib.clairb_host_alloc(ctypes.byref(ptr), nbytes), None, "clairb_host_alloc")
+    buf = (ctypes.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+    weakref.finalize(buf, lib.clairb_host_free, ptr)
+    return arr
+
+
+def _as_text_block(sam):
+    if isinstance(sam, (bytes, bytearray, memoryview)):
+        return bytes(sam)
+    if isinstance(sam, str):
+        return sam.encode("ascii", "replace")
+    rows = [r if isinstance(r, bytes) else r.encode("ascii", "replace") for r in sam]
+    return b"".join(r if r.endswith(b"\n") else r + b"\n" for r in rows)
+
+
+def encode_alignments(sam, min_mq=0, dcov=250, encoder="native", pinned=False):
+    """`samtools view` rows (an iterable of rows, or one text block) -> Alignments.
+
+    encoder="native": clairb_encode_sam (csrc/encode_host.cuh), multi-threaded host code; with pinned=True the arrays live
+    in page-locked memory.  encoder="python": the numpy restatement below, kept as the cross-check."""
+    if encoder == "python":
+        rows = sam.splitlines() if isinstance(sam, (str, bytes, bytearray)) else sam
+        return _encode_alignments_python(rows, min_mq, dcov)
+    if encoder != "native":
+        raise ValueError("encoder must be 'native' or 'python'")
+    lib = _lib.load()
+    text = _as_text_block(sam)
+    state = (ctypes.c_int32 * 3)(0, 0, -2 ** 31)
+    n = [ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()]
+    refs = [ctypes.byref(v) for v in n]
+    rc = lib.clairb_encode_sam(text, len(text), int(min_mq), int(dcov), state, 0, 0, 0, None, None, None, None, None, None, None,
+                               None, *refs)
+    _lib.check(rc, None, "clairb_encode_sam")
+    R, O, B = (int(v.value) for v in n)
+    empty = _pinned_empty if pinned else (lambda k, dt: np.empty(int(k), dt))
+    a = Alignments()
+    a.read_pos, a.read_end, a.read_op0 = empty(R, np.int32), empty(R, np.int32), empty(R + 1, np.int32)
+    a.read_strand = empty(R, np.uint8)
+    a.op_ref, a.op_qry, a.op_len = empty(O, np.int32), empty(O, np.int32), empty(O, np.int32)
+    a.seq = empty(B, np.uint8)
+    ptr = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.clairb_encode_sam(text, len(text), int(min_mq), int(dcov), state, R, O, B, ptr(a.read_pos), ptr(a.read_end),
+                               ptr(a.read_op0), ptr(a.read_strand), ptr(a.op_ref), ptr(a.op_qry), ptr(a.op_len), ptr(a.seq), *refs)
+    _lib.check(rc, None, "clairb_encode_sam")
+    return a
+
+
+def _encode_alignments_python(sam_lines, min_mq=0, dcov=250):
+    """The row filters are the reference's (CreateTensor.py:253-281); the CIGAR strings of all kept reads are parsed in one
+    vectorised numpy pass."""
     pos_l, strand_l, cigars, seqs = [], [], [], []
     previous_position, depth_cap = 0, 0
     for line in sam_lines:

@@ -22,6 +22,7 @@
 #include "decide_kernels.cuh"
 #include "decode_host.cuh"
 #include "create_tensor_kernels.cuh"
+#include "encode_host.cuh"
 
 using namespace clairb;
 
@@ -909,6 +910,29 @@ int clairb_predict_created(clairb_engine* e, const int64_t* rows, int64_t n, flo
   CU_TRY(e, cudaMemcpyAsync(out_host, e->ct_out.p, (size_t)n * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_TRY(e, cudaStreamSynchronize(st));
   return CLAIRB_OK;
+}
+
+int clairb_encode_sam(const char* text, int64_t text_len, int min_mq, int dcov, int32_t* state, int64_t cap_reads, int64_t cap_ops,
+                      int64_t cap_bases, int32_t* read_pos, int32_t* read_end, int32_t* read_op0, uint8_t* read_strand, int32_t* op_ref,
+                      int32_t* op_qry, int32_t* op_len, uint8_t* seq, int64_t* n_reads, int64_t* n_ops, int64_t* n_bases) {
+  if ((!text && text_len) || text_len < 0 || !state || !n_reads || !n_ops || !n_bases)
+    return fail(nullptr, CLAIRB_EINVAL, "encode_sam: bad arguments");
+  const bool fill = read_pos != nullptr;
+  if (fill && (!read_end || !read_op0 || !read_strand || (cap_ops && (!op_ref || !op_qry || !op_len)) || (cap_bases && !seq)))
+    return fail(nullptr, CLAIRB_EINVAL, "encode_sam: output arrays missing");
+  static const int threads = getenv("CLAIRB_DECODE_THREADS") ? atoi(getenv("CLAIRB_DECODE_THREADS")) : 4;
+  sam::Out out{read_pos, read_end, read_op0, read_strand, op_ref, op_qry, op_len, seq};
+  int64_t bad = -1;
+  const int rc = sam::encode(text, text_len, min_mq, dcov, state, fill ? &out : nullptr, cap_reads, cap_ops, cap_bases, n_reads, n_ops,
+                             n_bases, &bad, threads);
+  switch (rc) {
+    case sam::OK: return CLAIRB_OK;
+    case sam::MALFORMED: return fail(nullptr, CLAIRB_EINVAL, "encode_sam: row %lld is not a SAM alignment row (needs 10 columns, integer FLAG / POS / MAPQ)", (long long)bad);
+    case sam::UNSORTED: return fail(nullptr, CLAIRB_EINVAL, "encode_sam: row %lld: alignments are not coordinate-sorted", (long long)bad);
+    case sam::CIGAR_BEYOND_SEQ: return fail(nullptr, CLAIRB_EINVAL, "encode_sam: read %lld: CIGAR consumes more bases than SEQ holds", (long long)bad);
+    case sam::CAPACITY: return fail(nullptr, CLAIRB_EINVAL, "encode_sam: output arrays too small (%lld reads, %lld ops, %lld bases)", (long long)*n_reads, (long long)*n_ops, (long long)*n_bases);
+    default: return fail(nullptr, CLAIRB_EINVAL, "encode_sam: block too large for int32 offsets: split the region");
+  }
 }
 
 int clairb_decode_rows(const char* text, int64_t text_len, int64_t max_rows, int dtype, void* x_out, int32_t* info_off,

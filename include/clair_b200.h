@@ -181,6 +181,21 @@ int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const in
  * out_host: [n,90] float32 as clairb_predict. */
 int clairb_predict_created(clairb_engine* e, const int64_t* rows, int64_t n, float* out_host);
 
+/* Host-only (no device): `samtools view` text -> the arrays of clairb_alignments.  Replaces what the reference does per
+ * SAM row before and while it walks the CIGAR string (dataPrepScripts/CreateTensor.py:251-296): '@' rows skipped, the
+ * mapping-quality filter (:264), the per-POS depth cap (:274-281) and the CIGAR grammar (:283-366).
+ * state: [3] int32 carried across the blocks of one stream = previous_position, depthCap (:249-250; start both at 0) and
+ *   the POS of the last kept read (start at -2147483648); updated only by a filling call.
+ * With read_pos == NULL nothing is written: the call only reports n_reads / n_ops / n_bases so that the caller can size
+ * the arrays (read_op0 holds n_reads + 1 entries), e.g. in pinned memory from clairb_host_alloc.
+ * Rows must be complete lines; CLAIRB_EINVAL for a malformed row, unsorted rows, or a CIGAR that consumes more bases
+ * than SEQ holds (the reference raises IndexError there); message via clairb_last_error(NULL). */
+int clairb_encode_sam(const char* text, int64_t text_len, int min_mq, int dcov, int32_t* state,
+                      int64_t cap_reads, int64_t cap_ops, int64_t cap_bases,
+                      int32_t* read_pos, int32_t* read_end, int32_t* read_op0, uint8_t* read_strand,
+                      int32_t* op_ref, int32_t* op_qry, int32_t* op_len, uint8_t* seq,
+                      int64_t* n_reads, int64_t* n_ops, int64_t* n_bases);
+
 /* Host-only (no device): replaces the per-row `row.split()` + `np.array(columns, float32)` of
  * tensor_generator_from (clair/utils.py:81-98) for one predict-batch of text rows (CreateTensor.py:60-65).
  * Parses complete '\n'-terminated lines of `text` until max_rows lines are read; rows whose centre base

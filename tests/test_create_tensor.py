@@ -124,14 +124,15 @@ def test_kernel_rule_on_host_random_regions(host_rule):
 
 
 # ---- host encoder ----------------------------------------------------------------------------------------------------
-def test_encoder_filters_and_offsets():
+@pytest.mark.parametrize("encoder", ["native", "python"])
+def test_encoder_filters_and_offsets(encoder):
     sam = ["@HD\tVN:1.6",
            "r0\t0\tc\t11\t60\t2S3M1I2M2D1M3H\t*\t0\t0\tNNACGTTTA\t*",      # S skips 2 query bases, H skips nothing
            "r1\t16\tc\t11\t5\t4M\t*\t0\t0\tACGT\t*",                         # below minMQ
            "r2\t16\tc\t11\t60\t2M5N2M\t*\t0\t0\tacgt\t*",                    # N advances nothing (CreateTensor.py:283-366)
            "r3\t0\tc\t11\t60\t4M\t*\t0\t0\tACGT\t*",                         # third read at POS 10 -> depth cap 2 drops it
            "r4\t0\tc\t15\t60\t*\t*\t0\t0\tAC\t*"]
-    a = CT.encode_alignments(sam, min_mq=10, dcov=2)
+    a = CT.encode_alignments(sam, min_mq=10, dcov=2, encoder=encoder)
     assert a.read_pos.tolist() == [10, 10, 14] and a.read_strand.tolist() == [0, 1, 0]
     assert a.read_end.tolist() == [18, 14, 14]
     assert a.read_op0.tolist() == [0, 5, 7, 7]
@@ -139,12 +140,33 @@ def test_encoder_filters_and_offsets():
     assert a.op_ref.tolist() == [10, 13, 13, 15, 17, 10, 12]
     assert a.op_qry.tolist() == [2, 5, 6, 8, 8, 9, 11]
     assert bytes(a.seq) == b"NNACGTTTAacgtAC"
-    with pytest.raises(ValueError):
-        CT.encode_alignments(["r\t0\tc\t5\t60\t10M\t*\t0\t0\tACGT\t*"])
-    with pytest.raises(ValueError):
-        CT.encode_alignments(["a\t0\tc\t9\t60\t1M\t*\t0\t0\tA\t*", "b\t0\tc\t5\t60\t1M\t*\t0\t0\tA\t*"])
-    empty = CT.encode_alignments(["@SQ\tSN:c"])
+    with pytest.raises(ValueError):                       # CIGAR consumes more bases than SEQ holds
+        CT.encode_alignments(["r\t0\tc\t5\t60\t10M\t*\t0\t0\tACGT\t*"], encoder=encoder)
+    with pytest.raises(ValueError):                       # not coordinate-sorted
+        CT.encode_alignments(["a\t0\tc\t9\t60\t1M\t*\t0\t0\tA\t*", "b\t0\tc\t5\t60\t1M\t*\t0\t0\tA\t*"], encoder=encoder)
+    empty = CT.encode_alignments(["@SQ\tSN:c"], encoder=encoder)
     assert empty.n_reads == 0 and empty.n_ops == 0 and empty.read_op0.tolist() == [0]
+
+
+@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+def test_native_encoder_equals_python_encoder(case):
+    a = case["args"]
+    native = CT.encode_alignments(case["sam"], a["minMQ"], a["dcov"])
+    python = CT.encode_alignments(case["sam"], a["minMQ"], a["dcov"], encoder="python")
+    for field in CT.Alignments.__slots__:
+        assert np.array_equal(getattr(native, field), getattr(python, field)), field
+    # one text block, CRLF rows, no final newline: same arrays
+    block = "\r\n".join(case["sam"])
+    again = CT.encode_alignments(block, a["minMQ"], a["dcov"])
+    for field in CT.Alignments.__slots__:
+        assert np.array_equal(getattr(native, field), getattr(again, field)), field
+
+
+def test_native_encoder_rejects_malformed_rows():
+    with pytest.raises(ValueError):
+        CT.encode_alignments(["r\t0\tc\tnot_a_number\t60\t1M\t*\t0\t0\tA\t*"])
+    with pytest.raises(ValueError):
+        CT.encode_alignments(["r\t0\tc\t5\t60\t1M"])
 
 
 # ---- GPU -------------------------------------------------------------------------------------------------------------
