@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--batches-per-step", type=int, default=142)
     ap.add_argument("--cpu-baseline-batches", type=int, default=0, help="0 = auto (about 10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-create-tensor", action="store_true", help="skip the CreateTensor-stage line (SURVEY 8f row 4)")
     return ap.parse_args()
 
 
@@ -404,6 +405,14 @@ def main():
                         "kernel_share": {k: v["ms"] / max(1e-9, sum(p["ms"] for p in profile)) for k, v in prof.items()},
                         "note": "logit tolerance 1e-4 needs the 3-term fp16 split (3 MMAs per algorithmic MAC): attainable "
                                 "ceiling is 1/3 of peak, i.e. frac 0.333 = tensor pipe saturated"}
+        # ---- CreateTensor stage: alignments -> tensors on the device, outside the timed region ----
+        ct_info = ct_ctx = None
+        if world == 1 and not args.no_create_tensor:
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+            import ct_bench
+            launches_before_ct = m.kernel_launches()
+            ct_info, ct_ctx = ct_bench.device_part(m, 2000000, 5, True, measured_peaks()["hbm_gbs"])
+            ct_info["gpu_launches"] = m.kernel_launches() - launches_before_ct
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             nb = args.cpu_baseline_batches or 24
@@ -425,6 +434,8 @@ def main():
             assert np.array_equal(got, want) and np.array_equal(dec.max_probability[:ns], want_p), "decision parity failed"
             decision_info["cpu_python_restatement_sites_per_s"] = cpu_dec
             decision_info["cpu_sample"] = "%d sites, 1 core; device records bit-exact on them" % ns
+            if ct_info is not None:
+                ct_bench.cpu_part(ct_info, ct_ctx)
             cpu = {"value": v, "unit": "sites/s", "cores": threads, "kind": "port",
                    "sample": "%d predict-batches x %d sites of the same pool, %.1f s" % (nb, BATCH, dt),
                    "parity_vs_gpu": {"max_abs_prob_diff": err, "argmax_identical": True, "sites": BATCH},
@@ -448,6 +459,7 @@ def main():
                     "h2d_ceiling_sites_per_s": world * h2d_gbs * 1e9 / 4224,
                     "note": "float32 input (the reference generator's dtype): bounded by the pinned host->device copy"},
             "decision_stage": decision_info,
+            "create_tensor_stage": ct_info,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -33,6 +33,9 @@ for _ch in "M=X":
     _CODE[ord(_ch)] = OP_M
 _CODE[ord("I")] = OP_I
 _CODE[ord("D")] = OP_D
+_IS_IUPAC = np.zeros(256, bool)
+for _ch in IUPAC_BASES:
+    _IS_IUPAC[ord(_ch)] = True
 _REF_ADV = np.zeros(256, bool)
 _QRY_ADV = np.zeros(256, bool)
 for _ch in "M=XD":                               # CreateTensor.py:294,337: ops that advance the reference position
@@ -199,13 +202,22 @@ def _ptr(arr):
 class TensorBlock(object):
     """Result of one `create_tensors` call: the sites the reference would have printed, in its output order.
 
-    positions [n] (1-based centres), sequences [n] (the 33-base reference windows of the rows, :59), depth [n] (aligned
-    bases at the centre), rows [n] (index into the device-resident block), and - when fetched - x [n,33,8,4] int16."""
+    positions [n] (1-based centres), sequences [n] (the 33-base reference windows of the rows, :59; built on first use),
+    depth [n] (aligned bases at the centre), rows [n] (index into the device-resident block), and - when fetched -
+    x [n,33,8,4] int16."""
 
-    def __init__(self, model, ctg_name, positions, sequences, depth, rows, x, subtracted):
+    def __init__(self, model, ctg_name, positions, reference_sequence, window_start, depth, rows, x, subtracted):
         self.model, self.ctg_name = model, ctg_name
-        self.positions, self.sequences, self.depth, self.rows, self.x = positions, sequences, depth, rows, x
+        self.positions, self.depth, self.rows, self.x = positions, depth, rows, x
         self.subtracted = subtracted
+        self._reference, self._start, self._sequences = reference_sequence, window_start, None
+
+    @property
+    def sequences(self):
+        if self._sequences is None:
+            ref = self._reference
+            self._sequences = [ref[s:s + N_POS] for s in self._start.tolist()]                # CreateTensor.py:59
+        return self._sequences
 
     def __len__(self):
         return int(self.positions.shape[0])
@@ -221,7 +233,12 @@ class TensorBlock(object):
     def callable_sites(self):
         """Indices (into this block) of the sites tensor_generator_from keeps: centre base is an IUPAC code
         (clair/utils.py:90; a window cut short by the end of the contig fails the same test there by IndexError)."""
-        return np.array([i for i, s in enumerate(self.sequences) if len(s) > FLANK and s[FLANK] in IUPAC_BASES], np.int64)
+        ref = np.frombuffer(self._reference.encode("ascii", "replace"), np.uint8)
+        at = self._start + FLANK
+        inside = at < ref.shape[0]
+        ok = np.zeros(len(self), bool)
+        ok[inside] = _IS_IUPAC[ref[at[inside]]]
+        return np.flatnonzero(ok).astype(np.int64)
 
     def predict(self, which=None):
         """Forward pass over sites of this block without the tensors leaving the device -> [n,90] float32."""
@@ -246,14 +263,16 @@ def create_tensors(model, alignments, candidate_positions, reference_sequence, r
                    min_coverage=0, consider_left_edge=True, ctg_start=None, ctg_end=None, subtract=False, fetch=True):
     """Counts for every candidate site of one region -> TensorBlock.  `model` is a clair_b200.model.Clair (it owns the
     device handle; weights are only needed for TensorBlock.predict)."""
-    cand = np.unique(np.asarray(list(candidate_positions), np.int64))                     # ascending, duplicates are no-ops (:304)
+    if not isinstance(candidate_positions, np.ndarray):
+        candidate_positions = list(candidate_positions)
+    cand = np.unique(np.asarray(candidate_positions, np.int64))                              # ascending, duplicates are no-ops (:304)
     if ctg_start is not None and ctg_end is not None:
         cand = cand[(cand >= ctg_start) & (cand <= ctg_end)]                                # :83
     cand = cand[cand - reference_start_0_based - (FLANK + 1) >= 0]                          # :55
     ref = np.frombuffer(reference_sequence.encode("ascii", "replace"), np.uint8)
     n = int(cand.shape[0])
-    empty = TensorBlock(model, ctg_name, np.zeros(0, np.int64), [], np.zeros(0, np.int32), np.zeros(0, np.int64),
-                        np.zeros((0, N_POS, 8, 4), np.int16) if fetch else None, subtract)
+    empty = TensorBlock(model, ctg_name, np.zeros(0, np.int64), reference_sequence, np.zeros(0, np.int64), np.zeros(0, np.int32),
+                        np.zeros(0, np.int64), np.zeros((0, N_POS, 8, 4), np.int16) if fetch else None, subtract)
     if n == 0 or alignments.n_reads == 0 or ref.size == 0:
         return empty
     if cand.max() >= 2 ** 31 - 64:
@@ -274,9 +293,8 @@ def create_tensors(model, alignments, candidate_positions, reference_sequence, r
     rows = np.flatnonzero((meta[:, 0] > 0) & (meta[:, 1] >= min_coverage))                  # a row exists (:303) and :55
     positions = cand[rows]
     start = positions - reference_start_0_based - (FLANK + 1)
-    sequences = [reference_sequence[s:s + N_POS] for s in start.tolist()]                   # :59
-    return TensorBlock(model, ctg_name, positions, sequences, meta[rows, 1].copy(), rows.astype(np.int64),
-                       x[rows] if fetch else None, subtract)
+    return TensorBlock(model, ctg_name, positions, reference_sequence, start, meta[rows, 1].copy(), rows.astype(np.int64),
+                       (x if rows.shape[0] == n else x[rows]) if fetch else None, subtract)
 
 
 def created_tensor_generator_from(block, batch_size):

@@ -32,15 +32,28 @@ constexpr int THREADS = 128;
 
 // shared/utils.py:24-27 (IUPAC code -> A,C,G,T row), lower case folded as SEQ.upper() / sequence.upper() do
 // (CreateTensor.py:149,261); 255 = not a base, the record is skipped (:37-38)
+// Branch-free: fold the case bit, index the 26 letters into two packed constants (a switch here diverges per lane and was
+// 80 % of the kernel's instructions).
+__host__ __device__ constexpr uint32_t base_valid_mask() {
+  const char* k = "ACGTURYSWKMBDHVN";
+  uint32_t m = 0;
+  for (int i = 0; i < 16; ++i) m |= 1u << (k[i] - 'A');
+  return m;
+}
+__host__ __device__ constexpr uint64_t base_row_bits() {
+  const char* k = "ACGTURYSWKMBDHVN";
+  const int v[16] = {0, 1, 2, 3, 3, 0, 1, 1, 0, 2, 0, 1, 0, 0, 0, 0};
+  uint64_t b = 0;
+  for (int i = 0; i < 16; ++i) b |= (uint64_t)v[i] << (2 * (k[i] - 'A'));
+  return b;
+}
 __host__ __device__ __forceinline__ int base_row(uint8_t ch) {
-  if (ch >= 'a' && ch <= 'z') ch -= 32;
-  switch (ch) {
-    case 'A': case 'R': case 'W': case 'M': case 'D': case 'H': case 'V': case 'N': return 0;
-    case 'C': case 'Y': case 'S': case 'B': return 1;
-    case 'G': case 'K': return 2;
-    case 'T': case 'U': return 3;
-    default: return 255;
-  }
+  constexpr uint32_t VALID = base_valid_mask();
+  constexpr uint64_t ROWS = base_row_bits();
+  const unsigned t = (unsigned)(ch | 0x20) - (unsigned)'a';      // 'A'..'Z' and 'a'..'z' -> 0..25, everything else >= 26
+  const unsigned tc = t < 26u ? t : 26u;
+  const bool ok = t < 26u && ((VALID >> tc) & 1u);
+  return ok ? (int)((ROWS >> (2 * tc)) & 3u) : 255;
 }
 
 struct Alignments {
@@ -60,10 +73,18 @@ struct Alignments {
   int32_t n_reads;
 };
 
-// One read folded into one candidate's counters.  `Add` supplies add(int element): an atomic on shared memory in the
+// Rows of the reference bases under a candidate's window (255 = not a base / outside the loaded reference): the same 33
+// bytes serve every read of the site, so the kernel resolves them once per site into shared memory.
+__host__ __device__ __forceinline__ uint8_t window_row(const Alignments& a, int center, int i) {
+  const int ri = center - (FLANK + 1) + i - a.ref_start0;
+  return (uint8_t)((ri >= 0 && ri < a.ref_len) ? base_row(a.ref[ri]) : 255);
+}
+
+// One read folded into one candidate's counters; `win` = window_row(a, center, 0..32).  `Add` supplies add(int element): an atomic on shared memory in the
 // kernel, a plain increment when this header is compiled for the host by tests/harness.
 template <typename Add>
-__host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, int center, bool left_edge, Add& add) {
+__host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, int center, bool left_edge, const uint8_t* win,
+                                                   Add& add) {
   const int w0 = center - (FLANK + 1);                 // first window position (0-based)
   const int pos = a.read_pos[r], end = a.read_end[r];
   int q;
@@ -94,8 +115,7 @@ __host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, i
     if (code == OP_M) {
       const int s = p0 > q ? p0 : q, t = p0 + len < wend ? p0 + len : wend;
       for (int p = s; p < t; ++p) {
-        const int ri = p - a.ref_start0;
-        const int rb = (ri >= 0 && ri < a.ref_len) ? base_row(a.ref[ri]) : 255;
+        const int rb = win[p - w0];
         const int qb = base_row(a.seq[qo + (p - p0)]);
         if (rb == 255 || qb == 255) continue;
         const int cell = (p - w0) * 32 + strand * 4;
@@ -107,8 +127,7 @@ __host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, i
     } else if (code == OP_D) {
       const int s = p0 > q + 1 ? p0 : q + 1, t = p0 + len < wend ? p0 + len : wend;
       for (int p = s; p < t; ++p) {
-        const int ri = p - a.ref_start0;
-        const int rb = (ri >= 0 && ri < a.ref_len) ? base_row(a.ref[ri]) : 255;
+        const int rb = win[p - w0];
         if (rb == 255) continue;
         add.add((p - w0) * 32 + strand * 4 + rb * 4 + 2);
       }
@@ -145,6 +164,46 @@ __host__ __device__ __forceinline__ void read_range(const Alignments& a, int cen
   last = lo;
 }
 
+// read_range by the whole warp: both searches advance together, 32 probes per step each (33-ary search: 3 steps + a final
+// sweep for 10^4..10^5 reads instead of 2 x 14 dependent loads - the window's reads cannot be touched before this returns).
+__device__ __forceinline__ int warp_narrow(const int32_t* __restrict__ arr, int key, int lane, int& lo, int& hi) {
+  // one step on [lo, hi): probes p_i = lo + (hi-lo)(i+1)/33; predicate arr[p] > key is monotone
+  const int p = lo + (int)(((int64_t)(hi - lo) * (lane + 1)) / 33);
+  const unsigned m = __ballot_sync(0xffffffffu, arr[p] > key);
+  const int prev = __shfl_up_sync(0xffffffffu, p, 1);
+  int nlo, nhi;
+  if (m == 0) {
+    nlo = __shfl_sync(0xffffffffu, p, 31) + 1;
+    nhi = hi;
+  } else {
+    const int j = __ffs(m) - 1;
+    nhi = __shfl_sync(0xffffffffu, p, j);
+    nlo = j ? __shfl_sync(0xffffffffu, prev, j) + 1 : lo;
+  }
+  lo = nlo;
+  hi = nhi;
+  return hi - lo;
+}
+
+__device__ __forceinline__ int warp_finish(const int32_t* __restrict__ arr, int key, int lane, int lo, int hi) {
+  // hi - lo <= 32: the first index in [lo, hi) with arr[idx] > key, or hi
+  const int idx = lo + lane;
+  const unsigned m = __ballot_sync(0xffffffffu, idx < hi && arr[idx] > key);
+  return m ? lo + __ffs(m) - 1 : hi;
+}
+
+__device__ __forceinline__ void read_range_warp(const Alignments& a, int center, bool left_edge, int lane, int& first, int& last) {
+  const int w0 = center - (FLANK + 1);
+  const int last_open = left_edge ? w0 + 2 * FLANK + 1 : w0;
+  int lo1 = 0, hi1 = a.n_reads, lo2 = 0, hi2 = a.n_reads;
+  while (hi1 - lo1 > 32 || hi2 - lo2 > 32) {
+    if (hi1 - lo1 > 32) warp_narrow(a.read_maxend, w0, lane, lo1, hi1);
+    if (hi2 - lo2 > 32) warp_narrow(a.read_pos, last_open, lane, lo2, hi2);
+  }
+  first = warp_finish(a.read_maxend, w0, lane, lo1, hi1);
+  last = warp_finish(a.read_pos, last_open, lane, lo2, hi2);
+}
+
 struct SharedAdd {
   int* cnt;
   __device__ __forceinline__ void add(int i) { atomicAdd(cnt + i, 1); }
@@ -165,18 +224,21 @@ __global__ void __launch_bounds__(THREADS) create_tensors(Alignments a, const in
                                                           int flags, int16_t* __restrict__ x_out, int32_t* __restrict__ meta,
                                                           int* __restrict__ overflow) {
   __shared__ int cnt_all[SITES_PER_BLOCK][ELEMS];
+  __shared__ uint8_t win_all[SITES_PER_BLOCK][N_POS + 3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* cnt = cnt_all[warp];
+  uint8_t* win = win_all[warp];
   const bool left_edge = flags & F_LEFT_EDGE;
   for (int ci = blockIdx.x * SITES_PER_BLOCK + warp; ci < n_centers; ci += gridDim.x * SITES_PER_BLOCK) {
     const int center = centers[ci];
     for (int i = lane; i < ELEMS; i += 32) cnt[i] = 0;
+    for (int i = lane; i < N_POS; i += 32) win[i] = window_row(a, center, i);
     int first, last;
-    read_range(a, center, left_edge, first, last);       // warp-uniform: every lane walks the same two searches
+    read_range_warp(a, center, left_edge, lane, first, last);
     __syncwarp();
     SharedAdd add{cnt};
     int opened = 0;
-    for (int r = first + lane; r < last; r += 32) opened += fold_read(a, r, center, left_edge, add) ? 1 : 0;
+    for (int r = first + lane; r < last; r += 32) opened += fold_read(a, r, center, left_edge, win, add) ? 1 : 0;
     opened = __reduce_add_sync(0xffffffffu, opened);
     __syncwarp();
     // one row out: 528 words of two int16 = channels (0,1) or (2,3) of a cell

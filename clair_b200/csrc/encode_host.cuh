@@ -125,7 +125,19 @@ inline int encode(const char* text, int64_t len, int min_mq, int dcov, int32_t* 
       while (q < end && is_space(text[q])) ++q;
       if (q >= end) break;
       f[nf][0] = text + q;
-      while (q < end && !is_space(text[q])) ++q;
+      if (nf == 5 || nf == 9) {
+        // CIGAR and SEQ are the long columns: jump to the next tab, and only rescan byte by byte when the span holds
+        // another kind of white space (rows not written by samtools)
+        const char* tab = (const char*)memchr(text + q, '\t', (size_t)(end - q));
+        int64_t stop = tab ? tab - text : end;
+        if (stop > q && text[stop - 1] == '\r') --stop;
+        bool plain = true;
+        for (const char ws : {' ', '\r', '\v', '\f'}) plain = plain && !memchr(text + q, ws, (size_t)(stop - q));
+        if (plain) q = stop;
+        else while (q < end && !is_space(text[q])) ++q;
+      } else {
+        while (q < end && !is_space(text[q])) ++q;
+      }
       f[nf][1] = text + q;
       ++nf;
     }

@@ -6,6 +6,7 @@
 // neighbouring chunks overlapping the kernels on separate streams (double-buffered input/output).
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -831,11 +832,22 @@ int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const in
   }
   for (int64_t i = 1; i < n_centers; ++i)
     if (centers[i] <= centers[i - 1]) return fail(e, CLAIRB_EINVAL, "create_tensors: candidate positions must be strictly ascending");
-  for (int64_t k = 0; k < O; ++k) {
-    const int len = a->op_len[k] >> 2, code = a->op_len[k] & 3;
-    if (code != ct::OP_D && code != ct::OP_M && code != ct::OP_I) return fail(e, CLAIRB_EINVAL, "create_tensors: op %lld has an unknown code", (long long)k);
-    if (code != ct::OP_D && (a->op_qry[k] < 0 || (int64_t)a->op_qry[k] + len > a->seq_len))
-      return fail(e, CLAIRB_EINVAL, "create_tensors: op %lld reads past the end of its SEQ (the reference raises IndexError)", (long long)k);
+  {
+    // every op must stay inside `seq` (the kernel reads it unguarded); 10^7 ops per region, so on the host threads
+    static const int threads = getenv("CLAIRB_DECODE_THREADS") ? atoi(getenv("CLAIRB_DECODE_THREADS")) : 4;
+    constexpr int64_t CHUNK = 1 << 16;
+    std::atomic<int64_t> bad_code(-1), bad_seq(-1);
+    sam::parallel_for((O + CHUNK - 1) / CHUNK, threads, [&](int64_t c) {
+      const int64_t hi = (c + 1) * CHUNK < O ? (c + 1) * CHUNK : O;
+      for (int64_t k = c * CHUNK; k < hi; ++k) {
+        const int len = a->op_len[k] >> 2, code = a->op_len[k] & 3;
+        if (code != ct::OP_D && code != ct::OP_M && code != ct::OP_I) bad_code.store(k);
+        else if (len < 0 || (code != ct::OP_D && (a->op_qry[k] < 0 || (int64_t)a->op_qry[k] + len > a->seq_len))) bad_seq.store(k);
+      }
+    });
+    if (bad_code.load() >= 0) return fail(e, CLAIRB_EINVAL, "create_tensors: op %lld has an unknown code", (long long)bad_code.load());
+    if (bad_seq.load() >= 0)
+      return fail(e, CLAIRB_EINVAL, "create_tensors: op %lld reads past the end of its SEQ (the reference raises IndexError)", (long long)bad_seq.load());
   }
   CU_TRY(e, cudaSetDevice(e->device));
   cudaStream_t st = e->s_comp;

@@ -19,13 +19,15 @@ extern "C" int ct_host_sites(const int32_t* read_pos, const int32_t* read_end, c
   for (int ci = 0; ci < n_centers; ++ci) {
     PlainAdd add{counts + (size_t)ci * clairb::ct::ELEMS};
     int first, last, n = 0;
+    uint8_t win[clairb::ct::N_POS];
+    for (int i = 0; i < clairb::ct::N_POS; ++i) win[i] = clairb::ct::window_row(a, centers[ci], i);
     clairb::ct::read_range(a, centers[ci], left_edge != 0, first, last);
-    for (int r = first; r < last; ++r) n += clairb::ct::fold_read(a, r, centers[ci], left_edge != 0, add) ? 1 : 0;
+    for (int r = first; r < last; ++r) n += clairb::ct::fold_read(a, r, centers[ci], left_edge != 0, win, add) ? 1 : 0;
     // every read outside [first, last) must be rejected by the rule itself
     static int scratch[clairb::ct::ELEMS];
     PlainAdd sink{scratch};
     for (int r = 0; r < n_reads; ++r)
-      if ((r < first || r >= last) && clairb::ct::fold_read(a, r, centers[ci], left_edge != 0, sink)) return 1 + ci;
+      if ((r < first || r >= last) && clairb::ct::fold_read(a, r, centers[ci], left_edge != 0, win, sink)) return 1 + ci;
     opened[ci] = n;
   }
   return 0;
