@@ -73,6 +73,17 @@ struct Alignments {
   int32_t n_reads;
 };
 
+// Event slots of a (position, row) cell and the channels the reference derives from them (CreateTensor.py:41-50):
+//   channel 0 = aligned bases counted at the reference row, 1 = aligned at the query row + inserted bases,
+//   2 = aligned at the reference row + deleted bases, 3 = aligned at the query row.
+constexpr int SLOT_MREF = 0, SLOT_INS = 1, SLOT_DEL = 2, SLOT_MQRY = 3;
+__host__ __device__ __forceinline__ void channels_from_slots(const int* s, int* ch) {
+  ch[0] = s[SLOT_MREF];
+  ch[1] = s[SLOT_MQRY] + s[SLOT_INS];
+  ch[2] = s[SLOT_MREF] + s[SLOT_DEL];
+  ch[3] = s[SLOT_MQRY];
+}
+
 // Rows of the reference bases under a candidate's window (255 = not a base / outside the loaded reference): the same 33
 // bytes serve every read of the site, so the kernel resolves them once per site into shared memory.
 __host__ __device__ __forceinline__ uint8_t window_row(const Alignments& a, int center, int i) {
@@ -107,29 +118,42 @@ __host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, i
     const int e = a.op_ref[mid] + (((lc & 3) == OP_I) ? 0 : (lc >> 2));
     if (e > q) hi = mid; else lo = mid + 1;
   }
+  // The counters of a cell are kept as four event slots, two increments per aligned base instead of four:
+  //   SLOT_MREF aligned bases by reference row, SLOT_INS inserted bases, SLOT_DEL deleted bases, SLOT_MQRY aligned bases by
+  //   query row; channels_from_slots() turns them into the reference's four channels when the row is written.
+  if (lo >= op_end) return true;
+  int p0 = a.op_ref[lo], lc = a.op_len[lo], qo = a.op_qry[lo];
   for (int k = lo; k < op_end; ++k) {
-    const int p0 = a.op_ref[k];
     if (p0 >= wend) break;
-    const int lc = a.op_len[k], len = lc >> 2, code = lc & 3;
-    const int qo = a.op_qry[k];
+    // the next op's fields are requested before this op's bases are counted (one load latency per op, overlapped)
+    const int kn = k + 1 < op_end ? k + 1 : k;
+    const int np0 = a.op_ref[kn], nlc = a.op_len[kn], nqo = a.op_qry[kn];
+    const int len = lc >> 2, code = lc & 3;
     if (code == OP_M) {
       const int s = p0 > q ? p0 : q, t = p0 + len < wend ? p0 + len : wend;
-      for (int p = s; p < t; ++p) {
-        const int rb = win[p - w0];
-        const int qb = base_row(a.seq[qo + (p - p0)]);
-        if (rb == 255 || qb == 255) continue;
-        const int cell = (p - w0) * 32 + strand * 4;
-        add.add(cell + rb * 4 + 0);
-        add.add(cell + qb * 4 + 1);
-        add.add(cell + rb * 4 + 2);
-        add.add(cell + qb * 4 + 3);
+      const uint8_t* qs = a.seq + (qo - p0);
+      for (int pb = s; pb < t; pb += 8) {
+        uint8_t qch[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qch[j] = pb + j < t ? qs[pb + j] : (uint8_t)0;      // eight loads in flight
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int p = pb + j;
+          if (p >= t) break;
+          const int rb = win[p - w0];
+          const int qb = base_row(qch[j]);
+          if (rb == 255 || qb == 255) continue;
+          const int cell = (p - w0) * 32 + strand * 4;
+          add.add(cell + rb * 4 + SLOT_MREF);
+          add.add(cell + qb * 4 + SLOT_MQRY);
+        }
       }
     } else if (code == OP_D) {
       const int s = p0 > q + 1 ? p0 : q + 1, t = p0 + len < wend ? p0 + len : wend;
       for (int p = s; p < t; ++p) {
         const int rb = win[p - w0];
         if (rb == 255) continue;
-        add.add((p - w0) * 32 + strand * 4 + rb * 4 + 2);
+        add.add((p - w0) * 32 + strand * 4 + rb * 4 + SLOT_DEL);
       }
     } else if (p0 > q) {                               // insertion before reference position p0
       const int i0 = p0 - w0;
@@ -137,9 +161,10 @@ __host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, i
         const int qb = base_row(a.seq[qo + t]);
         if (qb == 255) continue;
         const int idx = i0 + t < N_POS - 1 ? i0 + t : N_POS - 1;     // min(position_index + queryAdv, 32), :46
-        add.add(idx * 32 + strand * 4 + qb * 4 + 1);
+        add.add(idx * 32 + strand * 4 + qb * 4 + SLOT_INS);
       }
     }
+    p0 = np0; lc = nlc; qo = nqo;
   }
   return true;
 }
@@ -245,13 +270,12 @@ __global__ void __launch_bounds__(THREADS) create_tensors(Alignments a, const in
     uint32_t* out = reinterpret_cast<uint32_t*>(x_out + (size_t)ci * ELEMS);
     bool ovf = false;
     for (int w = lane; w < ELEMS / 2; w += 32) {
-      const int cell = (w >> 1) * 4;
-      const int c0 = cnt[cell];
-      int v0, v1;
-      if (w & 1) { v0 = cnt[cell + 2]; v1 = cnt[cell + 3]; } else { v0 = c0; v1 = cnt[cell + 1]; }
+      int ch[4];
+      channels_from_slots(cnt + (w >> 1) * 4, ch);
+      int v0 = (w & 1) ? ch[2] : ch[0], v1 = (w & 1) ? ch[3] : ch[1];
       if (flags & F_SUBTRACT) {
-        if (w & 1) v0 -= c0;
-        v1 -= c0;
+        if (w & 1) v0 -= ch[0];
+        v1 -= ch[0];
       }
       ovf |= v0 > 32767 || v1 > 32767 || v0 < -32768 || v1 < -32768;
       out[w] = (uint32_t)(uint16_t)(int16_t)v0 | ((uint32_t)(uint16_t)(int16_t)v1 << 16);

@@ -29,6 +29,12 @@ extern "C" int ct_host_sites(const int32_t* read_pos, const int32_t* read_end, c
     for (int r = 0; r < n_reads; ++r)
       if ((r < first || r >= last) && clairb::ct::fold_read(a, r, centers[ci], left_edge != 0, win, sink)) return 1 + ci;
     opened[ci] = n;
+    // event slots -> the reference's channels, as the kernel does when it writes the row
+    for (int cell = 0; cell < clairb::ct::CELLS; ++cell) {
+      int ch[4];
+      clairb::ct::channels_from_slots(add.cnt + cell * 4, ch);
+      for (int j = 0; j < 4; ++j) add.cnt[cell * 4 + j] = ch[j];
+    }
   }
   return 0;
 }
