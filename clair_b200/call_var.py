@@ -66,6 +66,20 @@ def _take_one(gen):
         return []
 
 
+def call_variants_from_alignments(block, m, output_config, output_utilities, output_stage):
+    """call_variants fed by CreateTensor on the device (clair_b200.create_tensor.create_tensors(..., subtract=True)) instead of
+    its text rows: same batch loop, same (X, infos) hand-over, the tensors never leave the GPU - the pipe between the two
+    reference processes (clair/callVarBam.py:191-200) is gone."""
+    from . import create_tensor
+    output_utilities.output_header()
+    logging.info("Calling variants ...")
+    started = time()
+    run_batches(m, create_tensor.device_tensor_generator_from(block, param.predictBatchSize), output_stage, output_config,
+                output_utilities)
+    logging.info("Total time elapsed: %.2f s" % (time() - started))
+    output_utilities.close_opened_files()
+
+
 def call_variants(args, m, output_config, output_utilities, output_stage):
     """Reference signature plus the output stage to run (the reference picks batch_output or
     batch_output_for_ensemble itself, call_var.py:1320)."""

@@ -297,13 +297,36 @@ def create_tensors(model, alignments, candidate_positions, reference_sequence, r
                        (x if rows.shape[0] == n else x[rows]) if fetch else None, subtract)
 
 
-def created_tensor_generator_from(block, batch_size):
-    """What utils.tensor_generator_from yields per batch (clair/utils.py:72-109) minus the tensors themselves, which stay
-    on the device: (probabilities [n,90], [[ctg, pos, seq]] * n) for the sites of `block` the generator keeps."""
+class DeviceTensors(object):
+    """Stand-in for the X array of a predict-batch whose tensors live on the device: `Clair.predict` accepts it where
+    tensor_generator_from would have handed a [n,33,8,4] array (clair/call_var.py:1343)."""
+    __slots__ = ("block", "index")
+
+    def __init__(self, block, index):
+        self.block, self.index = block, index
+
+    @property
+    def shape(self):
+        return (int(self.index.shape[0]), N_POS, param.matrixRow, param.matrixNum)
+
+    def __len__(self):
+        return int(self.index.shape[0])
+
+
+def device_tensor_generator_from(block, batch_size):
+    """Drop-in for utils.tensor_generator_from (clair/utils.py:72-109) in the batch loop: yields (X, [[ctg, pos, seq]] * n)
+    per predict-batch for the sites of `block` the reference generator keeps (:90), X being a DeviceTensors."""
     keep = block.callable_sites()
+    sequences, positions = block.sequences, block.positions.tolist()
     for s in range(0, keep.shape[0], batch_size):
         idx = keep[s:s + batch_size]
-        yield block.predict(idx), [[block.ctg_name, str(int(block.positions[i])), block.sequences[i]] for i in idx]
+        yield DeviceTensors(block, idx), [[block.ctg_name, str(positions[i]), sequences[i]] for i in idx.tolist()]
+
+
+def created_tensor_generator_from(block, batch_size):
+    """The same batches with the forward already applied: (probabilities [n,90], [[ctg, pos, seq]] * n)."""
+    for X, infos in device_tensor_generator_from(block, batch_size):
+        yield block.predict(X.index), infos
 
 
 # ---- the reference's command (children as in CreateTensor.py:115-176) ---------------------------------------------

@@ -128,6 +128,14 @@ class Clair(object):
         """Reference clair/model.py:946-966: list of 4 float32 arrays, also stored in .prediction."""
         if not self._has_weights:
             raise RuntimeError("predict() before init()/restore_parameters()")
+        from .create_tensor import DeviceTensors
+        if isinstance(batchX, DeviceTensors):
+            # tensors that clairb_create_tensors left on the device (SURVEY.md 8f row 4): no host copy of X exists
+            packed = batchX.block.predict(batchX.index)
+            bounds = np.cumsum([0] + self.output_label_split)
+            prediction = [np.ascontiguousarray(packed[:, a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
+            self.prediction = prediction
+            return prediction
         X, _ = self.tensor_transform_function(batchX, None, "predict")      # clair/model.py:953
         X, dtype = self._as_input(X)
         n = X.shape[0]

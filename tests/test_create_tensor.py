@@ -228,6 +228,42 @@ def test_device_born_tensors_through_forward(model):
 
 
 @pytest.mark.gpu
+def test_batch_loop_over_device_born_tensors(model):
+    """call_var's loop (clair/call_var.py:1312-1367) fed by device_tensor_generator_from: same batches, same order, same
+    probabilities as the text route (tensor rows -> tensor_generator_from -> predict)."""
+    from clair_b200 import call_var
+
+    class Utilities(object):
+        calls = []
+
+        def output_header(self):
+            self.calls.append("header")
+
+        def close_opened_files(self):
+            self.calls.append("close")
+
+    rng = np.random.default_rng(80)
+    case = G.make_case(rng, "loop", 5000, 2500, 600)
+    block = device_block(model, case, subtract=True)
+    keep = block.callable_sites()
+    seen = []
+
+    def output_stage(batch, prediction, config, utilities):
+        X, infos = batch
+        assert len(X) == len(infos) == prediction[0].shape[0]
+        seen.append((infos, [p.copy() for p in prediction]))
+
+    util = Utilities()
+    call_var.call_variants_from_alignments(block, model, None, util, output_stage)
+    assert util.calls == ["header", "close"]
+    assert [i[1] for infos, _ in seen for i in infos] == [str(int(p)) for p in block.positions[keep]]
+    want = model.predict(block.x[keep])
+    for k in range(4):
+        assert np.array_equal(np.concatenate([pred[k] for _, pred in seen]), want[k])
+    assert [len(infos) for infos, _ in seen] == [1000] * (keep.shape[0] // 1000) + ([keep.shape[0] % 1000] if keep.shape[0] % 1000 else [])
+
+
+@pytest.mark.gpu
 def test_device_argument_errors(model):
     case = CASES[0]
     seq, start0 = reference_window(case)
