@@ -94,8 +94,8 @@ __host__ __device__ __forceinline__ uint8_t window_row(const Alignments& a, int 
 // One read folded into one candidate's counters; `win` = window_row(a, center, 0..32).  `Add` supplies add(int element): an atomic on shared memory in the
 // kernel, a plain increment when this header is compiled for the host by tests/harness.
 template <typename Add>
-__host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, int center, bool left_edge, const uint8_t* win,
-                                                   Add& add) {
+__host__ __device__ __forceinline__ bool fold_read_ops(const Alignments& a, int r, int center, bool left_edge, const uint8_t* win,
+                                                       Add& add) {
   const int w0 = center - (FLANK + 1);                 // first window position (0-based)
   const int pos = a.read_pos[r], end = a.read_end[r];
   int q;
@@ -167,6 +167,83 @@ __host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, i
     p0 = np0; lc = nlc; qo = nqo;
   }
   return true;
+}
+
+// The same rule walked position-major: all lanes of a site step through the window positions together (most reads cover the
+// whole window, so the lanes stay converged) and the op cursor advances as a side branch; the query base of the next
+// position is requested one iteration ahead.  A/B against fold_read_ops with -DCLAIRB_CT_FLAT.
+template <typename Add>
+__host__ __device__ __forceinline__ bool fold_read_flat(const Alignments& a, int r, int center, bool left_edge, const uint8_t* win,
+                                                        Add& add) {
+  const int w0 = center - (FLANK + 1);
+  const int pos = a.read_pos[r], end = a.read_end[r];
+  int q;
+  if (left_edge) {
+    if (pos > w0 + 2 * FLANK + 1 || end <= w0) return false;
+    q = pos > w0 ? pos : w0;
+  } else {
+    if (pos > w0 || end <= w0) return false;
+    q = w0;
+  }
+  if (q >= end) return false;
+  const int wend = w0 + N_POS;
+  const int strand = (a.read_strand[r] ? 4 : 0) * 4;
+  int lo = a.read_op0[r], hi = a.read_op0[r + 1];
+  const int op_end = hi;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int lc = a.op_len[mid];
+    const int e = a.op_ref[mid] + (((lc & 3) == OP_I) ? 0 : (lc >> 2));
+    if (e > q) hi = mid; else lo = mid + 1;
+  }
+  if (lo >= op_end) return true;
+  int k = lo;
+  int p0 = a.op_ref[k], lc = a.op_len[k], qo = a.op_qry[k];
+  int len = lc >> 2, code = lc & 3;                    // an M or D op that covers q
+  uint8_t ahead = 0;
+  bool have_ahead = false;
+  for (int p = q; p < wend; ++p) {
+    while (code == OP_I || p >= p0 + len) {            // move the cursor to the op that covers p
+      if (code == OP_I && p0 > q) {                    // inserted bases sit before reference position p0 == p
+        const int i0 = p0 - w0;
+        for (int t = 0; t < len; ++t) {
+          const int qb = base_row(a.seq[qo + t]);
+          if (qb == 255) continue;
+          const int idx = i0 + t < N_POS - 1 ? i0 + t : N_POS - 1;
+          add.add(idx * 32 + strand + qb * 4 + SLOT_INS);
+        }
+      }
+      if (++k >= op_end) return true;
+      p0 = a.op_ref[k]; lc = a.op_len[k]; qo = a.op_qry[k];
+      len = lc >> 2; code = lc & 3;
+      have_ahead = false;
+    }
+    const int rb = win[p - w0];
+    if (code == OP_M) {
+      const uint8_t* qs = a.seq + (qo - p0);
+      const uint8_t ch = have_ahead ? ahead : qs[p];
+      have_ahead = p + 1 < p0 + len && p + 1 < wend;
+      if (have_ahead) ahead = qs[p + 1];
+      const int qb = base_row(ch);
+      if (rb != 255 && qb != 255) {
+        const int cell = (p - w0) * 32 + strand;
+        add.add(cell + rb * 4 + SLOT_MREF);
+        add.add(cell + qb * 4 + SLOT_MQRY);
+      }
+    } else if (p > q && rb != 255) {
+      add.add((p - w0) * 32 + strand + rb * 4 + SLOT_DEL);
+    }
+  }
+  return true;
+}
+
+template <typename Add>
+__host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, int center, bool left_edge, const uint8_t* win, Add& add) {
+#ifdef CLAIRB_CT_FLAT
+  return fold_read_flat(a, r, center, left_edge, win, add);
+#else
+  return fold_read_ops(a, r, center, left_edge, win, add);
+#endif
 }
 
 // Reads that can open the window of `center`: [first, last) with first = the first read whose running maximum end reaches

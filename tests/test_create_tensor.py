@@ -61,13 +61,14 @@ def test_oracle_reproduces_reference_rows(case):
 
 
 # ---- the kernel's rule, compiled for the host ------------------------------------------------------------------------
-@pytest.fixture(scope="module")
-def host_rule(tmp_path_factory):
+@pytest.fixture(scope="module", params=["op-major walk", "position-major walk (-DCLAIRB_CT_FLAT)"])
+def host_rule(request, tmp_path_factory):
     out = str(tmp_path_factory.mktemp("ct_harness") / "ct_host.so")
     src = os.path.join(ROOT, "tests", "harness", "create_tensor_host.cu")
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", out, src],
-                   check=True)
+    variant = ["-DCLAIRB_CT_FLAT"] if "FLAT" in request.param else []
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + variant +
+                   ["-o", out, src], check=True)
     lib = ctypes.CDLL(out)
     lib.ct_host_sites.restype = ctypes.c_int
     return lib
