@@ -24,6 +24,7 @@
 #include "decode_host.cuh"
 #include "create_tensor_kernels.cuh"
 #include "encode_host.cuh"
+#include "blosc_host.cuh"
 
 using namespace clairb;
 
@@ -944,6 +945,21 @@ int clairb_encode_sam(const char* text, int64_t text_len, int min_mq, int dcov, 
     case sam::CIGAR_BEYOND_SEQ: return fail(nullptr, CLAIRB_EINVAL, "encode_sam: read %lld: CIGAR consumes more bases than SEQ holds", (long long)bad);
     case sam::CAPACITY: return fail(nullptr, CLAIRB_EINVAL, "encode_sam: output arrays too small (%lld reads, %lld ops, %lld bases)", (long long)*n_reads, (long long)*n_ops, (long long)*n_bases);
     default: return fail(nullptr, CLAIRB_EINVAL, "encode_sam: block too large for int32 offsets: split the region");
+  }
+}
+
+int clairb_blosc_decompress(const void* src, int64_t src_len, void* dst, int64_t dst_cap, int64_t* nbytes) {
+  if (!src || src_len < 0 || !nbytes || dst_cap < 0) return fail(nullptr, CLAIRB_EINVAL, "blosc_decompress: bad arguments");
+  blosc::Info h;
+  if (blosc::info((const uint8_t*)src, src_len, &h)) return fail(nullptr, CLAIRB_EINVAL, "blosc_decompress: shorter than a Blosc header");
+  *nbytes = h.nbytes;
+  if (!dst) return CLAIRB_OK;
+  switch (blosc::decompress((const uint8_t*)src, src_len, (uint8_t*)dst, dst_cap, nbytes)) {
+    case blosc::OK: return CLAIRB_OK;
+    case blosc::TRUNCATED: return fail(nullptr, CLAIRB_EINVAL, "blosc_decompress: frame is truncated (header says %lld bytes)", (long long)h.cbytes);
+    case blosc::UNSUPPORTED: return fail(nullptr, CLAIRB_EINVAL, "blosc_decompress: only LZ4 / stored frames without bit shuffle are read (flags 0x%02x)", h.flags);
+    case blosc::CAPACITY: return fail(nullptr, CLAIRB_EINVAL, "blosc_decompress: destination holds %lld bytes, frame needs %lld", (long long)dst_cap, (long long)h.nbytes);
+    default: return fail(nullptr, CLAIRB_EINVAL, "blosc_decompress: corrupt frame");
   }
 }
 

@@ -181,6 +181,12 @@ int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const in
  * out_host: [n,90] float32 as clairb_predict. */
 int clairb_predict_created(clairb_engine* e, const int64_t* rows, int64_t n, float* out_host);
 
+/* Host-only (no device): one Blosc1 frame of the reference's training / evaluation bins -> its bytes (a pickled numpy
+ * array: blosc.pack_array(array, cname='lz4hc', clevel=9, shuffle=NOSHUFFLE), clair/utils.py:47-48; read back by
+ * blosc.unpack_array in decompress_array, clair/utils.py:223-262).  Reads LZ4 / stored frames, split or not, byte-shuffled
+ * or not.  With dst == NULL only *nbytes (the uncompressed size from the header) is reported. */
+int clairb_blosc_decompress(const void* src, int64_t src_len, void* dst, int64_t dst_cap, int64_t* nbytes);
+
 /* Host-only (no device): `samtools view` text -> the arrays of clairb_alignments.  Replaces what the reference does per
  * SAM row before and while it walks the CIGAR string (dataPrepScripts/CreateTensor.py:251-296): '@' rows skipped, the
  * mapping-quality filter (:264), the per-POS depth cap (:274-281) and the CIGAR grammar (:283-366).
