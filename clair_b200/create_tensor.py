@@ -211,6 +211,7 @@ class TensorBlock(object):
         self.positions, self.depth, self.rows, self.x = positions, depth, rows, x
         self.subtracted = subtracted
         self._reference, self._start, self._sequences = reference_sequence, window_start, None
+        self._generation = getattr(model, "_ct_generation", 0)      # the device holds one block per handle: the latest
 
     @property
     def sequences(self):
@@ -244,6 +245,8 @@ class TensorBlock(object):
         """Forward pass over sites of this block without the tensors leaving the device -> [n,90] float32."""
         if not self.subtracted:
             raise ValueError("the forward pass takes channel-subtracted tensors: create_tensors(..., subtract=True)")
+        if getattr(self.model, "_ct_generation", 0) != self._generation:
+            raise RuntimeError("this TensorBlock is no longer resident: a later create_tensors call on the same model replaced it")
         which = np.arange(len(self), dtype=np.int64) if which is None else np.asarray(which, np.int64)
         rows = np.ascontiguousarray(self.rows[which])
         out = np.empty((rows.shape[0], _lib.N_OUT), np.float32)
@@ -286,6 +289,7 @@ def create_tensors(model, alignments, candidate_positions, reference_sequence, r
     x = np.empty((n, N_POS, 8, 4), np.int16) if fetch else None
     flags = (CT_LEFT_EDGE if consider_left_edge else 0) | (CT_SUBTRACT if subtract else 0)
     with model._lock:
+        model._ct_generation = getattr(model, "_ct_generation", 0) + 1
         rc = model._lib.clairb_create_tensors(model._h, ctypes.byref(ca), centers.ctypes.data_as(ctypes.c_void_p), n, flags,
                                               x.ctypes.data_as(ctypes.c_void_p) if fetch else None,
                                               meta.ctypes.data_as(ctypes.c_void_p))

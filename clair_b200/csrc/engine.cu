@@ -105,6 +105,7 @@ struct clairb_engine {
   DevBuf ct_in[12], ct_x, ct_meta, ct_gather, ct_rows_idx, ct_out;
   int* ct_overflow = nullptr;
   int64_t ct_rows = 0;
+  bool ct_subtracted = false;   // the resident block was written with CLAIRB_CT_SUBTRACT (what the forward takes)
 
   // optional per-kernel CUDA-event timing (bench.py's roofline leg)
   bool profiling = false;
@@ -896,6 +897,7 @@ int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const in
   CU_TRY(e, cudaStreamSynchronize(st));
   if (overflow) return fail(e, CLAIRB_EINVAL, "create_tensors: a count does not fit int16 (depth above 32767)");
   e->ct_rows = n_centers;
+  e->ct_subtracted = (flags & ct::F_SUBTRACT) != 0;
   return CLAIRB_OK;
 }
 
@@ -904,6 +906,8 @@ int clairb_predict_created(clairb_engine* e, const int64_t* rows, int64_t n, flo
   if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
   if (!rows || !out_host || n <= 0 || n > e->max_sites) return fail(e, CLAIRB_EINVAL, "predict_created: bad n or buffers");
   if (e->ct_rows <= 0) return fail(e, CLAIRB_EINVAL, "predict_created: no tensor block resident (call clairb_create_tensors first)");
+  if (!e->ct_subtracted)
+    return fail(e, CLAIRB_EINVAL, "predict_created: the resident block holds raw counts; create it with CLAIRB_CT_SUBTRACT (clair/utils.py:96-98)");
   for (int64_t i = 0; i < n; ++i)
     if (rows[i] < 0 || rows[i] >= e->ct_rows) return fail(e, CLAIRB_EINVAL, "predict_created: row %lld is outside the resident block", (long long)rows[i]);
   CU_TRY(e, cudaSetDevice(e->device));

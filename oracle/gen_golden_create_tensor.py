@@ -113,9 +113,9 @@ def random_read(rng, contig_len, pos0, style):
             c = "M" if rng.random() < 0.8 else ("=" if rng.random() < 0.5 else "X")
             n = int(rng.integers(1, 45))
         elif r < 0.75:
-            c, n = "I", int(rng.integers(1, 6)) if rng.random() < 0.9 else int(rng.integers(20, 60))
+            c, n = "I", int(rng.integers(1, 6)) if rng.random() < (0.5 if style == "long_indels" else 0.9) else int(rng.integers(20, 130))
         elif r < 0.95:
-            c, n = "D", int(rng.integers(1, 6)) if rng.random() < 0.9 else int(rng.integers(20, 60))
+            c, n = "D", int(rng.integers(1, 6)) if rng.random() < (0.5 if style == "long_indels" else 0.9) else int(rng.integers(20, 130))
         elif r < 0.98:
             c, n = "N", int(rng.integers(1, 30))
         else:
@@ -183,6 +183,14 @@ def make_cases():
         make_case(rng, "region_tight_ref", 2500, 260, 70, region=(700, 1800), expand=40, style="short"),
         make_case(rng, "no_left_edge", 1200, 200, 60, stop_left=True),
         make_case(rng, "no_reads", 400, 0, 10),
+        # second batch (appended: the cases above keep their random streams)
+        make_case(rng, "long_indels", 2000, 260, 120, style="long_indels"),
+        make_case(rng, "deep", 260, 600, 40, style="short"),
+        make_case(rng, "deep_long", 700, 500, 60),
+        make_case(rng, "contig_tail", 300, 120, 200, style="dense"),
+        make_case(rng, "dcov_one", 700, 200, 50, dup_rate=0.5, dcov=1),
+        make_case(rng, "region_from_one", 1500, 200, 80, region=(1, 700), expand=25),
+        make_case(rng, "no_left_edge_dense", 900, 260, 40, style="dense", stop_left=True, dup_rate=0.2, dcov=3),
     ]
 
 

@@ -170,6 +170,57 @@ def test_native_encoder_rejects_malformed_rows():
         CT.encode_alignments(["r\t0\tc\t5\t60\t1M"])
 
 
+# ---- the reference's command line (host plumbing; the device call is replaced by the oracle in THIS test only) ---------
+def _fake_children(case):
+    contig = case["contig"]
+
+    def popen(args, **kw):
+        if "faidx" in args:
+            region = args[-1]
+            lo, hi = 1, len(contig)
+            if ":" in region:
+                lo, hi = (int(v) for v in region.split(":")[1].split("-"))
+            seq = contig[lo - 1:hi]
+            return G._Proc([">%s\n" % region] + [seq[i:i + 60].lower() + "\n" for i in range(0, len(seq), 60)])
+        if "view" in args:
+            assert "-F" in args and str(CT.param.SAMTOOLS_VIEW_FILTER_FLAG) in args
+            return G._Proc([l + "\n" for l in case["sam"]])
+        if args[0] == "gzip":
+            return G._Proc([l + "\n" for l in case["candidates"]])
+        raise AssertionError("unexpected child process %r" % (args,))
+    return popen
+
+
+@pytest.mark.parametrize("name", ["whole", "region", "min_mq_cov", "no_left_edge", "contig_tail"])
+def test_output_aln_tensor_plumbing(monkeypatch, tmp_path, name):
+    """OutputAlnTensor(args): children, region strings, filters and row formatting (CreateTensor.py:179-394) with the counting
+    done by the oracle instead of the device - what is left is exactly the host code around clairb_create_tensors."""
+    import types
+    case = next(c for c in CASES if c["name"] == name)
+    a = case["args"]
+
+    def oracle_create_tensors(model, alignments, candidates, reference_sequence, start0=0, ctg_name="chr", min_coverage=0,
+                              consider_left_edge=True, ctg_start=None, ctg_end=None, subtract=False, fetch=True):
+        rows = O.create_tensors(case["sam"], sorted(set(candidates)), reference_sequence, start0, ctg_name, a["minMQ"], a["dcov"],
+                                min_coverage, consider_left_edge, ctg_start, ctg_end)
+        positions = np.array([r[1] for r in rows], np.int64)
+        x = np.stack([r[3] for r in rows]).astype(np.int16) if rows else np.zeros((0, 33, 8, 4), np.int16)
+        return CT.TensorBlock(model, ctg_name, positions, reference_sequence, positions - start0 - 17, x[:, 16, :, 0].sum(1),
+                              np.arange(len(rows)), x, False)
+
+    monkeypatch.setattr(CT, "create_tensors", oracle_create_tensors)
+    monkeypatch.setattr(CT.param, "expandReferenceRegion", a["expandReferenceRegion"])
+    args = types.SimpleNamespace(samtools="samtools", tensor_fn=str(tmp_path / "t.gz"), bam_fn="x.bam", ref_fn="x.fa", can_fn="x.can",
+                                 dcov=a["dcov"], stop_consider_left_edge=a["stop_consider_left_edge"], minCoverage=a["minCoverage"],
+                                 minMQ=a["minMQ"], ctgName=a["ctgName"], ctgStart=a["ctgStart"], ctgEnd=a["ctgEnd"])
+    out = []
+    CT.OutputAlnTensor(args, model=object(), popen=_fake_children(case), out=out)
+    assert out == case["expected"]
+    CT.OutputAlnTensor(args, model=object(), popen=_fake_children(case))                 # --tensor_fn FILE: gzip text
+    with gzip.open(args.tensor_fn, "rt") as f:
+        assert f.read().splitlines() == case["expected"]
+
+
 # ---- GPU -------------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def model():
