@@ -35,6 +35,8 @@ SYMBOLS = {
                                      _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                      _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
     "clairb_blosc_decompress": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.POINTER(_c.c_int64)]),
+    "clairb_format_tensor_rows": (_c.c_int, [_c.c_char_p, _c.c_void_p, _c.c_char_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_int64,
+                                             _c.c_void_p, _c.c_int64, _c.POINTER(_c.c_int64)]),
     "clairb_decode_rows": (_c.c_int, [_c.c_char_p, _c.c_int64, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p,
                                       _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
     "clairb_get_layer": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int64]),

@@ -223,13 +223,30 @@ class TensorBlock(object):
     def __len__(self):
         return int(self.positions.shape[0])
 
-    def text_rows(self):
-        """The rows CreateTensor.py prints (:57-62); needs raw counts fetched to the host."""
+    def text(self):
+        """The rows CreateTensor.py prints (:57-62) as one bytes block, formatted by the native library
+        (clairb_format_tensor_rows); needs raw counts fetched to the host."""
         if self.x is None or self.subtracted:
             raise ValueError("text rows need create_tensors(..., fetch=True, subtract=False)")
-        flat = self.x.reshape(len(self), N_POS * 8 * 4)
-        return ["%s %d %s %s" % (self.ctg_name, p, s, " ".join(map(str, r.tolist())))
-                for p, s, r in zip(self.positions.tolist(), self.sequences, flat)]
+        n = len(self)
+        if n == 0:
+            return b""
+        lib = _lib.load()
+        ref = self._reference.encode("ascii", "replace")
+        positions = np.ascontiguousarray(self.positions, np.int64)
+        start = np.ascontiguousarray(self._start, np.int64)
+        x = np.ascontiguousarray(self.x, np.int16)
+        need = ctypes.c_int64()
+        args = (self.ctg_name.encode(), positions.ctypes.data_as(ctypes.c_void_p), ref, len(ref), start.ctypes.data_as(ctypes.c_void_p),
+                x.ctypes.data_as(ctypes.c_void_p), n)
+        _lib.check(lib.clairb_format_tensor_rows(*args, None, 0, ctypes.byref(need)), None, "clairb_format_tensor_rows")
+        buf = ctypes.create_string_buffer(need.value)
+        _lib.check(lib.clairb_format_tensor_rows(*args, buf, need.value, ctypes.byref(need)), None, "clairb_format_tensor_rows")
+        return buf.raw[:need.value]
+
+    def text_rows(self):
+        """The same rows as a list of str (without the newlines)."""
+        return self.text().decode("ascii").splitlines()
 
     def callable_sites(self):
         """Indices (into this block) of the sites tensor_generator_from keeps: centre base is an IUPAC code
@@ -386,13 +403,13 @@ def OutputAlnTensor(args, model=None, popen=_popen, out=None):
     finally:
         if own:
             model.close()
-    rows = block.text_rows()
+    text = block.text()
     if out is not None:
-        out.extend(rows)
+        out.extend(text.decode("ascii").splitlines())
     elif args.tensor_fn == "PIPE":
-        sys.stdout.write("".join(r + "\n" for r in rows))
+        sys.stdout.write(text.decode("ascii"))
     else:
         import gzip
-        with gzip.open(args.tensor_fn, "wt") as f:
-            f.write("".join(r + "\n" for r in rows))
+        with gzip.open(args.tensor_fn, "wb") as f:
+            f.write(text)
     return block

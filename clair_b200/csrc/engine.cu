@@ -25,6 +25,7 @@
 #include "create_tensor_kernels.cuh"
 #include "encode_host.cuh"
 #include "blosc_host.cuh"
+#include "format_host.cuh"
 
 using namespace clairb;
 
@@ -965,6 +966,16 @@ int clairb_blosc_decompress(const void* src, int64_t src_len, void* dst, int64_t
     case blosc::CAPACITY: return fail(nullptr, CLAIRB_EINVAL, "blosc_decompress: destination holds %lld bytes, frame needs %lld", (long long)dst_cap, (long long)h.nbytes);
     default: return fail(nullptr, CLAIRB_EINVAL, "blosc_decompress: corrupt frame");
   }
+}
+
+int clairb_format_tensor_rows(const char* ctg_name, const int64_t* positions, const char* reference, int64_t reference_len,
+                              const int64_t* window_start, const int16_t* x, int64_t n, char* out, int64_t out_cap, int64_t* out_len) {
+  if (!ctg_name || n < 0 || !out_len || (n && (!positions || !reference || !window_start || !x)) || reference_len < 0 || out_cap < 0)
+    return fail(nullptr, CLAIRB_EINVAL, "format_tensor_rows: bad arguments");
+  static const int threads = getenv("CLAIRB_DECODE_THREADS") ? atoi(getenv("CLAIRB_DECODE_THREADS")) : 4;
+  if (fmt::rows(ctg_name, positions, reference, reference_len, window_start, x, n, out, out_cap, out_len, threads))
+    return fail(nullptr, CLAIRB_EINVAL, "format_tensor_rows: the rows need %lld bytes, the buffer holds %lld", (long long)*out_len, (long long)out_cap);
+  return CLAIRB_OK;
 }
 
 int clairb_decode_rows(const char* text, int64_t text_len, int64_t max_rows, int dtype, void* x_out, int32_t* info_off,

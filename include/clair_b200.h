@@ -187,6 +187,13 @@ int clairb_predict_created(clairb_engine* e, const int64_t* rows, int64_t n, flo
  * or not.  With dst == NULL only *nbytes (the uncompressed size from the header) is reported. */
 int clairb_blosc_decompress(const void* src, int64_t src_len, void* dst, int64_t dst_cap, int64_t* nbytes);
 
+/* Host-only (no device): the text rows CreateTensor.py prints (dataPrepScripts/CreateTensor.py:57-62), one per site:
+ * "<ctg_name> <position> <reference[window_start .. +33)> <1056 counts>\n" from raw counts x [n][1056] int16 (the x_host of
+ * clairb_create_tensors without CLAIRB_CT_SUBTRACT).  With out == NULL only *out_len (bytes needed) is reported. */
+int clairb_format_tensor_rows(const char* ctg_name, const int64_t* positions, const char* reference, int64_t reference_len,
+                              const int64_t* window_start, const int16_t* x, int64_t n, char* out, int64_t out_cap,
+                              int64_t* out_len);
+
 /* Host-only (no device): `samtools view` text -> the arrays of clairb_alignments.  Replaces what the reference does per
  * SAM row before and while it walks the CIGAR string (dataPrepScripts/CreateTensor.py:251-296): '@' rows skipped, the
  * mapping-quality filter (:264), the per-POS depth cap (:274-281) and the CIGAR grammar (:283-366).
