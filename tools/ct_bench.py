@@ -57,6 +57,12 @@ def device_part(m, contig_len=1000000, repeats=5, with_forward=True, hbm_peak_gb
     algo = in_bytes + n * (2112 + 8)
     out["kernel"] = {"name": "create_tensors", "ms": k_ms, "sites_per_s": n / (k_ms * 1e-3), "algorithmic_bytes": algo,
                      "achieved_gbs": algo / (k_ms * 1e-3) / 1e9, "bound": "hbm"}
+    try:                                                     # DRAM bytes of one launch of this workload, from the committed ncu capture
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_ct_s19.json")))["create_tensors"]
+        out["kernel"]["traffic"] = (t["dram_bytes_read"] + t["dram_bytes_write"]) if t["sites"] == n else None
+        out["kernel"]["traffic_source"] = t["source"]
+    except Exception:
+        out["kernel"]["traffic"] = None
     if hbm_peak_gbs:
         out["kernel"]["hbm_peak_gbs"] = hbm_peak_gbs
         out["kernel"]["frac"] = out["kernel"]["achieved_gbs"] / hbm_peak_gbs
