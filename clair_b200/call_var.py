@@ -69,7 +69,9 @@ def _take_one(gen):
 def call_variants_from_alignments(block, m, output_config, output_utilities, output_stage):
     """call_variants fed by CreateTensor on the device (clair_b200.create_tensor.create_tensors(..., subtract=True)) instead of
     its text rows: same batch loop, same (X, infos) hand-over, the tensors never leave the GPU - the pipe between the two
-    reference processes (clair/callVarBam.py:191-200) is gone."""
+    reference processes (clair/callVarBam.py:191-200) is gone.  An output stage that reads the tensors themselves, as the
+    reference's batch_output does for read depth and supporting reads (clair/call_var.py:1021-1151), iterates the batch's
+    DeviceTensors: create the block with fetch=True then (one device->host copy; the forward still reads the resident block)."""
     from . import create_tensor
     output_utilities.output_header()
     logging.info("Calling variants ...")

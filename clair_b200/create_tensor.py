@@ -333,6 +333,21 @@ class DeviceTensors(object):
     def __len__(self):
         return int(self.index.shape[0])
 
+    def _host_rows(self):
+        if self.block.x is None:
+            raise ValueError("this batch has no host copy of its tensors: an output stage that reads them (batch_output reads "
+                             "x[16] and x[17], clair/call_var.py:1021-1151) needs create_tensors(..., subtract=True, fetch=True)")
+        return self.block.x
+
+    def __getitem__(self, i):
+        """x of site i as the output stage indexes it ([33,8,4], channel-subtracted counts)."""
+        return self._host_rows()[self.index[i]]
+
+    def __iter__(self):
+        x = self._host_rows()
+        for i in self.index.tolist():
+            yield x[i]
+
 
 def device_tensor_generator_from(block, batch_size):
     """Drop-in for utils.tensor_generator_from (clair/utils.py:72-109) in the batch loop: yields (X, [[ctg, pos, seq]] * n)

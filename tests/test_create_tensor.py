@@ -170,6 +170,26 @@ def test_native_encoder_rejects_malformed_rows():
         CT.encode_alignments(["r\t0\tc\t5\t60\t1M"])
 
 
+def test_device_tensors_stand_in():
+    x = np.arange(6 * 1056, dtype=np.int16).reshape(6, 33, 8, 4)
+    block = CT.TensorBlock(None, "c", np.array([100, 150, 200, 250, 300, 350]), "ACGTN*" * 100, np.array([83, 133, 183, 233, 283, 333]),
+                           np.zeros(6, np.int32), np.arange(6), x, True)
+    assert block.sequences[0] == ("ACGTN*" * 100)[83:116] and len(block.sequences[0]) == 33
+    # centre bases (window start + 16): indices 99, 149, ... of the text; '*' is not an IUPAC code (clair/utils.py:90)
+    text = "ACGTN*" * 100
+    keep = block.callable_sites()
+    assert keep.tolist() == [i for i, s in enumerate([83, 133, 183, 233, 283, 333]) if text[s + 16] != "*"]
+    assert len(keep) == 4
+    batches = list(CT.device_tensor_generator_from(block, 3))
+    assert [len(X) for X, _ in batches] == [3, 1] and batches[0][0].shape == (3, 33, 8, 4)
+    X, infos = batches[0]
+    assert infos[0] == ["c", str(int(block.positions[keep[0]])), block.sequences[keep[0]]]
+    assert np.array_equal(np.stack(list(X)), x[keep[:3]]) and np.array_equal(X[1], x[keep[1]])
+    no_host = CT.DeviceTensors(CT.TensorBlock(None, "c", block.positions, text, block._start, block.depth, block.rows, None, True), keep)
+    with pytest.raises(ValueError):
+        list(no_host)
+
+
 # ---- the reference's command line (host plumbing; the device call is replaced by the oracle in THIS test only) ---------
 def _fake_children(case):
     contig = case["contig"]
