@@ -190,6 +190,40 @@ def test_device_tensors_stand_in():
         list(no_host)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="runs the reference's own batch_output; only where /root/reference exists")
+def test_reference_batch_output_accepts_device_tensors():
+    """The reference's unmodified output stage (clair/call_var.py:1199-1236 -> output_with -> output_from) prints the same VCF
+    rows from a DeviceTensors batch as from the numpy batch tensor_generator_from would have handed it."""
+    from oracle import gen_golden_decision as GD
+    from clair_b200 import synth
+    cv = GD.import_reference_call_var()
+    rng = np.random.default_rng(5)
+    n = 120
+    x = synth.synthetic_counts(n, seed=21)
+    x[..., 1:] -= x[..., 0:1]
+    text = "".join(rng.choice(list("ACGT"), size=50 * n + 100))
+    positions = np.arange(n, dtype=np.int64) * 50 + 40
+    block = CT.TensorBlock(None, "chr7", positions, text, positions - 17, np.zeros(n, np.int32), np.arange(n), x, True)
+    (X, infos), = list(CT.device_tensor_generator_from(block, 1000))
+    P = np.stack([np.concatenate([GD.softmax(rng.normal(0, 3.0, k)) for k in (21, 3, 33, 33)]) for _ in range(n)])
+    batch_Y = [P[:, 0:21], P[:, 21:24], P[:, 24:57], P[:, 57:90]]
+    config = cv.OutputConfig(is_show_reference=True, is_debug=False, is_haploid_precision_mode_enabled=False,
+                             is_haploid_sensitive_mode_enabled=False, is_output_for_ensemble=False, quality_score_for_pass=None)
+
+    def run(batch_x):
+        lines, rec = [], GD.Recorder()
+        util = cv.OutputUtilities(print_debug_message=lambda *a: lines.append(("debug", a[0], a[1], a[-1])),
+                                  insertion_bases_using=rec.insertion_bases_using, deletion_bases_using=rec.deletion_bases_using,
+                                  insertion_bases_using_pysam_using=rec.insertion_bases_using_pysam_using,
+                                  output=lines.append, output_header=lambda: None, close_opened_files=lambda: None)
+        cv.batch_output((batch_x, infos), batch_Y, config, util)
+        return lines
+
+    from_numpy = run(x[block.callable_sites()].astype(np.float32))
+    from_device_batch = run(X)
+    assert len(from_numpy) > n // 2 and from_device_batch == from_numpy
+
+
 # ---- the reference's command line (host plumbing; the device call is replaced by the oracle in THIS test only) ---------
 def _fake_children(case):
     contig = case["contig"]
