@@ -411,8 +411,11 @@ def main():
             sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
             import ct_bench
             launches_before_ct = m.kernel_launches()
-            ct_info, ct_ctx = ct_bench.device_part(m, 2000000, 5, True, measured_peaks()["hbm_gbs"])
-            ct_info["gpu_launches"] = m.kernel_launches() - launches_before_ct
+            try:
+                ct_info, ct_ctx = ct_bench.device_part(m, 2000000, 5, True, measured_peaks()["hbm_gbs"])
+                ct_info["gpu_launches"] = m.kernel_launches() - launches_before_ct
+            except Exception as exc:      # a side stage must not take the headline line down with it
+                ct_info, ct_ctx = {"error": "%s: %s" % (type(exc).__name__, exc)}, None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             nb = args.cpu_baseline_batches or 24
@@ -434,8 +437,11 @@ def main():
             assert np.array_equal(got, want) and np.array_equal(dec.max_probability[:ns], want_p), "decision parity failed"
             decision_info["cpu_python_restatement_sites_per_s"] = cpu_dec
             decision_info["cpu_sample"] = "%d sites, 1 core; device records bit-exact on them" % ns
-            if ct_info is not None:
-                ct_bench.cpu_part(ct_info, ct_ctx)
+            if ct_ctx is not None:
+                try:
+                    ct_bench.cpu_part(ct_info, ct_ctx)
+                except Exception as exc:
+                    ct_info["cpu_oracle"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
             cpu = {"value": v, "unit": "sites/s", "cores": threads, "kind": "port",
                    "sample": "%d predict-batches x %d sites of the same pool, %.1f s" % (nb, BATCH, dt),
                    "parity_vs_gpu": {"max_abs_prob_diff": err, "argmax_identical": True, "sites": BATCH},
