@@ -366,9 +366,9 @@ def created_tensor_generator_from(block, batch_size):
 
 
 # ---- the reference's command (children as in CreateTensor.py:115-176) ---------------------------------------------
-def _popen(args, **kw):
+def _popen(args, binary=False, **kw):
     from subprocess import PIPE, Popen
-    return Popen(args, stdout=PIPE, stderr=sys.stderr, bufsize=8388608, universal_newlines=True, **kw)
+    return Popen(args, stdout=PIPE, stderr=sys.stderr, bufsize=8388608, universal_newlines=not binary, **kw)
 
 
 def reference_sequence_from(samtools, reference_file_path, ctg_name, ctg_start, ctg_end, popen=_popen):
@@ -404,15 +404,19 @@ def OutputAlnTensor(args, model=None, popen=_popen, out=None):
     candidates = [int(row.split(maxsplit=2)[1]) for row in candidate_rows]
     have_region = args.ctgStart is not None and args.ctgEnd is not None
     region = ("%s:%d-%d" % (args.ctgName, args.ctgStart, args.ctgEnd)) if have_region else args.ctgName
-    view = popen(shlex.split("%s view -F %d %s %s" % (args.samtools, param.SAMTOOLS_VIEW_FILTER_FLAG, args.bam_fn, region)))
-    alignments = encode_alignments(view.stdout, args.minMQ, args.dcov)
-    view.stdout.close()
-    view.wait()
+    view_args = shlex.split("%s view -F %d %s %s" % (args.samtools, param.SAMTOOLS_VIEW_FILTER_FLAG, args.bam_fn, region))
     own = model is None
     if own:
         from .model import Clair
         model = Clair()
     try:
+        # the alignment rows go to the native encoder as one block of bytes (no per-row Python work), and from there to
+        # page-locked arrays when a device handle exists
+        view = popen(view_args, binary=True) if popen is _popen else popen(view_args)
+        rows = view.stdout.read() if hasattr(view.stdout, "read") else view.stdout
+        alignments = encode_alignments(rows, args.minMQ, args.dcov, pinned=getattr(model, "_h", None) is not None)
+        view.stdout.close()
+        view.wait()
         block = create_tensors(model, alignments, candidates, reference_sequence, reference_start_0_based, args.ctgName,
                                args.minCoverage, not args.stop_consider_left_edge, args.ctgStart, args.ctgEnd)
     finally:
