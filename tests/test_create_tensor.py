@@ -124,6 +124,28 @@ def test_kernel_rule_on_host_random_regions(host_rule):
             assert g[:3] == w[:3] and np.array_equal(g[3], w[3].reshape(-1))
 
 
+@pytest.mark.parametrize("shape", [dict(depth=60, read_len=150, ops_per_read=3, site_spacing=40),       # short reads, few ops
+                                   dict(depth=25, read_len=6000, ops_per_read=21, site_spacing=60),    # long accurate reads
+                                   dict(depth=30, read_len=3000, ops_per_read=601, site_spacing=25)])  # long noisy reads
+def test_kernel_rule_on_host_sequencing_shapes(host_rule, shape):
+    """The synthetic regions the bench uses (clair_b200.synth.synthetic_alignments) at three read shapes: the kernel's rule
+    on the host against the oracle, through SAM text and the native encoder."""
+    from clair_b200 import synth
+    aln, reference, sites = synth.synthetic_alignments(12000, seed=31, **shape)
+    sam = synth.alignments_to_sam(aln, name="syn")
+    again = CT.encode_alignments(sam)
+    for field in CT.Alignments.__slots__:
+        assert np.array_equal(getattr(aln, field), getattr(again, field)), field
+    case = {"sam": sam, "contig": reference, "candidates": ["syn\t%d" % p for p in sites],
+            "args": {"dcov": 250, "stop_consider_left_edge": False, "minCoverage": 0, "minMQ": 0, "ctgName": "syn",
+                     "ctgStart": None, "ctgEnd": None, "expandReferenceRegion": 1000000}}
+    want = oracle_rows(case)
+    got = host_rule_rows(host_rule, case)
+    assert len(want) > 100 and len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g[:3] == w[:3] and np.array_equal(g[3], w[3].reshape(-1))
+
+
 # ---- host encoder ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("encoder", ["native", "python"])
 def test_encoder_filters_and_offsets(encoder):
