@@ -138,3 +138,17 @@ def test_bin_batches_through_predict(tmp_path):
     got = np.concatenate([np.concatenate(m.predict(xb), axis=1) for xb, _ in bins.prediction_batches_from(bins.dataset_info_from(path), 500)])
     m.close()
     assert np.array_equal(got, want)
+
+
+def test_evaluate_model_prints_the_reference_report(tmp_path):
+    """clair_b200.evaluate.evaluate_model against what the reference's own evaluate_model printed for the same seeded bin and
+    stand-in model (tests/golden/evaluate_report.txt, oracle/gen_golden_evaluate.py)."""
+    from clair_b200 import evaluate
+    from oracle import gen_golden_evaluate as GE
+    info = GE.dataset_info(str(tmp_path))
+    assert info.dataset_size == GE.N_SITES and len(info.x_array_compressed) == 4
+    want = open(os.path.join(ROOT, "tests", "golden", "evaluate_report.txt")).read()
+    assert GE.report_of(evaluate.evaluate_model, info) == want
+    model = GE.FakeModel()
+    evaluate.evaluate_model(model, info)
+    assert model.calls == [1000, 730]                     # predict sees the batches the reference's walk produces
