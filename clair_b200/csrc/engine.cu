@@ -364,7 +364,7 @@ void free_all(clairb_engine* e) {
 
 extern "C" {
 
-const char* clairb_version(void) { return "clair_b200 0.3 sm_100a (tcgen05 BiLSTM, streamed layer-2 projection, decision stage)"; }
+const char* clairb_version(void) { return "clair_b200 0.4 sm_100a (tcgen05 BiLSTM, streamed layer-2 projection, decision stage, create_tensors)"; }
 
 const char* clairb_last_error(const clairb_engine* e) {
   if (e) return e->err.c_str();
