@@ -51,3 +51,45 @@ def snp_bases(aux):
     """(base1, base2) of a reference / SNP decision: the gt21 label (clair/call_var.py:60-67)."""
     label = GT21_LABELS[int(aux)]
     return label[0], label[1]
+
+
+class FirstChoice(object):
+    """Drop-in for the reference's `output_from` (clair/call_var.py:692-937) that answers from the device's decision records.
+
+    `output_with` (clair/call_var.py:1002-1197) calls `output_from(x, reference_sequence, contig, position, ...)` per site and
+    gets back the ten flags and (reference_base, alternate_base).  For the sites whose first choice is reference / homo SNP /
+    hetero SNP - the bulk of any call set - both follow from the record alone (category + gt21 label), without building the
+    ~1.2 k outcome products; every other site (indel categories, whose bases need the tensor / the BAM and may need the retry
+    loop) goes to `fallback`, the reference's own function.  A maintainer installs it as
+
+        first_choice = decision.FirstChoice(call_var.output_from); call_var.output_from = first_choice
+        ... per batch:  first_choice.load(batch_chr_pos_seq, dec)      # dec from m.predict_and_decide
+
+    Difference from the reference: when two categories tie EXACTLY for the maximum (never seen with real softmax outputs) the
+    reference's tuple carries a True flag for each of them; the record knows the first in its elif order only.
+    """
+
+    def __init__(self, fallback):
+        self.fallback = fallback
+        self.records = {}
+        self.served = self.deferred = 0
+
+    def load(self, batch_chr_pos_seq, decision):
+        category, aux = np.asarray(decision.category).tolist(), np.asarray(decision.aux).tolist()
+        self.records = {(info[0], int(info[1])): (category[i], aux[i]) for i, info in enumerate(batch_chr_pos_seq)}
+
+    def __call__(self, x, reference_sequence, contig, position, tensor_position_center, *rest, **kw):
+        record = self.records.get((contig, position))
+        if record is None or record[0] > 2:
+            self.deferred += 1
+            return self.fallback(x, reference_sequence, contig, position, tensor_position_center, *rest, **kw)
+        self.served += 1
+        category, aux = record
+        if category == 0:                                                     # clair/call_var.py:748-753
+            base = IUPAC_TO_ACGT[reference_sequence[tensor_position_center]]
+            return flags_tuple(0), (base, base)
+        base1, base2 = snp_bases(aux)
+        reference_base = reference_sequence[tensor_position_center]
+        if category == 2 and base1 != reference_base and base2 != reference_base:      # :771-776
+            return flags_tuple(2), (reference_base, "{},{}".format(base1, base2))
+        return flags_tuple(category), (reference_base, base1 if base1 != reference_base else base2)   # :766-769, 777-778

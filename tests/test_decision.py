@@ -140,3 +140,56 @@ def test_kernel_tie_breaking_on_quantised_probabilities(gpu_model):
     np.testing.assert_array_equal(np.stack([d.category, d.len1, d.len2, d.aux], axis=1), dec)
     np.testing.assert_array_equal(d.max_probability, maxp)
     assert len(set(dec[:, 0])) >= 6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="runs the reference's own batch_output; only where /root/reference exists")
+def test_first_choice_inside_the_reference_output_stage():
+    """decision.FirstChoice installed as call_var.output_from: the reference's batch_output prints the same VCF rows, with the
+    reference / SNP sites answered from the decision records (here from the decision oracle; on a GPU from predict_and_decide)."""
+    import time
+    from clair_b200 import decision, synth
+    from oracle import decision_oracle as DO
+    from oracle import gen_golden_decision as GD
+    cv = GD.import_reference_call_var()
+    rng = np.random.default_rng(8)
+    n = 400
+    x = synth.synthetic_tensors(n, seed=33)
+    infos = [["chr2", str(500 + 40 * i), "".join(rng.choice(list("ACGT"), size=33))] for i in range(n)]
+    heads = []
+    for i in range(n):                                     # a call set: mostly reference / SNP sites, some indels
+        z = [rng.normal(0, 1.5, k) for k in (21, 3, 33, 33)]
+        if i % 8:
+            z[0][rng.integers(0, 10)] += 7                 # an ACGT-pair label
+            z[2][16] += 6                                  # both lengths zero
+            z[3][16] += 6
+        heads.append(np.concatenate([GD.softmax(v) for v in z]))
+    P = np.stack(heads)
+    batch_Y = [P[:, 0:21], P[:, 21:24], P[:, 24:57], P[:, 57:90]]
+    records, max_p, depth = DO.decide(P, decision.ref_base_codes(infos), x)
+    dec = decision.Decision(records[:, 0], records[:, 1], records[:, 2], records[:, 3], max_p, depth)
+    config = cv.OutputConfig(is_show_reference=True, is_debug=False, is_haploid_precision_mode_enabled=False,
+                             is_haploid_sensitive_mode_enabled=False, is_output_for_ensemble=False, quality_score_for_pass=None)
+
+    def run():
+        lines, rec = [], GD.Recorder()
+        util = cv.OutputUtilities(print_debug_message=lambda *a: lines.append(("debug", a[0], a[1], a[-1])),
+                                  insertion_bases_using=rec.insertion_bases_using, deletion_bases_using=rec.deletion_bases_using,
+                                  insertion_bases_using_pysam_using=rec.insertion_bases_using_pysam_using,
+                                  output=lines.append, output_header=lambda: None, close_opened_files=lambda: None)
+        t = time.perf_counter()
+        cv.batch_output((x, infos), batch_Y, config, util)
+        return lines, time.perf_counter() - t
+
+    original = cv.output_from
+    want, t_reference = run()
+    first_choice = decision.FirstChoice(original)
+    first_choice.load(infos, dec)
+    cv.output_from = first_choice
+    try:
+        got, t_first_choice = run()
+    finally:
+        cv.output_from = original
+    assert got == want and len(want) > n // 2
+    assert first_choice.served + first_choice.deferred > n // 2 and first_choice.served > first_choice.deferred
+    print("batch_output: %.1f ms/site with the reference's output_from, %.2f ms/site with FirstChoice (%d of %d sites from records)"
+          % (1e3 * t_reference / n, 1e3 * t_first_choice / n, first_choice.served, first_choice.served + first_choice.deferred))
