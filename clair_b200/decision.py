@@ -53,14 +53,18 @@ def snp_bases(aux):
     return label[0], label[1]
 
 
+MIN_INFERRED_LENGTH, MAX_INFERRED_LENGTH = 16, 50      # clair/call_var.py:29-30 (maximum_variant_length_from, :480-484)
+
+
 class FirstChoice(object):
     """Drop-in for the reference's `output_from` (clair/call_var.py:692-937) that answers from the device's decision records.
 
     `output_with` (clair/call_var.py:1002-1197) calls `output_from(x, reference_sequence, contig, position, ...)` per site and
-    gets back the ten flags and (reference_base, alternate_base).  For the sites whose first choice is reference / homo SNP /
-    hetero SNP - the bulk of any call set - both follow from the record alone (category + gt21 label), without building the
-    ~1.2 k outcome products; every other site (indel categories, whose bases need the tensor / the BAM and may need the retry
-    loop) goes to `fallback`, the reference's own function.  A maintainer installs it as
+    gets back the ten flags and (reference_base, alternate_base).  Both follow from the record - category, variant lengths,
+    gt21 label / hetero base - without building the ~1.2 k outcome products: reference and SNP sites from the record alone,
+    indel sites with the same calls to the indel-base helpers of `output_utilities` the reference makes for its first choice
+    (:780-937).  Only when a helper comes back empty, where the reference's loop moves on to its next candidate, the site
+    goes to `fallback`, the reference's own function.  A maintainer installs it as
 
         first_choice = decision.FirstChoice(call_var.output_from); call_var.output_from = first_choice
         ... per batch:  first_choice.load(batch_chr_pos_seq, dec)      # dec from m.predict_and_decide
@@ -75,21 +79,75 @@ class FirstChoice(object):
         self.served = self.deferred = 0
 
     def load(self, batch_chr_pos_seq, decision):
-        category, aux = np.asarray(decision.category).tolist(), np.asarray(decision.aux).tolist()
-        self.records = {(info[0], int(info[1])): (category[i], aux[i]) for i, info in enumerate(batch_chr_pos_seq)}
+        fields = [np.asarray(f).tolist() for f in (decision.category, decision.len1, decision.len2, decision.aux)]
+        self.records = {(info[0], int(info[1])): (fields[0][i], fields[1][i], fields[2][i], fields[3][i])
+                        for i, info in enumerate(batch_chr_pos_seq)}
 
-    def __call__(self, x, reference_sequence, contig, position, tensor_position_center, *rest, **kw):
+    def __call__(self, x, reference_sequence, contig, position, tensor_position_center, gt21_probabilities,
+                 genotype_probabilities, variant_length_probabilities_1, variant_length_probabilities_2, output_config,
+                 output_utilities):
         record = self.records.get((contig, position))
-        if record is None or record[0] > 2:
+        answer = None if record is None else self._first_choice(x, reference_sequence, contig, position,
+                                                                tensor_position_center, output_utilities, *record)
+        if answer is None:
+            # no record, or the first choice did not yield bases: the reference's loop moves on to its next candidate
+            # (clair/call_var.py:803, 819, 838-839, 853, ... `continue`), which needs its full outcome lists
             self.deferred += 1
-            return self.fallback(x, reference_sequence, contig, position, tensor_position_center, *rest, **kw)
+            return self.fallback(x, reference_sequence, contig, position, tensor_position_center, gt21_probabilities,
+                                 genotype_probabilities, variant_length_probabilities_1, variant_length_probabilities_2,
+                                 output_config, output_utilities)
         self.served += 1
-        category, aux = record
+        return answer
+
+    @staticmethod
+    def _first_choice(x, reference_sequence, contig, position, center, util, category, len1, len2, aux):
+        """(flags, (REF, ALT)) of the first pass of output_from's loop, or None where the reference would `continue`."""
+        ref0 = reference_sequence[center]
         if category == 0:                                                     # clair/call_var.py:748-753
-            base = IUPAC_TO_ACGT[reference_sequence[tensor_position_center]]
+            base = IUPAC_TO_ACGT[ref0]
             return flags_tuple(0), (base, base)
-        base1, base2 = snp_bases(aux)
-        reference_base = reference_sequence[tensor_position_center]
-        if category == 2 and base1 != reference_base and base2 != reference_base:      # :771-776
-            return flags_tuple(2), (reference_base, "{},{}".format(base1, base2))
-        return flags_tuple(category), (reference_base, base1 if base1 != reference_base else base2)   # :766-769, 777-778
+        if category in (1, 2):                                                # :766-778
+            base1, base2 = snp_bases(aux)
+            if category == 2 and base1 != ref0 and base2 != ref0:
+                return flags_tuple(2), (ref0, "{},{}".format(base1, base2))
+            return flags_tuple(category), (ref0, base1 if base1 != ref0 else base2)
+        if category in (3, 4, 5, 9):                                          # an insertion is part of the call
+            insertion_bases, insertion_length = util.insertion_bases_using(
+                tensor_input=x, variant_length=len2 if category in (5, 9) else len1, contig=contig, position=position)
+            if category == 9:                                                 # :912-937
+                deletion_bases, deletion_length = util.deletion_bases_using(
+                    tensor_input=x, variant_length=len1, contig=contig, position=position, reference_sequence=reference_sequence)
+                if insertion_length == 0 or deletion_length == 0:
+                    return None
+                ref = ref0 + deletion_bases
+                return flags_tuple(9), (ref, "{},{}".format(ref[0], ref[0] + insertion_bases + ref[1:]))
+            if insertion_length == 0:
+                return None
+            alt = ref0 + insertion_bases
+            if category == 3:                                                 # :780-790
+                return flags_tuple(3), (ref0, alt)
+            if category == 4:                                                 # :792-810
+                hetero_base = "ACGT"[aux]
+                return flags_tuple(4), (ref0, "{},{}".format(hetero_base, alt) if hetero_base != ref0 else alt)
+            another = util.insertion_bases_using_pysam_using(                 # :812-840
+                contig=contig, position=position, minimum_insertion_length=len1,
+                maximum_insertion_length=MAX_INFERRED_LENGTH if len1 >= MIN_INFERRED_LENGTH else len1,
+                insertion_bases_to_ignore=insertion_bases) or insertion_bases[0:len1]
+            alt_1 = ref0 + another
+            return (flags_tuple(5), (ref0, "{},{}".format(alt_1, alt))) if alt_1 != alt else None
+        deletion_bases, deletion_length = util.deletion_bases_using(          # categories 6, 7, 8
+            tensor_input=x, variant_length=len2 if category == 8 else len1, contig=contig, position=position,
+            reference_sequence=reference_sequence)
+        if deletion_length == 0:
+            return None
+        ref = ref0 + deletion_bases
+        if category == 6:                                                     # :842-857
+            return flags_tuple(6), (ref, ref[0])
+        if category == 7:                                                     # :859-883
+            hetero_base = "ACGT"[aux]
+            alt = "{},{}".format(ref[0], hetero_base + ref[1:]) if hetero_base != ref[0] else ref[0]
+            return flags_tuple(7), (ref, alt)
+        alt_1, alt_2 = ref[0], ref[0] + ref[len1 + 1:]                        # :885-910
+        if alt_1 != alt_2 and ref != alt_1 and ref != alt_2:
+            return flags_tuple(8), (ref, "{},{}".format(alt_1, alt_2))
+        return None
