@@ -9,8 +9,8 @@ csrc/create_tensor_kernels.cuh).  `created_tensor_generator_from` / `TensorBlock
 and hand them straight to the forward pass, which removes the text hop between CreateTensor.py and call_var.py
 (clair/callVarBam.py:191-200) and the host->device copy.
 
-Not modelled: the 5,000,000-record memory guard (`available_slots`, :180,285-286), which only drops records when more
-than five million are outstanding.  Reads must be coordinate-sorted (as `samtools view` of a sorted BAM yields them; the
+Not modelled: the 5,000,000-record memory guard (`available_slots`, :180,285-286,306-308), which only drops records when
+more than five million are outstanding - which ones then depends on the iteration order of a Python set (:305).  Reads must be coordinate-sorted (as `samtools view` of a sorted BAM yields them; the
 reference's flush at :368-381 assumes the same) and a read whose CIGAR consumes more bases than SEQ holds is an error
 (the reference raises IndexError on it once a window is open).
 """
