@@ -152,3 +152,28 @@ def test_evaluate_model_prints_the_reference_report(tmp_path):
     model = GE.FakeModel()
     evaluate.evaluate_model(model, info)
     assert model.calls == [1000, 730]                     # predict sees the batches the reference's walk produces
+
+
+def test_decoder_survives_damaged_frames():
+    """Every byte of the container is attacker-controlled as far as the decoder is concerned: random damage must end in an
+    error or in bytes of the announced size, never in a read or write outside the buffers (the library would take the test
+    process down with it)."""
+    rng = np.random.default_rng(123)
+    data = (rng.integers(0, 6, size=70000).astype(np.uint8) * 9).tobytes()
+    frames = [bins.blosc_compress(data, typesize=4, split=True), bins.blosc_compress(data, typesize=4, split=False),
+              bins.blosc_compress(data[:5000], typesize=1)]
+    outcomes = {"error": 0, "bytes": 0}
+    for frame in frames:
+        for _ in range(400):
+            damaged = bytearray(frame)
+            for _ in range(int(rng.integers(1, 6))):
+                damaged[int(rng.integers(0, len(damaged)))] = int(rng.integers(0, 256))
+            if rng.random() < 0.2:
+                damaged = damaged[:int(rng.integers(0, len(damaged)))]
+            try:
+                out = bins.blosc_decompress(bytes(damaged))
+                assert isinstance(out, bytes)
+                outcomes["bytes"] += 1
+            except (ValueError, MemoryError):
+                outcomes["error"] += 1
+    assert outcomes["error"] > 100 and outcomes["bytes"] > 100

@@ -185,6 +185,39 @@ def test_native_encoder_equals_python_encoder(case):
         assert np.array_equal(getattr(native, field), getattr(again, field)), field
 
 
+def test_native_encoder_equals_python_encoder_on_odd_cigars():
+    """CIGAR strings the SAM specification does not produce but the reference's character loop defines anyway
+    (CreateTensor.py:283-366): unknown op letters, lower case, zero lengths, digits without an op, '*', very long lengths."""
+    rng = np.random.default_rng(404)
+    alphabet = list("MIDNSHP=XBmid*") + ["", "0"]
+    rows, pos = [], 3
+    for i in range(300):
+        pos += int(rng.integers(0, 4))
+        parts = []
+        for _ in range(int(rng.integers(0, 9))):
+            parts.append("%s%s" % (rng.choice(["", "0", "1", "3", "12", "007"]), rng.choice(alphabet)))
+        cigar = "".join(parts) + rng.choice(["", "5", "2M"])
+        if not cigar:
+            cigar = "*"
+        flag = int(rng.choice([0, 16, 2048, 272]))
+        sep = rng.choice(["\t", " ", "\t\t"])
+        row = sep.join(["q%d" % i, str(flag), "c", str(pos), str(int(rng.integers(0, 61))), cigar, "*", "0", "0",
+                        "".join(rng.choice(list("ACGTNacgt"), size=120)), "*", "NM:i:3 extra column"])
+        try:                                              # digits run together ("12" + "3M"): both encoders refuse a CIGAR
+            CT.encode_alignments([row], encoder="python")  # that consumes more bases than SEQ holds
+        except ValueError:
+            with pytest.raises(ValueError):
+                CT.encode_alignments([row])
+            continue
+        rows.append(row)
+    for min_mq, dcov in ((0, 250), (30, 2)):
+        native = CT.encode_alignments(rows, min_mq, dcov)
+        python = CT.encode_alignments(rows, min_mq, dcov, encoder="python")
+        assert native.n_reads > 50
+        for field in CT.Alignments.__slots__:
+            assert np.array_equal(getattr(native, field), getattr(python, field)), field
+
+
 def test_native_encoder_rejects_malformed_rows():
     with pytest.raises(ValueError):
         CT.encode_alignments(["r\t0\tc\tnot_a_number\t60\t1M\t*\t0\t0\tA\t*"])
