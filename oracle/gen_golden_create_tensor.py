@@ -136,7 +136,15 @@ def random_read(rng, contig_len, pos0, style):
     seq = rng.choice(list("ACGT"), size=qlen)
     for ch, rate in (("N", 0.01), ("c", 0.02), ("t", 0.02), ("Y", 0.004), (".", 0.003), ("=", 0.003)):
         seq[rng.random(qlen) < rate] = ch
-    return "".join("%d%s" % (n, c) for n, c in ops), "".join(seq)
+    cigar = "".join("%d%s" % (n, c) for n, c in ops)
+    if style == "odd":
+        # tokens the SAM specification does not produce; the reference's character loop (:283-366) gives them no effect
+        junk = ["3B", "0M", "2m", "7i", "*", "0D", "12d", "4Z", "0I"]
+        tokens = ["%d%s" % (n, c) for n, c in ops]
+        for _ in range(int(rng.integers(1, 5))):
+            tokens.insert(int(rng.integers(0, len(tokens) + 1)), junk[int(rng.integers(0, len(junk)))])
+        cigar = "".join(tokens)
+    return cigar, "".join(seq)
 
 
 def make_case(rng, name, contig_len, n_reads, n_cand, style="mixed", dcov=250, min_mq=0, min_cov=0,
@@ -191,6 +199,7 @@ def make_cases():
         make_case(rng, "dcov_one", 700, 200, 50, dup_rate=0.5, dcov=1),
         make_case(rng, "region_from_one", 1500, 200, 80, region=(1, 700), expand=25),
         make_case(rng, "no_left_edge_dense", 900, 260, 40, style="dense", stop_left=True, dup_rate=0.2, dcov=3),
+        make_case(rng, "odd_cigars", 900, 220, 60, style="odd"),
     ]
 
 
