@@ -4,6 +4,7 @@
 #include "../../clair_b200/csrc/blosc_host.cuh"
 #include "../../clair_b200/csrc/encode_host.cuh"
 #include "../../clair_b200/csrc/format_host.cuh"
+#include "../../clair_b200/csrc/decode_host.cuh"
 #include <cstdio>
 #include <random>
 #include <string>
@@ -64,6 +65,26 @@ int main() {
     (r2 == 0 ? ok : err)++;
   }
   printf("sam fuzz: ok=%d err=%d\n", ok, err);
+  // 2b) tensor-row decoder (clairb_decode_rows): valid rows with random damage and truncation
+  ok = err = 0;
+  for (int it = 0; it < 3000; ++it) {
+    std::string text;
+    int rows = 1 + rng() % 3;
+    for (int r = 0; r < rows; ++r) {
+      text += "chr1 " + std::to_string(rng() % 100000) + " ACGTACGTACGTACGTNACGTACGTACGTACGTA";
+      for (int k = 0; k < 1056; ++k) text += " " + std::to_string((int)(rng() % 200) - 20);
+      text += "\n";
+    }
+    int k = rng() % 4;
+    for (int j = 0; j < k; ++j) text[rng() % text.size()] = " \t-9aN.\n"[rng() % 9];
+    if (rng() % 4 == 0) text.resize(rng() % text.size());
+    std::vector<int16_t> xo((size_t)rows * 1056 + 1056);
+    std::vector<int32_t> info((size_t)(rows + 2) * 6);
+    int64_t rr = 0, rk = 0, cons = 0, bad = -1;
+    int r = decode::rows<int16_t>(text.data(), (int64_t)text.size(), rows, xo.data(), info.data(), &rr, &rk, &cons, &bad, 2);
+    (r == 0 ? ok : err)++;
+  }
+  printf("decode fuzz: ok=%d err=%d\n", ok, err);
   // 3) formatter at the edges of the reference text
   const char* ref = "ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT";
   int64_t positions[3] = {17, 30, 1000000000}, starts[3] = {0, 20, 39};

@@ -1,5 +1,5 @@
 """Host-side decoders of the C-ABI library under AddressSanitizer / UBSan (tests/harness/host_fuzz.cu): damaged Blosc frames,
-random and truncated SAM rows, the row formatter at the edges of the reference text.  Skipped where the sanitizer runtime is
+random and truncated SAM rows, damaged tensor rows, the row formatter at the edges of the reference text.  Skipped where the sanitizer runtime is
 not installed."""
 import os
 import subprocess
@@ -25,4 +25,4 @@ def test_host_decoders_under_sanitizers(tmp_path):
     assert "ERROR: AddressSanitizer" not in run.stderr and "runtime error" not in run.stderr, run.stderr[-3000:]
     out = run.stdout.splitlines()
     assert out[0].startswith("valid frame rc=0 n=205 first=a last=z")
-    assert "blosc fuzz" in out[1] and "sam fuzz" in out[2] and out[3].startswith("format rc=0")
+    assert "blosc fuzz" in out[1] and "sam fuzz" in out[2] and "decode fuzz" in out[3] and out[4].startswith("format rc=0")
