@@ -15,17 +15,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def device_part(m, contig_len=1000000, repeats=5, with_forward=True, hbm_peak_gbs=None):
+# read shapes of the three technologies the reference ships models for (README "Pretrained Models"); "ont" is the default
+SHAPES = {"ont": dict(depth=40, read_len=8000, ops_per_read=1001, site_spacing=50),
+          "ccs": dict(depth=30, read_len=14000, ops_per_read=61, site_spacing=300),
+          "illumina": dict(depth=60, read_len=150, ops_per_read=3, site_spacing=500)}
+
+
+def device_part(m, contig_len=1000000, repeats=5, with_forward=True, hbm_peak_gbs=None, shape="ont"):
     """-> (report, context for cpu_part).  `m` is a clair_b200.model.Clair (with weights when with_forward)."""
     from clair_b200 import create_tensor as CT, synth
     t0 = time.time()
-    aln, reference, sites = synth.synthetic_alignments(contig_len)
+    aln, reference, sites = synth.synthetic_alignments(contig_len, **SHAPES[shape])
     gen_s = time.time() - t0
     lib, h = m._lib, m._h
     n = int(sites.shape[0])
     if n > m.max_sites:
         raise ValueError("region holds %d sites, the model handle was sized for %d" % (n, m.max_sites))
-    out = {"workload": "synthetic ONT-like region: %d bp, depth 40, 8 kb reads, an indel every ~8 bases, a candidate every ~50 bp" % contig_len,
+    what = {"ont": "ONT-like region: %d bp, depth 40, 8 kb reads, an indel every ~8 bases, a candidate every ~50 bp",
+            "ccs": "CCS-like region: %d bp, depth 30, 14 kb reads, an indel every ~230 bases, a candidate every ~300 bp",
+            "illumina": "Illumina-like region: %d bp, depth 60, 150 bp reads, one indel per read, a candidate every ~500 bp"}[shape]
+    out = {"workload": "synthetic " + what % contig_len,
            "sites": n, "reads": aln.n_reads, "ops": aln.n_ops, "query_bases": int(aln.seq.size), "synth_seconds": round(gen_s, 2)}
     in_bytes = sum(int(getattr(aln, f).nbytes) for f in aln.__slots__) + len(reference) + 4 * n
     out["input_bytes"] = in_bytes
@@ -135,12 +144,13 @@ if __name__ == "__main__":
     ap.add_argument("--contig", type=int, default=1000000)
     ap.add_argument("--repeats", type=int, default=5)
     ap.add_argument("--no-forward", action="store_true")
+    ap.add_argument("--shape", default="ont", choices=sorted(SHAPES))
     args = ap.parse_args()
     from clair_b200 import weights as W
     from clair_b200.model import Clair
-    model = Clair(max_sites=max(4096, args.contig // 40), batch_sites=1000)
+    model = Clair(max_sites=max(4096, args.contig // 20), batch_sites=1000)
     if not args.no_forward:
         model.set_weights(W.random_weights(seed=1234))
-    report, context = device_part(model, args.contig, args.repeats, not args.no_forward, hbm_peak())
+    report, context = device_part(model, args.contig, args.repeats, not args.no_forward, hbm_peak(), args.shape)
     print(json.dumps(cpu_part(report, context)))
     model.close()
