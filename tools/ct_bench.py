@@ -75,6 +75,12 @@ def device_part(m, contig_len=1000000, repeats=5, with_forward=True, hbm_peak_gb
     if hbm_peak_gbs:
         out["kernel"]["hbm_peak_gbs"] = hbm_peak_gbs
         out["kernel"]["frac"] = out["kernel"]["achieved_gbs"] / hbm_peak_gbs
+        # the same numbers under the key names of bench.py's `roofline` object
+        out["roofline"] = {"bound": "hbm", "kernel": "create_tensors", "achieved": out["kernel"]["achieved_gbs"], "peak": hbm_peak_gbs,
+                           "unit": "GB/s", "frac": out["kernel"]["frac"], "traffic": out["kernel"]["traffic"],
+                           "algorithmic_bytes": algo, "avg_launch_ms": k_ms, "sites_per_launch": n,
+                           "note": "bytes are at the algorithmic minimum; the kernel is bound by instruction issue under divergence "
+                                   "(8.9 of 32 threads active per instruction, profiles/r01_s19_create_tensors.ncu_summary.txt)"}
     out["call_resident"] = {"seconds": call_s, "sites_per_s": n / call_s, "h2d_bytes": in_bytes,
                             "note": "clairb_create_tensors, encoded reads in pinned host memory (uploaded every call), tensors left on the device"}
     pg_s, _ = timed(aln, max(2, repeats // 2), subtract=True, fetch=False)
