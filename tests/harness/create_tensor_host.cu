@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE.  Compiles the __host__ __device__ halves of csrc/create_tensor_kernels.cuh (read_range, fold_read,
 // base_row) for the CPU so that the per-site rule the kernel applies can be checked against the reference-generated golden
-// rows on a machine without a GPU (tests/test_create_tensor.py, -m "not gpu").  Never linked into libclair_b200.so.
+// rows on a machine without a GPU (tests/test_widen_create_tensor.py, -m "not gpu").  Never linked into libclair_b200.so.
 #include "../../clair_b200/csrc/create_tensor_kernels.cuh"
 
 namespace {

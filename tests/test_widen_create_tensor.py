@@ -1,4 +1,5 @@
-"""CreateTensor on the device.
+"""CreateTensor on the device.  (The file name sorts after the forward-path tests on purpose: the
+driver runs `pytest -x`, and a widening row must not be able to hide the main path.)
 
 not gpu: the oracle restatement and the kernel's per-site rule (its __host__ __device__ half compiled for the CPU by
          tests/harness) against rows printed by the reference's own OutputAlnTensor (tests/golden/create_tensor_cases.json.gz,
