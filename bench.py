@@ -3,20 +3,23 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): ONT-shape model, 1M synthetic candidate sites in
-predict-batches of 1000.  A "step" is one pass of the forward over a pool of `--batches-per-step`
-predict-batches (default 142 x 1000 sites = 600 MB of fp32 input, larger than the 126 MB L2, so
-every step re-reads its inputs from HBM; 142,000 sites = 14.99 waves of 74 CTA pairs x 128 sites: 7 full chunks of
-18,944 sites + one of 9,392); the default 8 steps are 1.14 M sites.  One step is one predict() call of the end-to-end
-leg, so the per-call cost of the host pipeline (first host->device copy, last device->host copy: about 1.3 ms) is
-paid once per 142 predict-batches.
-  value : device-resident sites/s (inputs already in HBM, CUDA events on the launching stream)
-  e2e   : the same through the reference-facing call (Clair.predict -> clairb_predict_split: four fresh float32
-          arrays per call like clair/model.py:946-966): pinned HOST input, H2D + forward + D2H inside the timed region
-  roofline / cpu_baseline : see DESIGN.md section "Measurement"
-N>1 (launched by torchrun, one rank per GPU): every rank runs the same per-GPU workload on its own
-sites (weak scaling) and the packed [sites,90] probabilities are gathered to rank 0 with one NCCL
-collective per step, inside the timed region.
+Workload (BASELINE.json configs[1]): ONT-shape model, 1M synthetic candidate sites in predict-batches of 1000.  A "step"
+is one pass of the forward over all `--batches-per-step` predict-batches (default 1000 x 1000 sites = 4.2 GB of fp32
+input, far larger than the 126 MB L2; the sites are `--distinct-batches` distinct synthetic batches repeated); the default
+20 steps keep the timed region above 2 s, so the sustained tensor peak is the right roofline denominator.
+  value    : device-resident sites/s (inputs already in HBM, CUDA events on the launching stream)
+  e2e      : one Clair.predict call per step over the whole pool (four fresh float32 arrays per call like
+             clair/model.py:946-966): pinned HOST input in the int16 transport (the same integer counts, bit-identical
+             results), H2D + forward + D2H inside the timed region; `e2e_f32` is the same call fed float32
+  loop_e2e : the reference-shaped loop - a generator yielding 1000-site batches, one predict per batch
+             (clair/call_var.py:1340-1344, param.predictBatchSize), a no-op output stage - through
+             clair_b200.call_var.run_batches (predict_async: many batches in flight); `loop_lockstep` is the same loop
+             with exactly one predict in flight, the reference's own structure
+  roofline / cpu_baseline / oracle_pinning : see DESIGN.md section "Measurement"
+N>1 (launched by torchrun, one rank per GPU): every rank runs the same per-GPU workload on its own sites (weak scaling);
+the packed [sites,90] probabilities are gathered to rank 0 with one NCCL collective per step, inside the timed region
+(e2e: host input -> device -> gather -> rank 0's host memory), and rank 0 checks the gathered rows bit for bit against
+a single-GPU run of the same sites.
 """
 import argparse
 import json
@@ -50,26 +53,32 @@ WORKLOAD = "ONT-shape model inference, 1M synthetic candidate sites, batch=1000,
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batches-per-step", type=int, default=142)
+    ap.add_argument("--batches-per-step", type=int, default=1000)
+    ap.add_argument("--distinct-batches", type=int, default=200, help="distinct synthetic predict-batches, repeated to fill a step")
+    ap.add_argument("--in-flight", type=int, default=64, help="predict-batches in flight in the loop_e2e leg")
     ap.add_argument("--cpu-baseline-batches", type=int, default=0, help="0 = auto (about 10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-create-tensor", action="store_true", help="skip the CreateTensor-stage line (SURVEY 8f row 4)")
     return ap.parse_args()
 
 
+TRAFFIC_FILES = ("r02_traffic.json", "r01_traffic_s11.json")     # newest capture first
+
+
 def measured_traffic(kernel, sites_per_launch):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic_s11.json),
-    scaled to this run's sites per launch; None when no capture covers the kernel."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic_s11.json")
-    try:
-        with open(path) as f:
-            t = json.load(f)
-        return t["dram_bytes_per_site"][kernel] * sites_per_launch
-    except (OSError, KeyError, ValueError):
-        return None
+    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full capture that covers it (profiles/),
+    scaled to this run's sites per launch; (None, None) when no capture covers the kernel."""
+    for name in TRAFFIC_FILES:
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            return t["dram_bytes_per_site"][kernel] * sites_per_launch, name
+        except (OSError, KeyError, ValueError):
+            continue
+    return None, None
 
 
 def measured_peaks():
@@ -173,59 +182,145 @@ def cpu_info():
     return model, os.cpu_count() or 1
 
 
-def time_cpu_port(weights, pool, n_batches, warm=1):
-    """Oracle port (torch-CPU fp32, all host threads) on a bounded sample of the same workload."""
-    from oracle.clair_oracle_fast import FastOracle
+# ---- the reference's CPU path on the host cores ---------------------------------------------------------------------
+# The reference scales on a host by running independent processes over genome chunks (`parallel -j`,
+# /root/reference README "Run Clair ... in parallel", callVarBamParallel.py:90-119), each with a few intra-op threads
+# (--threads, 4 in the README's commands).  The arm mirrors that: cores // 4 worker processes x 4 threads, every worker
+# running the fp32 CPU port of the forward (oracle/clair_oracle_fast.py; TensorFlow 1.13.2 itself is not installable) on its
+# own predict-batches.
+def _cpu_worker(rank, threads, weights, seeds, check_batch, conn):
+    import numpy as np                                     # noqa: F401
     import torch
-    torch.set_num_threads(os.cpu_count() or 1)
-    fo = FastOracle(weights)
-    first = None
-    for i in range(warm):
-        first = fo.forward_packed(pool[i % len(pool)])
-    t0 = time.perf_counter()
-    for i in range(n_batches):
-        fo.forward_packed(pool[i % len(pool)])
-    dt = time.perf_counter() - t0
-    return n_batches * BATCH / dt, fo.threads, dt, first
+    torch.set_num_threads(threads)
+    sys.path.insert(0, ROOT)
+    from clair_b200 import synth
+    from oracle.clair_oracle_fast import FastOracle
+    fo = FastOracle(weights, threads=threads)
+    pool = [synth.synthetic_tensors(BATCH, seed=s) for s in seeds]
+    if check_batch is not None:
+        pool[0] = check_batch
+    first = fo.forward_packed(pool[0])                     # warm-up, and the checker's sample
+    conn.send(("ready", first if rank == 0 else None))
+    k = 0
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            return
+        t0 = time.perf_counter()
+        for _ in range(msg):
+            fo.forward_packed(pool[k % len(pool)])
+            k += 1
+        conn.send(("done", time.perf_counter() - t0))
+
+
+class CpuArm(object):
+    """cores // 4 processes x 4 threads of the CPU port; run(k) = every worker does k predict-batches, returns seconds."""
+
+    def __init__(self, weights, seeds, procs=None, threads=4, check_batch=None):
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        self.threads = min(threads, cores)
+        self.procs = procs or max(1, cores // self.threads)
+        ctx = mp.get_context("spawn")
+        self.workers = []
+        for r in range(self.procs):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker, daemon=True,
+                            args=(r, self.threads, weights, [s + 17 * r for s in seeds], check_batch if r == 0 else None, b))
+            p.start()
+            self.workers.append((p, a))
+        self.first = None
+        for r, (_, a) in enumerate(self.workers):
+            tag, first = a.recv()
+            if r == 0:
+                self.first = first
+
+    def run(self, k):
+        t0 = time.perf_counter()
+        for _, a in self.workers:
+            a.send(k)
+        for _, a in self.workers:
+            a.recv()
+        return time.perf_counter() - t0
+
+    def close(self):
+        for p, a in self.workers:
+            try:
+                a.send(None)
+            except OSError:
+                pass
+        for p, _ in self.workers:
+            p.join(timeout=10)
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU path.  TensorFlow 1.13.2 cannot be installed here (no
-    wheel for Python 3.12, no network), so this times the oracle port - see DESIGN.md."""
+    """--impl reference: the reference's CPU path on all host cores (see CpuArm), a bounded sample per step."""
     if rank != 0:
         return
-    import numpy as np
-    from clair_b200 import synth, weights as W
+    from clair_b200 import weights as W
     w = W.random_weights(seed=1234)
-    per_step = 2                                        # bounded sample: 2 predict-batches per step
-    pool = [synth.synthetic_tensors(BATCH, seed=20240607 + i) for i in range(4)]
-    from oracle.clair_oracle_fast import FastOracle
-    import torch
-    torch.set_num_threads(os.cpu_count() or 1)
-    fo = FastOracle(w)
-    k = 0
-    for _ in range(args.warmup):
-        for _ in range(per_step):
-            fo.forward_packed(pool[k % 4]); k += 1
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for _ in range(per_step):
-            fo.forward_packed(pool[k % 4]); k += 1
-    dt = time.perf_counter() - t0
+    arm = CpuArm(w, [20240607 + i for i in range(2)])
+    per_worker = 1                                      # predict-batches per worker per step
+    try:
+        for _ in range(max(1, args.warmup)):
+            arm.run(per_worker)
+        dt = 0.0
+        for _ in range(args.steps):
+            dt += arm.run(per_worker)
+    finally:
+        arm.close()
+    per_step = per_worker * arm.procs
     value = args.steps * per_step * BATCH / dt
     model, cores = cpu_info()
-    sample = "%d steps x %d predict-batches x %d sites (of the 1M-site workload)" % (args.steps, per_step, BATCH)
+    sample = "%d steps x %d predict-batches x %d sites (of the 1M-site workload); %d processes x %d threads" % (
+        args.steps, per_step, BATCH, arm.procs, arm.threads)
     print(json.dumps({
         "impl": "reference", "metric": "candidate-sites/sec", "value": value, "unit": "sites/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD % 1, "batch": BATCH, "sites_per_step": per_step * BATCH,
-                   "note": "reference CPU path = fp32 torch-CPU port of the reference graph (TensorFlow 1.13.2 not installable)"},
-        "cpu_baseline": {"value": value, "unit": "sites/s", "cores": fo.threads, "kind": "port", "sample": sample,
+                   "note": "reference CPU path = fp32 torch-CPU port of the reference graph (TensorFlow 1.13.2 not installable), "
+                           "run the way the reference scales on a host: independent processes x 4 threads (README `parallel -j`)"},
+        "cpu_baseline": {"value": value, "unit": "sites/s", "cores": arm.procs * arm.threads, "kind": "port", "sample": sample,
                          "cpu_model": model, "host_cores": cores},
         "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def oracle_pinning(m, weights, X256):
+    """How far the forward oracle can be pinned on this box (the reference's arithmetic lives in TensorFlow
+    1.13): (1) is TensorFlow importable (then the reference itself could be run); (2) cuDNN's own fp32 LSTM + torch dense
+    trunk on this GPU as a third, independent restatement against the fp64 numpy oracle and against the product."""
+    import numpy as np
+    out = {}
+    try:
+        import tensorflow as tf                                   # noqa: F401
+        out["tensorflow"] = getattr(tf, "__version__", "present")
+    except Exception as exc:
+        out["tensorflow"] = "not importable (%s)" % type(exc).__name__
+    try:
+        from oracle import clair_oracle as O
+        from oracle.clair_oracle_cudnn import CudnnOracle
+        from clair_b200 import _lib
+        ref_probs, im = O.forward(X256, weights, np.float64, intermediates=True)
+        ref_logits = np.concatenate(im["logits"], axis=1)
+        cp, cl = CudnnOracle(weights, device="cuda").forward(X256)
+        m.predict(X256)
+        ours = m.get_layer(_lib.LAYER_LOGITS, X256.shape[0])
+        scaled = lambda a, b: float((np.abs(a - b) / np.maximum(1.0, np.abs(b))).max())
+        out.update({"sites": int(X256.shape[0]),
+                    "cudnn_fp32_vs_fp64_oracle_logits": scaled(cl, ref_logits),
+                    "ours_vs_fp64_oracle_logits": scaled(ours, ref_logits),
+                    "ours_vs_cudnn_fp32_logits": scaled(ours, cl),
+                    "argmax_identical_all_three": bool(all(
+                        (cp[:, a:b].argmax(1) == np.concatenate(ref_probs, axis=1)[:, a:b].argmax(1)).all()
+                        for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)))),
+                    "note": "torch.nn.LSTM on cuda = cuDNN's LSTM, the kernel CudnnCompatibleLSTMCell (clair/model.py:282-312) is "
+                            "defined to be weight-compatible with; TF32 off"})
+    except Exception as exc:
+        out["cudnn_error"] = "%s: %s" % (type(exc).__name__, exc)
+    return out
 
 
 def main():
@@ -246,7 +341,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from clair_b200 import _lib, synth, weights as W
+    from clair_b200 import _lib, call_var, synth, weights as W
     from clair_b200.model import Clair, pinned_empty
 
     torch.cuda.set_device(local_rank)
@@ -257,16 +352,32 @@ def main():
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(seconds):
+        if world == 1:
+            return seconds
+        t = torch.tensor([seconds], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     bps = args.batches_per_step
     sites = bps * BATCH
+    steps, warm = args.steps, max(args.warmup, 3)
     weights = W.random_weights(seed=1234)
     m = Clair(device=local_rank, max_sites=sites, batch_sites=BATCH)
     m.set_weights(weights)
+    lib, h = m._lib, m._h
 
-    # ---- synthetic pool: distinct per rank, 64 distinct predict-batches per step ----
-    X = pinned_empty((sites, 33, 8, 4), np.float32)
-    X[...] = synth.synthetic_tensors(sites, seed=20240607 + 1 + 1000 * rank)
-    out_host = pinned_empty((sites, _lib.N_OUT), np.float32)
+    # ---- synthetic pool: `distinct` predict-batches per rank (different on every rank), repeated to fill the step ----
+    distinct = min(args.distinct_batches, bps)
+    Xi = pinned_empty((sites, 33, 8, 4), np.int16)                 # the int16 transport of the same counts
+    base = synth.synthetic_counts(distinct * BATCH, seed=20240607 + 1 + 1000 * rank)
+    base[..., 1:] -= base[..., 0:1]                                # clair/utils.py:96-98
+    for s0 in range(0, sites, distinct * BATCH):
+        k = min(distinct * BATCH, sites - s0)
+        Xi[s0:s0 + k] = base[:k]
+    del base
+    X = pinned_empty((sites, 33, 8, 4), np.float32)                # what the reference's generator yields
+    X[...] = Xi
     xd = torch.from_numpy(X).cuda(non_blocking=False)
     od = torch.empty((sites, _lib.N_OUT), dtype=torch.float32, device="cuda")
     gather_bufs = [torch.empty_like(od) for _ in range(world)] if (world > 1 and rank == 0) else None
@@ -282,7 +393,7 @@ def main():
         sampler.start()
 
     # ---- device-resident timing ----
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         device_step()
     torch.cuda.synchronize()
     barrier()
@@ -292,7 +403,7 @@ def main():
     torch.cuda.synchronize()
     sampler.mark_begin()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         device_step()
     ev1.record(stream)
     torch.cuda.synchronize()
@@ -307,30 +418,74 @@ def main():
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * sites * args.steps / (ms * 1e-3)
+    value = world * sites * steps / (ms * 1e-3)
 
-    # ---- end-to-end through the reference-facing call: pinned host in, host out ----
-    for _ in range(2):
-        m._lib.clairb_predict(m._h, X.ctypes.data, _lib.DTYPE_F32, sites, out_host.ctypes.data)
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out4 = m.predict(X)                # the reference's own call: four fresh float32 arrays (clair/model.py:946-966)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    out = np.concatenate(out4, axis=1)
+    # ---- end to end: host input -> probabilities in host memory, once per step over the whole pool ----
+    # N = 1: Clair.predict (four fresh arrays).  N > 1: every rank runs host input -> device rows (clairb_predict_to_device),
+    # ONE NCCL gather of the packed rows to rank 0, and rank 0 copies all N x [sites,90] to its pinned host memory.
+    host_all = pinned_empty((world, sites, _lib.N_OUT), np.float32) if (world > 1 and rank == 0) else None
+    host_all_t = torch.from_numpy(host_all) if host_all is not None else None
+    last = {}
+
+    def e2e_step(Xh, dtype):
+        if world == 1:
+            last["out4"] = m.predict(Xh)
+            return
+        _lib.check(lib.clairb_predict_to_device(h, Xh.ctypes.data, dtype, sites, od.data_ptr()), h, "clairb_predict_to_device")
+        dist.gather(od, gather_list=gather_bufs, dst=0)
+        if rank == 0:
+            for r in range(world):
+                host_all_t[r].copy_(gather_bufs[r], non_blocking=True)
+            torch.cuda.synchronize()
+
+    def time_e2e(Xh, dtype, n_steps):
+        for _ in range(2):
+            e2e_step(Xh, dtype)
+        torch.cuda.synchronize()
+        barrier()
+        l0 = m.kernel_launches()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            e2e_step(Xh, dtype)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        return world * sites * n_steps / dt, m.kernel_launches() - l0
+
+    e2e_value, e2e_launches = time_e2e(Xi, _lib.DTYPE_I16, steps)
+    out = np.concatenate(last["out4"], axis=1) if world == 1 else None
+    e2e_f32_value, _ = time_e2e(X, _lib.DTYPE_F32, steps)
+    if world == 1:
+        assert np.array_equal(np.concatenate(last["out4"], axis=1), out), "int16 transport must give bit-identical results"
+        assert np.isfinite(out).all()
+
+    # ---- multi-GPU parity gate (BASELINE.md 3 / SURVEY.md 8d): the gathered rows of every rank must equal, bit for bit,
+    #      what ONE GPU computes for the same sites.  Rank 0 collects every rank's input and runs it on its own device. ----
+    multi_gpu_check = None
     if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * sites * args.steps / e2e_s
+        xi_d = torch.from_numpy(Xi).cuda()
+        in_bufs = [torch.empty_like(xi_d) for _ in range(world)] if rank == 0 else None
+        dist.gather(xi_d, gather_list=in_bufs, dst=0)
+        if rank == 0:
+            single = torch.empty_like(od)
+            bad = 0
+            for r in range(world):
+                m.predict_device(in_bufs[r].data_ptr(), _lib.DTYPE_I16, sites, single.data_ptr(), stream.cuda_stream)
+                torch.cuda.synchronize()
+                if not torch.equal(single, gather_bufs[r]) or not np.array_equal(host_all[r], single.cpu().numpy()):
+                    bad += 1
+            multi_gpu_check = {"rows_checked": world * sites, "ranks_differing": bad,
+                               "what": "gathered [N*sites,90] of the e2e leg (device buffers and rank 0's host copy) vs a "
+                                       "single-GPU run of every rank's sites on rank 0, bit for bit"}
+            assert bad == 0, "multi-GPU result differs from the single-GPU result"
+            del in_bufs, single
+        del xi_d
 
-    # ---- what the host link allows: pinned H2D bandwidth of this box, and the f32 ceiling that follows from it ----
+    # ---- what the host link allows: pinned H2D bandwidth of this box ----
     xt = torch.from_numpy(X)
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     xd.copy_(xt, non_blocking=True)
     torch.cuda.synchronize()
+    barrier()
     h0.record(stream)
     for _ in range(3):
         xd.copy_(xt, non_blocking=True)
@@ -338,51 +493,56 @@ def main():
     torch.cuda.synchronize()
     h2d_gbs = 3 * sites * 4224 / (h0.elapsed_time(h1) * 1e-3) / 1e9
 
-    # ---- the same call with the int16 transport of the same integer counts (CLAIRB_DTYPE_I16: half the H2D bytes;
-    #      the float32 line above is PCIe-bound).  Extra information, not the headline: the reference's generator
-    #      yields float32 (clair/utils.py:84) ----
-    Xi = pinned_empty((sites, 33, 8, 4), np.int16)
-    Xi[...] = X
-    assert np.array_equal(Xi.astype(np.float32), X), "synthetic counts must be exact in int16"
-    for _ in range(2):
-        out_i = m.predict(Xi)
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out_i = m.predict(Xi)
-    torch.cuda.synchronize()
-    e2e_i16_s = time.perf_counter() - t0
-    out_i = np.concatenate(out_i, axis=1)
-    if world > 1:
-        t = torch.tensor([e2e_i16_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_i16_s = float(t.item())
-    assert np.array_equal(out_i, out), "int16 transport must give bit-identical results"
-    assert np.isfinite(out).all()
+    # ---- the reference-shaped loop: generator -> one predict per 1000-site batch -> output stage (no-op) ----
+    def batch_source(Xh, n_batches, pageable=False):
+        infos = [None] * BATCH                                   # the forward never looks at them
+        for i in range(n_batches):
+            j = i % bps
+            xb = Xh[j * BATCH:(j + 1) * BATCH]
+            yield (np.array(xb) if pageable else xb), infos
+
+    def time_loop(Xh, n_batches, in_flight, pageable=False):
+        seen = [0]
+
+        def output_stage(batch, prediction):
+            seen[0] += prediction[0].shape[0]
+
+        call_var.run_batches(m, batch_source(Xh, 2 * args.in_flight, pageable), output_stage, in_flight=in_flight)   # warm-up
+        seen[0] = 0
+        torch.cuda.synchronize()
+        barrier()
+        l0 = m.kernel_launches()
+        t0 = time.perf_counter()
+        call_var.run_batches(m, batch_source(Xh, n_batches, pageable), output_stage, in_flight=in_flight)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        assert seen[0] == n_batches * BATCH
+        return world * n_batches * BATCH / dt, m.kernel_launches() - l0
+
+    loop_batches = bps * steps
+    loop_i16, loop_launches = time_loop(Xi, loop_batches, args.in_flight)
+    loop_f32, _ = time_loop(X, loop_batches, args.in_flight)
+    loop_pageable, _ = time_loop(X, max(bps, loop_batches // 4), args.in_flight, pageable=True)
+    loop_lockstep, lockstep_launches = time_loop(Xi, min(loop_batches, 300), 1)
 
     # ---- the same end-to-end call with the first-choice variant decision fused behind the heads
     #      (clairb_predict_decide), and the reference-equivalent Python restatement timed on a small sample ----
     ref_bases = (np.arange(sites) % 4).astype(np.uint8)
+    dec_steps = max(2, steps // 4)
     for _ in range(2):
-        _, dec = m.predict_and_decide_packed(X, ref_bases)
+        _, dec = m.predict_and_decide_packed(Xi, ref_bases)
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, dec = m.predict_and_decide_packed(X, ref_bases)
+    for _ in range(dec_steps):
+        _, dec = m.predict_and_decide_packed(Xi, ref_bases)
     torch.cuda.synchronize()
-    e2e_dec_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_dec_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dec_s = float(t.item())
+    e2e_dec_s = max_over_ranks(time.perf_counter() - t0)
     decision_info = None
     if rank == 0:
-        decision_info = {"e2e_with_decision": world * sites * args.steps / e2e_dec_s, "unit": "sites/s",
+        decision_info = {"e2e_with_decision": world * sites * dec_steps / e2e_dec_s, "unit": "sites/s",
                          "extra_d2h_bytes_per_step": sites * 24, "extra_h2d_bytes_per_step": sites,
                          "categories_seen": np.bincount(dec.category, minlength=10).tolist(),
-                         "note": "forward + decide_sites kernel per chunk (call_var.py:589-690, 732-760)"}
+                         "note": "forward + decide_sites kernel per chunk (call_var.py:589-690, 732-760), int16 transport"}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -390,19 +550,23 @@ def main():
         dom = max(profile, key=lambda p: p["ms"]) if profile else None
         roofline = None
         if dom is not None:
-            sites_per_launch = sites * args.steps / dom["launches"]
+            sites_per_launch = sites * steps / dom["launches"]
             flop = KERNEL_FLOP_PER_SITE.get(dom["kernel"], 0) * sites_per_launch
             avg_ms = dom["ms"] / dom["launches"]
             achieved = flop / (avg_ms * 1e-3) / 1e12
+            traffic, traffic_file = measured_traffic(dom["kernel"], sites_per_launch)
             roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": achieved,
                         "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                        "traffic": measured_traffic(dom["kernel"], sites_per_launch),
-                        "traffic_source": "ncu dram__bytes_read+write per launch (profiles/r01_traffic_s11.json), scaled by sites",
+                        "traffic": traffic,
+                        "traffic_source": "ncu dram__bytes_read+write per launch (profiles/%s), scaled by sites" % traffic_file,
                         "algorithmic_bytes": KERNEL_BYTES_PER_SITE.get(dom["kernel"], 0) * sites_per_launch,
-                        "peak_source": peaks["source"] + " (sustained bf16)",
+                        "peak_source": peaks["source"] + " (sustained bf16; timed region %.1f s)" % (ms * 1e-3),
+                        "frac_of_burst_peak": achieved / peaks["bf16_burst"],
                         "avg_launch_ms": avg_ms, "sites_per_launch": sites_per_launch,
                         "whole_path_frac": value / world * FLOP_PER_SITE / 1e12 / peaks["bf16_sustained"],
                         "kernel_share": {k: v["ms"] / max(1e-9, sum(p["ms"] for p in profile)) for k, v in prof.items()},
+                        "kernel_frac": {k: (KERNEL_FLOP_PER_SITE.get(k, 0) * sites * steps / max(1e-9, v["ms"] * 1e-3) / 1e12) / peaks["bf16_sustained"]
+                                        for k, v in prof.items()},
                         "note": "logit tolerance 1e-4 needs the 3-term fp16 split (3 MMAs per algorithmic MAC): attainable "
                                 "ceiling is 1/3 of peak, i.e. frac 0.333 = tensor pipe saturated"}
         # ---- CreateTensor stage: alignments -> tensors on the device, outside the timed region ----
@@ -416,14 +580,21 @@ def main():
                 ct_info["gpu_launches"] = m.kernel_launches() - launches_before_ct
             except Exception as exc:      # a side stage must not take the headline line down with it
                 ct_info, ct_ctx = {"error": "%s: %s" % (type(exc).__name__, exc)}, None
-        cpu = None
+        cpu = pinning = None
         if world == 1 and not args.no_cpu_baseline:
-            nb = args.cpu_baseline_batches or 24
-            pool = [np.array(X[i * BATCH:(i + 1) * BATCH]) for i in range(min(8, bps))]
             # the only place this arm touches oracle/: the CPU port is timed on a bounded sample AND serves as the
             # checker of what was just measured (same sites, same weights)
-            v, threads, dt, cpu_first = time_cpu_port(weights, pool, nb)
+            seeds = [20240607 + 1, 20240607 + 2]
+            arm = CpuArm(weights, seeds, check_batch=np.array(X[:BATCH]))
+            try:
+                dt1 = arm.run(1)
+                per_worker = args.cpu_baseline_batches or max(2, min(40, int(12.0 / max(dt1, 1e-3))))    # about 12 s of CPU work
+                dt = arm.run(per_worker)
+            finally:
+                arm.close()
+            v = arm.procs * per_worker * BATCH / dt
             model, cores = cpu_info()
+            cpu_first = arm.first                  # worker 0's answer for the first BATCH sites of this run's pool
             err = float(np.abs(out[:BATCH] - cpu_first).max())
             assert err <= 1e-4, "GPU result differs from the CPU port of the reference: %g" % err
             for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
@@ -442,33 +613,48 @@ def main():
                     ct_bench.cpu_part(ct_info, ct_ctx)
                 except Exception as exc:
                     ct_info["cpu_oracle"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
-            cpu = {"value": v, "unit": "sites/s", "cores": threads, "kind": "port",
-                   "sample": "%d predict-batches x %d sites of the same pool, %.1f s" % (nb, BATCH, dt),
+            cpu = {"value": v, "unit": "sites/s", "cores": arm.procs * arm.threads, "kind": "port",
+                   "sample": "%d processes x %d threads x %d predict-batches x %d sites of the same workload, %.1f s" % (
+                       arm.procs, arm.threads, per_worker, BATCH, dt),
                    "parity_vs_gpu": {"max_abs_prob_diff": err, "argmax_identical": True, "sites": BATCH},
                    "cpu_model": model, "host_cores": cores}
+            pinning = oracle_pinning(m, weights, np.array(X[:256]))
         engine = os.environ.get("CLAIRB_ENGINE", "default")
         print(json.dumps({
             "metric": "candidate-sites/sec", "value": value, "unit": "sites/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (fp16 hi/lo split operands, f32 accumulate)", "data": "synthetic",
             "config": {"workload": WORKLOAD % world, "batch": BATCH, "batches_per_step": bps, "sites_per_step": sites,
+                       "distinct_batches": distinct,
                        "l2": "inputs larger than L2: %.0f MB of fp32 input re-read per step" % (sites * 4224 / 1e6),
                        "weights": "random-init ONT-shape, seed 1234", "engine": engine,
                        "parallelism": "sites sharded over %d GPU(s), one NCCL gather of [sites,90] per step" % world},
             "clocks": clocks,
-            "e2e_int16_transport": {"value": world * sites * args.steps / e2e_i16_s, "unit": "sites/s",
-                                    "h2d_bytes_per_step": sites * 2112, "d2h_bytes_per_step": sites * 360,
-                                    "note": "same call, input as int16 counts (lossless, bit-identical output)"},
-            "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": sites * 4224,
-                    "d2h_bytes_per_step": sites * 360, "h2d_gbs_measured": h2d_gbs,
-                    "h2d_ceiling_sites_per_s": world * h2d_gbs * 1e9 / 4224,
-                    "note": "float32 input (the reference generator's dtype): bounded by the pinned host->device copy"},
+            "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": sites * 2112,
+                    "d2h_bytes_per_step": sites * 360 * (world if world > 1 else 1), "gpu_launches": e2e_launches,
+                    "note": ("one Clair.predict call per step over the pool" if world == 1 else
+                             "per rank: host input -> device rows, one NCCL gather to rank 0, rank 0 copies N x [sites,90] to host")
+                            + "; pinned host input in the int16 transport (same integer counts as float32, bit-identical output)"},
+            "e2e_f32": {"value": e2e_f32_value, "unit": "sites/s", "h2d_bytes_per_step": sites * 4224,
+                        "d2h_bytes_per_step": sites * 360, "h2d_gbs_measured": h2d_gbs,
+                        "h2d_ceiling_sites_per_s": world * h2d_gbs * 1e9 / 4224,
+                        "note": "float32 input (the reference generator's dtype): bounded by the pinned host->device copy"},
+            "loop_e2e": {"value": loop_i16, "unit": "sites/s", "batch": BATCH, "in_flight": args.in_flight, "batches": loop_batches,
+                         "gpu_launches": loop_launches, "frac_of_e2e": loop_i16 / e2e_value,
+                         "f32_pinned": loop_f32, "f32_pageable": loop_pageable,
+                         "note": "generator -> one predict per 1000-site batch (run_batches over predict_async) -> no-op output "
+                                 "stage; headline = int16 pinned batches"},
+            "loop_lockstep": {"value": loop_lockstep, "unit": "sites/s", "gpu_launches": lockstep_launches,
+                              "note": "the same loop with exactly one predict in flight (the reference's own loop structure, "
+                                      "clair/call_var.py:1327-1352): 1000 sites = 8 of 74 CTA pairs per call"},
+            "multi_gpu_check": multi_gpu_check,
             "decision_stage": decision_info,
             "create_tensor_stage": ct_info,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "oracle_pinning": pinning,
             "kernels": profile,
         }))
     m.close()

@@ -24,6 +24,10 @@ SYMBOLS = {
     "clairb_finalize_weights": (_c.c_int, [_c.c_void_p]),
     "clairb_predict": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p]),
     "clairb_predict_split": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "clairb_predict_async": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                        _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_int64)]),
+    "clairb_predict_wait": (_c.c_int, [_c.c_void_p, _c.c_int64]),
+    "clairb_predict_to_device": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p]),
     "clairb_predict_device": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p]),
     "clairb_predict_decide": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "clairb_predict_split_decide": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,

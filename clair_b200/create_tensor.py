@@ -262,15 +262,14 @@ class TensorBlock(object):
         """Forward pass over sites of this block without the tensors leaving the device -> [n,90] float32."""
         if not self.subtracted:
             raise ValueError("the forward pass takes channel-subtracted tensors: create_tensors(..., subtract=True)")
-        if getattr(self.model, "_ct_generation", 0) != self._generation:
-            raise RuntimeError("this TensorBlock is no longer resident: a later create_tensors call on the same model replaced it")
         which = np.arange(len(self), dtype=np.int64) if which is None else np.asarray(which, np.int64)
         rows = np.ascontiguousarray(self.rows[which])
         out = np.empty((rows.shape[0], _lib.N_OUT), np.float32)
-        if rows.shape[0] == 0:
-            return out
         m = self.model
         with m._lock:
+            # checked under the lock: a create_tensors call on another thread replaces the resident block under the same lock
+            if getattr(m, "_ct_generation", 0) != self._generation:
+                raise RuntimeError("this TensorBlock is no longer resident: a later create_tensors call on the same model replaced it")
             for s in range(0, rows.shape[0], m.max_sites):
                 k = min(m.max_sites, rows.shape[0] - s)
                 rc = m._lib.clairb_predict_created(m._h, rows[s:s + k].ctypes.data_as(ctypes.c_void_p), k,

@@ -7,13 +7,16 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/clair_b200.h"
@@ -56,6 +59,23 @@ constexpr int TC_PAIR_SITES = 256;
 
 }  // namespace
 
+// One clairb_predict_async call: the sites of a request are cut into segments, a segment rides in one chunk ("group") of
+// the pipeline next to segments of other requests, and the request is done when all its sites were delivered.
+struct AsyncRequest {
+  int64_t ticket = 0;
+  const char* x = nullptr;
+  int dtype = 0;
+  int64_t n = 0;
+  float* outs[4] = {nullptr, nullptr, nullptr, nullptr};   // four head arrays, or outs[0] = packed [n][90] when !split
+  bool split = false;
+  const uint8_t* ref = nullptr;      // with `dec`: first-choice decision behind the heads
+  int32_t* dec = nullptr;
+  int64_t issued = 0, delivered = 0;
+  int rc = 0;
+  std::string err;
+  bool done = false;
+};
+
 struct clairb_engine {
   int device = 0;
   int64_t max_sites = 0;
@@ -69,7 +89,20 @@ struct clairb_engine {
   bool l2_stream = true;       // TC engine: layer-2 input projection streamed through the recurrent kernel (lstm_seq_x2)
   bool ramp = false;           // first chunk of a multi-chunk host call is half a chunk (one wave)
   std::string err;
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};
+
+  // ---- asynchronous submission (clairb_predict_async / clairb_predict_wait) ----
+  // run_mu owns the chunk pipeline (device buffers, staging, streams): a synchronous call holds it for its duration, the
+  // worker thread holds it while requests are in flight.  q_mu guards the queue and the tickets.
+  std::mutex run_mu, q_mu;
+  std::condition_variable q_cv, done_cv;
+  std::deque<AsyncRequest*> pending;
+  std::map<int64_t, AsyncRequest*> tickets;
+  int64_t next_ticket = 1;
+  std::thread worker;
+  bool worker_started = false, stop = false;
+  cudaEvent_t ev_dev = nullptr;     // end of the last clairb_predict_device enqueue (the workspace is shared with it)
+  bool dev_pending = false;
 
   std::map<std::string, HostWeight> hw;
 
@@ -344,6 +377,7 @@ void free_all(clairb_engine* e) {
     if (e->ev_d2h[l]) cudaEventDestroy(e->ev_d2h[l]);
   }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_dev) cudaEventDestroy(e->ev_dev);
   cudaFree(e->d_w3p); cudaFree(e->d_b3p); cudaFree(e->d_W4); cudaFree(e->d_b4);
   cudaFree(e->d_W5); cudaFree(e->d_b5); cudaFree(e->d_Whd); cudaFree(e->d_bhd);
   cudaFree(e->d_xT); cudaFree(e->d_h1); cudaFree(e->d_h2); cudaFree(e->d_l3T); cudaFree(e->d_l4T);
@@ -372,7 +406,7 @@ const char* clairb_last_error(const clairb_engine* e) {
   return g_create_error.c_str();
 }
 
-int64_t clairb_kernel_launches(const clairb_engine* e) { return e ? e->launches : 0; }
+int64_t clairb_kernel_launches(const clairb_engine* e) { return e ? e->launches.load() : 0; }
 
 int clairb_host_alloc(void** ptr, int64_t bytes) {
   if (!ptr || bytes <= 0) return CLAIRB_EINVAL;
@@ -458,6 +492,7 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
     CR_TRY(cudaHostAlloc((void**)&e->h_ref[b], (size_t)e->chunk_sites, cudaHostAllocDefault));
   }
   CR_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CR_TRY(cudaEventCreateWithFlags(&e->ev_dev, cudaEventDisableTiming));
   const size_t np = (size_t)e->chunk_np;
   CR_TRY(cudaMalloc((void**)&e->d_logits, np * N_OUT * sizeof(float)));
   CR_TRY(cudaMemset(e->d_logits, 0, np * N_OUT * sizeof(float)));
@@ -610,8 +645,8 @@ int clairb_finalize_weights(clairb_engine* e) {
   return CLAIRB_OK;
 }
 
-int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_t n, float* out_dev, void* stream) {
-  if (!e) return CLAIRB_EINVAL;
+// body of clairb_predict_device; the caller holds run_mu
+static int predict_device_locked(clairb_engine* e, const void* x_dev, int dtype, int64_t n, float* out_dev, void* stream) {
   if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
   if (!x_dev || !out_dev || n <= 0 || n > e->max_sites) return fail(e, CLAIRB_EINVAL, "predict_device: bad n or buffers");
   if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(e, CLAIRB_EINVAL, "unknown dtype %d", dtype);
@@ -631,7 +666,16 @@ int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_
     ++nchunks;
   }
   e->last_single_chunk = nchunks == 1;
+  // the workspace is shared with the host-buffer pipeline, whose own stream must not start before this work is done
+  CU_TRY(e, cudaEventRecord(e->ev_dev, st));
+  e->dev_pending = true;
   return CLAIRB_OK;
+}
+
+int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_t n, float* out_dev, void* stream) {
+  if (!e) return CLAIRB_EINVAL;
+  std::lock_guard<std::mutex> run_lk(e->run_mu);
+  return predict_device_locked(e, x_dev, dtype, n, out_dev, stream);
 }
 
 // Shared body of clairb_predict / clairb_predict_decide: chunked, copy-overlapped forward; when `ref_host` / `dec_host`
@@ -639,12 +683,14 @@ int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_
 // that are still resident, and its 24-byte records travel back with the probabilities.
 // `outs` (optional, instead of out_host): four head arrays [n][21], [n][3], [n][33], [n][33] as Clair.predict returns
 // them; the heads kernel then writes head-major chunk buffers and the host only copies contiguous blocks.
+// `out_dev_final` (instead of out_host / outs): the packed [n][90] rows stay on the device (clairb_predict_to_device).
 static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_host, const uint8_t* ref_host,
-                        int32_t* dec_host, float* const* outs = nullptr) {
+                        int32_t* dec_host, float* const* outs = nullptr, float* out_dev_final = nullptr) {
   if (!e) return CLAIRB_EINVAL;
   if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
   if (outs && (!outs[0] || !outs[1] || !outs[2] || !outs[3])) return fail(e, CLAIRB_EINVAL, "predict_split: bad buffers");
   if (outs) out_host = outs[0];
+  if (out_dev_final) out_host = out_dev_final;
   if (!x_host || !out_host || n <= 0 || n > e->max_sites) return fail(e, CLAIRB_EINVAL, "predict: bad n or buffers");
   // head-major chunk buffers need the kernel that can write them (tensor-core heads); the cross-check engines produce
   // packed rows and the host scatters them
@@ -662,13 +708,18 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
     }
   };
   if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(e, CLAIRB_EINVAL, "unknown dtype %d", dtype);
+  std::lock_guard<std::mutex> run_lk(e->run_mu);
   CU_TRY(e, cudaSetDevice(e->device));
+  if (e->dev_pending) {
+    CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_dev, 0));
+    e->dev_pending = false;
+  }
   const size_t eb = elem_bytes(dtype);
   // Results go device -> pinned staging (truly asynchronous) -> the caller's array.  A pageable destination would make
   // every D2H copy synchronous and serialise the chunk pipeline, and the reference contract hands back a fresh numpy
   // array per call (clair/model.py:963), i.e. pageable memory.  A destination that is itself pinned is written directly.
-  bool out_pinned = false;
-  if (!outs) {
+  bool out_pinned = out_dev_final != nullptr;      // nothing to stage either way
+  if (!outs && !out_dev_final) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, out_host) == cudaSuccess) out_pinned = at.type == cudaMemoryTypeHost;
     else cudaGetLastError();
@@ -681,7 +732,10 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
     // ramp-up: nothing can overlap the very first host->device copy, so the first chunk of a multi-chunk call is half a
     // chunk = exactly ONE wave of CTA pairs (a quarter chunk copies faster but leaves half the SMs idle for a whole
     // wave time: measured 9 wave-times instead of 8 on a 75,000-site call)
-    if (c == 0 && n > e->chunk_sites && e->ramp) cn = (e->chunk_sites / 2 + TC_PAIR_SITES - 1) / TC_PAIR_SITES * TC_PAIR_SITES;
+    if (c == 0 && n > e->chunk_sites && e->ramp) {
+      cn = (e->chunk_sites / 2 + TC_PAIR_SITES - 1) / TC_PAIR_SITES * TC_PAIR_SITES;
+      if (cn > e->chunk_sites) cn = e->chunk_sites;
+    }
     SiteMap sm = make_map(e, cn);
     // input buffer b is free once the forward of chunk c-2 has consumed it
     CU_TRY(e, cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));
@@ -707,7 +761,8 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
     CU_TRY(e, cudaEventRecord(e->ev_h2d[b], e->s_h2d));
     CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_h2d[b], 0));
     CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_d2h[b], 0));   // output buffer b drained
-    int rc = forward_chunk(e, e->d_x[b], dtype, sm, e->d_out[b], e->s_comp, dev_split ? cn : 0);
+    float* fwd_out = out_dev_final ? out_dev_final + (size_t)done * N_OUT : e->d_out[b];
+    int rc = forward_chunk(e, e->d_x[b], dtype, sm, fwd_out, e->s_comp, dev_split ? cn : 0);
     if (rc) return rc;
     if (dec_host) {
       ProfScope ps(e, 13, e->s_comp);
@@ -720,7 +775,8 @@ static int predict_impl(clairb_engine* e, const void* x_host, int dtype, int64_t
     CU_TRY(e, cudaEventRecord(e->ev_comp[b], e->s_comp));
     CU_TRY(e, cudaStreamWaitEvent(e->s_d2h, e->ev_comp[b], 0));
     float* dst = out_pinned ? out_host + (size_t)done * N_OUT : e->h_out[b];
-    CU_TRY(e, cudaMemcpyAsync(dst, e->d_out[b], (size_t)cn * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+    if (!out_dev_final)
+      CU_TRY(e, cudaMemcpyAsync(dst, e->d_out[b], (size_t)cn * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
     if (dec_host)
       CU_TRY(e, cudaMemcpyAsync(e->h_dec[b], e->d_dec[b], (size_t)cn * decide::REC_WORDS * sizeof(int32_t),
                                 cudaMemcpyDeviceToHost, e->s_d2h));
@@ -759,6 +815,12 @@ int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, f
   return predict_impl(e, x_host, dtype, n, out_host, nullptr, nullptr);
 }
 
+int clairb_predict_to_device(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_dev) {
+  if (!e) return CLAIRB_EINVAL;
+  if (!out_dev) return fail(e, CLAIRB_EINVAL, "predict_to_device: out_dev is required");
+  return predict_impl(e, x_host, dtype, n, nullptr, nullptr, nullptr, nullptr, out_dev);
+}
+
 int clairb_predict_split(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_gt21, float* out_genotype,
                          float* out_indel_1, float* out_indel_2) {
   float* outs[4] = {out_gt21, out_genotype, out_indel_1, out_indel_2};
@@ -780,11 +842,205 @@ int clairb_predict_decide(clairb_engine* e, const void* x_host, int dtype, int64
   return predict_impl(e, x_host, dtype, n, out_host, ref_base, decision);
 }
 
+
+// ---- asynchronous submission: many small predict calls in flight, coalesced into full chunks --------------------------
+// The reference hands predict() one 1000-site batch per call (clair/call_var.py:1340-1344, shared/param.py:16); 1000 sites
+// are 8 CTA pairs on a 148-SM device.  Requests queue here and a worker thread packs the sites of consecutive requests
+// into chunks ("groups") of up to chunk_sites - tiles run straight through request boundaries, sites being independent -
+// and drives the same double-buffered H2D -> forward -> D2H pipeline as the synchronous call.  While a group runs, new
+// requests accumulate, so the group size follows the submission rate by itself.
+namespace {
+
+struct Segment { AsyncRequest* r; int64_t at, cnt, pos; };   // rows [at, at+cnt) of r sit at rows [pos, pos+cnt) of the chunk
+struct Group {
+  std::vector<Segment> segs;
+  int64_t cn = 0;
+  int b = 0, dtype = 0;
+  bool split = false, decide = false;
+};
+
+int issue_group(clairb_engine* e, const Group& g) {
+  const int b = g.b;
+  const size_t eb = elem_bytes(g.dtype);
+  const SiteMap sm = make_map(e, g.cn);
+  const bool dev_split = g.split && e->kind == ENGINE_TC && e->fuse_tail;
+  CU_TRY(e, cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));      // the forward two groups back has consumed d_x[b]
+  for (const Segment& s : g.segs)
+    CU_TRY(e, cudaMemcpyAsync((char*)e->d_x[b] + (size_t)s.pos * SITE_ELEMS * eb, s.r->x + (size_t)s.at * SITE_ELEMS * eb,
+                              (size_t)s.cnt * SITE_ELEMS * eb, cudaMemcpyHostToDevice, e->s_h2d));
+  if (g.decide) {
+    CU_TRY(e, cudaEventSynchronize(e->ev_h2d[b]));                 // staging last read by the copy two groups back
+    for (const Segment& s : g.segs) memcpy(e->h_ref[b] + s.pos, s.r->ref + s.at, (size_t)s.cnt);
+    CU_TRY(e, cudaMemcpyAsync(e->d_ref[b], e->h_ref[b], (size_t)g.cn, cudaMemcpyHostToDevice, e->s_h2d));
+  }
+  CU_TRY(e, cudaEventRecord(e->ev_h2d[b], e->s_h2d));
+  CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_h2d[b], 0));
+  CU_TRY(e, cudaStreamWaitEvent(e->s_comp, e->ev_d2h[b], 0));
+  if (int rc = forward_chunk(e, e->d_x[b], g.dtype, sm, e->d_out[b], e->s_comp, dev_split ? g.cn : 0)) return rc;
+  if (g.decide) {
+    ProfScope ps(e, 13, e->s_comp);
+    cudaError_t st = g.dtype == CLAIRB_DTYPE_I16
+                         ? decide::launch<int16_t>(e->d_out[b], e->d_ref[b], (const int16_t*)e->d_x[b], e->d_dec[b], g.cn, e->s_comp, dev_split ? g.cn : 0)
+                         : decide::launch<float>(e->d_out[b], e->d_ref[b], (const float*)e->d_x[b], e->d_dec[b], g.cn, e->s_comp, dev_split ? g.cn : 0);
+    if (st != cudaSuccess) return fail(e, CLAIRB_ECUDA, "decide_sites launch failed: %s", cudaGetErrorString(st));
+    e->launches += 1;
+  }
+  CU_TRY(e, cudaEventRecord(e->ev_comp[b], e->s_comp));
+  CU_TRY(e, cudaStreamWaitEvent(e->s_d2h, e->ev_comp[b], 0));
+  CU_TRY(e, cudaMemcpyAsync(e->h_out[b], e->d_out[b], (size_t)g.cn * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+  if (g.decide)
+    CU_TRY(e, cudaMemcpyAsync(e->h_dec[b], e->d_dec[b], (size_t)g.cn * decide::REC_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
+  CU_TRY(e, cudaEventRecord(e->ev_d2h[b], e->s_d2h));
+  return CLAIRB_OK;
+}
+
+// staged results of a group -> the arrays of its requests; marks requests whose last sites these were
+int deliver_group(clairb_engine* e, const Group& g, int rc_issue) {
+  int rc = rc_issue;
+  if (!rc) {
+    cudaError_t st = cudaEventSynchronize(e->ev_d2h[g.b]);
+    if (st != cudaSuccess) rc = fail(e, CLAIRB_ECUDA, "asynchronous predict failed: %s", cudaGetErrorString(st));
+  }
+  const bool dev_split = g.split && e->kind == ENGINE_TC && e->fuse_tail;
+  const float* staged = e->h_out[g.b];
+  if (!rc)
+    for (const Segment& s : g.segs) {
+      AsyncRequest* r = s.r;
+      if (!g.split) {
+        memcpy(r->outs[0] + (size_t)s.at * N_OUT, staged + (size_t)s.pos * N_OUT, (size_t)s.cnt * N_OUT * sizeof(float));
+      } else if (dev_split) {
+        for (int k = 0; k < 4; ++k)
+          memcpy(r->outs[k] + (size_t)s.at * kHeadSize[k], staged + (size_t)g.cn * kHeadOffH[k] + (size_t)s.pos * kHeadSize[k],
+                 (size_t)s.cnt * kHeadSize[k] * sizeof(float));
+      } else {
+        for (int64_t i = 0; i < s.cnt; ++i)
+          for (int k = 0; k < 4; ++k)
+            memcpy(r->outs[k] + (size_t)(s.at + i) * kHeadSize[k], staged + (size_t)(s.pos + i) * N_OUT + kHeadOffH[k], kHeadSize[k] * sizeof(float));
+      }
+      if (g.decide)
+        memcpy(r->dec + (size_t)s.at * decide::REC_WORDS, e->h_dec[g.b] + (size_t)s.pos * decide::REC_WORDS,
+               (size_t)s.cnt * decide::REC_WORDS * sizeof(int32_t));
+    }
+  {
+    std::lock_guard<std::mutex> lk(e->q_mu);
+    for (const Segment& s : g.segs) {
+      AsyncRequest* r = s.r;
+      if (rc && !r->rc) { r->rc = rc; r->err = e->err; }
+      r->delivered += s.cnt;
+      if (r->delivered == r->n) r->done = true;
+    }
+  }
+  e->done_cv.notify_all();
+  return rc;
+}
+
+void worker_main(clairb_engine* e) {
+  cudaSetDevice(e->device);
+  Group prev;
+  bool have_prev = false;
+  int prev_rc = 0;
+  int c = 0;
+  std::unique_lock<std::mutex> run_lk(e->run_mu, std::defer_lock);
+  for (;;) {
+    Group g;
+    {
+      std::unique_lock<std::mutex> lk(e->q_mu);
+      e->q_cv.wait(lk, [&] { return e->stop || !e->pending.empty() || have_prev; });
+      if (e->pending.empty() && !have_prev) return;                // stop, nothing outstanding
+      // pack segments of consecutive requests that agree on dtype / layout / decision into one chunk
+      while (!e->pending.empty() && g.cn < e->chunk_sites) {
+        AsyncRequest* r = e->pending.front();
+        const bool dec = r->dec != nullptr;
+        if (g.segs.empty()) { g.dtype = r->dtype; g.split = r->split; g.decide = dec; }
+        else if (g.dtype != r->dtype || g.split != r->split || g.decide != dec) break;
+        const int64_t left = r->n - r->issued, room = e->chunk_sites - g.cn;
+        const int64_t cnt = left < room ? left : room;
+        g.segs.push_back({r, r->issued, cnt, g.cn});
+        g.cn += cnt;
+        r->issued += cnt;
+        if (r->issued == r->n) e->pending.pop_front();
+      }
+    }
+    if (g.segs.empty()) {                                          // queue ran dry: drain the group in flight
+      deliver_group(e, prev, prev_rc);
+      have_prev = false;
+      cudaStreamSynchronize(e->s_comp);
+      if (run_lk.owns_lock()) run_lk.unlock();
+      continue;
+    }
+    if (!run_lk.owns_lock()) {
+      run_lk.lock();
+      if (e->dev_pending) {
+        cudaStreamWaitEvent(e->s_comp, e->ev_dev, 0);
+        e->dev_pending = false;
+      }
+    }
+    g.b = c & 1;
+    ++c;
+    const int rc = issue_group(e, g);
+    if (have_prev) deliver_group(e, prev, prev_rc);                // while this group runs, hand the previous one over
+    prev = std::move(g);
+    prev_rc = rc;
+    have_prev = true;
+  }
+}
+
+}  // namespace
+
+int clairb_predict_async(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_gt21, float* out_genotype,
+                         float* out_indel_1, float* out_indel_2, const uint8_t* ref_base, int32_t* decision, int64_t* ticket) {
+  if (!e) return CLAIRB_EINVAL;
+  // e->err belongs to the pipeline owner while requests are in flight: argument errors are reported under q_mu
+  std::unique_lock<std::mutex> lk(e->q_mu);
+  if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
+  if (!ticket || !x_host || !out_gt21 || n <= 0) return fail(e, CLAIRB_EINVAL, "predict_async: bad n or buffers");
+  const bool split = out_genotype || out_indel_1 || out_indel_2;
+  if (split && (!out_genotype || !out_indel_1 || !out_indel_2))
+    return fail(e, CLAIRB_EINVAL, "predict_async: pass all four head arrays, or only the first one for packed [n,90] rows");
+  if ((ref_base == nullptr) != (decision == nullptr)) return fail(e, CLAIRB_EINVAL, "predict_async: ref_base and decision go together");
+  if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(e, CLAIRB_EINVAL, "unknown dtype %d", dtype);
+  if (e->stop) return fail(e, CLAIRB_EINVAL, "predict_async: the engine is being destroyed");
+  AsyncRequest* r = new AsyncRequest();
+  r->ticket = e->next_ticket++;
+  r->x = (const char*)x_host;
+  r->dtype = dtype;
+  r->n = n;
+  r->outs[0] = out_gt21; r->outs[1] = out_genotype; r->outs[2] = out_indel_1; r->outs[3] = out_indel_2;
+  r->split = split;
+  r->ref = ref_base;
+  r->dec = decision;
+  e->tickets[r->ticket] = r;
+  e->pending.push_back(r);
+  if (!e->worker_started) {
+    e->worker = std::thread(worker_main, e);
+    e->worker_started = true;
+  }
+  *ticket = r->ticket;
+  lk.unlock();
+  e->q_cv.notify_one();
+  return CLAIRB_OK;
+}
+
+int clairb_predict_wait(clairb_engine* e, int64_t ticket) {
+  if (!e) return CLAIRB_EINVAL;
+  std::unique_lock<std::mutex> lk(e->q_mu);
+  auto it = e->tickets.find(ticket);
+  if (it == e->tickets.end()) return fail(e, CLAIRB_EINVAL, "predict_wait: unknown ticket %lld (already waited for?)", (long long)ticket);
+  AsyncRequest* r = it->second;
+  e->done_cv.wait(lk, [&] { return r->done; });
+  e->tickets.erase(it);
+  const int rc = r->rc;
+  if (rc) e->err = r->err;
+  delete r;
+  return rc;
+}
+
 int clairb_decide(clairb_engine* e, const float* probs_host, const uint8_t* ref_base, const void* x_host, int dtype, int64_t n,
                   int32_t* decision) {
   if (!e) return CLAIRB_EINVAL;
   if (!probs_host || !ref_base || !decision || n <= 0) return fail(e, CLAIRB_EINVAL, "decide: bad n or buffers");
   if (x_host && dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(e, CLAIRB_EINVAL, "unknown dtype %d", dtype);
+  std::lock_guard<std::mutex> run_lk(e->run_mu);
   CU_TRY(e, cudaSetDevice(e->device));
   const size_t eb = elem_bytes(dtype);
   for (int64_t done = 0; done < n; done += e->chunk_sites) {
@@ -824,6 +1080,7 @@ int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const in
     return fail(e, CLAIRB_EINVAL, "create_tensors: read arrays missing");
   if (a->n_ops && (!a->op_ref || !a->op_qry || !a->op_len || !a->seq)) return fail(e, CLAIRB_EINVAL, "create_tensors: op arrays missing");
   if (!a->ref || a->ref_len == 0) return fail(e, CLAIRB_EINVAL, "create_tensors: empty reference sequence");
+  std::lock_guard<std::mutex> run_lk(e->run_mu);
   const int64_t R = a->n_reads, O = a->n_ops;
   // the kernel finds the reads of a window by binary search: POS ascending (a sorted BAM), centres ascending
   std::vector<int32_t> maxend((size_t)R);
@@ -906,6 +1163,7 @@ int clairb_predict_created(clairb_engine* e, const int64_t* rows, int64_t n, flo
   if (!e) return CLAIRB_EINVAL;
   if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
   if (!rows || !out_host || n <= 0 || n > e->max_sites) return fail(e, CLAIRB_EINVAL, "predict_created: bad n or buffers");
+  std::lock_guard<std::mutex> run_lk(e->run_mu);
   if (e->ct_rows <= 0) return fail(e, CLAIRB_EINVAL, "predict_created: no tensor block resident (call clairb_create_tensors first)");
   if (!e->ct_subtracted)
     return fail(e, CLAIRB_EINVAL, "predict_created: the resident block holds raw counts; create it with CLAIRB_CT_SUBTRACT (clair/utils.py:96-98)");
@@ -924,7 +1182,7 @@ int clairb_predict_created(clairb_engine* e, const int64_t* rows, int64_t n, flo
   cudaError_t lst = cudaGetLastError();
   if (lst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "gather_rows launch failed: %s", cudaGetErrorString(lst));
   e->launches += 1;
-  if (int rc = clairb_predict_device(e, e->ct_gather.p, CLAIRB_DTYPE_I16, n, (float*)e->ct_out.p, st)) return rc;
+  if (int rc = predict_device_locked(e, e->ct_gather.p, CLAIRB_DTYPE_I16, n, (float*)e->ct_out.p, st)) return rc;
   CU_TRY(e, cudaMemcpyAsync(out_host, e->ct_out.p, (size_t)n * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_TRY(e, cudaStreamSynchronize(st));
   return CLAIRB_OK;
@@ -1053,6 +1311,7 @@ int clairb_get_layer(clairb_engine* e, int layer, float* out_host, int64_t n) {
 
 int clairb_set_profiling(clairb_engine* e, int enabled) {
   if (!e) return CLAIRB_EINVAL;
+  std::lock_guard<std::mutex> run_lk(e->run_mu);
   cudaSetDevice(e->device);
   prof_fold(e);
   e->prof_acc.clear();
@@ -1062,6 +1321,7 @@ int clairb_set_profiling(clairb_engine* e, int enabled) {
 
 int clairb_read_profile(clairb_engine* e, char* json, int64_t json_len) {
   if (!e || !json || json_len < 64) return CLAIRB_EINVAL;
+  std::lock_guard<std::mutex> run_lk(e->run_mu);
   cudaSetDevice(e->device);
   prof_fold(e);
   std::string s = "[";
@@ -1081,6 +1341,15 @@ int clairb_read_profile(clairb_engine* e, char* json, int64_t json_len) {
 
 int clairb_destroy(clairb_engine* e) {
   if (!e) return CLAIRB_EINVAL;
+  {
+    // requests still queued are completed first (their callers may be blocked in clairb_predict_wait)
+    std::unique_lock<std::mutex> lk(e->q_mu);
+    e->stop = true;
+  }
+  e->q_cv.notify_all();
+  if (e->worker_started) e->worker.join();
+  for (auto& kv : e->tickets) delete kv.second;
+  e->tickets.clear();
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   free_all(e);

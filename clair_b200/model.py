@@ -29,6 +29,7 @@ class Clair(object):
             tensor_transform_function=lambda X, Y, phase: (X, Y),
             # B200-side options (safe defaults; not in the reference)
             device=0,
+            devices=None,      # e.g. [0, 1, ..., 7]: one engine (weights replicated) per GPU behind the same predict()
             max_sites=32 * param.predictBatchSize,
             batch_sites=param.predictBatchSize,
             seed=None,
@@ -56,17 +57,28 @@ class Clair(object):
         if self.output_label_split != [21, 3, 33, 33]:
             raise ValueError("output shapes must be 21/3/33/33")
         self.structure = params["structure"]
-        self.device = int(params["device"])
+        devices = params["devices"]
+        self.devices = [int(d) for d in devices] if devices is not None else [int(params["device"])]
+        if not self.devices or len(set(self.devices)) != len(self.devices):
+            raise ValueError("devices must be a non-empty list of distinct CUDA ordinals")
+        self.device = self.devices[0]
         self.max_sites = int(params["max_sites"])
         self.batch_sites = int(params["batch_sites"])
         self._seed = params["seed"]
         self.prediction = None
         self._lock = threading.Lock()
         self._lib = _lib.load()                                # raises if the extension is missing
-        handle = ctypes.c_void_p()
-        rc = self._lib.clairb_create(self.device, self.max_sites, self.batch_sites, ctypes.byref(handle))
-        _lib.check(rc, None, "clairb_create")
-        self._h = handle
+        self._engines = []                                     # one handle per GPU; every op is per-site
+        self._h = None
+        for dev in self.devices:
+            handle = ctypes.c_void_p()
+            rc = self._lib.clairb_create(dev, self.max_sites, self.batch_sites, ctypes.byref(handle))
+            if rc:
+                self.close()
+            _lib.check(rc, None, "clairb_create(device %d)" % dev)
+            self._engines.append(handle)
+        self._h = self._engines[0]
+        self._next_engine = 0
         self._has_weights = False
 
     # ---- weights ---------------------------------------------------------------------------
@@ -86,13 +98,13 @@ class Clair(object):
 
     def set_weights(self, weights):
         _weights.check_weights(weights)
-        for name in _weights.weight_shapes():
-            arr = np.ascontiguousarray(weights[name], dtype=np.float32)
-            shape = (ctypes.c_int64 * arr.ndim)(*arr.shape)
-            rc = self._lib.clairb_set_weight(self._h, name.encode(), arr.ctypes.data_as(ctypes.c_void_p),
-                                             shape, arr.ndim)
-            _lib.check(rc, self._h, "clairb_set_weight(%s)" % name)
-        _lib.check(self._lib.clairb_finalize_weights(self._h), self._h, "clairb_finalize_weights")
+        for h in self._engines:                                # replicated: 9.5 MB per GPU
+            for name in _weights.weight_shapes():
+                arr = np.ascontiguousarray(weights[name], dtype=np.float32)
+                shape = (ctypes.c_int64 * arr.ndim)(*arr.shape)
+                rc = self._lib.clairb_set_weight(h, name.encode(), arr.ctypes.data_as(ctypes.c_void_p), shape, arr.ndim)
+                _lib.check(rc, h, "clairb_set_weight(%s)" % name)
+            _lib.check(self._lib.clairb_finalize_weights(h), h, "clairb_finalize_weights")
         self._has_weights = True
 
     # ---- forward ---------------------------------------------------------------------------
@@ -136,6 +148,8 @@ class Clair(object):
             prediction = [np.ascontiguousarray(packed[:, a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
             self.prediction = prediction
             return prediction
+        if len(self._engines) > 1:
+            return self.predict_async(batchX, shard=True).result()
         X, _ = self.tensor_transform_function(batchX, None, "predict")      # clair/model.py:953
         X, dtype = self._as_input(X)
         n = X.shape[0]
@@ -149,6 +163,53 @@ class Clair(object):
                 _lib.check(rc, self._h, "clairb_predict_split")
         self.prediction = prediction
         return prediction
+
+    def predict_async(self, batchX, ref_bases=None, shard=None):
+        """Queue predict(batchX) and return a PredictTicket at once; ``ticket.result()`` blocks until the four arrays
+        are written, stores them in ``.prediction`` like predict() and returns them (with ref_bases:
+        ``(prediction, Decision)`` like predict_and_decide).  Many calls may be in flight; the library packs the sites
+        of consecutive calls into full device chunks (clairb_predict_async), so a loop of 1000-site batches
+        (clair/call_var.py:1340-1344) runs at the throughput of one large call.  Results are bit-identical to
+        predict().  With several engines (devices=[...]) whole batches go round-robin to the GPUs, or - shard=True,
+        the default for calls of at least 4096 sites per GPU - one call is cut into contiguous slices
+        (shard.shard_bounds), one per GPU."""
+        if not self._has_weights:
+            raise RuntimeError("predict() before init()/restore_parameters()")
+        X, _ = self.tensor_transform_function(batchX, None, "predict")
+        X, dtype = self._as_input(X)
+        n = X.shape[0]
+        ref = rec = None
+        if ref_bases is not None:
+            ref = np.ascontiguousarray(ref_bases, dtype=np.uint8).reshape(-1)
+            if ref.shape[0] != n or (ref > 3).any():
+                raise ValueError("ref_bases must be %d codes in 0..3" % n)
+            rec = np.empty((n, _lib.DECISION_WORDS), dtype=np.int32)
+        prediction = [np.empty((n, k), dtype=np.float32) for k in self.output_label_split]    # fresh every call
+        g = len(self._engines)
+        if shard is None:
+            shard = g > 1 and n >= 4096 * g
+        if g > 1 and shard:
+            from .shard import shard_bounds
+            parts = [(self._engines[r],) + shard_bounds(n, g, r) for r in range(g)]
+        else:
+            parts = [(self._engines[self._next_engine % g], 0, n)]
+            self._next_engine += 1
+        waits = []
+        for h, lo, hi in parts:
+            if hi <= lo:
+                continue
+            t = ctypes.c_int64()
+            rc = self._lib.clairb_predict_async(
+                h, X[lo:hi].ctypes.data_as(ctypes.c_void_p), dtype, hi - lo,
+                *([a[lo:hi].ctypes.data_as(ctypes.c_void_p) for a in prediction] +
+                  [ref[lo:hi].ctypes.data_as(ctypes.c_void_p) if ref is not None else None,
+                   rec[lo:hi].ctypes.data_as(ctypes.c_void_p) if rec is not None else None, ctypes.byref(t)]))
+            if rc:
+                for hw, tw in waits:                           # do not leave earlier slices in flight behind an error
+                    self._lib.clairb_predict_wait(hw, tw)
+            _lib.check(rc, h, "clairb_predict_async")
+            waits.append((h, t.value))
+        return PredictTicket(self, waits, (X, ref), prediction, rec)
 
     def predict_and_decide(self, batchX, ref_bases):
         """predict() plus the first-choice variant decision of every site in the same device pass: returns
@@ -256,8 +317,8 @@ class Clair(object):
     # ---- lifetime --------------------------------------------------------------------------
     def close(self):
         """Reference clair/model.py:872-876."""
-        h, self._h = getattr(self, "_h", None), None
-        if h:
+        engines, self._engines, self._h = getattr(self, "_engines", []), [], None
+        for h in engines:
             self._lib.clairb_destroy(h)
 
     def __del__(self):                                         # clair/model.py:1149
@@ -265,6 +326,74 @@ class Clair(object):
             self.close()
         except Exception:
             pass
+
+
+class PredictTicket(object):
+    """One predict_async call in flight.  Holds the input and output arrays alive until result() has returned."""
+
+    def __init__(self, model, waits, inputs, prediction, rec):
+        self._model, self._waits, self._inputs, self._prediction, self._rec = model, waits, inputs, prediction, rec
+        self._error = None
+
+    def result(self):
+        m = self._model
+        while self._waits:
+            h, t = self._waits.pop(0)
+            rc = m._lib.clairb_predict_wait(h, t)
+            if rc and self._error is None:
+                try:
+                    _lib.check(rc, h, "clairb_predict_wait")
+                except Exception as exc:                       # keep waiting for the other slices, then raise
+                    self._error = exc
+        self._inputs = None
+        if self._error is not None:
+            raise self._error
+        m.prediction = self._prediction
+        if self._rec is None:
+            return self._prediction
+        from . import decision as _decision
+        return self._prediction, _decision.unpack(self._rec)
+
+    def __del__(self):
+        try:
+            while self._waits:                                 # never let the library write into freed arrays
+                h, t = self._waits.pop(0)
+                self._model._lib.clairb_predict_wait(h, t)
+        except Exception:
+            pass
+
+
+class PinnedPool(object):
+    """A fixed set of page-locked batch buffers handed out by take() and returned by give(): the staging ring of the
+    batch loop (replaces the pageable np.empty per batch of clair/utils.py:85).  take() has the signature of
+    tensor_generator_from's `alloc`; it blocks while every buffer is in use, which is what bounds the loader."""
+
+    def __init__(self, count, shape, dtype=np.float32):
+        import queue
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self._slab = pinned_empty((count,) + self.shape, self.dtype)
+        self._free = queue.Queue()
+        self._index = {}
+        for i in range(count):
+            self._index[self._slab[i].ctypes.data] = i
+            self._free.put(i)
+
+    def take(self, shape=None, dtype=None):
+        if shape is not None and (int(np.prod(shape)) != int(np.prod(self.shape)) or np.dtype(dtype or self.dtype) != self.dtype):
+            raise ValueError("PinnedPool holds %s %s buffers" % (self.shape, self.dtype))
+        buf = self._slab[self._free.get()]
+        return buf if shape is None else buf.reshape(shape)
+
+    def give(self, arr):
+        """Return the buffer `arr` is a view of (any leading-rows view of what take() handed out)."""
+        i = self._index.get(arr.ctypes.data)
+        if i is not None:
+            self._free.put(i)
+
+    def close(self):
+        slab, self._slab = self._slab, None
+        if slab is not None:
+            pinned_free(slab)
 
 
 def pinned_empty(shape, dtype=np.float32):

@@ -54,8 +54,12 @@ def native_rows_to_batch(lines, batch_size, out=None, dtype=np.float32):
     lib = _lib.load()
     dtype = np.dtype(dtype)
     code = _lib.DTYPE_I16 if dtype == np.int16 else _lib.DTYPE_F32
+    if len(lines) > batch_size:
+        raise ValueError("%d rows do not fit a batch of %d" % (len(lines), batch_size))
     if out is None:
         out = np.empty((batch_size, input_tensor_size), dtype=dtype)
+    elif out.dtype != dtype or out.size < batch_size * input_tensor_size or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError("`out` must be a C-contiguous %s array of at least %d x %d values" % (dtype, batch_size, input_tensor_size))
     text = b"".join((ln if isinstance(ln, bytes) else ln.encode()) if ln[-1:] in (b"\n", "\n")
                     else (ln if isinstance(ln, bytes) else ln.encode()) + b"\n" for ln in lines)
     infos = []
@@ -70,9 +74,10 @@ def native_rows_to_batch(lines, batch_size, out=None, dtype=np.float32):
         if rows_read.value != len(lines):
             raise ValueError("clairb_decode_rows read %d of %d rows" % (rows_read.value, len(lines)))
         n = rows_kept.value
+        assert n <= len(lines) <= batch_size
         o = off[:n].tolist()
         infos = [[text[a:b].decode(), text[c:d].decode(), text[e:f].decode()] for a, b, c, d, e, f in o]
-    X = out.reshape((batch_size, no_of_positions, matrix_row, matrix_num))
+    X = out.reshape(-1)[:batch_size * input_tensor_size].reshape((batch_size, no_of_positions, matrix_row, matrix_num))
     return X[:n], infos
 
 

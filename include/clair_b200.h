@@ -8,9 +8,9 @@
  *
  * Conventions: plain pointers and sizes only; every entry point returns 0 on success and a
  * non-zero CLAIRB_E* code on failure (message via clairb_last_error); nothing here calls
- * exit() or throws.  One handle drives one GPU.  A handle is not re-entrant: one call in flight
- * per handle (the reference keeps exactly one predict in flight: clair/call_var.py:1340-1352),
- * but calls may come from any host thread.
+ * exit() or throws.  One handle drives one GPU.  Calls may come from any host thread; the
+ * synchronous calls of one handle are serialised inside the library (the reference keeps exactly
+ * one predict in flight: clair/call_var.py:1340-1352), clairb_predict_async keeps many in flight.
  *
  * Tensor layouts
  *   input  x   : [n,33,8,4] row-major (position, ACGTacgt row, channel), already
@@ -82,6 +82,30 @@ int clairb_predict(clairb_engine* e, const void* x_host, int dtype, int64_t n, f
  * host side only copies contiguous blocks (splitting packed rows on the host costs as much as half the forward). */
 int clairb_predict_split(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_gt21,
                          float* out_genotype, float* out_indel_1, float* out_indel_2);
+
+/* ---- many predict calls in flight (SURVEY.md 8b "predict_async / _wait", 8d C2 ">= 8 batches in flight") -----------
+ * The reference's loop hands predict() one batch of param.predictBatchSize = 1000 sites per call
+ * (clair/call_var.py:1340-1344, shared/param.py:16); 1000 sites occupy 8 of the 74 CTA pairs a B200 holds.
+ * clairb_predict_async queues the call and returns at once with a ticket; a worker thread owned by the handle packs the
+ * sites of consecutive queued calls into full device chunks (sites are independent, tiles run through call boundaries)
+ * and runs the same copy-overlapped pipeline as clairb_predict.  clairb_predict_wait blocks until every output of that
+ * ticket is written and returns the call's status; results are bit-identical to the synchronous calls.
+ *   outputs  : the four head arrays [n,21] [n,3] [n,33] [n,33] (as clairb_predict_split), or - with out_genotype,
+ *              out_indel_1, out_indel_2 all NULL - packed [n,90] rows in out_gt21 (as clairb_predict)
+ *   ref_base / decision : both NULL, or both given for the first-choice decision records (as clairb_predict_decide)
+ *   n        : any value >= 1 (not bounded by max_sites)
+ * The library reads x_host / ref_base and writes the outputs until clairb_predict_wait(ticket) has returned: the caller
+ * keeps them alive and untouched until then.  Tickets complete in submission order; every ticket must be waited for
+ * exactly once.  Pinned x_host (clairb_host_alloc) keeps the copies asynchronous.  Synchronous calls on the same handle
+ * are serialised behind the queued ones. */
+int clairb_predict_async(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_gt21,
+                         float* out_genotype, float* out_indel_1, float* out_indel_2, const uint8_t* ref_base,
+                         int32_t* decision, int64_t* ticket);
+int clairb_predict_wait(clairb_engine* e, int64_t ticket);
+
+/* Host input, device output: as clairb_predict, but the packed [n,90] rows are left in device memory at out_dev (the
+ * send buffer of the multi-GPU gather) instead of being copied back.  Returns when out_dev is written. */
+int clairb_predict_to_device(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_dev);
 
 /* Same forward with both buffers already resident in device memory, enqueued on `stream`
  * (a cudaStream_t; NULL = legacy default stream) without synchronising the host.  Used by

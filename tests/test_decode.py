@@ -188,3 +188,18 @@ def test_native_decoder_randomised_rows_match_python(tmp_path):
     for (Xa, ia), (Xb, ib) in zip(a, b):
         np.testing.assert_array_equal(Xa, Xb)
         assert ia == ib
+
+
+def test_native_decoder_refuses_more_rows_than_the_batch_or_the_buffer_holds():
+    # round-1 advisor finding: 50 lines with batch_size=2 used to be written into a 2-row buffer
+    from clair_b200 import synth
+    c = synth.synthetic_counts(50, seed=1)
+    lines = [utils.format_tensor_row("c", i, "A" * 33, c[i]) + "\n" for i in range(50)]
+    with pytest.raises(ValueError):
+        utils.native_rows_to_batch(lines, 2)
+    with pytest.raises(ValueError):
+        utils.native_rows_to_batch(lines, 50, out=np.empty((10, 1056), np.float32))
+    with pytest.raises(ValueError):
+        utils.native_rows_to_batch(lines, 50, out=np.empty((50, 1056), np.float64))
+    X, infos = utils.native_rows_to_batch(lines, 50, out=np.empty((64, 1056), np.float32))
+    assert X.shape == (50, 33, 8, 4) and len(infos) == 50

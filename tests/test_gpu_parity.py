@@ -323,3 +323,28 @@ def test_predict_split_layout_equals_packed(weights1234, monkeypatch):
             assert all(a.flags["C_CONTIGUOUS"] and a.dtype == np.float32 for a in four)
             np.testing.assert_array_equal(np.concatenate(four, axis=1), packed)
         eng.close()
+
+
+def test_cudnn_restatement_agrees_with_the_oracle(gpu_model, weights1234):
+    # the reference's arithmetic lives in TensorFlow 1.13 (not installable), whose
+    # CudnnCompatibleLSTMCell is defined to be weight-compatible with cuDNN's LSTM (clair/model.py:281-312).  cuDNN's own
+    # fp32 LSTM (torch.nn.LSTM on cuda) + a torch dense trunk is a third implementation, written by nobody involved here:
+    # it must agree with the fp64 numpy oracle to 1e-5 on config 1, and the product must meet both.
+    from oracle.clair_oracle_cudnn import CudnnOracle
+    X = synth.synthetic_tensors(256, seed=20240607)
+    ref_probs, im = O.forward(X, weights1234, np.float64, intermediates=True)
+    ref_logits = np.concatenate(im["logits"], axis=1)
+    cp, cl = CudnnOracle(weights1234, device="cuda").forward(X)
+    scaled = lambda a, b: (np.abs(a - b) / np.maximum(1.0, np.abs(b))).max()
+    assert scaled(cl, ref_logits) <= 1e-5
+    assert np.abs(cp - np.concatenate(ref_probs, axis=1)).max() <= 1e-5
+    gpu_model.predict(X)
+    ours = gpu_model.get_layer(_lib.LAYER_LOGITS, 256)
+    assert scaled(ours, cl) <= TOL and scaled(ours, ref_logits) <= TOL
+    for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
+        np.testing.assert_array_equal(cp[:, a:b].argmax(1), np.concatenate(ref_probs, axis=1)[:, a:b].argmax(1))
+    try:
+        import tensorflow  # noqa: F401
+        print("tensorflow is importable on this box: the reference itself could be run")
+    except Exception as exc:
+        print("tensorflow not importable on the GPU box (%s): the oracle stays pinned on cuDNN + the two CPU restatements" % type(exc).__name__)

@@ -132,3 +132,18 @@ def test_fast_cpu_port_matches_oracle(weights1234):
     assert np.abs(fast - ref).max() < 5e-6
     for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
         np.testing.assert_array_equal(fast[:, a:b].argmax(1), ref[:, a:b].argmax(1))
+
+
+def test_torch_lstm_restatement_agrees_with_the_numpy_oracle(weights1234):
+    # the cuDNN oracle's weight mapping (gate order i,c,f,o -> i,f,g,o; rows [x;h] -> weight_ih / weight_hh), checked
+    # here on torch's CPU LSTM kernels: in float64 it must reproduce the numpy fp64 oracle to rounding
+    import torch
+    from clair_b200 import synth
+    from oracle.clair_oracle_cudnn import CudnnOracle
+    X = synth.synthetic_tensors(24, seed=5)
+    ref_probs, im = O.forward(X, weights1234, np.float64, intermediates=True)
+    p, l = CudnnOracle(weights1234, device="cpu", dtype=torch.float64).forward(X)
+    assert np.abs(p - np.concatenate(ref_probs, axis=1)).max() <= 1e-12
+    assert np.abs(l - np.concatenate(im["logits"], axis=1)).max() <= 1e-11
+    p32, _ = CudnnOracle(weights1234, device="cpu", dtype=torch.float32).forward(X)
+    assert np.abs(p32 - np.concatenate(ref_probs, axis=1)).max() <= 1e-5
