@@ -427,16 +427,22 @@ def main():
     host_all_t = torch.from_numpy(host_all) if host_all is not None else None
     last = {}
 
+    E2E_SLICES = 8      # N > 1: gather + rank 0's device->host copy of slice j run while slice j+1 is computed
+
     def e2e_step(Xh, dtype):
         if world == 1:
             last["out4"] = m.predict(Xh)
             return
-        _lib.check(lib.clairb_predict_to_device(h, Xh.ctypes.data, dtype, sites, od.data_ptr()), h, "clairb_predict_to_device")
-        dist.gather(od, gather_list=gather_bufs, dst=0)
-        if rank == 0:
-            for r in range(world):
-                host_all_t[r].copy_(gather_bufs[r], non_blocking=True)
-            torch.cuda.synchronize()
+        per = -(-sites // E2E_SLICES)
+        for lo in range(0, sites, per):
+            hi = min(sites, lo + per)
+            _lib.check(lib.clairb_predict_to_device(h, Xh[lo:hi].ctypes.data, dtype, hi - lo, od[lo:hi].data_ptr()), h,
+                       "clairb_predict_to_device")
+            dist.gather(od[lo:hi], gather_list=[b[lo:hi] for b in gather_bufs] if rank == 0 else None, dst=0)
+            if rank == 0:
+                for r in range(world):
+                    host_all_t[r, lo:hi].copy_(gather_bufs[r][lo:hi], non_blocking=True)
+        torch.cuda.synchronize()
 
     def time_e2e(Xh, dtype, n_steps):
         for _ in range(2):
@@ -462,7 +468,7 @@ def main():
     #      what ONE GPU computes for the same sites.  Rank 0 collects every rank's input and runs it on its own device. ----
     multi_gpu_check = None
     if world > 1:
-        xi_d = torch.from_numpy(Xi).cuda()
+        xi_d = torch.from_numpy(Xi).cuda().view(torch.uint8)          # NCCL has no int16: the bytes travel
         in_bufs = [torch.empty_like(xi_d) for _ in range(world)] if rank == 0 else None
         dist.gather(xi_d, gather_list=in_bufs, dst=0)
         if rank == 0:
@@ -634,7 +640,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": sites * 2112,
                     "d2h_bytes_per_step": sites * 360 * (world if world > 1 else 1), "gpu_launches": e2e_launches,
                     "note": ("one Clair.predict call per step over the pool" if world == 1 else
-                             "per rank: host input -> device rows, one NCCL gather to rank 0, rank 0 copies N x [sites,90] to host")
+                             "per rank: host input -> device rows, NCCL gather to rank 0 (%d slices per step, overlapped with the next "
+                             "slice's forward), rank 0 copies N x [sites,90] to host" % E2E_SLICES)
                             + "; pinned host input in the int16 transport (same integer counts as float32, bit-identical output)"},
             "e2e_f32": {"value": e2e_f32_value, "unit": "sites/s", "h2d_bytes_per_step": sites * 4224,
                         "d2h_bytes_per_step": sites * 360, "h2d_gbs_measured": h2d_gbs,
