@@ -136,6 +136,244 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
                   *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
 }
 
+// the three stages of transpose8x8_h as separate calls, so that the epilogue can spread them between its cell updates
+__device__ __forceinline__ void t8_stage1(uint32_t* w, int lane) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t p = __shfl_xor_sync(0xffffffffu, w[k], 1);
+    w[k] = (lane & 1) ? __byte_perm(w[k], p, 0x3276) : __byte_perm(w[k], p, 0x5410);
+  }
+}
+__device__ __forceinline__ void t8_stage2(uint32_t* w, int lane) {
+#pragma unroll
+  for (int k1 = 0; k1 < 2; ++k1) {
+    const bool up = lane & 2;
+    const uint32_t send = up ? w[2 * k1] : w[2 * k1 + 1];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+    if (up) w[2 * k1] = recv; else w[2 * k1 + 1] = recv;
+  }
+}
+__device__ __forceinline__ void t8_stage3(uint32_t* w, int lane) {
+#pragma unroll
+  for (int k0 = 0; k0 < 2; ++k0) {
+    const bool up = lane & 4;
+    const uint32_t send = up ? w[k0] : w[2 + k0];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 4);
+    if (up) w[k0] = recv; else w[2 + k0] = recv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue of the recurrent kernels (lstm_seq<FUSE_X> of layer 1, lstm_seq_x2 of layer 2): all 33 steps of one epilogue
+// warp.  G warps per TMEM lane quarter; warp `sub` of a quarter owns units sub*UW..+UW (UW = 32/G) of every gate block and
+// walks them in slices of 8 units.  Per block: wait for the accumulator, pull the warp's whole share into registers, hand
+// the accumulator back, then per slice the cell update (7 MUFU per cell: the pipe that bounds this code) and its TAIL:
+//   A: h_t -> fp16 hi/lo words -> tcgen05.st into the h buffer (next step's A operand) [-> publish the block on hq[b]]
+//   B: the same words -> the next layer's operand tile in global memory (OUT 0: K-major; OUT 2: MN-major, 8x8 transposes)
+// The tail of a slice is not run behind its cells (all warps of a scheduler then convert / shuffle / store in lockstep while
+// the MUFU pipe idles: measured 2 x 300 of 3.2 k cycles per block), it is issued piecewise BETWEEN the cell updates of the
+// NEXT slice.  Only the last slice of a step cannot wait - the next step's first gate block contracts over it - so its part
+// A runs at once and its part B rides with the first slice of the next step.
+// ---------------------------------------------------------------------------------------------
+struct EpiArgs {
+  uint32_t tmem;
+  uint64_t* acc_full;                    // [2] this CTA's "gate block complete" barriers
+  uint32_t leader_hq, leader_acc_empty0, leader_acc_empty1;    // cluster addresses in the leader CTA
+  uint32_t bias_base;                    // shared-memory address of [128 units][4 gates] floats (BIAS)
+  void* Hout;
+  int NT;
+  int64_t np;
+  int dir, tile;
+  long long* trace;                      // CLAIRB_TRACE builds: [33 steps][64] clock64 stamps of epilogue warp 1 (events 16 + 8b + k)
+};
+
+// PIPE = false keeps the tail of a slice right behind its own cells (layer 2: measured 5 % faster that way - the chip runs
+// this kernel at its 1000 W cap, and the deferred publish / extra live registers cost more than the overlap returns).
+template <int OUT, int G, bool BIAS, bool PIPE>
+__device__ __forceinline__ void lstm_epilogue(const EpiArgs& a, int warp, int lane) {
+#ifdef CLAIRB_TRACE
+  const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32;
+  auto stamp = [&](int s, int ev) { if (tr_on) a.trace[s * 64 + ev] = clock64(); };
+#else
+  auto stamp = [&](int, int) {};
+#endif
+  static_assert(OUT == 0 || OUT == 1 || OUT == 2, "unknown output layout");
+  constexpr int UW = 32 / G, NSL = UW / 8;
+  const int ew = warp - 1;
+  const int quarter = warp & 3;                        // TMEM lane quarter this warp may touch
+  const int sub = ew >> 2;                             // 0..G-1
+  const int r = quarter * 32 + lane;
+  const uint32_t lane_base = a.tmem + ((uint32_t)(quarter * 32) << 16);
+  float c[4][UW];
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+#pragma unroll
+    for (int i = 0; i < UW; ++i) c[b][i] = 0.f;
+  uint32_t use0 = 0, use1 = 0;
+  uint32_t dhi[4] = {0, 0, 0, 0}, dlo[4] = {0, 0, 0, 0};      // part B owed for the last slice of the previous step
+  int t_prev = 0;
+
+  auto out_ptr = [&](int t, int u0) -> uint8_t* {      // where the 16-byte hi chunk of this lane goes (lo: see lo_off)
+    if (OUT == 0) {
+      return (uint8_t*)((__half*)a.Hout + ((size_t)t * a.NT + a.tile) * (2 * 32 * KCH) + (size_t)(a.dir * 16 + (u0 >> 3)) * KCH + r * 8);
+    } else {
+      // OUT == 2: MN-major SWIZZLE_128B tiles for the slice-dense MMA (K = time, M = site), per channel
+      //   H2t[tile][c][hl][t/8 (5)][site/64 (2)][t%8][16-byte chunk ((site%64)/8) ^ (t%8)][site%8]
+      // after the 8x8 transposes every lane holds one channel x 8 sites = one 16-byte chunk
+      const int ch = a.dir * H + u0 + (lane & 7);
+      const int rg = r >> 3;                                    // site group of 8 within the tile (0..15)
+      return (uint8_t*)a.Hout + ((size_t)a.tile * 2 * H + ch) * L3A_BYTES + (size_t)(t >> 3) * 2048 + (rg >> 3) * 1024 +
+             (t & 7) * 128 + (((rg & 7) ^ (t & 7)) << 4);
+    }
+  };
+  constexpr size_t lo_off = OUT == 0 ? (size_t)32 * KCH * 2 : (size_t)L3A_BYTES / 2;
+  auto publish = [&](int b) {                          // this warp's units of block b of h_t are in tensor memory
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster_relaxed(a.leader_hq + b * 8);
+  };
+  auto pack_pair = [&](const float* hv, uint32_t* whi, uint32_t* wlo, int k) {
+    const __half2 h2 = __floats2half2_rn(hv[2 * k], hv[2 * k + 1]);
+    const float2 back = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(hv[2 * k] - back.x, hv[2 * k + 1] - back.y);
+    whi[k] = *reinterpret_cast<const uint32_t*>(&h2);
+    wlo[k] = *reinterpret_cast<const uint32_t*>(&l2);
+  };
+
+  for (int s = 0; s < T_STEPS; ++s) {
+    const int t = a.dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
+    const uint32_t h_st = lane_base + 256 + (s & 1) * 128;
+    float hv_p[8];                                     // h_t of the previous slice, tail still to do
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = b & 1;
+      {
+        uint32_t& use = i ? use1 : use0;
+        mbar_wait(&a.acc_full[i], use & 1);
+        ++use;
+        tc_fence_after();
+      }
+      stamp(s, 16 + b * 8);
+      // this warp's whole share of the accumulator -> registers, then hand the accumulator back at once
+      float v[4 * UW];
+#pragma unroll
+      for (int k = 0; k < UW / 4; ++k) tmem_ld16(lane_base + i * 128 + sub * UW * 4 + k * 16, v + 16 * k);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(i ? a.leader_acc_empty1 : a.leader_acc_empty0);
+      stamp(s, 16 + b * 8 + 1);
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        const bool first = b == 0 && sl == 0;          // compile-time after unrolling
+        const int u0 = b * 32 + sub * UW + sl * 8;     // first hidden unit of this slice
+        const int pb = sl ? b : b - 1, psl = sl ? sl - 1 : NSL - 1;     // the slice whose tail rides along
+        const int pu0 = pb * 32 + sub * UW + psl * 8;
+        float hv[8];
+        uint32_t whi[4], wlo[4];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float* vv = v + (sl * 8 + k) * 4;
+#ifdef CLAIRB_EPI_NOCELL                                // timing probe: no transcendental work
+          hv[k] = c[b][sl * 8 + k] = fmaf(vv[0], vv[1], fmaf(vv[2], vv[3], c[b][sl * 8 + k]));
+#else
+          if (BIAS) {
+            const float4 bq = lds4(a.bias_base + (u0 + k) * 16);
+            hv[k] = lstm_cell(vv[0] + bq.x, vv[1] + bq.y, vv[2] + bq.z, vv[3] + bq.w, c[b][sl * 8 + k]);
+          } else {
+            hv[k] = lstm_cell(vv[0], vv[1], vv[2], vv[3], c[b][sl * 8 + k]);
+          }
+#endif
+          if (OUT == 1 || !PIPE) continue;             // plain tail below
+#ifdef CLAIRB_EPI_NOTAIL                                // timing probe: no tail (h is not carried: results are wrong)
+          if (!first && k == 3 && psl == NSL - 1) publish(pb);
+          continue;
+#endif
+          if (!first) {
+            if (k < 4) pack_pair(hv_p, whi, wlo, k);
+            if (k == 3) {
+              tmem_st4(h_st + (pu0 >> 1), whi);
+              tmem_st4(h_st + 64 + (pu0 >> 1), wlo);
+              if (psl == NSL - 1) publish(pb);
+            }
+            if (OUT == 2) {
+              if (k == 4) { t8_stage1(whi, lane); t8_stage1(wlo, lane); }
+              if (k == 5) { t8_stage2(whi, lane); t8_stage2(wlo, lane); }
+              if (k == 6) { t8_stage3(whi, lane); t8_stage3(wlo, lane); }
+            }
+            if (k == 7) {
+              uint8_t* out = out_ptr(t, pu0);
+              *reinterpret_cast<uint4*>(out) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+              *reinterpret_cast<uint4*>(out + lo_off) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+            }
+          } else {
+            // part B of the previous step's last slice (nothing is owed at s = 0)
+            if (OUT == 2) {
+              if (k == 2) { t8_stage1(dhi, lane); t8_stage1(dlo, lane); }
+              if (k == 3) { t8_stage2(dhi, lane); t8_stage2(dlo, lane); }
+              if (k == 4) { t8_stage3(dhi, lane); t8_stage3(dlo, lane); }
+            }
+            if (k == 5 && s > 0) {
+              uint8_t* out = out_ptr(t_prev, 3 * 32 + sub * UW + (NSL - 1) * 8);
+              *reinterpret_cast<uint4*>(out) = make_uint4(dhi[0], dhi[1], dhi[2], dhi[3]);
+              *reinterpret_cast<uint4*>(out + lo_off) = make_uint4(dlo[0], dlo[1], dlo[2], dlo[3]);
+            }
+          }
+        }
+        if (OUT == 1) {
+          uint32_t w1[4], w2[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pack_pair(hv, w1, w2, k);
+          tmem_st4(h_st + (u0 >> 1), w1);
+          tmem_st4(h_st + 64 + (u0 >> 1), w2);
+          float* out = (float*)a.Hout + ((size_t)t * 2 * H + a.dir * H + u0) * a.np + (size_t)a.tile * 128 + r;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) out[(size_t)k * a.np] = hv[k];
+          if (sl == NSL - 1) publish(b);
+        } else if (!PIPE) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pack_pair(hv, whi, wlo, k);
+          tmem_st4(h_st + (u0 >> 1), whi);
+          tmem_st4(h_st + 64 + (u0 >> 1), wlo);
+          if (OUT == 2) {
+            transpose8x8_h(whi, lane);
+            transpose8x8_h(wlo, lane);
+          }
+          uint8_t* out = out_ptr(t, u0);
+          *reinterpret_cast<uint4*>(out) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+          *reinterpret_cast<uint4*>(out + lo_off) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+          if (sl == NSL - 1) publish(b);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) hv_p[k] = hv[k];
+        }
+        stamp(s, 16 + b * 8 + 2 + sl);
+      }
+    }
+    if (OUT != 1 && PIPE) {
+      // last slice of the step: part A now, part B with the next step's first slice
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pack_pair(hv_p, dhi, dlo, k);
+      const int lu0 = 3 * 32 + sub * UW + (NSL - 1) * 8;
+      tmem_st4(h_st + (lu0 >> 1), dhi);
+      tmem_st4(h_st + 64 + (lu0 >> 1), dlo);
+      publish(3);
+      t_prev = t;
+    }
+    stamp(s, 16 + 3 * 8 + 7);
+  }
+  if (OUT != 1 && PIPE) {
+    if (OUT == 2) {
+      transpose8x8_h(dhi, lane);
+      transpose8x8_h(dlo, lane);
+    }
+    uint8_t* out = out_ptr(t_prev, 3 * 32 + sub * UW + (NSL - 1) * 8);
+    *reinterpret_cast<uint4*>(out) = make_uint4(dhi[0], dhi[1], dhi[2], dhi[3]);
+    *reinterpret_cast<uint4*>(out + lo_off) = make_uint4(dlo[0], dlo[1], dlo[2], dlo[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // xproj_pair<KC>: Gx[a][dir][unit][row][gate] = A[a] . Wx[:, dir, unit*4+gate] + b      (a = t*NT + tile)
 //   A tiles  : [a][hl][KC][128][8] fp16          (KC = K/8: 4 for layer 1, 32 for layer 2)
@@ -383,7 +621,7 @@ constexpr size_t seq_smem_bytes() {
 template <bool FUSE_X, int OUT, int G>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (2 + 4 * G), 1)
 lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __half* __restrict__ X48,
-         const float* __restrict__ Gx, void* __restrict__ Hout, int NT, int64_t np, int pf_dist) {
+         const float* __restrict__ Gx, void* __restrict__ Hout, int NT, int64_t np, int pf_dist, const int* __restrict__ x_lo_flag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* Ws = smem;                                            // [hl][b][kc 16][64][8]
@@ -410,6 +648,14 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
   const uint32_t rank = cluster_ctarank();
   const int dir = blockIdx.y;
   const int tile = blockIdx.x;                                   // = 2*pair + rank
+#ifdef CLAIRB_TRACE
+  // timeline probe (CLAIRB_S1_TRACE): the fused-x launch has no Gx, its parameter slot carries the stamp buffer
+  long long* trace = FUSE_X ? (long long*)Gx : nullptr;
+  const bool tr_on = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  auto stamp = [&](int s, int ev) { if (tr_on) trace[s * 64 + ev] = clock64(); };
+#else
+  auto stamp = [&](int, int) {};
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -454,6 +700,8 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
       const uint64_t wxdesc = make_smem_desc(smem_u32(Wxs), 1024, 128);      // input kernel (FUSE_X)
       const uint64_t xdesc = make_smem_desc(smem_u32(Xs), KCH_BYTES, 128);   // x_t tile: 128-row k-chunks
       uint32_t use0 = 0, use1 = 0;
+      // FUSE_X: prep_tiles48 reports whether any input value has a non-zero fp16 low part (never, for integer counts)
+      const bool x_has_lo = FUSE_X && x_lo_flag != nullptr && *reinterpret_cast<const volatile int*>(x_lo_flag) != 0;
       for (int s = 0; s < T_STEPS; ++s) {
         if (!FUSE_X && s == 0) continue;               // h_{-1} = 0 and no x part: nothing to accumulate
         const uint32_t h_hi = tmem + 256 + ((s - 1) & 1) * 128, h_lo = h_hi + 64;
@@ -480,9 +728,11 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
           for (int j = 0; j < 3; ++j) {
             const uint64_t a_hi = desc_advance(a_hi0, j * 2 * KCH_BYTES), a_lo = desc_advance(a_lo0, j * 2 * KCH_BYTES);
             const uint64_t b_hi = desc_advance(b_hi0, j * 2 * 1024), b_lo = desc_advance(b_lo0, j * 2 * 1024);
+            if (FUSE_X && (pf_dist & 2)) continue;     // timing experiment (CLAIRB_SEQ1_DBG): no tensor work
             umma_f16_pair(d, a_hi, b_hi, idesc, j != 0);
-            umma_f16_pair(d, a_lo, b_hi, idesc, 1);
-            umma_f16_pair(d, a_hi, b_lo, idesc, 1);
+            // k-step 2 holds the constant-one columns against the bias rows: both low parts are zero by construction
+            if (j < 2 && x_has_lo) umma_f16_pair(d, a_lo, b_hi, idesc, 1);
+            if (j < 2) umma_f16_pair(d, a_hi, b_lo, idesc, 1);
           }
         };
         auto h_part = [&](int b, int j0, int j1) {     // k-steps j0..j1-1 of h_{s-1} . W_h for block b
@@ -492,6 +742,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
           for (int j = 0; j < 8; ++j) {
             if (j < j0 || j >= j1) continue;
             const uint64_t b_hi = desc_advance(b_hi0, j * 2 * 1024), b_lo = desc_advance(b_lo0, j * 2 * 1024);
+            if (FUSE_X && (pf_dist & 2)) continue;
             umma_f16_pair_ts(d, h_hi + j * 8, b_hi, idesc, (FUSE_X || j != 0) ? 1u : 0u);
             umma_f16_pair_ts(d, h_lo + j * 8, b_hi, idesc, 1);
             umma_f16_pair_ts(d, h_hi + j * 8, b_lo, idesc, 1);
@@ -520,25 +771,31 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
           }
         } else {
           acquire_acc(0);
+          stamp(s, 0);
           x_part(0);
-          wait_h(0); h_part(0, 0, 2);
+          wait_h(0); stamp(s, 2); h_part(0, 0, 2);
           wait_h(1); h_part(0, 2, 4);
           wait_h(2); h_part(0, 4, 6);
           acquire_acc(1);
+          stamp(s, 1);
           x_part(1);
           h_part(1, 0, 6);
           wait_h(3);
+          stamp(s, 3);
           h_part(0, 6, 8);
           umma_commit_pair(&acc_full[0], 0b11);
           h_part(1, 6, 8);
           umma_commit_pair(&acc_full[1], 0b11);
+          stamp(s, 4);
 #pragma unroll
           for (int b = 2; b < 4; ++b) {
             acquire_acc(b);
+            stamp(s, 6 + b);
             x_part(b);
             h_part(b, 0, 8);
             umma_commit_pair(&acc_full[b & 1], 0b11);
           }
+          stamp(s, 12);
         }
         if (FUSE_X) umma_commit_pair(&x_empty[s & 1], 0b11);
       }
@@ -574,10 +831,31 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
       }
     }
     __syncwarp();
+  } else if constexpr (FUSE_X) {
+    // ---- epilogue warps (lstm_epilogue: pipelined cell updates / tails, see there) ----
+    static_assert(EARLY, "the shared epilogue publishes h_t block by block");
+    EpiArgs ea;
+    ea.tmem = tmem;
+    ea.acc_full = acc_full;
+    ea.leader_hq = map_to_cta(smem_u32(hq), 0);
+    ea.leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
+    ea.leader_acc_empty1 = map_to_cta(smem_u32(&acc_empty[1]), 0);
+    ea.bias_base = 0;
+    ea.Hout = Hout;
+    ea.NT = NT;
+    ea.np = np;
+    ea.dir = dir;
+    ea.tile = tile;
+#ifdef CLAIRB_TRACE
+    ea.trace = trace;
+#else
+    ea.trace = nullptr;
+#endif
+    lstm_epilogue<OUT, G, false, true>(ea, warp, lane);
   } else {
-    // ---- epilogue warps: G warps per TMEM lane quarter; a gate block (32 units) is two half-blocks of 16 units
-    //      (= one Gx ring stage), and every warp takes UPS = 16/G units of EACH half-block, so all warps walk the
-    //      ring stages in the same order ----
+    // ---- epilogue warps of the Gx-fed cross-check kernel: G warps per TMEM lane quarter; a gate block (32 units) is two
+    //      half-blocks of 16 units (= one Gx ring stage), and every warp takes UPS = 16/G units of EACH half-block, so
+    //      all warps walk the ring stages in the same order ----
     constexpr int UPS = 16 / G;
     const int ew = warp - 1;
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
@@ -848,6 +1126,7 @@ lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap t
           for (int j = 0; j < 8; ++j) {
             if (j < j0 || j >= j1) continue;
             const uint64_t b_hi = desc_advance(b_hi0, j * 2 * 1024), b_lo = desc_advance(b_lo0, j * 2 * 1024);
+            if (dbg & 2) continue;                     // timing experiment: no tensor work
             umma_f16_pair_ts(d, h_hi + j * 8, b_hi, idesc_h, (fresh && j == 0) ? 0u : 1u);
             umma_f16_pair_ts(d, h_lo + j * 8, b_hi, idesc_h, 1);
             umma_f16_pair_ts(d, h_hi + j * 8, b_lo, idesc_h, 1);
@@ -864,6 +1143,7 @@ lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap t
             for (int kk = 0; kk < SX_KC / 2; ++kk) {
               const uint64_t a_hi = desc_advance(a_hi0, kk * 2 * KCH_BYTES), a_lo = desc_advance(a_lo0, kk * 2 * KCH_BYTES);
               const uint64_t b_hi = desc_advance(b_hi0, kk * 2 * KCH_BYTES), b_lo = desc_advance(b_lo0, kk * 2 * KCH_BYTES);
+              if (dbg & 2) continue;
               umma_f16_pair(tmem, a_hi, b_hi, idesc_x, (fresh && st == 0 && kk == 0) ? 0u : 1u);
               umma_f16_pair(tmem, a_lo, b_hi, idesc_x, 1);
               umma_f16_pair(tmem, a_hi, b_lo, idesc_x, 1);
@@ -954,117 +1234,21 @@ lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap t
     }
     __syncwarp();
   } else {
-    // ---- epilogue warps: G warps per TMEM lane quarter; warp `sub` of a quarter owns units sub*UW..+UW of every gate
-    //      block (UW = 32/G) and handles them in slices of 8 ----
-    constexpr int UW = 32 / G, NSL = UW / 8;
-    const int ew = warp - 1;
-    const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
-    const int sub = ew >> 2;                           // 0..G-1
-    const int r = quarter * 32 + lane;
-    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t leader_hq = map_to_cta(smem_u32(hq), 0);
-    const uint32_t leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
-    const uint32_t leader_acc_empty1 = map_to_cta(smem_u32(&acc_empty[1]), 0);
-    const uint32_t bias_base = smem_u32(bias_s);
-    float c[4][UW];
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-      for (int i = 0; i < UW; ++i) c[b][i] = 0.f;
-
-    // With G = 4 the two warp pairs of a scheduler run half a block out of phase: warps sub >= 2 ("lagging") defer the
-    // non-MUFU tail of block b (pack, tcgen05.st, transposes, global stores) until they have drained block b+1, so it
-    // overlaps the other pair's cell math instead of leaving the MUFU pipe idle while all warps pack in lockstep.
-    constexpr bool SKEW = (G == 4);
-    const bool lag = SKEW && sub >= 2;
-    uint32_t use0 = 0, use1 = 0;
-    for (int s = 0; s < T_STEPS; ++s) {
-      const int t = dir ? (T_STEPS - 1 - s) : s;       // bw consumes t = 32..0 (model.py:306-312)
-      const uint32_t h_st = lane_base + 256 + (s & 1) * 128;
-      // tail of one slice: h_t -> fp16 hi/lo -> tensor memory (next step's A operand) and -> the next layer's tiles
-      auto post = [&](int b, int sl, const float* hv) {
-        const int u0 = b * 32 + sub * UW + sl * 8;     // first hidden unit of this slice
-        uint32_t whi[4], wlo[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const __half2 h2 = __floats2half2_rn(hv[2 * k], hv[2 * k + 1]);
-          const float2 back = __half22float2(h2);
-          const __half2 l2 = __floats2half2_rn(hv[2 * k] - back.x, hv[2 * k + 1] - back.y);
-          whi[k] = *reinterpret_cast<const uint32_t*>(&h2);
-          wlo[k] = *reinterpret_cast<const uint32_t*>(&l2);
-        }
-        tmem_st4(h_st + (u0 >> 1), whi);
-        tmem_st4(h_st + 64 + (u0 >> 1), wlo);
-        if (OUT == 1) {
-          float* out = (float*)Hout + ((size_t)t * 2 * H + dir * H + u0) * np + (size_t)tile * 128 + r;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) out[(size_t)k * np] = hv[k];
-        } else {
-          // OUT == 2: MN-major SWIZZLE_128B tiles for the slice-dense MMA (see lstm_seq)
-          transpose8x8_h(whi, lane);
-          transpose8x8_h(wlo, lane);
-          const int ch = dir * H + u0 + (lane & 7);
-          const int rg = r >> 3;                                  // site group of 8 within the tile (0..15)
-          uint8_t* out = (uint8_t*)Hout + ((size_t)tile * 2 * H + ch) * L3A_BYTES + (size_t)(t >> 3) * 2048 +
-                         (rg >> 3) * 1024 + (t & 7) * 128 + (((rg & 7) ^ (t & 7)) << 4);
-          *reinterpret_cast<uint4*>(out) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
-          *reinterpret_cast<uint4*>(out + L3A_BYTES / 2) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
-        }
-      };
-      // this warp's slice of block b of h_t is in tensor memory: the MMA issuer may start contracting over it
-      auto publish = [&](int b) {
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(leader_hq + b * 8);
-      };
-      float hv_prev[8];                                // lagging warps: h_t of the previous block, tail still to do
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int i = b & 1;
-        {
-          uint32_t& use = i ? use1 : use0;
-          mbar_wait(&acc_full[i], use & 1);
-          ++use;
-          tc_fence_after();
-        }
-        if (threadIdx.x == 32) stamp(s, 16 + b * 8);
-        // this warp's whole share of the accumulator -> registers, then hand the accumulator back at once
-        float v[4 * UW];
-#pragma unroll
-        for (int k = 0; k < UW / 4; ++k) tmem_ld16(lane_base + i * 128 + sub * UW * 4 + k * 16, v + 16 * k);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(i ? leader_acc_empty1 : leader_acc_empty0);
-        if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 1);
-        if (SKEW && b > 0 && lag) {
-          post(b - 1, 0, hv_prev);
-          publish(b - 1);
-        }
-#pragma unroll
-        for (int sl = 0; sl < NSL; ++sl) {
-          const int u0 = b * 32 + sub * UW + sl * 8;
-          float hv[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float4 bq = lds4(bias_base + (u0 + k) * 16);
-            const float* vv = v + (sl * 8 + k) * 4;
-            hv[k] = lstm_cell(vv[0] + bq.x, vv[1] + bq.y, vv[2] + bq.z, vv[3] + bq.w, c[b][sl * 8 + k]);
-          }
-          if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 2 + sl * 2);
-          if (SKEW && b < 3 && lag) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) hv_prev[k] = hv[k];
-          } else {
-            post(b, sl, hv);
-          }
-          if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 3 + sl * 2);
-        }
-        if (!(SKEW && b < 3 && lag)) publish(b);
-        if (threadIdx.x == 32) stamp(s, 16 + b * 8 + 7);
-      }
-    }
+    // ---- epilogue warps (lstm_epilogue: pipelined cell updates / tails, see there) ----
+    EpiArgs ea;
+    ea.tmem = tmem;
+    ea.acc_full = acc_full;
+    ea.leader_hq = map_to_cta(smem_u32(hq), 0);
+    ea.leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
+    ea.leader_acc_empty1 = map_to_cta(smem_u32(&acc_empty[1]), 0);
+    ea.bias_base = smem_u32(bias_s);
+    ea.Hout = Hout;
+    ea.NT = NT;
+    ea.np = np;
+    ea.dir = dir;
+    ea.tile = tile;
+    ea.trace = trace;
+    lstm_epilogue<OUT, G, true, false>(ea, warp, lane);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -1073,7 +1257,8 @@ lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap t
 
 // prep for the fused layer-1 kernel: like prep_tiles but K = 48 (k = 32, 33 are the constant-one bias columns)
 template <typename TIn>
-__global__ void __launch_bounds__(128) prep_tiles48(const TIn* __restrict__ x, __half* __restrict__ X48, int64_t n, int NT) {
+__global__ void __launch_bounds__(128) prep_tiles48(const TIn* __restrict__ x, __half* __restrict__ X48, int64_t n, int NT,
+                                                   int* __restrict__ lo_flag) {
   const int tile = blockIdx.x, t = blockIdx.y, r = threadIdx.x;
   const int64_t site = (int64_t)tile * 128 + r;
   float v[32];
@@ -1099,13 +1284,17 @@ __global__ void __launch_bounds__(128) prep_tiles48(const TIn* __restrict__ x, _
     for (int i = 0; i < 32; ++i) v[i] = 0.f;
   }
   __half* base = X48 + ((size_t)t * NT + tile) * X48_TILE_HALVES;
+  uint32_t any_lo = 0;
 #pragma unroll
   for (int kc = 0; kc < 4; ++kc) {
     uint4 hi, lo;
     split8(v + 8 * kc, hi, lo);
     *reinterpret_cast<uint4*>(base + kc * KCH + r * 8) = hi;
     *reinterpret_cast<uint4*>(base + 6 * KCH + kc * KCH + r * 8) = lo;
+    any_lo |= (lo.x | lo.y | lo.z | lo.w) & 0x7fff7fffu;        // -0.0 is still zero
   }
+  // the generator's integer counts are exact in fp16 (|x| <= 2048): the layer-1 kernel then skips the x_lo . W_hi products
+  if (any_lo) *lo_flag = 1;
   const uint4 zero = make_uint4(0, 0, 0, 0);
   *reinterpret_cast<uint4*>(base + 4 * KCH + r * 8) = make_uint4(0x3C003C00u, 0, 0, 0);     // k = 32, 33: fp16 1.0
   *reinterpret_cast<uint4*>(base + 5 * KCH + r * 8) = zero;
@@ -1638,6 +1827,8 @@ struct Workspace {
   CUtensorMap tmH1;          // H1 as [rows][1 KB], box = 4 rows (hi or lo half of one ring stage of A)
   long long* lf_trace = nullptr;   // CLAIRB_LF_TRACE=<file>: [256 channels][16] clock64 stamps of tile 0 of l3l4_fused
   long long* trace = nullptr; // CLAIRB_SX_TRACE=<file>: [33][64] clock64 stamps of one CTA pair of lstm_seq_x2 (dumped at destroy)
+  int* x_lo_flag = nullptr;    // set by prep_tiles48 when an input value is not exact in fp16 (cleared before every chunk)
+  long long* trace1 = nullptr; // CLAIRB_S1_TRACE=<file>: the same for the layer-1 launch of lstm_seq (CLAIRB_TRACE builds)
 };
 
 inline bool available() { return true; }
@@ -1846,6 +2037,7 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device, bo
   // time steps 33..39 of the last time group are never written by lstm_seq and must read as zeros
   if ((st = cudaMemset(ws.H2t, 0, NT * 2 * H * (size_t)L3A_BYTES)) != cudaSuccess) return st;
   if ((st = cudaMalloc((void**)&ws.L4t, NT * (size_t)HD_A4_BYTES)) != cudaSuccess) return st;
+  if ((st = cudaMalloc((void**)&ws.x_lo_flag, sizeof(int))) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(heads_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem_bytes())) != cudaSuccess) return st;
   cudaDeviceGetAttribute(&ws.sm_count, cudaDevAttrMultiProcessorCount, device);
   if (getenv("CLAIRB_LF_TRACE")) {
@@ -1855,6 +2047,10 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device, bo
   if (getenv("CLAIRB_SX_TRACE")) {
     if ((st = cudaMalloc((void**)&ws.trace, T_STEPS * 64 * sizeof(long long))) != cudaSuccess) return st;
     cudaMemset(ws.trace, 0, T_STEPS * 64 * sizeof(long long));
+  }
+  if (getenv("CLAIRB_S1_TRACE")) {
+    if ((st = cudaMalloc((void**)&ws.trace1, T_STEPS * 64 * sizeof(long long))) != cudaSuccess) return st;
+    cudaMemset(ws.trace1, 0, T_STEPS * 64 * sizeof(long long));
   }
   if ((st = cudaFuncSetAttribute(xproj_pair<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<32>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq<true, 0, SEQ1_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
@@ -1879,6 +2075,18 @@ inline void free_workspace(Workspace& ws) {
     cudaFree(ws.lf_trace);
     ws.lf_trace = nullptr;
   }
+  if (ws.trace1) {
+    std::vector<long long> h(T_STEPS * 64);
+    if (cudaMemcpy(h.data(), ws.trace1, h.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      if (FILE* f = fopen(getenv("CLAIRB_S1_TRACE") ? getenv("CLAIRB_S1_TRACE") : "/dev/null", "w")) {
+        for (int s = 0; s < T_STEPS; ++s)
+          for (int e = 0; e < 64; ++e) fprintf(f, "%lld%c", h[s * 64 + e], e == 63 ? '\n' : ' ');
+        fclose(f);
+      }
+    }
+    cudaFree(ws.trace1);
+    ws.trace1 = nullptr;
+  }
   if (ws.trace) {
     std::vector<long long> h(T_STEPS * 64);
     if (cudaMemcpy(h.data(), ws.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
@@ -1892,7 +2100,8 @@ inline void free_workspace(Workspace& ws) {
     cudaFree(ws.trace);
     ws.trace = nullptr;
   }
-  cudaFree(ws.X48); cudaFree(ws.Gx); cudaFree(ws.H1); cudaFree(ws.H2t); cudaFree(ws.L4t);
+  cudaFree(ws.X48); cudaFree(ws.Gx); cudaFree(ws.H1); cudaFree(ws.H2t); cudaFree(ws.L4t); cudaFree(ws.x_lo_flag);
+  ws.x_lo_flag = nullptr;
   ws.L4t = nullptr; ws.X48 = nullptr; ws.Gx = nullptr; ws.H1 = nullptr; ws.H2t = nullptr;
 }
 
@@ -1915,14 +2124,16 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   static const int l3_pf = getenv("CLAIRB_L3_PF") ? atoi(getenv("CLAIRB_L3_PF")) : 8;   // l3l4 L2 prefetch distance (channels)
   static const int xp_dbg = getenv("CLAIRB_XP_DBG") ? atoi(getenv("CLAIRB_XP_DBG")) : 0;   // timing experiments only
   static const int sx_dbg = getenv("CLAIRB_SX_DBG") ? atoi(getenv("CLAIRB_SX_DBG")) : 0;   // timing experiments only
+  static const int s1_dbg = getenv("CLAIRB_SEQ1_DBG") ? atoi(getenv("CLAIRB_SEQ1_DBG")) : 0; // timing experiments only
   dim3 gprep((unsigned)NT, T_STEPS);
   dim3 grec((unsigned)NT, 2);
+  cudaMemsetAsync(ws.x_lo_flag, 0, sizeof(int), st);
   hook(0, true);
-  if (dtype_is_i16) prep_tiles48<int16_t><<<gprep, 128, 0, st>>>((const int16_t*)x_dev, ws.X48, n, NT);
-  else prep_tiles48<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X48, n, NT);
+  if (dtype_is_i16) prep_tiles48<int16_t><<<gprep, 128, 0, st>>>((const int16_t*)x_dev, ws.X48, n, NT, ws.x_lo_flag);
+  else prep_tiles48<float><<<gprep, 128, 0, st>>>((const float*)x_dev, ws.X48, n, NT, ws.x_lo_flag);
   hook(0, false);
   hook(1, true);   // layer 1: input projection fused into the recurrent kernel (no Gx round trip)
-  lstm_seq<true, 0, SEQ1_G><<<grec, 32 * (2 + 4 * SEQ1_G), seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, nullptr, ws.H1, NT, np, 0);
+  lstm_seq<true, 0, SEQ1_G><<<grec, 32 * (2 + 4 * SEQ1_G), seq_smem_bytes<true>(), st>>>(w.Whs[0], w.Wxf, ws.X48, (const float*)ws.trace1, ws.H1, NT, np, s1_dbg, ws.x_lo_flag);
   hook(1, false);
   // layer 2: input projection streamed through the recurrent kernel (default), or the two-kernel path
   // xproj_pair -> Gx -> lstm_seq (CLAIRB_L2_STREAM=0: on-device cross-check)
@@ -1937,8 +2148,8 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
     xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx2, w.bx2, ws.Gx, num_row_pairs, xp_dbg);
     hook(2, false);
     hook(3, true);
-    if (fuse_tail) lstm_seq<false, 2, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2t, NT, np, gx_pf);
-    else lstm_seq<false, 1, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np, gx_pf);
+    if (fuse_tail) lstm_seq<false, 2, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, ws.H2t, NT, np, gx_pf, nullptr);
+    else lstm_seq<false, 1, SEQ_G><<<grec, SEQ_THREADS, seq_smem_bytes<false>(), st>>>(w.Whs[1], nullptr, nullptr, ws.Gx, h2_planes, NT, np, gx_pf, nullptr);
     hook(3, false);
     *launches += 4;
   }

@@ -348,3 +348,25 @@ def test_cudnn_restatement_agrees_with_the_oracle(gpu_model, weights1234):
         print("tensorflow is importable on this box: the reference itself could be run")
     except Exception as exc:
         print("tensorflow not importable on the GPU box (%s): the oracle stays pinned on cuDNN + the two CPU restatements" % type(exc).__name__)
+
+
+def test_inputs_that_are_not_exact_in_fp16_keep_their_low_parts(gpu_model, weights1234):
+    # the layer-1 kernel skips the x_lo . W_hi tensor-core products when prep_tiles48 saw only fp16-exact inputs (the
+    # generator's integer counts); fractional or large inputs must switch them back on, per chunk
+    rng = np.random.default_rng(11)
+    exact = synth.synthetic_tensors(300, seed=12)
+    frac = (exact + rng.normal(0, 0.37, exact.shape)).astype(np.float32)         # 24-bit mantissas
+    big = exact.copy()
+    big[7, 16, 2, 0] = 4099.0                                                      # an integer fp16 cannot hold
+    for X in (frac, big, exact, frac):                                             # the flag must not stick either way
+        got = gpu_model.predict_packed(X)
+        logits = gpu_model.get_layer(_lib.LAYER_LOGITS, len(X))
+        ref_probs, im = O.forward(X, weights1234, np.float64, intermediates=True)
+        ref_logits = np.concatenate(im["logits"], axis=1)
+        assert (np.abs(logits - ref_logits) / np.maximum(1.0, np.abs(ref_logits))).max() <= TOL
+        assert np.abs(got - np.concatenate(ref_probs, axis=1)).max() <= TOL
+    i16 = np.clip(exact, -32768, 32767).astype(np.int16)
+    i16[3, 10, 1, 0] = 30001                                                       # int16 transport, beyond fp16's integers
+    got = gpu_model.predict_packed(i16)
+    ref = O.forward_packed(i16.astype(np.float32), weights1234, np.float64)
+    assert np.abs(got - ref).max() <= TOL
