@@ -8,6 +8,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CLAIRB_LIB") or os.path.join(_HERE, "lib", "libclair_b200.so")   # CLAIRB_LIB: A/B builds
+# the cross-check build (-DCLAIRB_CROSSCHECK: tensor-core engine + fp32 CUDA-core engines selected by CLAIRB_ENGINE /
+# CLAIRB_FUSED_TAIL / CLAIRB_L2_STREAM); only tests load it: Clair(library=_lib.XCHECK_PATH)
+XCHECK_PATH = os.path.join(_HERE, "lib", "libclair_b200_xcheck.so")
 
 OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, EWEIGHTS = range(6)
 DTYPE_F32, DTYPE_I16 = 0, 1
@@ -54,36 +57,36 @@ SYMBOLS = {
     "clairb_destroy": (_c.c_int, [_c.c_void_p]),
 }
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Load the shared library and attach prototypes.  Raises if it was never built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(path=None):
+    """Load the shared library (default: the product build) and attach prototypes.  Raises if it was never built."""
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
         raise RuntimeError(
             "clair_b200: %s not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(there is no CPU fallback)" % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+            "(there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    _libs[path] = lib
     return lib
 
 
-def last_error(handle=None):
-    msg = load().clairb_last_error(handle)
+def last_error(handle=None, lib=None):
+    msg = (lib or load()).clairb_last_error(handle)
     return msg.decode("utf-8", "replace") if msg else ""
 
 
-def check(rc, handle=None, what=""):
+def check(rc, handle=None, what="", lib=None):
     if rc == OK:
         return
-    msg = "%s: %s" % (what, last_error(handle)) if what else last_error(handle)
+    msg = "%s: %s" % (what, last_error(handle, lib)) if what else last_error(handle, lib)
     if rc in (EINVAL, EWEIGHTS):
         raise ValueError(msg)
     if rc == ENOMEM:

@@ -21,7 +21,11 @@
 
 #include "../../include/clair_b200.h"
 #include "common.cuh"
+// The product library carries ONE engine: the tensor-core path (tc_kernels.cuh).  -DCLAIRB_CROSSCHECK adds the fp32
+// CUDA-core kernels and the two-kernel layer 2 as on-device cross-checks (libclair_b200_xcheck.so, loaded by tests only).
+#ifdef CLAIRB_CROSSCHECK
 #include "simt_kernels.cuh"
+#endif
 #include "tc_kernels.cuh"
 #include "decide_kernels.cuh"
 #include "decode_host.cuh"
@@ -279,6 +283,7 @@ struct ProfScope {
 };
 
 // ---- forward on one chunk, all launches on `st` ------------------------------------------------
+#ifdef CLAIRB_CROSSCHECK
 int forward_tail(clairb_engine* e, SiteMap sm, float* out_dev, cudaStream_t st);
 int forward_heads(clairb_engine* e, SiteMap sm, float* out_dev, cudaStream_t st);
 
@@ -336,6 +341,8 @@ int forward_heads(clairb_engine* e, SiteMap sm, float* out_dev, cudaStream_t st)
   return CLAIRB_OK;
 }
 
+#endif  // CLAIRB_CROSSCHECK
+
 int forward_chunk(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, float* out_dev, cudaStream_t st,
                   int64_t split_rows = 0) {
   if (e->kind == ENGINE_TC) {
@@ -350,9 +357,15 @@ int forward_chunk(clairb_engine* e, const void* x_dev, int dtype, SiteMap sm, fl
     e->launches += nl;
     if (cst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "tensor-core forward failed: %s", cudaGetErrorString(cst));
     if (e->fuse_tail) return CLAIRB_OK;
+#ifdef CLAIRB_CROSSCHECK
     return forward_tail(e, sm, out_dev, st);
+#endif
   }
+#ifdef CLAIRB_CROSSCHECK
   return forward_simt(e, x_dev, dtype, sm, out_dev, st);
+#else
+  return fail(e, CLAIRB_EINVAL, "this build carries the tensor-core engine only");
+#endif
 }
 
 size_t elem_bytes(int dtype) { return dtype == CLAIRB_DTYPE_I16 ? 2 : 4; }
@@ -398,7 +411,13 @@ void free_all(clairb_engine* e) {
 
 extern "C" {
 
-const char* clairb_version(void) { return "clair_b200 0.4 sm_100a (tcgen05 BiLSTM, streamed layer-2 projection, decision stage, create_tensors)"; }
+const char* clairb_version(void) {
+#ifdef CLAIRB_CROSSCHECK
+  return "clair_b200 0.5 sm_100a cross-check build (tcgen05 engine + fp32 CUDA-core engines)";
+#else
+  return "clair_b200 0.5 sm_100a (tcgen05 BiLSTM, streamed layer-2 projection, async batch queue, decision stage, create_tensors)";
+#endif
+}
 
 const char* clairb_last_error(const clairb_engine* e) {
   if (e) return e->err.c_str();
@@ -431,13 +450,25 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
   e->max_sites = max_sites;
   e->batch = batch_sites;
   e->bp = (batch_sites + TILE - 1) / TILE * TILE;
-  const char* kind = getenv("CLAIRB_ENGINE");
-  e->kind = (kind && !strcmp(kind, "simt")) ? ENGINE_SIMT : (tc::available() ? ENGINE_TC : ENGINE_SIMT);
-  if (e->kind == ENGINE_TC) {
+  e->kind = ENGINE_TC;
+  e->fuse_tail = true;
+  e->l2_stream = true;
+  {
+    const char* kind = getenv("CLAIRB_ENGINE");
     const char* ft = getenv("CLAIRB_FUSED_TAIL");
-    e->fuse_tail = !(ft && !strcmp(ft, "0"));
     const char* ls = getenv("CLAIRB_L2_STREAM");
-    e->l2_stream = !(ls && !strcmp(ls, "0"));
+    const bool want_simt = kind && !strcmp(kind, "simt"), no_fuse = ft && !strcmp(ft, "0"), no_stream = ls && !strcmp(ls, "0");
+#ifdef CLAIRB_CROSSCHECK
+    if (want_simt) e->kind = ENGINE_SIMT;
+    e->fuse_tail = !no_fuse;
+    e->l2_stream = !no_stream;
+#else
+    if (want_simt || no_fuse || no_stream) {
+      delete e;
+      return fail(nullptr, CLAIRB_EINVAL, "clairb_create: CLAIRB_ENGINE / CLAIRB_FUSED_TAIL / CLAIRB_L2_STREAM select the cross-check "
+                  "engines, which this library was built without (they live in libclair_b200_xcheck.so, -DCLAIRB_CROSSCHECK)");
+    }
+#endif
     const char* rp = getenv("CLAIRB_RAMP");
     e->ramp = !(rp && !strcmp(rp, "0"));
   }
@@ -503,6 +534,7 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
     CR_TRY(cudaMalloc((void**)&e->d_l3T, np * L3_K * sizeof(float)));
   }
   CR_TRY(cudaMalloc((void**)&e->d_l4T, np * L4_UNITS * sizeof(float)));
+#ifdef CLAIRB_CROSSCHECK
   CR_TRY(cudaFuncSetAttribute(simt::l4_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt::l4_smem_bytes()));
   CR_TRY(cudaFuncSetAttribute(simt::tail_heads, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)simt::tail_smem_bytes()));
@@ -513,7 +545,9 @@ int clairb_create(int device, int64_t max_sites, int batch_sites, clairb_engine*
                                 (int)simt::lstm_smem_bytes<F_IN>()));
     CR_TRY(cudaFuncSetAttribute(simt::lstm_layer<2 * H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)simt::lstm_smem_bytes<2 * H>()));
-  } else {
+  } else
+#endif
+  {
     CR_TRY(tc::alloc_workspace(e->tcws, e->chunk_np, device, !e->l2_stream));
   }
 #undef CR_TRY
@@ -607,12 +641,15 @@ int clairb_finalize_weights(clairb_engine* e) {
   drop(e->d_w3p); drop(e->d_b3p); drop(e->d_W4); drop(e->d_b4);
   drop(e->d_W5); drop(e->d_b5); drop(e->d_Whd); drop(e->d_bhd);
   int rc = 0;
-  // small tail weights are shared by both engines
+  if ((rc = upload(e, &e->d_b4, b4->data))) return rc;                // read by l3l4_fused
+#ifdef CLAIRB_CROSSCHECK
+  // fp32 layouts of the CUDA-core tail (slice-dense, L4, L5 / heads)
   if ((rc = upload(e, &e->d_W5, W5)) || (rc = upload(e, &e->d_b5, b5)) || (rc = upload(e, &e->d_Whd, Whd)) ||
-      (rc = upload(e, &e->d_bhd, bhd)) || (rc = upload(e, &e->d_b4, b4->data)))
+      (rc = upload(e, &e->d_bhd, bhd)))
     return rc;
   if ((rc = upload(e, &e->d_w3p, w3p)) || (rc = upload(e, &e->d_b3p, b3p)) || (rc = upload(e, &e->d_W4, W4->data)))
     return rc;
+#endif
   if (e->kind == ENGINE_SIMT) {
     for (int l = 0; l < 2; ++l)
       if ((rc = upload(e, &e->d_Wp[l], Wp[l])) || (rc = upload(e, &e->d_bp[l], bp[l]))) return rc;

@@ -1851,6 +1851,7 @@ inline cudaError_t upload_vec(Tp** dptr, const std::vector<Tp>& h) {
 inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
   const int kx[2] = {F_IN, 2 * H};
   cudaError_t st;
+#ifdef CLAIRB_CROSSCHECK
   // ---- layer-2 input projection (xproj_pair<32>): N-blocks of 256 gate columns, 128 rows per CTA ----
   {
     const int KC = 32;
@@ -1879,6 +1880,7 @@ inline cudaError_t build_weights(Weights& w, const HostModel& hm) {
     if ((st = upload_vec(&w.Wx2, wx)) != cudaSuccess) return st;
     if ((st = upload_vec(&w.bx2, bx)) != cudaSuccess) return st;
   }
+#endif
   // ---- layer-2 input projection streamed through lstm_seq_x2: per CTA q and block pair bp, row r = gate column
   //      (2bp+q)*128 + r; ring stages of K = 8*SX_KC: [hl][kc][128][8] ----
   {
@@ -2052,12 +2054,14 @@ inline cudaError_t alloc_workspace(Workspace& ws, int64_t np_max, int device, bo
     if ((st = cudaMalloc((void**)&ws.trace1, T_STEPS * 64 * sizeof(long long))) != cudaSuccess) return st;
     cudaMemset(ws.trace1, 0, T_STEPS * 64 * sizeof(long long));
   }
+#ifdef CLAIRB_CROSSCHECK
   if ((st = cudaFuncSetAttribute(xproj_pair<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xproj_smem_bytes<32>())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(lstm_seq<true, 0, SEQ1_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq<false, 1, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq<false, 2, SEQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<false>())) != cudaSuccess) return st;
-  if ((st = cudaFuncSetAttribute(l3l4_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3l4_smem_bytes())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq_x2<1, SX_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seqx_smem_bytes())) != cudaSuccess) return st;
+#endif
+  if ((st = cudaFuncSetAttribute(lstm_seq<true, 0, SEQ1_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes<true>())) != cudaSuccess) return st;
+  if ((st = cudaFuncSetAttribute(l3l4_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3l4_smem_bytes())) != cudaSuccess) return st;
   if ((st = cudaFuncSetAttribute(lstm_seq_x2<2, SX_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seqx_smem_bytes())) != cudaSuccess) return st;
   return cudaSuccess;
 }
@@ -2140,10 +2144,14 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
   if (l2_stream) {
     hook(6, true);
     if (fuse_tail) lstm_seq_x2<2, SX_G><<<grec, SX_THREADS, seqx_smem_bytes(), st>>>(w.Whs[1], ws.tmH1, w.tmWx, w.bx2s, ws.H1, ws.H2t, NT, np, sx_dbg, ws.trace);
+#ifdef CLAIRB_CROSSCHECK
     else lstm_seq_x2<1, SX_G><<<grec, SX_THREADS, seqx_smem_bytes(), st>>>(w.Whs[1], ws.tmH1, w.tmWx, w.bx2s, ws.H1, h2_planes, NT, np, sx_dbg, ws.trace);
+#endif
     hook(6, false);
     *launches += 3;
-  } else {
+  }
+#ifdef CLAIRB_CROSSCHECK
+  else {
     hook(2, true);
     xproj_pair<32><<<2 * ncl, XP_THREADS, xproj_smem_bytes<32>(), st>>>(ws.H1, w.Wx2, w.bx2, ws.Gx, num_row_pairs, xp_dbg);
     hook(2, false);
@@ -2153,6 +2161,7 @@ inline cudaError_t forward_lstm(const Weights& w, Workspace& ws, const void* x_d
     hook(3, false);
     *launches += 4;
   }
+#endif
   if (fuse_tail) {
     hook(4, true);
     l3l4_fused<<<(unsigned)NT, LF_THREADS, l3l4_smem_bytes(), st>>>(ws.H2t, w.l3l4, w.b4, l4T, ws.L4t, np, nullptr, l3_pf, ws.lf_trace, w.w4_unscale);

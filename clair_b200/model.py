@@ -30,6 +30,7 @@ class Clair(object):
             # B200-side options (safe defaults; not in the reference)
             device=0,
             devices=None,      # e.g. [0, 1, ..., 7]: one engine (weights replicated) per GPU behind the same predict()
+            library=None,      # another build of the C-ABI library (tests: the cross-check build, _lib.XCHECK_PATH)
             max_sites=32 * param.predictBatchSize,
             batch_sites=param.predictBatchSize,
             seed=None,
@@ -67,7 +68,7 @@ class Clair(object):
         self._seed = params["seed"]
         self.prediction = None
         self._lock = threading.Lock()
-        self._lib = _lib.load()                                # raises if the extension is missing
+        self._lib = _lib.load(params["library"])               # raises if the extension is missing
         self._engines = []                                     # one handle per GPU; every op is per-site
         self._h = None
         for dev in self.devices:
@@ -75,7 +76,7 @@ class Clair(object):
             rc = self._lib.clairb_create(dev, self.max_sites, self.batch_sites, ctypes.byref(handle))
             if rc:
                 self.close()
-            _lib.check(rc, None, "clairb_create(device %d)" % dev)
+            _lib.check(rc, None, "clairb_create(device %d)" % dev, self._lib)
             self._engines.append(handle)
         self._h = self._engines[0]
         self._next_engine = 0
@@ -103,8 +104,8 @@ class Clair(object):
                 arr = np.ascontiguousarray(weights[name], dtype=np.float32)
                 shape = (ctypes.c_int64 * arr.ndim)(*arr.shape)
                 rc = self._lib.clairb_set_weight(h, name.encode(), arr.ctypes.data_as(ctypes.c_void_p), shape, arr.ndim)
-                _lib.check(rc, h, "clairb_set_weight(%s)" % name)
-            _lib.check(self._lib.clairb_finalize_weights(h), h, "clairb_finalize_weights")
+                _lib.check(rc, h, "clairb_set_weight(%s)" % name, self._lib)
+            _lib.check(self._lib.clairb_finalize_weights(h), h, "clairb_finalize_weights", self._lib)
         self._has_weights = True
 
     # ---- forward ---------------------------------------------------------------------------
@@ -133,7 +134,7 @@ class Clair(object):
                 m = min(self.max_sites, n - s)
                 rc = self._lib.clairb_predict(self._h, X[s:s + m].ctypes.data_as(ctypes.c_void_p), dtype, m,
                                               out[s:s + m].ctypes.data_as(ctypes.c_void_p))
-                _lib.check(rc, self._h, "clairb_predict")
+                _lib.check(rc, self._h, "clairb_predict", self._lib)
         return out
 
     def predict(self, batchX):
@@ -160,7 +161,7 @@ class Clair(object):
                 rc = self._lib.clairb_predict_split(
                     self._h, X[s:s + m].ctypes.data_as(ctypes.c_void_p), dtype, m,
                     *[a[s:s + m].ctypes.data_as(ctypes.c_void_p) for a in prediction])
-                _lib.check(rc, self._h, "clairb_predict_split")
+                _lib.check(rc, self._h, "clairb_predict_split", self._lib)
         self.prediction = prediction
         return prediction
 
@@ -207,7 +208,7 @@ class Clair(object):
             if rc:
                 for hw, tw in waits:                           # do not leave earlier slices in flight behind an error
                     self._lib.clairb_predict_wait(hw, tw)
-            _lib.check(rc, h, "clairb_predict_async")
+            _lib.check(rc, h, "clairb_predict_async", self._lib)
             waits.append((h, t.value))
         return PredictTicket(self, waits, (X, ref), prediction, rec)
 
@@ -232,7 +233,7 @@ class Clair(object):
                 rc = self._lib.clairb_predict_split_decide(
                     self._h, X[s:s + m].ctypes.data_as(ctypes.c_void_p), dtype, m, ref[s:s + m].ctypes.data_as(ctypes.c_void_p),
                     *([a[s:s + m].ctypes.data_as(ctypes.c_void_p) for a in prediction] + [rec[s:s + m].ctypes.data_as(ctypes.c_void_p)]))
-                _lib.check(rc, self._h, "clairb_predict_split_decide")
+                _lib.check(rc, self._h, "clairb_predict_split_decide", self._lib)
         self.prediction = prediction
         return prediction, _decision.unpack(rec)
 
@@ -260,7 +261,7 @@ class Clair(object):
                     self._h, X[s:s + m].ctypes.data_as(ctypes.c_void_p), dtype, m,
                     ref[s:s + m].ctypes.data_as(ctypes.c_void_p), out[s:s + m].ctypes.data_as(ctypes.c_void_p),
                     rec[s:s + m].ctypes.data_as(ctypes.c_void_p))
-                _lib.check(rc, self._h, "clairb_predict_decide")
+                _lib.check(rc, self._h, "clairb_predict_decide", self._lib)
         return out, _decision.unpack(rec)
 
     def decide(self, probs, ref_bases, batchX=None):
@@ -283,7 +284,7 @@ class Clair(object):
         with self._lock:
             rc = self._lib.clairb_decide(self._h, P.ctypes.data_as(ctypes.c_void_p), ref.ctypes.data_as(ctypes.c_void_p),
                                          xp, dtype, n, rec.ctypes.data_as(ctypes.c_void_p))
-            _lib.check(rc, self._h, "clairb_decide")
+            _lib.check(rc, self._h, "clairb_decide", self._lib)
         return _decision.unpack(rec)
 
     def get_layer(self, layer, n):
@@ -292,26 +293,26 @@ class Clair(object):
                   _lib.LAYER_L4: (n, 192), _lib.LAYER_LOGITS: (n, 90)}
         out = np.empty(shapes[layer], dtype=np.float32)
         rc = self._lib.clairb_get_layer(self._h, layer, out.ctypes.data_as(ctypes.c_void_p), n)
-        _lib.check(rc, self._h, "clairb_get_layer")
+        _lib.check(rc, self._h, "clairb_get_layer", self._lib)
         return out
 
     def predict_device(self, x_ptr, dtype, n, out_ptr, stream=0):
         """Device-resident forward on `stream` (raw pointers; used by bench.py / shard path)."""
         rc = self._lib.clairb_predict_device(self._h, ctypes.c_void_p(x_ptr), dtype, n, ctypes.c_void_p(out_ptr),
                                              ctypes.c_void_p(stream))
-        _lib.check(rc, self._h, "clairb_predict_device")
+        _lib.check(rc, self._h, "clairb_predict_device", self._lib)
 
     def kernel_launches(self):
         return int(self._lib.clairb_kernel_launches(self._h))
 
     def set_profiling(self, enabled):
-        _lib.check(self._lib.clairb_set_profiling(self._h, int(bool(enabled))), self._h, "clairb_set_profiling")
+        _lib.check(self._lib.clairb_set_profiling(self._h, int(bool(enabled))), self._h, "clairb_set_profiling", self._lib)
 
     def read_profile(self):
         """[{kernel, launches, ms}] since profiling was enabled / last read."""
         import json
         buf = ctypes.create_string_buffer(1 << 16)
-        _lib.check(self._lib.clairb_read_profile(self._h, buf, len(buf)), self._h, "clairb_read_profile")
+        _lib.check(self._lib.clairb_read_profile(self._h, buf, len(buf)), self._h, "clairb_read_profile", self._lib)
         return json.loads(buf.value.decode())
 
     # ---- lifetime --------------------------------------------------------------------------
@@ -342,7 +343,7 @@ class PredictTicket(object):
             rc = m._lib.clairb_predict_wait(h, t)
             if rc and self._error is None:
                 try:
-                    _lib.check(rc, h, "clairb_predict_wait")
+                    _lib.check(rc, h, "clairb_predict_wait", m._lib)
                 except Exception as exc:                       # keep waiting for the other slices, then raise
                     self._error = exc
         self._inputs = None

@@ -209,7 +209,7 @@ def test_reference_call_variants_runs_unmodified_against_clair_b200_model(monkey
     want = run(StraightFromOracle())
 
     lib = OracleLib()
-    monkeypatch.setattr(_lib, "load", lambda: lib)
+    monkeypatch.setattr(_lib, "load", lambda path=None: lib)
     m = Clair()                                   # reference: Clair() then restore_parameters / init
     m.set_weights(weights1234)
     got = run(m)

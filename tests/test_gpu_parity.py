@@ -143,7 +143,10 @@ def test_cross_check_engines(weights1234, monkeypatch, env):
     from clair_b200.model import Clair
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    alt = Clair(max_sites=1024, batch_sites=1000)
+    with pytest.raises(ValueError, match="cross-check"):       # the product library carries one engine and says so
+        Clair(max_sites=1024, batch_sites=1000)
+    alt = Clair(max_sites=1024, batch_sites=1000, library=_lib.XCHECK_PATH)
+    assert b"cross-check" in alt._lib.clairb_version()
     for k in env:
         monkeypatch.delenv(k)
     alt.set_weights(weights1234)
@@ -310,7 +313,7 @@ def test_predict_split_layout_equals_packed(weights1234, monkeypatch):
     monkeypatch.setenv("CLAIRB_CHUNK_SITES", "1024")
     m = Clair(max_sites=4096, batch_sites=1000)
     monkeypatch.setenv("CLAIRB_FUSED_TAIL", "0")
-    alt = Clair(max_sites=4096, batch_sites=1000)
+    alt = Clair(max_sites=4096, batch_sites=1000, library=_lib.XCHECK_PATH)
     monkeypatch.delenv("CLAIRB_FUSED_TAIL")
     monkeypatch.delenv("CLAIRB_CHUNK_SITES")
     for eng in (m, alt):
