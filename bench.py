@@ -323,6 +323,11 @@ def oracle_pinning(m, weights, X256):
     return out
 
 
+def _decision_codes(infos):
+    from clair_b200 import decision
+    return decision.ref_base_codes(infos)
+
+
 def main():
     args = parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -543,10 +548,73 @@ def main():
         _, dec = m.predict_and_decide_packed(Xi, ref_bases)
     torch.cuda.synchronize()
     e2e_dec_s = max_over_ranks(time.perf_counter() - t0)
+    # the batched VCF output stage behind it (clair_b200.output.BatchOutput in place of call_var.batch_output): rows of
+    # reference / SNP calls formatted natively, insertion / deletion calls through the indel-base helpers (stand-ins here)
+    output_info = None
+    if rank == 0:
+        import types
+        from clair_b200 import output as _output
+        nb_out = min(64, bps)
+        infos_pool = [[["chr20", str(1000 * b + j + 1), "ACGT"[(b + j) % 4] * 33] for j in range(BATCH)] for b in range(4)]
+        helper = types.SimpleNamespace(
+            insertion_bases_using=lambda tensor_input, variant_length, contig, position: ("A" * variant_length, variant_length),
+            deletion_bases_using=lambda tensor_input, variant_length, contig, position, reference_sequence: (("CGTA" * 5)[:variant_length], variant_length),
+            insertion_bases_using_pysam_using=lambda **kw: "C" * kw["minimum_insertion_length"],
+            print_debug_message=lambda *a: None)
+        out_bytes = [0]
+        helper.output = lambda s: out_bytes.__setitem__(0, out_bytes[0] + len(s))
+        cfg = types.SimpleNamespace(is_show_reference=True, is_debug=False, is_haploid_precision_mode_enabled=False,
+                                    is_haploid_sensitive_mode_enabled=False, is_output_for_ensemble=False, quality_score_for_pass=None)
+        stage = _output.BatchOutput(cfg, helper, fallback=lambda *a: None)
+        preds = []
+        for b in range(nb_out):
+            xb = Xi[b * BATCH:(b + 1) * BATCH]
+            infos_b = infos_pool[b % 4]
+            preds.append((xb, infos_b) + m.predict_and_decide(xb, _decision_codes(infos_b)))
+        t0 = time.perf_counter()
+        for xb, infos_b, pred, dec_b in preds:
+            stage((xb, infos_b), pred, dec_b)
+        dt_out = time.perf_counter() - t0
+        # a random-init network answers "insertion + deletion" almost everywhere; a call set is reference / SNP calls with a
+        # few indels.  Heads shaped like that (peaked ACGT-pair label, both lengths zero, 1 site in 50 an indel) -> records from
+        # the device's decision kernel (clairb_decide) -> the same stage
+        rng = np.random.default_rng(5)
+        z = rng.normal(0, 1.0, (nb_out * BATCH, 90)).astype(np.float32)
+        z[np.arange(len(z)), rng.integers(0, 10, len(z))] += 9.0
+        z[:, 24 + 16] += 8.0
+        z[:, 57 + 16] += 8.0
+        indel = rng.random(len(z)) < 0.02
+        z[indel, 15] += 14.0
+        z[indel, 24 + 18] += 12.0
+        z[indel, 57 + 18] += 12.0
+        Pc = np.empty_like(z)
+        for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
+            ez = np.exp(z[:, a:b] - z[:, a:b].max(1, keepdims=True))
+            Pc[:, a:b] = ez / ez.sum(1, keepdims=True)
+        stage_c = _output.BatchOutput(cfg, helper, fallback=lambda *a: None)
+        calls = []
+        for b in range(nb_out):
+            sl = slice(b * BATCH, (b + 1) * BATCH)
+            infos_b = infos_pool[b % 4]
+            pb = Pc[sl]
+            calls.append((Xi[sl], infos_b, [pb[:, 0:21], pb[:, 21:24], pb[:, 24:57], pb[:, 57:90]],
+                          m.decide(pb, _decision_codes(infos_b), Xi[sl])))
+        t0 = time.perf_counter()
+        for xb, infos_b, pred, dec_b in calls:
+            stage_c((xb, infos_b), pred, dec_b)
+        dt_call = time.perf_counter() - t0
+        output_info = {"value": nb_out * BATCH / dt_call, "unit": "sites/s", "sites": nb_out * BATCH,
+                       "rows_native": stage_c.fast_rows, "rows_python": stage_c.slow_rows, "sites_to_fallback": stage_c.fallback_sites,
+                       "what": "call-like heads (reference / SNP calls, 2 % insertions), every site prints a row (show reference calls)",
+                       "random_init_model": {"value": nb_out * BATCH / dt_out, "rows_native": stage.fast_rows, "rows_python": stage.slow_rows,
+                                             "note": "the bench's random-init network calls 'insertion + deletion' on 80 % of the sites: the "
+                                                     "per-site Python path (indel-base helper calls) carries them"},
+                       "note": "BatchOutput on the device's decision records, one host thread + 4 formatter threads; the reference's "
+                               "batch_output spends ~1 ms of Python per site (SURVEY.md 8f)"}
     decision_info = None
     if rank == 0:
         decision_info = {"e2e_with_decision": world * sites * dec_steps / e2e_dec_s, "unit": "sites/s",
-                         "extra_d2h_bytes_per_step": sites * 24, "extra_h2d_bytes_per_step": sites,
+                         "extra_d2h_bytes_per_step": sites * 32, "extra_h2d_bytes_per_step": sites,
                          "categories_seen": np.bincount(dec.category, minlength=10).tolist(),
                          "note": "forward + decide_sites kernel per chunk (call_var.py:589-690, 732-760), int16 transport"}
 
@@ -612,6 +680,8 @@ def main():
             cpu_dec = ns / (time.perf_counter() - t0)
             got = np.stack([dec.category, dec.len1, dec.len2, dec.aux], axis=1)[:ns]
             assert np.array_equal(got, want) and np.array_equal(dec.max_probability[:ns], want_p), "decision parity failed"
+            for i in range(0, ns, 7):                  # record words 6 / 7 (quality score) against the restatement
+                assert dec.quality[i] == DO.quality_of_first_choice(out[i], int(want[i, 0]), int(want[i, 3])), "quality parity failed"
             decision_info["cpu_python_restatement_sites_per_s"] = cpu_dec
             decision_info["cpu_sample"] = "%d sites, 1 core; device records bit-exact on them" % ns
             if ct_ctx is not None:
@@ -657,6 +727,7 @@ def main():
                                       "clair/call_var.py:1327-1352): 1000 sites = 8 of 74 CTA pairs per call"},
             "multi_gpu_check": multi_gpu_check,
             "decision_stage": decision_info,
+            "output_stage": output_info,
             "create_tensor_stage": ct_info,
             "gpu_launches": launches,
             "roofline": roofline,

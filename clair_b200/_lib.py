@@ -15,7 +15,7 @@ XCHECK_PATH = os.path.join(_HERE, "lib", "libclair_b200_xcheck.so")
 OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, EWEIGHTS = range(6)
 DTYPE_F32, DTYPE_I16 = 0, 1
 N_OUT = 90
-DECISION_WORDS = 6
+DECISION_WORDS = 8
 SITE_ELEMS = 1056
 LAYER_LSTM1, LAYER_LSTM2, LAYER_L3, LAYER_L4, LAYER_LOGITS = 1, 2, 3, 4, 5
 
@@ -44,6 +44,8 @@ SYMBOLS = {
     "clairb_blosc_decompress": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.POINTER(_c.c_int64)]),
     "clairb_format_tensor_rows": (_c.c_int, [_c.c_char_p, _c.c_void_p, _c.c_char_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_int64,
                                              _c.c_void_p, _c.c_int64, _c.POINTER(_c.c_int64)]),
+    "clairb_format_vcf_rows": (_c.c_int, [_c.c_int64, _c.c_char_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                          _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.POINTER(_c.c_int64), _c.c_void_p]),
     "clairb_decode_rows": (_c.c_int, [_c.c_char_p, _c.c_int64, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p,
                                       _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
     "clairb_get_layer": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int64]),

@@ -9,8 +9,13 @@
 // entry with the largest value and, among equal values, the smallest (category rank, index in the reference's list).
 //
 // One warp per site: the 90 probabilities sit in shared memory, every lane walks a 32-strided share of the 1179
-// entries, then a shuffle reduction picks the winner.  HBM traffic is 360 B (+128 B of the centre row of x) in and
-// 24 B out per site; the arithmetic (about 3.6 k multiplies per site) is negligible next to it.
+// entries, then a shuffle reduction picks the winner.  HBM traffic is 360 B (+256 B: rows 16 and 17 of x) in and
+// 32 B out per site; the arithmetic (about 3.6 k multiplies per site) is negligible next to it.
+//
+// Behind the winner, lane 0 also evaluates what output_with (clair/call_var.py:1002-1197) derives from it without any
+// string in hand: the quality score (quality_score_from :568-586: float32 product p of the gt21 and genotype probabilities
+// of the call, then float64 as the reference's pinned numpy 1.18 computes it - `1.0 - p` with a Python float promotes a
+// float32 scalar to float64 there) and the supporting-read count (:1100-1151: sums over rows 16 / 17 of the tensor).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,7 +26,10 @@ namespace clairb {
 namespace decide {
 
 constexpr int WARPS_PER_BLOCK = 8;
-constexpr int REC_WORDS = 6;          // category, len1, len2, aux, max probability (f32 bits), read depth (f32 bits)
+constexpr int REC_WORDS = 8;          // category, len1, len2, aux, max probability (f32 bits), read depth (f32 bits),
+                                      // quality score, supporting reads (f32 bits)
+// -10 * log(e, 10) as CPython evaluates it (clair/call_var.py:581): math.log(math.e, 10) = 0.4342944819032518
+constexpr double QUAL_SCALE = -4.342944819032518;
 
 struct Best {
   float v;
@@ -143,10 +151,57 @@ decide_sites(const float* __restrict__ probs, const uint8_t* __restrict__ ref_ba
       const TIn* row = x + site * SITE_ELEMS + 16 * F_IN;
       for (int r = 0; r < 8; ++r) depth = __fadd_rn(depth, __fadd_rn((float)row[r * 4 + 2], (float)row[r * 4 + 0]));
     }
+    // quality score of the call (:568-586).  The gt21 label / genotype the reference derives from its REF, ALT and genotype
+    // strings (clair/task/gt21.py:64-108, genotype.py:20-33) follow from the category alone: reference -> (ref ref, 0/0);
+    // SNPs -> (the label, 1/1 or 0/1 | 1/2 -> hetero); insertions -> InsIns / <base>Ins; deletions -> DelDel / <base>Del;
+    // Ins+Del -> InsDel; every two-allele call scores with the hetero genotype (genotype_enum_for_task).
+    const int q_gt21 = cat <= 2 ? aux : cat == 3 || cat == 5 ? 15 : cat == 4 ? 16 + aux : cat == 6 || cat == 8 ? 10 : cat == 7 ? 11 + aux : 20;
+    const int q_geno = cat == 0 ? 0 : (cat == 1 || cat == 3 || cat == 6) ? 1 : 2;
+    const double pq = (double)__fmul_rn(gt21[q_gt21], p[21 + q_geno]);
+    double tq = QUAL_SCALE * log(((1.0 - pq) + 1e-300) / (pq + 1e-300)) + 16.0;
+    tq = tq > 0.0 ? tq : 0.0;
+    const int quality = (int)rint(tq * tq);                  // Python 3 round(): half to even
+    // supporting reads (:1100-1151), sums in the reference's order (integer counts: exact in float32 either way)
+    float support = 0.f;
+    if (x != nullptr) {
+      const TIn* c16 = x + site * SITE_ELEMS + 16 * F_IN;
+      const TIn* c17 = c16 + F_IN;
+      auto snp_support = [&](int base) {                     // SNP + reference channel of both strands of one base
+        return __fadd_rn(__fadd_rn(__fadd_rn((float)c16[base * 4 + 3], (float)c16[(base + 4) * 4 + 3]), (float)c16[base * 4 + 0]),
+                         (float)c16[(base + 4) * 4 + 0]);
+      };
+      auto column = [&](int channel) {
+        float t = 0.f;
+        for (int r = 0; r < 8; ++r) t = __fadd_rn(t, (float)c17[r * 4 + channel]);
+        return t;
+      };
+      // label bases of a gt21 pair label 0..9 (AA AC AG AT CC CG CT GG GT TT)
+      const int l1 = aux < 4 ? 0 : aux < 7 ? 1 : aux < 9 ? 2 : 3, l2 = aux < 4 ? aux : aux < 7 ? aux - 3 : aux < 9 ? aux - 5 : 3;
+      if (cat == 0) {
+        support = __fadd_rn((float)c16[rb * 4 + 0], (float)c16[(rb + 4) * 4 + 0]);
+      } else if (cat == 1) {
+        support = snp_support(l1);
+      } else if (cat == 2) {
+        if (l1 != rb && l2 != rb) support = __fadd_rn(snp_support(l1), snp_support(l2));
+        else support = snp_support(l1 != rb ? l1 : l2);
+      } else if (cat == 3 || cat == 5) {
+        support = __fsub_rn(column(1), column(3));
+      } else if (cat == 4) {
+        support = __fadd_rn(__fsub_rn(column(1), column(3)), aux != rb ? snp_support(aux) : 0.f);
+      } else if (cat == 6 || cat == 8) {
+        support = column(2);
+      } else if (cat == 7) {
+        support = __fadd_rn(column(2), aux != rb ? snp_support(aux) : 0.f);
+      } else {
+        support = __fsub_rn(__fadd_rn(column(1), column(2)), column(3));
+      }
+    }
     int32_t* o = rec + site * REC_WORDS;
     o[0] = cat; o[1] = len1; o[2] = len2; o[3] = aux;
     o[4] = __float_as_int(b.v);
     o[5] = __float_as_int(depth);
+    o[6] = quality;
+    o[7] = __float_as_int(support);
   }
 }
 

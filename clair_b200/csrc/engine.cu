@@ -1273,6 +1273,22 @@ int clairb_format_tensor_rows(const char* ctg_name, const int64_t* positions, co
   return CLAIRB_OK;
 }
 
+int clairb_format_vcf_rows(int64_t n, const char* ctg_blob, const int32_t* ctg_off, const int64_t* pos, const uint8_t* ref,
+                           const uint8_t* alt, const int32_t* quality, const uint8_t* filter_code, const uint8_t* gt_code,
+                           const int32_t* depth, const double* af, char* out, int64_t out_cap, int64_t* out_len, int64_t* row_end) {
+  if (n < 0 || !out_len || out_cap < 0 || (n && (!ctg_blob || !ctg_off || !pos || !ref || !alt || !quality || !filter_code || !gt_code || !depth || !af)))
+    return fail(nullptr, CLAIRB_EINVAL, "format_vcf_rows: bad arguments");
+  if (out && n && !row_end) return fail(nullptr, CLAIRB_EINVAL, "format_vcf_rows: row_end is required with out");
+  for (int64_t i = 0; i < n; ++i) {
+    if (filter_code[i] > 2 || gt_code[i] > 5 || ctg_off[i + 1] < ctg_off[i] || !memchr(alt + 4 * i, 0, 4))
+      return fail(nullptr, CLAIRB_EINVAL, "format_vcf_rows: row %lld has an unknown filter / genotype code, a negative contig length or an unterminated ALT", (long long)i);
+  }
+  static const int threads = getenv("CLAIRB_DECODE_THREADS") ? atoi(getenv("CLAIRB_DECODE_THREADS")) : 4;
+  if (fmt::vcf_rows(n, ctg_blob, ctg_off, pos, ref, alt, quality, filter_code, gt_code, depth, af, out, out_cap, out_len, row_end, threads))
+    return fail(nullptr, CLAIRB_EINVAL, "format_vcf_rows: the rows need %lld bytes, the buffer holds %lld", (long long)*out_len + 1, (long long)out_cap);
+  return CLAIRB_OK;
+}
+
 int clairb_decode_rows(const char* text, int64_t text_len, int64_t max_rows, int dtype, void* x_out, int32_t* info_off,
                        int64_t* rows_read, int64_t* rows_kept, int64_t* consumed) {
   if (!text || text_len < 0 || max_rows <= 0 || !x_out || !info_off || !rows_read || !rows_kept || !consumed)

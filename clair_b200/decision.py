@@ -22,7 +22,8 @@ GT21_LABELS = ("AA", "AC", "AG", "AT", "CC", "CG", "CT", "GG", "GT", "TT", "DelD
 IUPAC_TO_ACGT = dict(zip("ACGTURYSWKMBDHVN", "ACGTTACCAGACAAAA"))
 BASIC_BASES = frozenset("ACGTU")                                                         # shared/utils.py:31
 
-Decision = collections.namedtuple("Decision", "category len1 len2 aux max_probability read_depth")
+Decision = collections.namedtuple("Decision", "category len1 len2 aux max_probability read_depth quality supported_reads",
+                                  defaults=(None, None))
 
 
 def ref_base_codes(non_tensor_infos, centre=16):
@@ -35,11 +36,11 @@ def ref_base_codes(non_tensor_infos, centre=16):
 
 
 def unpack(records):
-    """[n,6] int32 device records -> Decision of column views into them (the two float fields are bit-cast back;
-    no copies: splitting 142,000 records into six contiguous arrays costs as much as 10 % of their forward pass)."""
+    """[n,8] int32 device records -> Decision of column views into them (the float fields are bit-cast back;
+    no copies: splitting 142,000 records into contiguous arrays costs as much as 10 % of their forward pass)."""
     r = np.ascontiguousarray(records, dtype=np.int32).reshape(-1, _lib.DECISION_WORDS)
     f = r.view(np.float32)
-    return Decision(r[:, 0], r[:, 1], r[:, 2], r[:, 3], f[:, 4], f[:, 5])
+    return Decision(r[:, 0], r[:, 1], r[:, 2], r[:, 3], f[:, 4], f[:, 5], r[:, 6], f[:, 7])
 
 
 def flags_tuple(category):

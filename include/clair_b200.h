@@ -131,8 +131,13 @@ int clairb_predict_device(clairb_engine* e, const void* x_dev, int dtype, int64_
  *                  ACGT+Ins/Del: the hetero base 0..3
  *              [4] maximum probability, float32 bits     [5] read depth
  *                  sum(x[16,:,delete] + x[16,:,reference]) (clair/call_var.py:1021-1024), float32 bits
+ *              [6] quality score of that call, int(round(max(-10 log10(e) ln((1-p+1e-300)/(p+1e-300)) + 16, 0)^2))
+ *                  (quality_score_from, clair/call_var.py:568-586; p = float32 product, the rest in float64)
+ *              [7] supporting-read count of that call (clair/call_var.py:1100-1151), float32 bits; the allele
+ *                  frequency the VCF row prints is [7] / [5] in float64, capped at 1 (:1152-1154)
+ *              [6] and [7] assume the first choice stands (indel-base lookups come back non-empty, :780-929).
  */
-#define CLAIRB_DECISION_WORDS 6
+#define CLAIRB_DECISION_WORDS 8
 
 /* Forward + decision in one pass: as clairb_predict, and the decision kernel runs on every chunk while its
  * probabilities and input tensor are still in device memory. */
@@ -217,6 +222,18 @@ int clairb_blosc_decompress(const void* src, int64_t src_len, void* dst, int64_t
 int clairb_format_tensor_rows(const char* ctg_name, const int64_t* positions, const char* reference, int64_t reference_len,
                               const int64_t* window_start, const int16_t* x, int64_t n, char* out, int64_t out_cap,
                               int64_t* out_len);
+
+/* Host-only (no device): the VCF rows output_with prints for reference / SNP calls (clair/call_var.py:1184-1197),
+ * "<ctg>\t<pos>\t.\t<REF>\t<ALT>\t<QUAL>\t<FILTER>\t.\tGT:GQ:DP:AF\t<GT>:<QUAL>:<DP>:<AF %.4f>", n rows joined by '\n'.
+ *   ctg_blob / ctg_off [n+1] : contig names back to back and their offsets      pos [n]
+ *   ref [n] : one character      alt [n][4] : "X" or "X,Y", NUL-terminated
+ *   filter_code [n] : 0 ".", 1 "PASS", 2 "LowQual" (filtration_value_from, :70-75)
+ *   gt_code [n] : 0 "0/0", 1 "1/1", 2 "0/1", 3 "1/2", 4 "0", 5 "1" (clair/task/genotype.py:3; the haploid modes, :1164-1166)
+ * row_end [n] : offset one past each row.  With out == NULL only *out_len (bytes needed, +1 for out_cap) is reported. */
+int clairb_format_vcf_rows(int64_t n, const char* ctg_blob, const int32_t* ctg_off, const int64_t* pos, const uint8_t* ref,
+                           const uint8_t* alt, const int32_t* quality, const uint8_t* filter_code, const uint8_t* gt_code,
+                           const int32_t* depth, const double* af, char* out, int64_t out_cap, int64_t* out_len,
+                           int64_t* row_end);
 
 /* Host-only (no device): `samtools view` text -> the arrays of clairb_alignments.  Replaces what the reference does per
  * SAM row before and while it walks the CIGAR string (dataPrepScripts/CreateTensor.py:251-296): '@' rows skipped, the

@@ -119,3 +119,71 @@ def decide(probs, ref_bases, X=None):
         if X is not None:
             depth[i] = read_depth(X[i])
     return dec, maxp, depth
+
+
+# ---- what output_with derives from the first choice without any string in hand (record words 6, 7) --------------------
+# quality_score_from (clair/call_var.py:568-586) needs the gt21 label and genotype of the call; gt21_enum_from
+# (clair/task/gt21.py:92-108) reads them off the REF / ALT / genotype strings, but for a first choice that stands they follow
+# from the category: reference -> (ref ref, 0/0); SNPs -> (the label, 1/1 | 0/1 | 1/2); homo Ins / InsIns -> InsIns;
+# ACGT+Ins -> <base>Ins; homo Del / DelDel -> DelDel; ACGT+Del -> <base>Del; Ins+Del -> InsDel; two-allele calls score with
+# the hetero genotype (genotype_enum_for_task, clair/task/genotype.py:30-33).  tests/test_output.py pins this against the
+# rows the reference's own output_with printed.
+QUALITY_GT21 = {3: GT_INSINS, 5: GT_INSINS, 6: GT_DELDEL, 8: GT_DELDEL, 9: GT_INSDEL}
+QUALITY_GENOTYPE = (HOMO_REF, HOMO_VAR, HETERO_VAR, HOMO_VAR, HETERO_VAR, HETERO_VAR, HOMO_VAR, HETERO_VAR, HETERO_VAR, HETERO_VAR)
+LABEL_BASES = ((0, 0), (0, 1), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 3))    # AA AC AG AT CC CG CT GG GT TT
+
+
+def quality_of_first_choice(probs90, category, aux):
+    """int(round(max(-10 log10(e) ln((1-p+1e-300)/(p+1e-300)) + 16, 0)^2)), p the float32 product (call_var.py:568-586)."""
+    from math import e, log
+    p90 = np.asarray(probs90, dtype=F)
+    gt21 = aux if category <= 2 else GT_AINS + aux if category == 4 else GT_ADEL + aux if category == 7 else QUALITY_GT21[category]
+    p = float(p90[gt21] * p90[21 + QUALITY_GENOTYPE[category]])
+    tmp = max((-10 * log(e, 10)) * log(((1.0 - p) + 1e-300) / (p + 1e-300)) + 16, 0)
+    return int(round(tmp * tmp))
+
+
+def support_of_first_choice(x, ref_base, category, aux):
+    """Supporting-read count of the first choice (call_var.py:1087-1151); x one [33,8,4] tensor, ref_base 0..3."""
+    x = np.asarray(x, dtype=np.float64)
+    snp = lambda b: x[16, b, 3] + x[16, b + 4, 3] + x[16, b, 0] + x[16, b + 4, 0]
+    ins, dele, snp17 = x[17, :, 1].sum(), x[17, :, 2].sum(), x[17, :, 3].sum()
+    if category == 0:
+        return F(x[16, ref_base, 0] + x[16, ref_base + 4, 0])
+    if category == 1:
+        return F(snp(LABEL_BASES[aux][0]))
+    if category == 2:
+        b1, b2 = LABEL_BASES[aux]
+        return F(snp(b1) + snp(b2)) if (b1 != ref_base and b2 != ref_base) else F(snp(b1 if b1 != ref_base else b2))
+    if category in (3, 5):
+        return F(ins - snp17)
+    if category == 4:
+        return F((ins - snp17) + (snp(aux) if aux != ref_base else 0))
+    if category in (6, 8):
+        return F(dele)
+    if category == 7:
+        return F(dele + (snp(aux) if aux != ref_base else 0))
+    return F(ins + dele - snp17)
+
+
+def decide_full(probs, ref_bases, X):
+    """decide() plus the two derived words: -> (dec [n,4], maxp [n], depth [n], quality int32 [n], support float32 [n])."""
+    dec, maxp, depth = decide(probs, ref_bases, X)
+    n = len(probs)
+    quality = np.zeros(n, np.int32)
+    support = np.zeros(n, F)
+    for i in range(n):
+        quality[i] = quality_of_first_choice(probs[i], int(dec[i, 0]), int(dec[i, 3]))
+        support[i] = support_of_first_choice(X[i], int(ref_bases[i]), int(dec[i, 0]), int(dec[i, 3]))
+    return dec, maxp, depth, quality, support
+
+
+def categories_holding_the_maximum(probs90, ref_base):
+    """How many of the ten outcome lists contain the maximum.  More than one = an exact tie between categories: the
+    reference's flags tuple then carries several True entries (clair/call_var.py:750-758 tests every list), and the
+    elif chains of output_with (:1076-1151) may follow a different flag than the one output_from built REF / ALT from.
+    Never seen with real softmax outputs; the golden cases with probabilities quantised to powers of two are full of them."""
+    p = np.asarray(probs90, dtype=F)
+    lists = outcome_lists(p[0:21], p[21:24], p[24:57], p[57:90], int(ref_base))
+    maximum = max(max(e[0] for e in lst) for lst in lists)
+    return sum(1 for lst in lists if any(e[0] == maximum for e in lst))

@@ -58,11 +58,14 @@ def test_host_helpers():
     assert codes.tolist() == ["ACGT".index(c) for c in "ACGTTACCAGACAAAA"]          # shared/utils.py:19-29
     assert decision.flags_tuple(4) == (False,) * 4 + (True,) + (False,) * 5
     assert decision.snp_bases(6) == ("C", "T")
-    rec = np.zeros((2, 6), np.int32)
+    rec = np.zeros((2, _lib.DECISION_WORDS), np.int32)
     rec[0, :4] = (5, 2, 7, 0)
-    rec.view(np.float32)[0, 4:] = (0.25, 31.0)
+    rec.view(np.float32)[0, 4:6] = (0.25, 31.0)
+    rec[0, 6] = 411
+    rec.view(np.float32)[0, 7] = 12.0
     d = decision.unpack(rec)
     assert (d.category[0], d.len1[0], d.len2[0], d.max_probability[0], d.read_depth[0]) == (5, 2, 7, 0.25, 31.0)
+    assert (d.quality[0], d.supported_reads[0]) == (411, 12.0)
 
 
 # ---- GPU ----------------------------------------------------------------------------------------------------------
