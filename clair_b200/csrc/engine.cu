@@ -1283,7 +1283,8 @@ int clairb_format_vcf_rows(int64_t n, const char* ctg_blob, const int32_t* ctg_o
     if (filter_code[i] > 2 || gt_code[i] > 5 || ctg_off[i + 1] < ctg_off[i] || !memchr(alt + 4 * i, 0, 4))
       return fail(nullptr, CLAIRB_EINVAL, "format_vcf_rows: row %lld has an unknown filter / genotype code, a negative contig length or an unterminated ALT", (long long)i);
   }
-  static const int threads = getenv("CLAIRB_DECODE_THREADS") ? atoi(getenv("CLAIRB_DECODE_THREADS")) : 4;
+  static const int max_threads = getenv("CLAIRB_DECODE_THREADS") ? atoi(getenv("CLAIRB_DECODE_THREADS")) : 4;
+  const int threads = n < 16384 ? 1 : max_threads;      // a predict-batch of 1000 rows is ~60 us of work: no thread is worth spawning
   if (fmt::vcf_rows(n, ctg_blob, ctg_off, pos, ref, alt, quality, filter_code, gt_code, depth, af, out, out_cap, out_len, row_end, threads))
     return fail(nullptr, CLAIRB_EINVAL, "format_vcf_rows: the rows need %lld bytes, the buffer holds %lld", (long long)*out_len + 1, (long long)out_cap);
   return CLAIRB_OK;

@@ -144,22 +144,31 @@ class BatchOutput(object):
             filt = np.zeros(n, np.uint8)
         else:
             filt = np.where(quality >= cfg.quality_score_for_pass, 1, 2).astype(np.uint8)
-        names = [infos[i][0].encode() for i in idx.tolist()]
-        ctg_off = np.zeros(n + 1, np.int32)
-        np.cumsum([len(s) for s in names], out=ctg_off[1:])
-        blob_in = b"".join(names)
-        pos = np.array([int(infos[i][1]) for i in idx.tolist()], np.int64)
+        contigs = [info[0] for info in infos]
+        if contigs.count(contigs[0]) == len(contigs):                 # one contig per batch is the rule
+            name = contigs[0].encode()
+            blob_in = name * n
+            ctg_off = (np.arange(n + 1, dtype=np.int64) * len(name)).astype(np.int32)
+        else:
+            names = [contigs[i].encode() for i in idx.tolist()]
+            ctg_off = np.zeros(n + 1, np.int32)
+            np.cumsum([len(s) for s in names], out=ctg_off[1:])
+            blob_in = b"".join(names)
+        pos = np.fromstring(" ".join(info[1] for info in infos), dtype=np.int64, sep=" ")       # one C-level parse per batch
+        if pos.shape[0] != len(infos):
+            raise ValueError("positions of the batch are not plain integers")
+        pos = np.ascontiguousarray(pos[idx])
         refc = np.ascontiguousarray(_BASE_CHAR[ref])
         depth_i = np.ascontiguousarray(depth.astype(np.int32))                                      # "%d" of a float truncates
         af = np.ascontiguousarray(af, dtype=np.float64)
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         need = ctypes.c_int64()
-        args = (n, blob_in, p(ctg_off), p(pos), p(refc), p(alt), p(quality), p(filt), p(gt), p(depth_i), p(af))
-        _lib.check(self._lib.clairb_format_vcf_rows(*args, None, 0, ctypes.byref(need), None), None, "clairb_format_vcf_rows")
-        out = ctypes.create_string_buffer(need.value + 1)
+        cap = len(blob_in) + 128 * n + 1                  # every field of a row but the contig is bounded: one call, no measuring pass
+        out = ctypes.create_string_buffer(cap)
         row_end = np.empty(n, np.int64)
-        _lib.check(self._lib.clairb_format_vcf_rows(*args, out, need.value + 1, ctypes.byref(need), p(row_end)), None,
-                   "clairb_format_vcf_rows")
+        rc = self._lib.clairb_format_vcf_rows(n, blob_in, p(ctg_off), p(pos), p(refc), p(alt), p(quality), p(filt), p(gt), p(depth_i),
+                                              p(af), out, cap, ctypes.byref(need), p(row_end))
+        _lib.check(rc, None, "clairb_format_vcf_rows")
         return idx, out.raw[:need.value], row_end
 
     # ---- everything else, a site at a time ------------------------------------------------------------------------
