@@ -313,18 +313,109 @@ def read_bundle(prefix, names=None, verify=True):
     return out
 
 
+# ---- which entries are the forward path's variables ------------------------------------------------------------------------
+# The dense layers carry explicit names (clair/model.py:240, 482-618: "L3/Unit_c", "L4", "L5_k", "Prediction/..."), but the
+# names of the LSTM variables depend on which branch of adaptive_LSTM_layer built the graph that was SAVED:
+#   * CPU branch (clair/model.py:298-312): "LSTM1/stack_bidirectional_rnn/cell_0/bidirectional_rnn/{fw,bw}/
+#     cudnn_compatible_lstm_cell/{kernel,bias}" - what SURVEY.md 8a lists and weights.lstm_name() produces;
+#   * cuDNN branch (clair/model.py:281-296, the one the released models were trained with): the CudnnLSTM layer keeps ONE
+#     opaque parameter buffer whose saveable writes either the same canonical tensors under the layer's own scope
+#     ("LSTM1/cudnn_lstm/stack_bidirectional_rnn/.../kernel") or, saved raw, the buffer itself ("LSTM1/cudnn_lstm/opaque_kernel").
+# So the LSTM variables are DISCOVERED: by scope ("LSTM1/" ... "/fw/" ... "/kernel"), shape and - last - the opaque buffer.
+_SLOT_SUFFIXES = ("/Adam", "/Adam_1", "/Momentum", "/RMSProp", "/RMSProp_1", "/Adagrad", "/ExponentialMovingAverage")
+
+
+def _is_slot(name):
+    return name.endswith(_SLOT_SUFFIXES)
+
+
+def discover_lstm_names(entries):
+    """{canonical name (weights.lstm_name): name in the checkpoint} for the 8 LSTM variables, or {canonical: ("opaque",
+    name, direction index)} where only the cuDNN parameter buffer of the layer was saved.  Raises ValueError naming the
+    candidates when a variable cannot be identified uniquely."""
+    from . import weights as W
+    found = {}
+    for layer, fin in ((1, W.F), (2, 2 * W.H)):
+        scope = "LSTM%d/" % layer
+        inside = [n for n in entries if n.startswith(scope) and not _is_slot(n) and entries[n]["dtype"] == DT_FLOAT]
+        for di, d in enumerate(("fw", "bw")):
+            for var, shape in (("kernel", (fin + W.H, 4 * W.H)), ("bias", (4 * W.H,))):
+                canonical = W.lstm_name(layer, d, var)
+                if canonical in entries:
+                    found[canonical] = canonical
+                    continue
+                cands = [n for n in inside if n.endswith("/" + var) and ("/%s/" % d) in n and tuple(entries[n]["shape"]) == shape]
+                if len(cands) == 1:
+                    found[canonical] = cands[0]
+                    continue
+                opaque = [n for n in inside if n.endswith("opaque_kernel") and
+                          tuple(entries[n]["shape"]) == (cudnn_opaque_size(fin, W.H),)]
+                if not cands and len(opaque) == 1:
+                    found[canonical] = ("opaque", opaque[0], di)
+                    continue
+                raise ValueError("cannot identify %s in the checkpoint: %s under %r" % (
+                    canonical, ("candidates %s" % cands) if cands else "no variable of shape %s" % (shape,), scope))
+    return found
+
+
+def cudnn_opaque_size(fin, units):
+    """Floats in the parameter buffer of a one-layer bidirectional cuDNN LSTM: per direction 4 input matrices [units, fin],
+    4 recurrent matrices [units, units] and 8 bias vectors [units]."""
+    return 2 * (4 * units * fin + 4 * units * units + 8 * units)
+
+
+def cudnn_opaque_to_canonical(buf, fin, units):
+    """cuDNN LSTM parameter buffer (one bidirectional layer) -> [(kernel [(fin+units), 4 units], bias [4 units]) for fw, bw]
+    in the TF LSTMBlockCell / CudnnCompatibleLSTMCell layout.
+
+    Buffer layout (cuDNN canonical order, as TensorFlow 1.13's cudnn_rnn_ops.CudnnOpaqueParamsSaveable unpacks it): all
+    weights first - per direction W_i, W_f, W_c, W_o ([units, fin] each, row-major) then R_i, R_f, R_c, R_o ([units, units]) -
+    then all biases - per direction b_Wi, b_Wf, b_Wc, b_Wo, b_Ri, b_Rf, b_Rc, b_Ro.  The TF cell wants ONE kernel with rows
+    [x ; h] and gate columns i, c, f, o, and ONE bias = b_W + b_R (tf.contrib.cudnn_rnn: _cudnn_to_tf_weights / _biases).
+    Unverified against a cuDNN-written buffer (none ships with the reference)."""
+    buf = np.asarray(buf, dtype=np.float32).reshape(-1)
+    if buf.size != cudnn_opaque_size(fin, units):
+        raise ValueError("opaque LSTM buffer holds %d floats, expected %d" % (buf.size, cudnn_opaque_size(fin, units)))
+    per_dir_w = 4 * units * fin + 4 * units * units
+    out = []
+    for di in range(2):
+        w = buf[di * per_dir_w:(di + 1) * per_dir_w]
+        W_ = w[:4 * units * fin].reshape(4, units, fin)                    # i, f, c, o
+        R_ = w[4 * units * fin:].reshape(4, units, units)
+        b = buf[2 * per_dir_w + di * 8 * units:2 * per_dir_w + (di + 1) * 8 * units].reshape(2, 4, units)
+        order = (0, 2, 1, 3)                                               # TF gate order i, c, f, o
+        kernel = np.concatenate([np.concatenate([W_[g].T for g in order], axis=1),
+                                 np.concatenate([R_[g].T for g in order], axis=1)], axis=0)
+        bias = np.concatenate([b[0, g] + b[1, g] for g in order])
+        out.append((np.ascontiguousarray(kernel, dtype=np.float32), np.ascontiguousarray(bias, dtype=np.float32)))
+    return out
+
+
 def load_checkpoint(prefix, verify=True):
-    """The forward path's variables of a reference checkpoint as a float32 weight blob
-    (what Clair.restore_parameters feeds to clairb_set_weight)."""
+    """The forward path's variables of a reference checkpoint as a float32 weight blob keyed by the canonical names
+    (what Clair.restore_parameters feeds to clairb_set_weight).  Dense variables are taken by name, LSTM variables are
+    discovered (discover_lstm_names)."""
     from . import weights as W
     shapes = W.weight_shapes()
     _, entries = read_index((str(prefix)[:-6] if str(prefix).endswith(".index") else str(prefix)) + ".index", verify)
-    missing = [k for k in shapes if k not in entries]
+    lstm = discover_lstm_names(entries)
+    missing = [k for k in shapes if k not in entries and k not in lstm]
     if missing:
         raise ValueError("checkpoint %s lacks %d forward-path variables, e.g. %s (has e.g. %s)"
                          % (prefix, len(missing), missing[0], sorted(entries)[:3]))
-    w = read_bundle(prefix, names=set(shapes), verify=verify)
-    w = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in w.items()}
+    source = {k: (lstm[k] if k in lstm else k) for k in shapes}
+    wanted = {v if isinstance(v, str) else v[1] for v in source.values()}
+    raw = read_bundle(prefix, names=wanted, verify=verify)
+    w, opaque_cache = {}, {}
+    for k, v in source.items():
+        if isinstance(v, str):
+            w[k] = np.ascontiguousarray(raw[v], dtype=np.float32)
+            continue
+        _, name, di = v
+        if name not in opaque_cache:
+            layer = 1 if name.startswith("LSTM1/") else 2
+            opaque_cache[name] = cudnn_opaque_to_canonical(raw[name], W.F if layer == 1 else 2 * W.H, W.H)
+        w[k] = opaque_cache[name][di][0 if k.endswith("/kernel") else 1]
     W.check_weights(w)
     return w
 

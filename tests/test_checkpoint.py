@@ -110,3 +110,66 @@ def test_restore_parameters_from_a_bundle(tmp_path, weights1234):
     np.testing.assert_array_equal(a.predict_packed(X), b.predict_packed(X))
     a.close()
     b.close()
+
+
+# ---- LSTM variable discovery (the released models were saved through the cuDNN branch, clair/model.py:281-296) -------------
+def _renamed(w, rename):
+    return {rename(k): v for k, v in w.items()}
+
+
+@pytest.mark.parametrize("scheme", ["cpu_graph", "cudnn_layer_scope", "other_cell_name", "opaque_buffer"])
+def test_lstm_variables_are_discovered_under_every_naming_scheme(tmp_path, scheme):
+    w = W.random_weights(seed=11)
+    lstm_keys = [k for k in w if k.startswith("LSTM")]
+    if scheme == "cpu_graph":
+        saved = dict(w)
+    elif scheme == "cudnn_layer_scope":            # canonical tensors written by the CudnnLSTM layer's saveable, under its scope
+        saved = _renamed(w, lambda k: k.replace("/stack_bidirectional_rnn/", "/cudnn_lstm/stack_bidirectional_rnn/") if k in lstm_keys else k)
+    elif scheme == "other_cell_name":
+        saved = _renamed(w, lambda k: k.replace("cudnn_compatible_lstm_cell", "lstm_cell") if k in lstm_keys else k)
+    else:                                          # only the raw cuDNN parameter buffer of each layer
+        saved = {k: v for k, v in w.items() if k not in lstm_keys}
+        for layer, fin in ((1, 32), (2, 256)):
+            parts_w, parts_b = [], []
+            for d in ("fw", "bw"):
+                k, b = w[W.lstm_name(layer, d, "kernel")], w[W.lstm_name(layer, d, "bias")]
+                gates = np.split(k, 4, axis=1)                     # TF columns i, c, f, o
+                cudnn = [gates[0], gates[2], gates[1], gates[3]]   # cuDNN order i, f, c, o
+                parts_w += [g[:fin].T.reshape(-1) for g in cudnn] + [g[fin:].T.reshape(-1) for g in cudnn]
+                bg = np.split(b, 4)
+                bc = [bg[0], bg[2], bg[1], bg[3]]
+                parts_b += [0.25 * x for x in bc] + [0.75 * x for x in bc]      # b_W + b_R = the TF bias
+            saved["LSTM%d/cudnn_lstm/opaque_kernel" % layer] = np.concatenate(parts_w + parts_b).astype(np.float32)
+    # what every training checkpoint also holds: optimiser slots next to the variables, step counters
+    for k in list(saved):
+        if k.endswith("/kernel") and saved[k].ndim == 2:
+            saved[k + "/Adam"] = np.zeros_like(saved[k])
+            saved[k + "/Adam_1"] = np.zeros_like(saved[k])
+    saved["global_step"] = np.array(3, dtype=np.int64)
+    prefix = str(tmp_path / scheme)
+    C.write_bundle(prefix, saved)
+    got = C.load_checkpoint(prefix)
+    assert set(got) == set(w)
+    for k in w:
+        if scheme == "opaque_buffer" and k.endswith("/bias") and k.startswith("LSTM"):
+            np.testing.assert_allclose(got[k], w[k], rtol=1e-6, atol=1e-7)      # 0.25 b + 0.75 b in float32
+        else:
+            np.testing.assert_array_equal(got[k], w[k], err_msg=k)
+
+
+def test_ambiguous_or_missing_lstm_variables_are_reported(tmp_path):
+    w = W.random_weights(seed=12)
+    twice = dict(w)
+    k = W.lstm_name(1, "fw", "kernel")
+    del twice[k]
+    twice["LSTM1/a/fw/cell/kernel"] = w[k]
+    twice["LSTM1/b/fw/cell/kernel"] = w[k]
+    C.write_bundle(str(tmp_path / "twice"), twice)
+    with pytest.raises(ValueError, match="candidates"):
+        C.load_checkpoint(str(tmp_path / "twice"))
+    gone = {n: v for n, v in w.items() if n != W.lstm_name(2, "bw", "bias")}
+    C.write_bundle(str(tmp_path / "gone"), gone)
+    with pytest.raises(ValueError, match="cannot identify LSTM2"):
+        C.load_checkpoint(str(tmp_path / "gone"))
+    with pytest.raises(ValueError):
+        C.cudnn_opaque_to_canonical(np.zeros(17, np.float32), 32, 128)
