@@ -16,7 +16,8 @@ rd, wr, nm = col("dram__bytes_read.sum"), col("dram__bytes_write.sum"), hdr.inde
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 acc = {}
 for r in rows[2:]:
-    key = next((v for k, v in KERNELS.items() if r[nm].startswith(k) or ("::" + k) in r[nm]), None)
+    base = r[nm].replace("void ", "").split("(")[0].split("<")[0].split("::")[-1].strip()
+    key = KERNELS.get(base)
     if key is None:
         continue
     b = float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]]
