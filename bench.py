@@ -432,7 +432,7 @@ def main():
     host_all_t = torch.from_numpy(host_all) if host_all is not None else None
     last = {}
 
-    E2E_SLICES = 8      # N > 1: gather + rank 0's device->host copy of slice j run while slice j+1 is computed
+    E2E_SLICES = 16     # N > 1: gather + rank 0's device->host copy of slice j run while slice j+1 is computed
 
     def e2e_step(Xh, dtype):
         if world == 1:
