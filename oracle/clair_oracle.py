@@ -6,12 +6,23 @@ This file is a CPU *restatement* (numpy) of what the reference computes when
 product package ``clair_b200`` imports it.  Only ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s cpu_baseline / ``--impl reference`` leg may import it.
 
-PARITY UNPINNED: the arithmetic of the reference lives in TensorFlow 1.13.2 (pinned only in
-prose, reference README.md:127), which is neither vendored under /root/reference nor
-installable here (no wheel for Python 3.12, no network), and the reference ships no tests,
-golden vectors, fixtures or checkpoints.  The restatement is therefore anchored on the
-reference's call sites and on the documented TF-1.13 semantics of the ops it calls, and is
-cross-checked in tests/ against an independent ``torch.nn.LSTM``-based restatement.
+PARITY: pinned on the reference's own model code, NOT on TensorFlow's kernels.  The arithmetic of the
+reference lives in TensorFlow 1.13.2 (pinned only in prose, reference README.md:127), which is neither
+vendored under /root/reference nor installable here (no wheel for Python 3.12, no network), and the
+reference ships no tests, golden vectors, fixtures or checkpoints.  What pins this restatement:
+  (1) tests/golden/reference_model_forward.npz - the reference's UNMODIFIED clair/model.py (Clair() ->
+      init -> restore_parameters -> predict) executed over a numpy stand-in for the ~60 TensorFlow
+      symbols it touches (oracle/tf_standin/, oracle/gen_golden_reference_model.py).  Graph wiring,
+      axis conventions, activations, flatten order, variable scopes / names and the output order are
+      the reference's own code there; this file reproduces its float64 evaluation to 1e-12
+      (tests/test_oracle.py).  The stand-in's op semantics - notably the LSTMBlockCell arithmetic
+      behind CudnnCompatibleLSTMCell - are TensorFlow's documented ones, restated; so
+  (2) on the GPU box, cuDNN's own fp32 LSTM (the kernel CudnnCompatibleLSTMCell is defined to be
+      weight-compatible with) + a torch dense trunk must agree with this file to 1e-5
+      (oracle/clair_oracle_cudnn.py, tests/test_gpu_parity.py, bench.py `oracle_pinning`), and
+  (3) an independent torch.nn.LSTM CPU restatement agrees to 1e-6 (oracle/clair_oracle_fast.py).
+"Parity unpinned" in the strict sense - no output of TensorFlow itself has ever been compared - still
+applies to the op kernels; DESIGN.md section 5 says so.
 
 Semantics followed (reference file:line -> what it means here)
   clair/utils.py:96-98      channels 1..3 -= channel 0 happens in the generator, NOT in predict

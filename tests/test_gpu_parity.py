@@ -373,3 +373,16 @@ def test_inputs_that_are_not_exact_in_fp16_keep_their_low_parts(gpu_model, weigh
     got = gpu_model.predict_packed(i16)
     ref = O.forward_packed(i16.astype(np.float32), weights1234, np.float64)
     assert np.abs(got - ref).max() <= TOL
+
+
+def test_device_forward_against_the_reference_model_code(gpu_model):
+    # the reference's own clair/model.py run over the TensorFlow stand-in (tests/golden/reference_model_forward.npz, see
+    # tests/test_oracle.py): the device's probabilities against its float64 evaluation
+    import os
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_model_forward.npz")) as z:
+        X, want64 = z["X"], z["probs_f64"]
+    for Xin in (X.astype(np.float32), X):                         # float32 like the reference's generator, and the int16 transport
+        got = gpu_model.predict_packed(Xin)
+        assert np.abs(got - want64).max() <= TOL
+        for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
+            np.testing.assert_array_equal(got[:, a:b].argmax(1), want64[:, a:b].argmax(1))

@@ -147,3 +147,20 @@ def test_torch_lstm_restatement_agrees_with_the_numpy_oracle(weights1234):
     assert np.abs(l - np.concatenate(im["logits"], axis=1)).max() <= 1e-11
     p32, _ = CudnnOracle(weights1234, device="cpu", dtype=torch.float32).forward(X)
     assert np.abs(p32 - np.concatenate(ref_probs, axis=1)).max() <= 1e-5
+
+
+def test_oracle_reproduces_the_reference_model_code_run_over_the_tf_standin(weights1234):
+    # tests/golden/reference_model_forward.npz: the REFERENCE's unmodified clair/model.py (Clair() -> init -> restore_parameters
+    # -> predict) executed over the numpy stand-in for TensorFlow (oracle/tf_standin, oracle/gen_golden_reference_model.py).
+    # Everything above the TF ops - reshape / transpose order, slice-dense axes, flatten order, activations, variable
+    # scopes, output order - is the reference's own code there; the restatement must land on the same numbers.
+    import os
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_model_forward.npz")) as z:
+        X, want32, want64, names = z["X"].astype(np.float32), z["probs_f32"], z["probs_f64"], z["variable_names"].tolist()
+    assert names == sorted(W.weight_shapes())                      # the names the reference's scopes produce = ours
+    got64 = O.forward_packed(X, weights1234, np.float64)
+    assert np.abs(got64 - want64).max() <= 1e-12
+    got32 = O.forward_packed(X, weights1234, np.float32)
+    assert np.abs(got32 - want32).max() <= 2e-6
+    for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
+        np.testing.assert_array_equal(got64[:, a:b].argmax(1), want64[:, a:b].argmax(1))
