@@ -388,19 +388,31 @@ def reference_sequence_from(samtools, reference_file_path, ctg_name, ctg_start, 
 
 
 def OutputAlnTensor(args, model=None, popen=_popen, out=None):
-    """The reference's entry point (CreateTensor.py:179-394): same arguments, same rows on `--tensor_fn` (PIPE = stdout)."""
+    """The reference's entry point (CreateTensor.py:179-394): same arguments, same rows on `--tensor_fn` (PIPE = stdout).
+
+    Two differences from the reference, both by construction of the one-kernel design: (1) the alignments of the requested
+    region are encoded as ONE block (the kernel finds a site's reads by binary search over all of them), so host memory
+    grows with the region - about 2.4 bytes per aligned base - where the reference streams rows and flushes finished
+    windows; a whole contig is processed the way the reference's own drivers cut it, in --ctgStart/--ctgEnd chunks
+    (clair/callVarBamParallel.py:90-119), and a block beyond 2^31 ops or bases is refused with "split the region".
+    (2) rows come out in ascending position (candidates are sorted and de-duplicated), which is the order of the
+    reference for the sorted candidate files its own pipeline produces (ExtractVariantCandidates.py walks a sorted BAM)."""
     reference_sequence, reference_start_0_based = reference_sequence_from(
         args.samtools, args.ref_fn, args.ctgName, args.ctgStart, args.ctgEnd, popen)
     if not reference_sequence:
         print("Failed to load reference seqeunce. Please check if the provided reference fasta %s and the ctgName %s are correct." % (
             args.ref_fn, args.ctgName), file=sys.stderr)
         sys.exit(1)
+    cand_proc = None
     if args.can_fn == "PIPE":
         candidate_rows = sys.stdin
     else:
         cand_proc = popen(shlex.split("gzip -fdc %s" % args.can_fn))
         candidate_rows = cand_proc.stdout
     candidates = [int(row.split(maxsplit=2)[1]) for row in candidate_rows]
+    if cand_proc is not None:                            # CreateTensor.py:383-385 closes and waits for its children
+        cand_proc.stdout.close()
+        cand_proc.wait()
     have_region = args.ctgStart is not None and args.ctgEnd is not None
     region = ("%s:%d-%d" % (args.ctgName, args.ctgStart, args.ctgEnd)) if have_region else args.ctgName
     view_args = shlex.split("%s view -F %d %s %s" % (args.samtools, param.SAMTOOLS_VIEW_FILTER_FLAG, args.bam_fn, region))

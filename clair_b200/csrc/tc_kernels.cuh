@@ -604,6 +604,9 @@ xproj_pair(const __half* __restrict__ A, const __half* __restrict__ Wx, const fl
 #ifndef CLAIRB_SEQ1_G
 #define CLAIRB_SEQ1_G 2
 #endif
+#ifndef CLAIRB_SEQ1_ORDER
+#define CLAIRB_SEQ1_ORDER 1   // issue order of blocks 0 / 1 in layer 1 (A/B switch; see the issuer)
+#endif
 constexpr int SEQ1_G = CLAIRB_SEQ1_G;                              // ... of the layer-1 launch (A/B switch)
 constexpr int SEQ_G = 2;                                // epilogue warps per TMEM lane quarter (2 or 4)
 constexpr int SEQ_THREADS = 32 * (2 + 4 * SEQ_G);
@@ -770,6 +773,7 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
             umma_commit_pair(&acc_full[b & 1], 0b11);
           }
         } else {
+#if CLAIRB_SEQ1_ORDER == 0
           acquire_acc(0);
           stamp(s, 0);
           x_part(0);
@@ -787,6 +791,27 @@ lstm_seq(const __half* __restrict__ Wh, const __half* __restrict__ Wx, const __h
           h_part(1, 6, 8);
           umma_commit_pair(&acc_full[1], 0b11);
           stamp(s, 4);
+#else
+          // Block 0 is completed as soon as the last quarter of h_{s-1} is published, and only then block 1 is issued: the
+          // epilogue (which idled 2.4 k cycles per step behind the 54 recurrence-independent MMAs the old order issued
+          // first) starts on block 0 one block's worth of tensor time earlier, and block 1 completes while it works.
+          acquire_acc(0);
+          stamp(s, 0);
+          x_part(0);
+          wait_h(0); stamp(s, 2); h_part(0, 0, 2);
+          wait_h(1); h_part(0, 2, 4);
+          wait_h(2); h_part(0, 4, 6);
+          wait_h(3);
+          stamp(s, 3);
+          h_part(0, 6, 8);
+          umma_commit_pair(&acc_full[0], 0b11);
+          acquire_acc(1);
+          stamp(s, 1);
+          x_part(1);
+          h_part(1, 0, 8);
+          umma_commit_pair(&acc_full[1], 0b11);
+          stamp(s, 4);
+#endif
 #pragma unroll
           for (int b = 2; b < 4; ++b) {
             acquire_acc(b);
