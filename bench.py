@@ -22,6 +22,7 @@ the packed [sites,90] probabilities are gathered to rank 0 with one NCCL collect
 a single-GPU run of the same sites.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -432,6 +433,7 @@ def main():
     host_all_t = torch.from_numpy(host_all) if host_all is not None else None
     last = {}
 
+    d2h_stream = torch.cuda.Stream() if world > 1 else None
     E2E_SLICES = 16     # N > 1: gather + rank 0's device->host copy of slice j run while slice j+1 is computed
 
     def e2e_step(Xh, dtype):
@@ -439,14 +441,24 @@ def main():
             last["out4"] = m.predict(Xh)
             return
         per = -(-sites // E2E_SLICES)
-        for lo in range(0, sites, per):
-            hi = min(sites, lo + per)
-            _lib.check(lib.clairb_predict_to_device(h, Xh[lo:hi].ctypes.data, dtype, hi - lo, od[lo:hi].data_ptr()), h,
-                       "clairb_predict_to_device")
+        bounds = [(lo, min(sites, lo + per)) for lo in range(0, sites, per)]
+        tickets = []
+        for lo, hi in bounds:                          # every slice is queued at once: the pipeline of the handle never drains
+            t = ctypes.c_int64()
+            _lib.check(lib.clairb_predict_async_to_device(h, Xh[lo:hi].ctypes.data, dtype, hi - lo, od[lo:hi].data_ptr(),
+                                                          ctypes.byref(t)), h, "clairb_predict_async_to_device")
+            tickets.append(t.value)
+        for (lo, hi), t in zip(bounds, tickets):
+            _lib.check(lib.clairb_predict_wait(h, t), h, "clairb_predict_wait")
             dist.gather(od[lo:hi], gather_list=[b[lo:hi] for b in gather_bufs] if rank == 0 else None, dst=0)
             if rank == 0:
-                for r in range(world):
-                    host_all_t[r, lo:hi].copy_(gather_bufs[r][lo:hi], non_blocking=True)
+                # rank 0's copies to the host go out on their own stream: the next slice's gather must not queue behind them
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                d2h_stream.wait_event(ev)
+                with torch.cuda.stream(d2h_stream):
+                    for r in range(world):
+                        host_all_t[r, lo:hi].copy_(gather_bufs[r][lo:hi], non_blocking=True)
         torch.cuda.synchronize()
 
     def time_e2e(Xh, dtype, n_steps):
@@ -710,8 +722,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": sites * 2112,
                     "d2h_bytes_per_step": sites * 360 * (world if world > 1 else 1), "gpu_launches": e2e_launches,
                     "note": ("one Clair.predict call per step over the pool" if world == 1 else
-                             "per rank: host input -> device rows, NCCL gather to rank 0 (%d slices per step, overlapped with the next "
-                             "slice's forward), rank 0 copies N x [sites,90] to host" % E2E_SLICES)
+                             "per rank: host input -> device rows (clairb_predict_async_to_device, %d slices queued per step), NCCL gather of "
+                             "every slice to rank 0 behind the forward of the next ones, rank 0 copies N x [sites,90] to host" % E2E_SLICES)
                             + "; pinned host input in the int16 transport (same integer counts as float32, bit-identical output)"},
             "e2e_f32": {"value": e2e_f32_value, "unit": "sites/s", "h2d_bytes_per_step": sites * 4224,
                         "d2h_bytes_per_step": sites * 360, "h2d_gbs_measured": h2d_gbs,

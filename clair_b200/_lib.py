@@ -30,6 +30,7 @@ SYMBOLS = {
     "clairb_predict_async": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                         _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_int64)]),
     "clairb_predict_wait": (_c.c_int, [_c.c_void_p, _c.c_int64]),
+    "clairb_predict_async_to_device": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.POINTER(_c.c_int64)]),
     "clairb_predict_to_device": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p]),
     "clairb_predict_device": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p]),
     "clairb_predict_decide": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p]),

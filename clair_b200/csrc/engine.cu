@@ -72,6 +72,7 @@ struct AsyncRequest {
   int64_t n = 0;
   float* outs[4] = {nullptr, nullptr, nullptr, nullptr};   // four head arrays, or outs[0] = packed [n][90] when !split
   bool split = false;
+  float* out_dev = nullptr;          // instead of outs: packed [n][90] rows left in device memory (clairb_predict_async_to_device)
   const uint8_t* ref = nullptr;      // with `dec`: first-choice decision behind the heads
   int32_t* dec = nullptr;
   int64_t issued = 0, delivered = 0;
@@ -893,7 +894,7 @@ struct Group {
   std::vector<Segment> segs;
   int64_t cn = 0;
   int b = 0, dtype = 0;
-  bool split = false, decide = false;
+  bool split = false, decide = false, to_device = false;
 };
 
 int issue_group(clairb_engine* e, const Group& g) {
@@ -924,7 +925,14 @@ int issue_group(clairb_engine* e, const Group& g) {
   }
   CU_TRY(e, cudaEventRecord(e->ev_comp[b], e->s_comp));
   CU_TRY(e, cudaStreamWaitEvent(e->s_d2h, e->ev_comp[b], 0));
-  CU_TRY(e, cudaMemcpyAsync(e->h_out[b], e->d_out[b], (size_t)g.cn * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+  if (g.to_device) {
+    // the rows stay on the device: every segment goes straight to its request's buffer
+    for (const Segment& s : g.segs)
+      CU_TRY(e, cudaMemcpyAsync(s.r->out_dev + (size_t)s.at * N_OUT, e->d_out[b] + (size_t)s.pos * N_OUT, (size_t)s.cnt * N_OUT * sizeof(float),
+                                cudaMemcpyDeviceToDevice, e->s_d2h));
+  } else {
+    CU_TRY(e, cudaMemcpyAsync(e->h_out[b], e->d_out[b], (size_t)g.cn * N_OUT * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+  }
   if (g.decide)
     CU_TRY(e, cudaMemcpyAsync(e->h_dec[b], e->d_dec[b], (size_t)g.cn * decide::REC_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
   CU_TRY(e, cudaEventRecord(e->ev_d2h[b], e->s_d2h));
@@ -940,7 +948,7 @@ int deliver_group(clairb_engine* e, const Group& g, int rc_issue) {
   }
   const bool dev_split = g.split && e->kind == ENGINE_TC && e->fuse_tail;
   const float* staged = e->h_out[g.b];
-  if (!rc)
+  if (!rc && !g.to_device)
     for (const Segment& s : g.segs) {
       AsyncRequest* r = s.r;
       if (!g.split) {
@@ -988,8 +996,9 @@ void worker_main(clairb_engine* e) {
       while (!e->pending.empty() && g.cn < e->chunk_sites) {
         AsyncRequest* r = e->pending.front();
         const bool dec = r->dec != nullptr;
-        if (g.segs.empty()) { g.dtype = r->dtype; g.split = r->split; g.decide = dec; }
-        else if (g.dtype != r->dtype || g.split != r->split || g.decide != dec) break;
+        const bool dev = r->out_dev != nullptr;
+        if (g.segs.empty()) { g.dtype = r->dtype; g.split = r->split; g.decide = dec; g.to_device = dev; }
+        else if (g.dtype != r->dtype || g.split != r->split || g.decide != dec || g.to_device != dev) break;
         const int64_t left = r->n - r->issued, room = e->chunk_sites - g.cn;
         const int64_t cnt = left < room ? left : room;
         g.segs.push_back({r, r->issued, cnt, g.cn});
@@ -1046,6 +1055,31 @@ int clairb_predict_async(clairb_engine* e, const void* x_host, int dtype, int64_
   r->split = split;
   r->ref = ref_base;
   r->dec = decision;
+  e->tickets[r->ticket] = r;
+  e->pending.push_back(r);
+  if (!e->worker_started) {
+    e->worker = std::thread(worker_main, e);
+    e->worker_started = true;
+  }
+  *ticket = r->ticket;
+  lk.unlock();
+  e->q_cv.notify_one();
+  return CLAIRB_OK;
+}
+
+int clairb_predict_async_to_device(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_dev, int64_t* ticket) {
+  if (!e) return CLAIRB_EINVAL;
+  std::unique_lock<std::mutex> lk(e->q_mu);
+  if (!e->finalized) return fail(e, CLAIRB_EINVAL, "predict before clairb_finalize_weights");
+  if (!ticket || !x_host || !out_dev || n <= 0) return fail(e, CLAIRB_EINVAL, "predict_async_to_device: bad n or buffers");
+  if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return fail(e, CLAIRB_EINVAL, "unknown dtype %d", dtype);
+  if (e->stop) return fail(e, CLAIRB_EINVAL, "predict_async_to_device: the engine is being destroyed");
+  AsyncRequest* r = new AsyncRequest();
+  r->ticket = e->next_ticket++;
+  r->x = (const char*)x_host;
+  r->dtype = dtype;
+  r->n = n;
+  r->out_dev = out_dev;
   e->tickets[r->ticket] = r;
   e->pending.push_back(r);
   if (!e->worker_started) {

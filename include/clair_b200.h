@@ -107,6 +107,12 @@ int clairb_predict_wait(clairb_engine* e, int64_t ticket);
  * send buffer of the multi-GPU gather) instead of being copied back.  Returns when out_dev is written. */
 int clairb_predict_to_device(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_dev);
 
+/* The queued form of it (tickets as clairb_predict_async): consecutive calls keep the copy / compute pipeline of the handle
+ * full, so a gather of slice j (NCCL, the caller's business) overlaps the forward of slice j+1.  clairb_predict_wait
+ * returns when the rows of that ticket are in out_dev. */
+int clairb_predict_async_to_device(clairb_engine* e, const void* x_host, int dtype, int64_t n, float* out_dev,
+                                   int64_t* ticket);
+
 /* Same forward with both buffers already resident in device memory, enqueued on `stream`
  * (a cudaStream_t; NULL = legacy default stream) without synchronising the host.  Used by
  * bench.py for the device-resident number and by the multi-GPU shard path. */

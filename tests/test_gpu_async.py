@@ -260,3 +260,25 @@ def test_reference_call_variants_unmodified_on_the_device(gpu_model, weights1234
                               output_header=lambda: None, close_opened_files=lambda: None)
     cv.call_variants(types.SimpleNamespace(tensor_fn=str(path)), gpu_model, config, util)
     assert len(lines) == n
+
+
+def test_queued_calls_with_device_output(gpu_model):
+    import torch
+    lib = _lib.load()
+    X = synth.synthetic_tensors(5000, seed=123).astype(np.int16)
+    od = torch.zeros((5000, 90), dtype=torch.float32, device="cuda")
+    bounds = [(0, 700), (700, 3300), (3300, 5000)]
+    tickets = []
+    for lo, hi in bounds:
+        t = ctypes.c_int64()
+        rc = lib.clairb_predict_async_to_device(gpu_model._h, X[lo:hi].ctypes.data_as(ctypes.c_void_p), _lib.DTYPE_I16, hi - lo,
+                                                ctypes.c_void_p(od[lo:hi].data_ptr()), ctypes.byref(t))
+        assert rc == 0
+        tickets.append(t.value)
+    mixed = gpu_model.predict_async(X[:100])                     # a host-output call in the same queue
+    for t in tickets:
+        assert lib.clairb_predict_wait(gpu_model._h, t) == 0
+    np.testing.assert_array_equal(od.cpu().numpy(), gpu_model.predict_packed(X))
+    np.testing.assert_array_equal(np.concatenate(mixed.result(), axis=1), gpu_model.predict_packed(X[:100]))
+    t = ctypes.c_int64()
+    assert lib.clairb_predict_async_to_device(gpu_model._h, X.ctypes.data_as(ctypes.c_void_p), 1, 10, None, ctypes.byref(t)) == _lib.EINVAL
