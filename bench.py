@@ -190,6 +190,7 @@ def cpu_info():
 # running the fp32 CPU port of the forward (oracle/clair_oracle_fast.py; TensorFlow 1.13.2 itself is not installable) on its
 # own predict-batches.
 def _cpu_worker(rank, threads, weights, seeds, check_batch, conn):
+    """seeds: the synthetic predict-batches of this worker (clair_b200.synth.synthetic_tensors(BATCH, seed))"""
     import numpy as np                                     # noqa: F401
     import torch
     torch.set_num_threads(threads)
@@ -207,11 +208,16 @@ def _cpu_worker(rank, threads, weights, seeds, check_batch, conn):
         msg = conn.recv()
         if msg is None:
             return
+        keep = isinstance(msg, tuple)                    # ("keep", n): also hand back the results (parity sample)
+        n_batches = msg[1] if keep else msg
+        outs = []
         t0 = time.perf_counter()
-        for _ in range(msg):
-            fo.forward_packed(pool[k % len(pool)])
+        for _ in range(n_batches):
+            o = fo.forward_packed(pool[k % len(pool)])
+            if keep:
+                outs.append(o)
             k += 1
-        conn.send(("done", time.perf_counter() - t0))
+        conn.send(("done", time.perf_counter() - t0, outs))
 
 
 class CpuArm(object):
@@ -227,7 +233,7 @@ class CpuArm(object):
         for r in range(self.procs):
             a, b = ctx.Pipe()
             p = ctx.Process(target=_cpu_worker, daemon=True,
-                            args=(r, self.threads, weights, [s + 17 * r for s in seeds], check_batch if r == 0 else None, b))
+                            args=(r, self.threads, weights, [s + 1000 * r for s in seeds], check_batch if r == 0 else None, b))
             p.start()
             self.workers.append((p, a))
         self.first = None
@@ -236,13 +242,14 @@ class CpuArm(object):
             if r == 0:
                 self.first = first
 
-    def run(self, k):
+    def run(self, k, keep=False):
+        """every worker does k predict-batches; seconds (and, with keep, the [k*BATCH,90] results of every worker)"""
         t0 = time.perf_counter()
         for _, a in self.workers:
-            a.send(k)
-        for _, a in self.workers:
-            a.recv()
-        return time.perf_counter() - t0
+            a.send(("keep", k) if keep else k)
+        outs = [a.recv()[2] for _, a in self.workers]
+        dt = time.perf_counter() - t0
+        return (dt, outs) if keep else dt
 
     def close(self):
         for p, a in self.workers:
@@ -670,14 +677,40 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             # the only place this arm touches oracle/: the CPU port is timed on a bounded sample AND serves as the
             # checker of what was just measured (same sites, same weights)
-            seeds = [20240607 + 1, 20240607 + 2]
+            # every worker owns 25 distinct synthetic predict-batches (seeds below): 100 k distinct sites on a 16-core box,
+            # the "100 k-site sample" of SURVEY.md 8d's parity gate
+            n_own = 25
+            seeds = [20240607 + 100 + i for i in range(n_own)]
             arm = CpuArm(weights, seeds, check_batch=np.array(X[:BATCH]))
             try:
                 dt1 = arm.run(1)
-                per_worker = args.cpu_baseline_batches or max(2, min(40, int(12.0 / max(dt1, 1e-3))))    # about 12 s of CPU work
-                dt = arm.run(per_worker)
+                per_worker = args.cpu_baseline_batches or max(2, min(n_own, int(12.0 / max(dt1, 1e-3))))    # about 12 s of CPU work
+                dt, kept = arm.run(per_worker, keep=True)
             finally:
                 arm.close()
+            # the same sites through the device: worker r ran pool[0] in the calibration run, then pool[(1 + j) % n_own] for j < per_worker
+            sample_sites = worst = flips = flips_outside_margin = 0
+            for r in range(arm.procs):
+                for j in range(per_worker):
+                    idx = (1 + j) % n_own
+                    if r == 0 and idx == 0:
+                        continue                       # worker 0's first batch is the check batch, compared above
+                    xb = synth.synthetic_tensors(BATCH, seed=seeds[idx] + 1000 * r)
+                    got = m.predict_packed(xb)
+                    want = kept[r][j]
+                    worst = max(worst, float(np.abs(got - want).max()))
+                    for a, b in ((0, 21), (21, 24), (24, 57), (57, 90)):
+                        diff = np.flatnonzero(got[:, a:b].argmax(1) != want[:, a:b].argmax(1))
+                        flips += int(diff.size)
+                        top2 = np.sort(want[diff, a:b], axis=1)[:, -2:]
+                        flips_outside_margin += int(((top2[:, 1] - top2[:, 0]) > 2e-4).sum())
+                    sample_sites += BATCH
+            assert worst <= 1e-4, "GPU result differs from the CPU port on the parity sample: %g" % worst
+            assert flips_outside_margin == 0, "arg-max differs from the CPU port where its two best classes are more than 2e-4 apart"
+            parity_sample = {"sites": sample_sites, "max_abs_prob_diff": worst, "argmax_differences": flips,
+                             "argmax_differences_outside_2e-4_margin": flips_outside_margin,
+                             "note": "distinct synthetic sites computed by the CPU port (fp32) and by the device; an arg-max may "
+                                     "only differ where the port's own two best classes are within 2e-4 of each other"}
             v = arm.procs * per_worker * BATCH / dt
             model, cores = cpu_info()
             cpu_first = arm.first                  # worker 0's answer for the first BATCH sites of this run's pool
@@ -705,6 +738,7 @@ def main():
                    "sample": "%d processes x %d threads x %d predict-batches x %d sites of the same workload, %.1f s" % (
                        arm.procs, arm.threads, per_worker, BATCH, dt),
                    "parity_vs_gpu": {"max_abs_prob_diff": err, "argmax_identical": True, "sites": BATCH},
+                   "parity_sample": parity_sample,
                    "cpu_model": model, "host_cores": cores}
             pinning = oracle_pinning(m, weights, np.array(X[:256]))
         engine = os.environ.get("CLAIRB_ENGINE", "default")
