@@ -55,6 +55,21 @@ SYMBOLS = {
     "clairb_kernel_launches": (_c.c_int64, [_c.c_void_p]),
     "clairb_set_profiling": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "clairb_read_profile": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_int64]),
+    "clairb_trainer_create": (_c.c_int, [_c.c_int, _c.c_int64, _c.POINTER(_c.c_void_p)]),
+    "clairb_trainer_set_weight": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.POINTER(_c.c_int64), _c.c_int]),
+    "clairb_trainer_get": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_char_p, _c.c_void_p, _c.c_int64]),
+    "clairb_trainer_set_grad_buffer": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "clairb_trainer_set_dropout_rates": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "clairb_trainer_num_params": (_c.c_int64, [_c.c_void_p]),
+    "clairb_trainer_dense_offset": (_c.c_int64, [_c.c_void_p]),
+    "clairb_trainer_forward_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_uint64,
+                                                   _c.c_void_p]),
+    "clairb_trainer_backward_lstm": (_c.c_int, [_c.c_void_p]),
+    "clairb_trainer_apply": (_c.c_int, [_c.c_void_p, _c.c_float, _c.c_float, _c.c_float, _c.c_int64, _c.POINTER(_c.c_double)]),
+    "clairb_trainer_get_probabilities": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64]),
+    "clairb_trainer_kernel_launches": (_c.c_int64, [_c.c_void_p]),
+    "clairb_trainer_last_error": (_c.c_char_p, [_c.c_void_p]),
+    "clairb_trainer_destroy": (_c.c_int, [_c.c_void_p]),
     "clairb_version": (_c.c_char_p, []),
     "clairb_last_error": (_c.c_char_p, [_c.c_void_p]),
     "clairb_destroy": (_c.c_int, [_c.c_void_p]),

@@ -1446,3 +1446,6 @@ int clairb_destroy(clairb_engine* e) {
 }
 
 }  // extern "C"
+
+// ---- training step: its own handle type and entry points ----
+#include "train_engine.cuh"

@@ -1273,7 +1273,13 @@ lstm_seq_x2(const __half* __restrict__ Wh, const __grid_constant__ CUtensorMap t
     ea.dir = dir;
     ea.tile = tile;
     ea.trace = trace;
+#ifdef CLAIRB_X2_PROBE_PLAIN                            // timing probe: layer 2 with layer 1's tail (no bias, no transposes); results are garbage
+    lstm_epilogue<0, G, false, false>(ea, warp, lane);
+#elif defined(CLAIRB_X2_PROBE_NOBIAS)
+    lstm_epilogue<OUT, G, false, false>(ea, warp, lane);
+#else
     lstm_epilogue<OUT, G, true, false>(ea, warp, lane);
+#endif
   }
   tc_fence_before();
   cluster_sync_all();

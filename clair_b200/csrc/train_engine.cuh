@@ -1,0 +1,536 @@
+// Host orchestration + C-ABI of the training step (kernels in train_kernels.cuh).  Included by engine.cu.
+//
+// One clairb_trainer drives one GPU.  Parameters, gradients and the two Adam moments are flat fp32 device buffers in the
+// order of clair_b200/weights.py:weight_shapes() (LSTM1 fw / bw, LSTM2 fw / bw: kernel, bias; L3/Unit_0..255: kernel, bias;
+// L4; L5_1..4; the four heads), so the gradient of a data-parallel step is ONE contiguous buffer for the all-reduce, with the
+// dense layers - whose gradients are complete first - at its tail.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/clair_b200.h"
+#include "train_kernels.cuh"
+
+struct clairb_trainer {
+  int device = 0;
+  int64_t max_batch = 0, np_max = 0;
+  std::string err;
+  int64_t launches = 0;
+  cudaStream_t st = nullptr;
+  struct Param { std::string name; int64_t off, rows, cols; };       // bias: rows = 1
+  std::vector<Param> params;
+  std::map<std::string, int> index;
+  int64_t n_params = 0, dense_off = 0;                                 // dense_off: first parameter behind the LSTMs
+  float *P = nullptr, *G = nullptr, *G_own = nullptr, *M1 = nullptr, *M2 = nullptr;
+  uint8_t* is_kernel = nullptr;
+  bool weights_set = false;
+  // activations / gradients (sized for np_max sites)
+  float *x_tm = nullptr, *xin = nullptr, *lout[2] = {nullptr, nullptr}, *dlout[2] = {nullptr, nullptr};
+  struct Dir { float *xin, *pre, *gates, *hbuf, *cbuf, *dZ, *dh_out, *dh_rec, *dc, *WhT, *dxin; } dir[2][2] = {};
+  float *a3 = nullptr, *da3 = nullptr, *a4 = nullptr, *a4d = nullptr, *da4 = nullptr, *a5[4] = {}, *a5d[4] = {}, *da5[4] = {};
+  float *zall = nullptr, *dzall = nullptr, *probs = nullptr, *target = nullptr;
+  void* x_in = nullptr;
+  uint8_t* mask[6] = {};                                               // lstm2 [33][n][256], l4 [n][192], l5_1..4 [n][96]
+  double* d_loss = nullptr;                                            // [4 focal sums, L2 sum, gradient sum of squares]
+  int64_t last_n = 0, last_np = 0;
+  bool lstm_pending = false;
+  float rates[6] = {0.5f, 0.5f, 0.2f, 0.2f, 0.2f, 0.2f};
+};
+
+namespace {
+
+using namespace clairb;
+
+std::string g_trainer_error;
+
+int tfail(clairb_trainer* t, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (t) t->err = buf; else g_trainer_error = buf;
+  return code;
+}
+#define TR_TRY(t, call)                                                                              \
+  do {                                                                                               \
+    cudaError_t _st = (call);                                                                        \
+    if (_st != cudaSuccess)                                                                          \
+      return tfail((t), _st == cudaErrorMemoryAllocation ? CLAIRB_ENOMEM : CLAIRB_ECUDA, "%s failed: %s (%s:%d)", #call, \
+                   cudaGetErrorString(_st), __FILE__, __LINE__);                                     \
+  } while (0)
+
+inline unsigned blocks_for(int64_t count, int threads = 256) { return (unsigned)((count + threads - 1) / threads); }
+
+void trainer_layout(clairb_trainer* t) {
+  const int head_n[4] = {21, 3, 33, 33};
+  const char* head_names[4] = {"Y_base_change_logits", "Y_genotype_logits", "Y_indel_length_logits_1", "Y_indel_length_logits_2"};
+  int64_t off = 0;
+  auto add = [&](const std::string& name, int64_t rows, int64_t cols) {
+    t->index[name] = (int)t->params.size();
+    t->params.push_back({name, off, rows, cols});
+    off += rows * cols;
+  };
+  for (int l = 0; l < 2; ++l)
+    for (int d = 0; d < 2; ++d) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "LSTM%d/stack_bidirectional_rnn/cell_0/bidirectional_rnn/%s/cudnn_compatible_lstm_cell/", l + 1, d ? "bw" : "fw");
+      add(std::string(buf) + "kernel", (l ? 2 * H : F_IN) + H, G4);
+      add(std::string(buf) + "bias", 1, G4);
+    }
+  t->dense_off = off;
+  for (int c = 0; c < 2 * H; ++c) {
+    add("L3/Unit_" + std::to_string(c) + "/kernel", T_STEPS, L3_UNITS);
+    add("L3/Unit_" + std::to_string(c) + "/bias", 1, L3_UNITS);
+  }
+  add("L4/kernel", L3_K, L4_UNITS);
+  add("L4/bias", 1, L4_UNITS);
+  for (int k = 0; k < 4; ++k) {
+    add("L5_" + std::to_string(k + 1) + "/kernel", L4_UNITS, L5_UNITS);
+    add("L5_" + std::to_string(k + 1) + "/bias", 1, L5_UNITS);
+  }
+  for (int k = 0; k < 4; ++k) {
+    add(std::string("Prediction/") + head_names[k] + "/kernel", L5_UNITS, head_n[k]);
+    add(std::string("Prediction/") + head_names[k] + "/bias", 1, head_n[k]);
+  }
+  t->n_params = off;
+}
+
+const clairb_trainer::Param& tp(clairb_trainer* t, const std::string& name) { return t->params[t->index.at(name)]; }
+std::string lstm_prefix(int l, int d) {
+  char buf[256];
+  snprintf(buf, sizeof buf, "LSTM%d/stack_bidirectional_rnn/cell_0/bidirectional_rnn/%s/cudnn_compatible_lstm_cell/", l + 1, d ? "bw" : "fw");
+  return buf;
+}
+
+void trainer_free(clairb_trainer* t) {
+  cudaSetDevice(t->device);
+  auto drop = [](auto*& p) { cudaFree(p); p = nullptr; };
+  drop(t->P); drop(t->G_own); drop(t->M1); drop(t->M2); drop(t->is_kernel);
+  drop(t->x_tm); drop(t->lout[0]); drop(t->lout[1]); drop(t->dlout[0]); drop(t->dlout[1]);
+  for (int l = 0; l < 2; ++l)
+    for (int d = 0; d < 2; ++d) {
+      auto& q = t->dir[l][d];
+      drop(q.xin); drop(q.pre); drop(q.gates); drop(q.hbuf); drop(q.cbuf); drop(q.dZ); drop(q.dh_out); drop(q.dh_rec); drop(q.dc); drop(q.WhT); drop(q.dxin);
+    }
+  drop(t->a3); drop(t->da3); drop(t->a4); drop(t->a4d); drop(t->da4);
+  for (int k = 0; k < 4; ++k) { drop(t->a5[k]); drop(t->a5d[k]); drop(t->da5[k]); }
+  drop(t->zall); drop(t->dzall); drop(t->probs); drop(t->target); drop(t->d_loss);
+  cudaFree(t->x_in); t->x_in = nullptr;
+  for (int i = 0; i < 6; ++i) drop(t->mask[i]);
+  if (t->st) cudaStreamDestroy(t->st);
+}
+
+// backward through the two directions of one BiLSTM layer: dlout[l] (gradient of the layer's output) -> parameter gradients,
+// and (layer 2 only) the gradient of the layer's input accumulated into dlout[0]
+int lstm_layer_backward(clairb_trainer* t, int l, int64_t np) {
+  using namespace clairb::train;
+  cudaStream_t st = t->st;
+  const int K = l ? 2 * H : F_IN;
+  const int64_t rows = (int64_t)T_STEPS * np;
+  split_bidirectional<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->dlout[l], t->dir[l][0].dh_out, t->dir[l][1].dh_out, (int)np);
+  ++t->launches;
+  if (l == 1) TR_TRY(t, cudaMemsetAsync(t->dlout[0], 0, (size_t)rows * 2 * H * sizeof(float), st));
+  for (int d = 0; d < 2; ++d) {
+    auto& q = t->dir[l][d];
+    const auto& pk = tp(t, lstm_prefix(l, d) + "kernel");
+    const auto& pb = tp(t, lstm_prefix(l, d) + "bias");
+    TR_TRY(t, cudaMemsetAsync(q.dh_rec, 0, (size_t)np * H * sizeof(float), st));
+    TR_TRY(t, cudaMemsetAsync(q.dc, 0, (size_t)np * H * sizeof(float), st));
+    for (int s = T_STEPS - 1; s >= 0; --s) {
+      lstm_step_backward<<<(unsigned)(np / ROWS), H, 0, st>>>(q.dh_out + (size_t)s * np * H, q.dh_rec, q.dc, q.gates + (size_t)s * np * G4,
+                                                               q.cbuf + (size_t)(s + 1) * np * H, q.cbuf + (size_t)s * np * H, q.WhT,
+                                                               q.dZ + (size_t)s * np * G4, (int)np);
+      ++t->launches;
+    }
+    float* gk = t->G + pk.off;
+    // dW_x = x_in^T . dZ (all steps at once), dW_h = h_prev^T . dZ, db = column sums
+    gemm(true, false, K, G4, (int)rows, q.xin, K, q.dZ, G4, 0.f, gk, G4, st, &t->launches);
+    gemm(true, false, H, G4, (int)rows, q.hbuf, H, q.dZ, G4, 0.f, gk + (size_t)K * G4, G4, st, &t->launches);
+    TR_TRY(t, cudaMemsetAsync(t->G + pb.off, 0, G4 * sizeof(float), st));
+    column_sums<<<dim3(blocks_for(G4, 128), 64), 128, 0, st>>>(q.dZ, rows, G4, t->G + pb.off);
+    ++t->launches;
+    if (l == 1) {
+      // d(input) = dZ . W_x^T, back in time order, summed over the two directions
+      gemm(false, true, (int)rows, K, G4, q.dZ, G4, t->P + pk.off, G4, 0.f, q.dxin, K, st, &t->launches);
+      if (d == 0) {
+        TR_TRY(t, cudaMemcpyAsync(t->dlout[0], q.dxin, (size_t)rows * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      } else {
+        reverse_time<<<blocks_for(rows * K), 256, 0, st>>>(q.dxin, t->dlout[0], (int)np, K, 1);
+        ++t->launches;
+      }
+    }
+  }
+  return CLAIRB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int clairb_trainer_create(int device, int64_t max_batch, clairb_trainer** out) {
+  using namespace clairb::train;
+  if (!out || max_batch <= 0) return tfail(nullptr, CLAIRB_EINVAL, "clairb_trainer_create: bad arguments");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return tfail(nullptr, CLAIRB_ENODEVICE, "clairb_trainer_create: CUDA device %d not available (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+    return tfail(nullptr, CLAIRB_ENODEVICE, "clairb_trainer_create: device %d is not compute capability 10.x (sm_100a only, no fallback)", device);
+  clairb_trainer* t = new clairb_trainer();
+  t->device = device;
+  t->max_batch = max_batch;
+  t->np_max = (max_batch + ROWS - 1) / ROWS * ROWS;
+  trainer_layout(t);
+  auto bail = [&](int rc) {
+    g_trainer_error = t->err;
+    trainer_free(t);
+    delete t;
+    return rc;
+  };
+  const size_t np = (size_t)t->np_max, TS = T_STEPS;
+#define TC_TRY(call)                                                                 \
+  do {                                                                               \
+    cudaError_t _st = (call);                                                        \
+    if (_st != cudaSuccess) {                                                        \
+      tfail(t, CLAIRB_ECUDA, "%s failed: %s", #call, cudaGetErrorString(_st));       \
+      return bail(_st == cudaErrorMemoryAllocation ? CLAIRB_ENOMEM : CLAIRB_ECUDA);  \
+    }                                                                                \
+  } while (0)
+#define TC_ALLOC(p, count) TC_TRY(cudaMalloc((void**)&(p), (size_t)(count) * sizeof(*(p))))
+  TC_TRY(cudaSetDevice(device));
+  TC_TRY(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
+  TC_ALLOC(t->P, t->n_params); TC_ALLOC(t->G_own, t->n_params); TC_ALLOC(t->M1, t->n_params); TC_ALLOC(t->M2, t->n_params);
+  TC_ALLOC(t->is_kernel, t->n_params);
+  t->G = t->G_own;
+  TC_TRY(cudaMemset(t->M1, 0, t->n_params * sizeof(float)));
+  TC_TRY(cudaMemset(t->M2, 0, t->n_params * sizeof(float)));
+  TC_TRY(cudaMemset(t->G, 0, t->n_params * sizeof(float)));
+  {
+    std::vector<uint8_t> flag((size_t)t->n_params, 0);
+    for (const auto& p : t->params)
+      if (p.rows > 1 || p.name.find("bias") == std::string::npos) std::fill(flag.begin() + p.off, flag.begin() + p.off + p.rows * p.cols, 1);
+    TC_TRY(cudaMemcpy(t->is_kernel, flag.data(), flag.size(), cudaMemcpyHostToDevice));
+  }
+  TC_ALLOC(t->x_tm, TS * np * F_IN);
+  TC_TRY(cudaMalloc(&t->x_in, np * SITE_ELEMS * sizeof(float)));
+  for (int l = 0; l < 2; ++l) {
+    TC_ALLOC(t->lout[l], TS * np * 2 * H);
+    TC_ALLOC(t->dlout[l], TS * np * 2 * H);
+    const size_t K = l ? 2 * H : F_IN;
+    for (int d = 0; d < 2; ++d) {
+      auto& q = t->dir[l][d];
+      TC_ALLOC(q.xin, TS * np * K); TC_ALLOC(q.pre, TS * np * G4); TC_ALLOC(q.gates, TS * np * G4);
+      TC_ALLOC(q.hbuf, (TS + 1) * np * H); TC_ALLOC(q.cbuf, (TS + 1) * np * H);
+      TC_ALLOC(q.dZ, TS * np * G4); TC_ALLOC(q.dh_out, TS * np * H); TC_ALLOC(q.dh_rec, np * H); TC_ALLOC(q.dc, np * H);
+      TC_ALLOC(q.WhT, (size_t)G4 * H); TC_ALLOC(q.dxin, TS * np * K);
+    }
+  }
+  TC_ALLOC(t->a3, np * L3_K); TC_ALLOC(t->da3, np * L3_K);
+  TC_ALLOC(t->a4, np * L4_UNITS); TC_ALLOC(t->a4d, np * L4_UNITS); TC_ALLOC(t->da4, np * L4_UNITS);
+  for (int k = 0; k < 4; ++k) { TC_ALLOC(t->a5[k], np * L5_UNITS); TC_ALLOC(t->a5d[k], np * L5_UNITS); TC_ALLOC(t->da5[k], np * L5_UNITS); }
+  TC_ALLOC(t->zall, np * N_OUT); TC_ALLOC(t->dzall, np * N_OUT); TC_ALLOC(t->probs, np * N_OUT); TC_ALLOC(t->target, np * N_OUT);
+  TC_ALLOC(t->d_loss, 8);
+  const size_t mask_count[6] = {TS * np * 2 * H, np * L4_UNITS, np * L5_UNITS, np * L5_UNITS, np * L5_UNITS, np * L5_UNITS};
+  for (int i = 0; i < 6; ++i) TC_ALLOC(t->mask[i], mask_count[i]);
+#undef TC_ALLOC
+#undef TC_TRY
+  *out = t;
+  return CLAIRB_OK;
+}
+
+int64_t clairb_trainer_num_params(const clairb_trainer* t) { return t ? t->n_params : 0; }
+int64_t clairb_trainer_dense_offset(const clairb_trainer* t) { return t ? t->dense_off : 0; }
+int64_t clairb_trainer_kernel_launches(const clairb_trainer* t) { return t ? t->launches : 0; }
+const char* clairb_trainer_last_error(const clairb_trainer* t) { return t ? t->err.c_str() : g_trainer_error.c_str(); }
+
+int clairb_trainer_set_weight(clairb_trainer* t, const char* tf_name, const float* data, const int64_t* shape, int rank) {
+  if (!t) return CLAIRB_EINVAL;
+  if (!tf_name || !data || !shape || rank < 1 || rank > 2) return tfail(t, CLAIRB_EINVAL, "trainer_set_weight: bad arguments");
+  auto it = t->index.find(tf_name);
+  if (it == t->index.end()) return tfail(t, CLAIRB_EWEIGHTS, "trainer_set_weight: %s is not a variable of the graph", tf_name);
+  const auto& p = t->params[it->second];
+  const int64_t rows = rank == 2 ? shape[0] : 1, cols = rank == 2 ? shape[1] : shape[0];
+  if (rows != p.rows || cols != p.cols) return tfail(t, CLAIRB_EWEIGHTS, "trainer_set_weight: %s has the wrong shape", tf_name);
+  TR_TRY(t, cudaSetDevice(t->device));
+  TR_TRY(t, cudaMemcpy(t->P + p.off, data, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice));
+  t->weights_set = true;
+  return CLAIRB_OK;
+}
+
+// which = 0 weights, 1 gradients of the last step, 2 / 3 Adam moments
+int clairb_trainer_get(clairb_trainer* t, int which, const char* tf_name, float* out, int64_t count) {
+  if (!t || !tf_name || !out || which < 0 || which > 3) return CLAIRB_EINVAL;
+  auto it = t->index.find(tf_name);
+  if (it == t->index.end()) return tfail(t, CLAIRB_EWEIGHTS, "trainer_get: %s is not a variable of the graph", tf_name);
+  const auto& p = t->params[it->second];
+  if (count != p.rows * p.cols) return tfail(t, CLAIRB_EINVAL, "trainer_get: %s holds %lld values", tf_name, (long long)(p.rows * p.cols));
+  TR_TRY(t, cudaSetDevice(t->device));
+  TR_TRY(t, cudaStreamSynchronize(t->st));
+  const float* src = which == 0 ? t->P : which == 1 ? t->G : which == 2 ? t->M1 : t->M2;
+  TR_TRY(t, cudaMemcpy(out, src + p.off, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+  return CLAIRB_OK;
+}
+
+int clairb_trainer_set_grad_buffer(clairb_trainer* t, float* dev_ptr) {
+  if (!t) return CLAIRB_EINVAL;
+  t->G = dev_ptr ? dev_ptr : t->G_own;
+  return CLAIRB_OK;
+}
+
+int clairb_trainer_set_dropout_rates(clairb_trainer* t, const float* rates6) {
+  if (!t || !rates6) return CLAIRB_EINVAL;
+  for (int i = 0; i < 6; ++i) {
+    if (!(rates6[i] >= 0.f && rates6[i] < 1.f)) return tfail(t, CLAIRB_EINVAL, "trainer_set_dropout_rates: rates must lie in [0, 1)");
+    t->rates[i] = rates6[i];
+  }
+  return CLAIRB_OK;
+}
+
+// Forward in training mode, loss, and the backward pass down to the gradient of the LSTM2 output: on return the gradients of
+// the dense layers (flat offsets >= clairb_trainer_dense_offset) are complete - a data-parallel caller starts their all-reduce
+// now - and losses[0..4] hold the four focal-loss sums and the L2 sum without lambda.  clairb_trainer_backward_lstm finishes.
+int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int dtype, const float* y_host, int64_t n,
+                                    const uint8_t* const* masks, uint64_t seed, double* losses) {
+  using namespace clairb::train;
+  if (!t) return CLAIRB_EINVAL;
+  if (!t->weights_set) return tfail(t, CLAIRB_EINVAL, "train step before the weights were set");
+  if (!x_host || !y_host || !losses || n <= 0 || n > t->max_batch) return tfail(t, CLAIRB_EINVAL, "train step: bad n or buffers");
+  if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return tfail(t, CLAIRB_EINVAL, "unknown dtype %d", dtype);
+  TR_TRY(t, cudaSetDevice(t->device));
+  cudaStream_t st = t->st;
+  const int64_t np = (n + ROWS - 1) / ROWS * ROWS;
+  const int64_t rows = (int64_t)T_STEPS * np;
+  t->last_n = n;
+  t->last_np = np;
+  const size_t eb = dtype == CLAIRB_DTYPE_I16 ? 2 : 4;
+  // inputs (padding sites: zero tensors, zero targets -> zero loss and zero gradient)
+  TR_TRY(t, cudaMemsetAsync(t->x_in, 0, (size_t)np * SITE_ELEMS * eb, st));
+  TR_TRY(t, cudaMemcpyAsync(t->x_in, x_host, (size_t)n * SITE_ELEMS * eb, cudaMemcpyHostToDevice, st));
+  TR_TRY(t, cudaMemsetAsync(t->target, 0, (size_t)np * N_OUT * sizeof(float), st));
+  TR_TRY(t, cudaMemcpyAsync(t->target, y_host, (size_t)n * N_OUT * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (dtype == CLAIRB_DTYPE_I16) input_time_major<int16_t><<<blocks_for(np * SITE_ELEMS), 256, 0, st>>>((const int16_t*)t->x_in, t->x_tm, (int)np);
+  else input_time_major<float><<<blocks_for(np * SITE_ELEMS), 256, 0, st>>>((const float*)t->x_in, t->x_tm, (int)np);
+  ++t->launches;
+  // dropout masks: the caller's (parity tests) or drawn from the seed
+  const int64_t mask_count[6] = {rows * 2 * H, np * L4_UNITS, np * L5_UNITS, np * L5_UNITS, np * L5_UNITS, np * L5_UNITS};
+  const int64_t mask_real[6] = {0, n * L4_UNITS, n * L5_UNITS, n * L5_UNITS, n * L5_UNITS, n * L5_UNITS};
+  for (int i = 0; i < 6; ++i) {
+    if (masks && masks[i]) {
+      if (i == 0) {
+        // [33][n][256] -> [33][np][256]
+        TR_TRY(t, cudaMemsetAsync(t->mask[0], 1, (size_t)mask_count[0], st));
+        TR_TRY(t, cudaMemcpy2DAsync(t->mask[0], (size_t)np * 2 * H, masks[0], (size_t)n * 2 * H, (size_t)n * 2 * H, T_STEPS, cudaMemcpyHostToDevice, st));
+      } else {
+        TR_TRY(t, cudaMemsetAsync(t->mask[i], 1, (size_t)mask_count[i], st));
+        TR_TRY(t, cudaMemcpyAsync(t->mask[i], masks[i], (size_t)mask_real[i], cudaMemcpyHostToDevice, st));
+      }
+    } else {
+      make_mask<<<blocks_for(mask_count[i]), 256, 0, st>>>(t->mask[i], mask_count[i], t->rates[i], seed, (uint64_t)i);
+      ++t->launches;
+    }
+  }
+  TR_TRY(t, cudaMemsetAsync(t->d_loss, 0, 8 * sizeof(double), st));
+  // ---- forward ----
+  for (int l = 0; l < 2; ++l) {
+    const int K = l ? 2 * H : F_IN;
+    const float* in = l ? t->lout[0] : t->x_tm;             // LSTM1_dropout_rate is 0 (clair/model.py:95): no mask between the layers
+    for (int d = 0; d < 2; ++d) {
+      auto& q = t->dir[l][d];
+      const auto& pk = tp(t, lstm_prefix(l, d) + "kernel");
+      const auto& pb = tp(t, lstm_prefix(l, d) + "bias");
+      if (d == 0) TR_TRY(t, cudaMemcpyAsync(q.xin, in, (size_t)rows * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      else { reverse_time<<<blocks_for(rows * K), 256, 0, st>>>(in, q.xin, (int)np, K, 0); ++t->launches; }
+      transpose_matrix<<<blocks_for((int64_t)H * G4), 256, 0, st>>>(t->P + pk.off + (size_t)K * G4, q.WhT, H, G4);
+      fill_rows<<<blocks_for(rows * G4), 256, 0, st>>>(q.pre, t->P + pb.off, rows, G4);
+      t->launches += 2;
+      gemm(false, false, (int)rows, G4, K, q.xin, K, t->P + pk.off, G4, 1.f, q.pre, G4, st, &t->launches);
+      TR_TRY(t, cudaMemsetAsync(q.hbuf, 0, (size_t)np * H * sizeof(float), st));
+      TR_TRY(t, cudaMemsetAsync(q.cbuf, 0, (size_t)np * H * sizeof(float), st));
+      for (int s = 0; s < T_STEPS; ++s) {
+        lstm_step_forward<<<(unsigned)(np / ROWS), H, 0, st>>>(q.pre + (size_t)s * np * G4, t->P + pk.off + (size_t)K * G4, q.hbuf + (size_t)s * np * H,
+                                                                q.cbuf + (size_t)s * np * H, q.gates + (size_t)s * np * G4, q.cbuf + (size_t)(s + 1) * np * H,
+                                                                q.hbuf + (size_t)(s + 1) * np * H, (int)np);
+        ++t->launches;
+      }
+    }
+    assemble_bidirectional<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->dir[l][0].hbuf + (size_t)np * H, t->dir[l][1].hbuf + (size_t)np * H, t->lout[l], (int)np);
+    ++t->launches;
+  }
+  if (t->rates[0] > 0.f) {
+    dropout_scale<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->lout[1], t->mask[0], 1.f / (1.f - t->rates[0]), rows * 2 * H);
+    ++t->launches;
+  }
+  const auto& p3 = tp(t, "L3/Unit_0/kernel");
+  l3_forward<<<dim3(2 * H, blocks_for(np, 128)), 128, 0, st>>>(t->lout[1], t->P + p3.off, t->a3, (int)np);
+  ++t->launches;
+  auto alpha_ab = [](float rate, float* a, float* b) {
+    const double q = 1.0 - rate, al = (double)ALPHA_DROPOUT;
+    *a = (float)std::sqrt(1.0 / (q * ((1.0 - q) * al * al + 1.0)));
+    *b = (float)(-(double)*a * (1.0 - q) * al);
+  };
+  const auto& p4k = tp(t, "L4/kernel");
+  const auto& p4b = tp(t, "L4/bias");
+  gemm(false, false, (int)np, L4_UNITS, L3_K, t->a3, L3_K, t->P + p4k.off, L4_UNITS, 0.f, t->a4, L4_UNITS, st, &t->launches);
+  bias_selu<<<blocks_for(np * L4_UNITS), 256, 0, st>>>(t->a4, t->P + p4b.off, np, L4_UNITS);
+  TR_TRY(t, cudaMemcpyAsync(t->a4d, t->a4, (size_t)np * L4_UNITS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ++t->launches;
+  if (t->rates[1] > 0.f) {
+    float a, b;
+    alpha_ab(t->rates[1], &a, &b);
+    alpha_dropout_forward<<<blocks_for(np * L4_UNITS), 256, 0, st>>>(t->a4d, t->mask[1], a, b, np * L4_UNITS);
+    ++t->launches;
+  }
+  const int head_n[4] = {21, 3, 33, 33}, head_off[4] = {0, 21, 24, 57};
+  const char* head_names[4] = {"Y_base_change_logits", "Y_genotype_logits", "Y_indel_length_logits_1", "Y_indel_length_logits_2"};
+  float* zk[4];
+  for (int k = 0; k < 4; ++k) {
+    const auto& p5k = tp(t, "L5_" + std::to_string(k + 1) + "/kernel");
+    const auto& p5b = tp(t, "L5_" + std::to_string(k + 1) + "/bias");
+    const auto& phk = tp(t, std::string("Prediction/") + head_names[k] + "/kernel");
+    const auto& phb = tp(t, std::string("Prediction/") + head_names[k] + "/bias");
+    gemm(false, false, (int)np, L5_UNITS, L4_UNITS, t->a4d, L4_UNITS, t->P + p5k.off, L5_UNITS, 0.f, t->a5[k], L5_UNITS, st, &t->launches);
+    bias_selu<<<blocks_for(np * L5_UNITS), 256, 0, st>>>(t->a5[k], t->P + p5b.off, np, L5_UNITS);
+    TR_TRY(t, cudaMemcpyAsync(t->a5d[k], t->a5[k], (size_t)np * L5_UNITS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ++t->launches;
+    if (t->rates[2 + k] > 0.f) {
+      float a, b;
+      alpha_ab(t->rates[2 + k], &a, &b);
+      alpha_dropout_forward<<<blocks_for(np * L5_UNITS), 256, 0, st>>>(t->a5d[k], t->mask[2 + k], a, b, np * L5_UNITS);
+      ++t->launches;
+    }
+    // head k: its post-SELU logits live in their own [np][n_k] block of da5-sized scratch (da3 is free until the backward)
+    zk[k] = t->da3 + (size_t)np * head_off[k];
+    gemm(false, false, (int)np, head_n[k], L5_UNITS, t->a5d[k], L5_UNITS, t->P + phk.off, head_n[k], 0.f, zk[k], head_n[k], st, &t->launches);
+    bias_selu<<<blocks_for(np * head_n[k]), 256, 0, st>>>(zk[k], t->P + phb.off, np, head_n[k]);
+    ++t->launches;
+    // side by side in zall [np][90] for the loss kernel
+    TR_TRY(t, cudaMemcpy2DAsync(t->zall + head_off[k], N_OUT * sizeof(float), zk[k], head_n[k] * sizeof(float), head_n[k] * sizeof(float), (size_t)np,
+                                cudaMemcpyDeviceToDevice, st));
+  }
+  TR_TRY(t, cudaMemsetAsync(t->dzall, 0, (size_t)np * N_OUT * sizeof(float), st));      // padding sites: no gradient
+  focal_loss_heads<<<blocks_for(np, 128), 128, 0, st>>>(t->zall, t->target, t->probs, t->dzall, t->d_loss, (int)n);
+  sum_squares<<<256, 256, 0, st>>>(t->P, t->is_kernel, t->n_params, t->d_loss + 4);
+  t->launches += 2;
+  // ---- backward: heads, L5, L4, slice-dense ----
+  TR_TRY(t, cudaMemsetAsync(t->G + t->dense_off, 0, (size_t)(t->n_params - t->dense_off) * sizeof(float), st));
+  float* dzk = t->da3 + (size_t)np * N_OUT;                  // scratch behind the four logit blocks
+  for (int k = 0; k < 4; ++k) {
+    const auto& p5k = tp(t, "L5_" + std::to_string(k + 1) + "/kernel");
+    const auto& p5b = tp(t, "L5_" + std::to_string(k + 1) + "/bias");
+    const auto& phk = tp(t, std::string("Prediction/") + head_names[k] + "/kernel");
+    const auto& phb = tp(t, std::string("Prediction/") + head_names[k] + "/bias");
+    // gradient w.r.t. the head's pre-activation: dz (from the loss, in dzall) * selu'(z)
+    TR_TRY(t, cudaMemcpy2DAsync(dzk, head_n[k] * sizeof(float), t->dzall + head_off[k], N_OUT * sizeof(float), head_n[k] * sizeof(float), (size_t)np,
+                                cudaMemcpyDeviceToDevice, st));
+    selu_backward<<<blocks_for(np * head_n[k]), 256, 0, st>>>(dzk, zk[k], np * head_n[k]);
+    ++t->launches;
+    gemm(true, false, L5_UNITS, head_n[k], (int)np, t->a5d[k], L5_UNITS, dzk, head_n[k], 0.f, t->G + phk.off, head_n[k], st, &t->launches);
+    column_sums<<<dim3(blocks_for(head_n[k], 128), 16), 128, 0, st>>>(dzk, np, head_n[k], t->G + phb.off);
+    gemm(false, true, (int)np, L5_UNITS, head_n[k], dzk, head_n[k], t->P + phk.off, head_n[k], 0.f, t->da5[k], L5_UNITS, st, &t->launches);
+    ++t->launches;
+    if (t->rates[2 + k] > 0.f) {
+      float a, b;
+      alpha_ab(t->rates[2 + k], &a, &b);
+      alpha_dropout_backward<<<blocks_for(np * L5_UNITS), 256, 0, st>>>(t->da5[k], t->mask[2 + k], a, np * L5_UNITS);
+      ++t->launches;
+    }
+    selu_backward<<<blocks_for(np * L5_UNITS), 256, 0, st>>>(t->da5[k], t->a5[k], np * L5_UNITS);
+    ++t->launches;
+    gemm(true, false, L4_UNITS, L5_UNITS, (int)np, t->a4d, L4_UNITS, t->da5[k], L5_UNITS, 0.f, t->G + p5k.off, L5_UNITS, st, &t->launches);
+    column_sums<<<dim3(blocks_for(L5_UNITS, 128), 16), 128, 0, st>>>(t->da5[k], np, L5_UNITS, t->G + p5b.off);
+    ++t->launches;
+    gemm(false, true, (int)np, L4_UNITS, L5_UNITS, t->da5[k], L5_UNITS, t->P + p5k.off, L5_UNITS, k ? 1.f : 0.f, t->da4, L4_UNITS, st, &t->launches);
+  }
+  if (t->rates[1] > 0.f) {
+    float a, b;
+    alpha_ab(t->rates[1], &a, &b);
+    alpha_dropout_backward<<<blocks_for(np * L4_UNITS), 256, 0, st>>>(t->da4, t->mask[1], a, np * L4_UNITS);
+    ++t->launches;
+  }
+  selu_backward<<<blocks_for(np * L4_UNITS), 256, 0, st>>>(t->da4, t->a4, np * L4_UNITS);
+  ++t->launches;
+  gemm(true, false, L3_K, L4_UNITS, (int)np, t->a3, L3_K, t->da4, L4_UNITS, 0.f, t->G + p4k.off, L4_UNITS, st, &t->launches);
+  column_sums<<<dim3(blocks_for(L4_UNITS, 128), 16), 128, 0, st>>>(t->da4, np, L4_UNITS, t->G + p4b.off);
+  ++t->launches;
+  gemm(false, true, (int)np, L3_K, L4_UNITS, t->da4, L4_UNITS, t->P + p4k.off, L4_UNITS, 0.f, t->da3, L3_K, st, &t->launches);
+  l3_backward_input<<<dim3(2 * H, blocks_for(np, 128)), 128, 0, st>>>(t->da3, t->a3, t->P + p3.off, t->dlout[1], (int)np);
+  l3_backward_weights<<<2 * H, 1024, 0, st>>>(t->lout[1], t->da3, t->G + p3.off, (int)np);
+  t->launches += 2;
+  if (t->rates[0] > 0.f) {
+    dropout_scale<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->dlout[1], t->mask[0], 1.f / (1.f - t->rates[0]), rows * 2 * H);
+    ++t->launches;
+  }
+  TR_TRY(t, cudaGetLastError());
+  TR_TRY(t, cudaMemcpyAsync(losses, t->d_loss, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TR_TRY(t, cudaStreamSynchronize(st));
+  losses[4] *= 0.5;                                          // sum ||v||^2 / 2 (tf.nn.l2_loss)
+  t->lstm_pending = true;
+  return CLAIRB_OK;
+}
+
+// BPTT through LSTM2 and LSTM1: completes the gradient buffer (flat offsets < clairb_trainer_dense_offset).
+int clairb_trainer_backward_lstm(clairb_trainer* t) {
+  if (!t) return CLAIRB_EINVAL;
+  if (!t->lstm_pending) return tfail(t, CLAIRB_EINVAL, "backward_lstm: no forward_backward call is pending");
+  TR_TRY(t, cudaSetDevice(t->device));
+  if (int rc = lstm_layer_backward(t, 1, t->last_np)) return rc;
+  if (int rc = lstm_layer_backward(t, 0, t->last_np)) return rc;
+  TR_TRY(t, cudaGetLastError());
+  TR_TRY(t, cudaStreamSynchronize(t->st));
+  t->lstm_pending = false;
+  return CLAIRB_OK;
+}
+
+// L2 gradient, global-norm clip, Adam (clair/model.py:689-694, 717-728).  `step` is the 1-based Adam step (bias corrections).
+// grad_norm (optional) receives the global norm before clipping.
+int clairb_trainer_apply(clairb_trainer* t, float learning_rate, float l2_lambda, float clip_norm, int64_t step, double* grad_norm) {
+  using namespace clairb::train;
+  if (!t) return CLAIRB_EINVAL;
+  if (t->lstm_pending) return tfail(t, CLAIRB_EINVAL, "apply: clairb_trainer_backward_lstm has not run for the pending step");
+  if (step < 1 || !(clip_norm > 0.f)) return tfail(t, CLAIRB_EINVAL, "apply: step must be >= 1 and clip_norm > 0");
+  TR_TRY(t, cudaSetDevice(t->device));
+  cudaStream_t st = t->st;
+  if (l2_lambda != 0.f) {
+    add_l2_gradient<<<blocks_for(t->n_params), 256, 0, st>>>(t->G, t->P, t->is_kernel, l2_lambda, t->n_params);
+    ++t->launches;
+  }
+  TR_TRY(t, cudaMemsetAsync(t->d_loss + 5, 0, sizeof(double), st));
+  sum_squares<<<256, 256, 0, st>>>(t->G, nullptr, t->n_params, t->d_loss + 5);
+  const double lr_t = (double)learning_rate * std::sqrt(1.0 - std::pow(0.999, (double)step)) / (1.0 - std::pow(0.9, (double)step));
+  adam_update<<<blocks_for(t->n_params), 256, 0, st>>>(t->P, t->G, t->M1, t->M2, t->d_loss + 5, clip_norm, (float)lr_t, t->n_params);
+  t->launches += 2;
+  TR_TRY(t, cudaGetLastError());
+  double ss = 0.0;
+  TR_TRY(t, cudaMemcpyAsync(&ss, t->d_loss + 5, sizeof(double), cudaMemcpyDeviceToHost, st));
+  TR_TRY(t, cudaStreamSynchronize(st));
+  if (grad_norm) *grad_norm = std::sqrt(ss);
+  return CLAIRB_OK;
+}
+
+// probabilities [n][90] of the last forward (training phase: with its dropout masks)
+int clairb_trainer_get_probabilities(clairb_trainer* t, float* out, int64_t n) {
+  if (!t || !out || n != t->last_n) return CLAIRB_EINVAL;
+  TR_TRY(t, cudaSetDevice(t->device));
+  TR_TRY(t, cudaMemcpy(out, t->probs, (size_t)n * N_OUT * sizeof(float), cudaMemcpyDeviceToHost));
+  return CLAIRB_OK;
+}
+
+int clairb_trainer_destroy(clairb_trainer* t) {
+  if (!t) return CLAIRB_EINVAL;
+  cudaSetDevice(t->device);
+  cudaDeviceSynchronize();
+  trainer_free(t);
+  delete t;
+  return CLAIRB_OK;
+}
+
+}  // extern "C"

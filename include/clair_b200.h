@@ -297,6 +297,40 @@ const char* clairb_last_error(const clairb_engine* e);
 /* Replaces Clair.close / __del__ (clair/model.py:872,1149). */
 int clairb_destroy(clairb_engine* e);
 
+/* ---- training step ------------------------------------------------------------------------------
+ * Replaces, per call of Clair.train (clair/model.py:913-945): the forward in training phase (tf.layers.dropout behind LSTM2,
+ * selu.dropout_selu behind L4 / L5_k: :434-578, clair/selu.py:43-74), the focal loss of the four heads (:783-805), the L2 term
+ * (:689-694), the gradients of every trainable variable (BPTT through both BiLSTMs), clip_by_global_norm(5.0) and the Adam
+ * update (:717-728).  fp32 on the device.  One clairb_trainer drives one GPU; parameters, gradients and Adam moments are flat
+ * buffers in the order of the TF variable list (LSTM1 fw / bw, LSTM2 fw / bw: kernel, bias; L3/Unit_0..255; L4; L5_1..4; heads).
+ * A step is three calls, so that a data-parallel caller can all-reduce the gradient buffer (set_grad_buffer: a device buffer of
+ * its own, e.g. a torch tensor handed to NCCL) in two pieces that overlap the backward pass:
+ *   clairb_trainer_forward_backward : forward, loss, backward through heads / L5 / L4 / slice-dense; on return the gradients at
+ *                                     flat offsets >= clairb_trainer_dense_offset() are complete; losses[5] = the four focal-loss
+ *                                     sums and sum ||kernel||^2 / 2
+ *   clairb_trainer_backward_lstm    : BPTT through LSTM2 and LSTM1 (offsets < dense_offset)
+ *   clairb_trainer_apply            : g += lambda * w on kernels, clip by global norm, Adam step `step` (1-based)
+ * masks: NULL (drawn on the device from `seed`, one stream per dropout) or six uint8 keep-masks [33][n][256], [n][192],
+ * 4 x [n][96] (parity tests: TensorFlow's random stream cannot be reproduced, both sides are handed the same masks).
+ * clairb_trainer_get: which = 0 weights, 1 gradients of the last step, 2 / 3 Adam moments, by TF variable name. */
+typedef struct clairb_trainer clairb_trainer;
+int clairb_trainer_create(int device, int64_t max_batch, clairb_trainer** out);
+int clairb_trainer_set_weight(clairb_trainer* t, const char* tf_name, const float* data, const int64_t* shape, int rank);
+int clairb_trainer_get(clairb_trainer* t, int which, const char* tf_name, float* out, int64_t count);
+int clairb_trainer_set_grad_buffer(clairb_trainer* t, float* dev_ptr);
+int clairb_trainer_set_dropout_rates(clairb_trainer* t, const float* rates6);
+int64_t clairb_trainer_num_params(const clairb_trainer* t);
+int64_t clairb_trainer_dense_offset(const clairb_trainer* t);
+int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int dtype, const float* y_host, int64_t n,
+                                    const uint8_t* const* masks, uint64_t seed, double* losses);
+int clairb_trainer_backward_lstm(clairb_trainer* t);
+int clairb_trainer_apply(clairb_trainer* t, float learning_rate, float l2_lambda, float clip_norm, int64_t step,
+                         double* grad_norm);
+int clairb_trainer_get_probabilities(clairb_trainer* t, float* out, int64_t n);
+int64_t clairb_trainer_kernel_launches(const clairb_trainer* t);
+const char* clairb_trainer_last_error(const clairb_trainer* t);
+int clairb_trainer_destroy(clairb_trainer* t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,7 +84,7 @@ class _AnyShape(object):
 
 class Variable(Tensor):
     def __init__(self, name, shape, dtype):
-        Tensor.__init__(self, lambda f, c: self.value, name + ":0", dtype)
+        Tensor.__init__(self, lambda f, c: self.value.astype(COMPUTE_DTYPE) if COMPUTE_DTYPE else self.value, name + ":0", dtype)
         self.var_name, self.shape = name, tuple(shape)
         self.value = np.zeros(self.shape, dtype)
         self.op = type("Op", (), {"name": name})()
