@@ -23,7 +23,8 @@ struct clairb_trainer {
   int64_t max_batch = 0, np_max = 0;
   std::string err;
   int64_t launches = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, st2 = nullptr;          // the two directions of a BiLSTM layer run side by side (st: fw, st2: bw)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   struct Param { std::string name; int64_t off, rows, cols; };       // bias: rows = 1
   std::vector<Param> params;
   std::map<std::string, int> index;
@@ -126,6 +127,9 @@ void trainer_free(clairb_trainer* t) {
   cudaFree(t->x_in); t->x_in = nullptr;
   for (int i = 0; i < 6; ++i) drop(t->mask[i]);
   if (t->st) cudaStreamDestroy(t->st);
+  if (t->st2) cudaStreamDestroy(t->st2);
+  if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+  if (t->ev_join) cudaEventDestroy(t->ev_join);
 }
 
 // backward through the two directions of one BiLSTM layer: dlout[l] (gradient of the layer's output) -> parameter gradients,
@@ -137,36 +141,39 @@ int lstm_layer_backward(clairb_trainer* t, int l, int64_t np) {
   const int64_t rows = (int64_t)T_STEPS * np;
   split_bidirectional<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->dlout[l], t->dir[l][0].dh_out, t->dir[l][1].dh_out, (int)np);
   ++t->launches;
-  if (l == 1) TR_TRY(t, cudaMemsetAsync(t->dlout[0], 0, (size_t)rows * 2 * H * sizeof(float), st));
+  TR_TRY(t, cudaEventRecord(t->ev_fork, st));
+  TR_TRY(t, cudaStreamWaitEvent(t->st2, t->ev_fork, 0));
   for (int d = 0; d < 2; ++d) {
+    cudaStream_t sd = d ? t->st2 : st;
     auto& q = t->dir[l][d];
     const auto& pk = tp(t, lstm_prefix(l, d) + "kernel");
     const auto& pb = tp(t, lstm_prefix(l, d) + "bias");
-    TR_TRY(t, cudaMemsetAsync(q.dh_rec, 0, (size_t)np * H * sizeof(float), st));
-    TR_TRY(t, cudaMemsetAsync(q.dc, 0, (size_t)np * H * sizeof(float), st));
+    TR_TRY(t, cudaMemsetAsync(q.dh_rec, 0, (size_t)np * H * sizeof(float), sd));
+    TR_TRY(t, cudaMemsetAsync(q.dc, 0, (size_t)np * H * sizeof(float), sd));
     for (int s = T_STEPS - 1; s >= 0; --s) {
-      lstm_step_backward<<<(unsigned)(np / ROWS), H, 0, st>>>(q.dh_out + (size_t)s * np * H, q.dh_rec, q.dc, q.gates + (size_t)s * np * G4,
+      lstm_step_backward<<<(unsigned)(np / ROWS), H, 0, sd>>>(q.dh_out + (size_t)s * np * H, q.dh_rec, q.dc, q.gates + (size_t)s * np * G4,
                                                                q.cbuf + (size_t)(s + 1) * np * H, q.cbuf + (size_t)s * np * H, q.WhT,
                                                                q.dZ + (size_t)s * np * G4, (int)np);
       ++t->launches;
     }
     float* gk = t->G + pk.off;
     // dW_x = x_in^T . dZ (all steps at once), dW_h = h_prev^T . dZ, db = column sums
-    gemm(true, false, K, G4, (int)rows, q.xin, K, q.dZ, G4, 0.f, gk, G4, st, &t->launches);
-    gemm(true, false, H, G4, (int)rows, q.hbuf, H, q.dZ, G4, 0.f, gk + (size_t)K * G4, G4, st, &t->launches);
-    TR_TRY(t, cudaMemsetAsync(t->G + pb.off, 0, G4 * sizeof(float), st));
-    column_sums<<<dim3(blocks_for(G4, 128), 64), 128, 0, st>>>(q.dZ, rows, G4, t->G + pb.off);
+    gemm(true, false, K, G4, (int)rows, q.xin, K, q.dZ, G4, 0.f, gk, G4, sd, &t->launches);
+    gemm(true, false, H, G4, (int)rows, q.hbuf, H, q.dZ, G4, 0.f, gk + (size_t)K * G4, G4, sd, &t->launches);
+    TR_TRY(t, cudaMemsetAsync(t->G + pb.off, 0, G4 * sizeof(float), sd));
+    column_sums<<<dim3(blocks_for(G4, 128), 64), 128, 0, sd>>>(q.dZ, rows, G4, t->G + pb.off);
     ++t->launches;
     if (l == 1) {
-      // d(input) = dZ . W_x^T, back in time order, summed over the two directions
-      gemm(false, true, (int)rows, K, G4, q.dZ, G4, t->P + pk.off, G4, 0.f, q.dxin, K, st, &t->launches);
-      if (d == 0) {
-        TR_TRY(t, cudaMemcpyAsync(t->dlout[0], q.dxin, (size_t)rows * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      } else {
-        reverse_time<<<blocks_for(rows * K), 256, 0, st>>>(q.dxin, t->dlout[0], (int)np, K, 1);
-        ++t->launches;
-      }
+      // d(input) = dZ . W_x^T per direction (in its processing order); summed in time order below
+      gemm(false, true, (int)rows, K, G4, q.dZ, G4, t->P + pk.off, G4, 0.f, q.dxin, K, sd, &t->launches);
     }
+  }
+  TR_TRY(t, cudaEventRecord(t->ev_join, t->st2));
+  TR_TRY(t, cudaStreamWaitEvent(st, t->ev_join, 0));
+  if (l == 1) {
+    TR_TRY(t, cudaMemcpyAsync(t->dlout[0], t->dir[1][0].dxin, (size_t)rows * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    reverse_time<<<blocks_for(rows * K), 256, 0, st>>>(t->dir[1][1].dxin, t->dlout[0], (int)np, K, 1);
+    ++t->launches;
   }
   return CLAIRB_OK;
 }
@@ -208,6 +215,9 @@ int clairb_trainer_create(int device, int64_t max_batch, clairb_trainer** out) {
 #define TC_ALLOC(p, count) TC_TRY(cudaMalloc((void**)&(p), (size_t)(count) * sizeof(*(p))))
   TC_TRY(cudaSetDevice(device));
   TC_TRY(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
+  TC_TRY(cudaStreamCreateWithFlags(&t->st2, cudaStreamNonBlocking));
+  TC_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+  TC_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
   TC_ALLOC(t->P, t->n_params); TC_ALLOC(t->G_own, t->n_params); TC_ALLOC(t->M1, t->n_params); TC_ALLOC(t->M2, t->n_params);
   TC_ALLOC(t->is_kernel, t->n_params);
   t->G = t->G_own;
@@ -343,25 +353,30 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
   for (int l = 0; l < 2; ++l) {
     const int K = l ? 2 * H : F_IN;
     const float* in = l ? t->lout[0] : t->x_tm;             // LSTM1_dropout_rate is 0 (clair/model.py:95): no mask between the layers
+    TR_TRY(t, cudaEventRecord(t->ev_fork, st));
+    TR_TRY(t, cudaStreamWaitEvent(t->st2, t->ev_fork, 0));
     for (int d = 0; d < 2; ++d) {
+      cudaStream_t sd = d ? t->st2 : st;
       auto& q = t->dir[l][d];
       const auto& pk = tp(t, lstm_prefix(l, d) + "kernel");
       const auto& pb = tp(t, lstm_prefix(l, d) + "bias");
-      if (d == 0) TR_TRY(t, cudaMemcpyAsync(q.xin, in, (size_t)rows * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      else { reverse_time<<<blocks_for(rows * K), 256, 0, st>>>(in, q.xin, (int)np, K, 0); ++t->launches; }
-      transpose_matrix<<<blocks_for((int64_t)H * G4), 256, 0, st>>>(t->P + pk.off + (size_t)K * G4, q.WhT, H, G4);
-      fill_rows<<<blocks_for(rows * G4), 256, 0, st>>>(q.pre, t->P + pb.off, rows, G4);
+      if (d == 0) TR_TRY(t, cudaMemcpyAsync(q.xin, in, (size_t)rows * K * sizeof(float), cudaMemcpyDeviceToDevice, sd));
+      else { reverse_time<<<blocks_for(rows * K), 256, 0, sd>>>(in, q.xin, (int)np, K, 0); ++t->launches; }
+      transpose_matrix<<<blocks_for((int64_t)H * G4), 256, 0, sd>>>(t->P + pk.off + (size_t)K * G4, q.WhT, H, G4);
+      fill_rows<<<blocks_for(rows * G4), 256, 0, sd>>>(q.pre, t->P + pb.off, rows, G4);
       t->launches += 2;
-      gemm(false, false, (int)rows, G4, K, q.xin, K, t->P + pk.off, G4, 1.f, q.pre, G4, st, &t->launches);
-      TR_TRY(t, cudaMemsetAsync(q.hbuf, 0, (size_t)np * H * sizeof(float), st));
-      TR_TRY(t, cudaMemsetAsync(q.cbuf, 0, (size_t)np * H * sizeof(float), st));
+      gemm(false, false, (int)rows, G4, K, q.xin, K, t->P + pk.off, G4, 1.f, q.pre, G4, sd, &t->launches);
+      TR_TRY(t, cudaMemsetAsync(q.hbuf, 0, (size_t)np * H * sizeof(float), sd));
+      TR_TRY(t, cudaMemsetAsync(q.cbuf, 0, (size_t)np * H * sizeof(float), sd));
       for (int s = 0; s < T_STEPS; ++s) {
-        lstm_step_forward<<<(unsigned)(np / ROWS), H, 0, st>>>(q.pre + (size_t)s * np * G4, t->P + pk.off + (size_t)K * G4, q.hbuf + (size_t)s * np * H,
+        lstm_step_forward<<<(unsigned)(np / ROWS), H, 0, sd>>>(q.pre + (size_t)s * np * G4, t->P + pk.off + (size_t)K * G4, q.hbuf + (size_t)s * np * H,
                                                                 q.cbuf + (size_t)s * np * H, q.gates + (size_t)s * np * G4, q.cbuf + (size_t)(s + 1) * np * H,
                                                                 q.hbuf + (size_t)(s + 1) * np * H, (int)np);
         ++t->launches;
       }
     }
+    TR_TRY(t, cudaEventRecord(t->ev_join, t->st2));
+    TR_TRY(t, cudaStreamWaitEvent(st, t->ev_join, 0));
     assemble_bidirectional<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->dir[l][0].hbuf + (size_t)np * H, t->dir[l][1].hbuf + (size_t)np * H, t->lout[l], (int)np);
     ++t->launches;
   }

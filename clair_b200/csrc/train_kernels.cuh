@@ -23,29 +23,34 @@ namespace clairb {
 namespace train {
 
 constexpr int ROWS = 8;                  // sites per CTA of the per-step recurrent kernels
+constexpr int WT = 16;                   // rows of the recurrent kernel staged in shared memory at a time
 constexpr float ALPHA_DROPOUT = -1.7580993408473766f;     // clair/selu.py:43
 
 // ---- C[M,N] = alpha * op(A)[M,K] . op(B)[K,N] + beta * C     (row-major; TA: A is stored [K][M]; TB: B is stored [N][K]) ----
 constexpr int GM = 64, GN = 64, GK = 16;
+// gridDim.z > 1: split-K - slice z of the contraction is added to C with atomics (C holds beta * C already; the weight-gradient
+// GEMMs contract over 33 * n rows into a few hundred outputs and would otherwise run on a handful of CTAs)
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
-                                             const float* __restrict__ B, int ldb, float beta, float* __restrict__ C, int ldc) {
+                                             const float* __restrict__ B, int ldb, float beta, float* __restrict__ C, int ldc, int k_per_slice) {
   __shared__ float As[GK][GM + 4], Bs[GK][GN + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  const int k_begin = blockIdx.z * k_per_slice;
+  const int k_end = min(K, k_begin + k_per_slice);
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  for (int k0 = k_begin; k0 < k_end; k0 += GK) {
     for (int i = threadIdx.x; i < GM * GK; i += 256) {
       int m, k;
       if (TA) { m = i % GM; k = i / GM; } else { k = i % GK; m = i / GK; }
       const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < M && gk < K) ? (TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk]) : 0.f;
+      As[k][m] = (gm < M && gk < k_end) ? (TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk]) : 0.f;
     }
     for (int i = threadIdx.x; i < GN * GK; i += 256) {
       int nn, k;
       if (TB) { k = i % GK; nn = i / GK; } else { nn = i % GN; k = i / GN; }
       const int gn = n0 + nn, gk = k0 + k;
-      Bs[k][nn] = (gn < N && gk < K) ? (TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn]) : 0.f;
+      Bs[k][nn] = (gn < N && gk < k_end) ? (TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -67,18 +72,39 @@ __global__ void __launch_bounds__(256) sgemm(int M, int N, int K, float alpha, c
       const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
       if (gm < M && gn < N) {
         float* c = C + (size_t)gm * ldc + gn;
-        *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
+        if (gridDim.z > 1) atomicAdd(c, alpha * acc[i][j]);
+        else *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
       }
     }
+}
+
+// rows of C (M x N, leading dimension ldc) <- beta * C, before a split-K GEMM adds its slices
+__global__ void scale_matrix(float* __restrict__ C, int M, int N, int ldc, float beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)M * N) {
+    float* c = C + (i / N) * ldc + i % N;
+    *c = beta != 0.f ? beta * *c : 0.f;
+  }
 }
 
 inline void gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc,
                  cudaStream_t st, int64_t* launches) {
   dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
-  if (!ta && !tb) sgemm<false, false><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc);
-  else if (ta && !tb) sgemm<true, false><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc);
-  else if (!ta && tb) sgemm<false, true><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc);
-  else sgemm<true, true><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc);
+  // split the contraction when the output tiles alone cannot fill the machine (592 = 4 CTAs per SM on 148 SMs)
+  int slices = 1;
+  const int tiles = (int)(grid.x * grid.y);
+  if (tiles < 296 && K >= 2048) slices = min(64, max(1, min(592 / tiles, K / 512)));
+  int k_per_slice = ((K + slices - 1) / slices + GK - 1) / GK * GK;
+  slices = (K + k_per_slice - 1) / k_per_slice;
+  grid.z = slices;
+  if (slices > 1) {
+    scale_matrix<<<(unsigned)(((int64_t)M * N + 255) / 256), 256, 0, st>>>(C, M, N, ldc, beta);
+    ++*launches;
+  }
+  if (!ta && !tb) sgemm<false, false><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, k_per_slice);
+  else if (ta && !tb) sgemm<true, false><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, k_per_slice);
+  else if (!ta && tb) sgemm<false, true><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, k_per_slice);
+  else sgemm<true, true><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, k_per_slice);
   ++*launches;
 }
 
@@ -180,23 +206,30 @@ __global__ void __launch_bounds__(H) lstm_step_forward(const float* __restrict__
                                                        const float* __restrict__ c_prev, float* __restrict__ gates, float* __restrict__ c_out,
                                                        float* __restrict__ h_out, int n) {
   __shared__ float hs[ROWS][H];
+  __shared__ float ws[WT][G4];                           // WT rows of W_h at a time, loaded by the whole CTA (coalesced)
   const int u = threadIdx.x, r0 = blockIdx.x * ROWS;
   for (int r = 0; r < ROWS; ++r) hs[r][u] = h_prev[(size_t)(r0 + r) * H + u];
-  __syncthreads();
   float z[ROWS][4];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r)
 #pragma unroll
     for (int g = 0; g < 4; ++g) z[r][g] = pre[(size_t)(r0 + r) * G4 + g * H + u];
-  for (int k = 0; k < H; ++k) {
-    float w[4];
+  for (int k0 = 0; k0 < H; k0 += WT) {
+    __syncthreads();
+    for (int i = u; i < WT * G4 / 4; i += H)
+      reinterpret_cast<float4*>(&ws[0][0])[i] = reinterpret_cast<const float4*>(Wh + (size_t)k0 * G4)[i];
+    __syncthreads();
 #pragma unroll
-    for (int g = 0; g < 4; ++g) w[g] = Wh[(size_t)k * G4 + g * H + u];
+    for (int kk = 0; kk < WT; ++kk) {
+      float w[4];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const float hv = hs[r][k];
+      for (int g = 0; g < 4; ++g) w[g] = ws[kk][g * H + u];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) z[r][g] = fmaf(hv, w[g], z[r][g]);
+      for (int r = 0; r < ROWS; ++r) {
+        const float hv = hs[r][k0 + kk];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) z[r][g] = fmaf(hv, w[g], z[r][g]);
+      }
     }
   }
 #pragma unroll
@@ -229,12 +262,19 @@ __global__ void __launch_bounds__(H) lstm_step_backward(const float* __restrict_
     dz_s[r][u] = dzi; dz_s[r][H + u] = dzg; dz_s[r][2 * H + u] = dzf; dz_s[r][3 * H + u] = dzo;
     dZ[row * G4 + u] = dzi; dZ[row * G4 + H + u] = dzg; dZ[row * G4 + 2 * H + u] = dzf; dZ[row * G4 + 3 * H + u] = dzo;
   }
-  __syncthreads();
+  __shared__ float wts[4 * WT][H];                        // 64 rows of W_h^T at a time
   float acc[ROWS] = {};
-  for (int k = 0; k < G4; ++k) {
-    const float w = WhT[(size_t)k * H + u];
+  for (int k0 = 0; k0 < G4; k0 += 4 * WT) {
+    __syncthreads();                                     // also orders the dz_s writes above before the first reads
+    for (int i = u; i < 4 * WT * H / 4; i += H)
+      reinterpret_cast<float4*>(&wts[0][0])[i] = reinterpret_cast<const float4*>(WhT + (size_t)k0 * H)[i];
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 4 * WT; ++kk) {
+      const float w = wts[kk][u];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(dz_s[r][k], w, acc[r]);
+      for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(dz_s[r][k0 + kk], w, acc[r]);
+    }
   }
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) dh_rec[(size_t)(r0 + r) * H + u] = acc[r];

@@ -48,7 +48,7 @@ def test_losses_and_gradients_equal_autograd(weights1234, n):
     t2 = Trainer(max_batch=64)
     t2.set_weights(weights1234)
     parts16 = t2.forward_backward(X.astype(np.int16), Y, masks)
-    np.testing.assert_allclose(parts16, parts, rtol=1e-9)         # (sums are accumulated with atomics: order varies)
+    np.testing.assert_allclose(parts16, parts, rtol=1e-6)         # (split-K sums are accumulated with atomics: order varies)
     t.close()
     t2.close()
 
@@ -85,7 +85,7 @@ def test_device_drawn_masks_and_a_short_run(weights1234):
     for t in (a, b, c):
         t.set_weights(weights1234)
     la, lb, lc = a.train(X, Y), b.train(X, Y), c.train(X, Y)
-    assert abs(la - lb) <= 1e-9 * abs(la) and abs(la - lc) > 1e-6 * abs(la)      # the mask stream is a function of (seed, step)
+    assert abs(la - lb) <= 1e-6 * abs(la) and abs(la - lc) > 1e-4 * abs(la)      # the mask stream is a function of (seed, step)
     first = la
     for _ in range(14):
         last = a.train(X, Y)
