@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--cpu-baseline-batches", type=int, default=0, help="0 = auto (about 10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-create-tensor", action="store_true", help="skip the CreateTensor-stage line (SURVEY 8f row 4)")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step line (SURVEY 8f row 5)")
     return ap.parse_args()
 
 
@@ -637,6 +638,16 @@ def main():
                          "categories_seen": np.bincount(dec.category, minlength=10).tolist(),
                          "note": "forward + decide_sites kernel per chunk (call_var.py:589-690, 732-760), int16 transport"}
 
+    # ---- training step (BASELINE.json configs[4]: batch 512 per GPU, data-parallel): outside the headline's
+    #      timed region; every rank takes part (NCCL all-reduce of the gradient buffer) ----
+    train_info = None
+    if not args.no_train:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_bench
+        try:
+            train_info = train_bench.device_part(512, steps=12, warm=3, device=local_rank, data_parallel=world > 1)
+        except Exception as exc:                       # a side stage must not take the headline line down with it
+            train_info = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if rank == 0:
         peaks = measured_peaks()
         prof = {p["kernel"]: p for p in profile}
@@ -741,6 +752,11 @@ def main():
                    "parity_sample": parity_sample,
                    "cpu_model": model, "host_cores": cores}
             pinning = oracle_pinning(m, weights, np.array(X[:256]))
+            if train_info is not None and "error" not in train_info:
+                try:
+                    train_bench.cpu_part(train_info)
+                except Exception as exc:
+                    train_info["cpu_oracle"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         engine = os.environ.get("CLAIRB_ENGINE", "default")
         print(json.dumps({
             "metric": "candidate-sites/sec", "value": value, "unit": "sites/s", "n_gpus": world,
@@ -775,6 +791,7 @@ def main():
             "decision_stage": decision_info,
             "output_stage": output_info,
             "create_tensor_stage": ct_info,
+            "train_stage": train_info,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
