@@ -34,7 +34,7 @@ struct clairb_trainer {
   bool weights_set = false;
   // activations / gradients (sized for np_max sites)
   float *x_tm = nullptr, *xin = nullptr, *lout[2] = {nullptr, nullptr}, *dlout[2] = {nullptr, nullptr};
-  struct Dir { float *xin, *pre, *gates, *hbuf, *cbuf, *dZ, *dh_out, *dh_rec, *dc, *WhT, *dxin; } dir[2][2] = {};
+  struct Dir { float *xin, *pre, *gates, *hbuf, *cbuf, *dZ, *dh_out, *dxin; } dir[2][2] = {};
   float *a3 = nullptr, *da3 = nullptr, *a4 = nullptr, *a4d = nullptr, *da4 = nullptr, *a5[4] = {}, *a5d[4] = {}, *da5[4] = {};
   float *zall = nullptr, *dzall = nullptr, *probs = nullptr, *target = nullptr;
   void* x_in = nullptr;
@@ -69,6 +69,8 @@ int tfail(clairb_trainer* t, int code, const char* fmt, ...) {
   } while (0)
 
 inline unsigned blocks_for(int64_t count, int threads = 256) { return (unsigned)((count + threads - 1) / threads); }
+// one cluster of SEQ_CTAS CTAs per SEQ_ROWS sites (lstm_seq_forward / lstm_seq_backward)
+inline unsigned seq_grid(int64_t np) { return (unsigned)((np + clairb::train::SEQ_ROWS - 1) / clairb::train::SEQ_ROWS * clairb::train::SEQ_CTAS); }
 
 void trainer_layout(clairb_trainer* t) {
   const int head_n[4] = {21, 3, 33, 33};
@@ -119,7 +121,7 @@ void trainer_free(clairb_trainer* t) {
   for (int l = 0; l < 2; ++l)
     for (int d = 0; d < 2; ++d) {
       auto& q = t->dir[l][d];
-      drop(q.xin); drop(q.pre); drop(q.gates); drop(q.hbuf); drop(q.cbuf); drop(q.dZ); drop(q.dh_out); drop(q.dh_rec); drop(q.dc); drop(q.WhT); drop(q.dxin);
+      drop(q.xin); drop(q.pre); drop(q.gates); drop(q.hbuf); drop(q.cbuf); drop(q.dZ); drop(q.dh_out); drop(q.dxin);
     }
   drop(t->a3); drop(t->da3); drop(t->a4); drop(t->a4d); drop(t->da4);
   for (int k = 0; k < 4; ++k) { drop(t->a5[k]); drop(t->a5d[k]); drop(t->da5[k]); }
@@ -148,21 +150,13 @@ int lstm_layer_backward(clairb_trainer* t, int l, int64_t np) {
     auto& q = t->dir[l][d];
     const auto& pk = tp(t, lstm_prefix(l, d) + "kernel");
     const auto& pb = tp(t, lstm_prefix(l, d) + "bias");
-    TR_TRY(t, cudaMemsetAsync(q.dh_rec, 0, (size_t)np * H * sizeof(float), sd));
-    TR_TRY(t, cudaMemsetAsync(q.dc, 0, (size_t)np * H * sizeof(float), sd));
-    for (int s = T_STEPS - 1; s >= 0; --s) {
-      lstm_step_backward<<<(unsigned)(np / ROWS), H, 0, sd>>>(q.dh_out + (size_t)s * np * H, q.dh_rec, q.dc, q.gates + (size_t)s * np * G4,
-                                                               q.cbuf + (size_t)(s + 1) * np * H, q.cbuf + (size_t)s * np * H, q.WhT,
-                                                               q.dZ + (size_t)s * np * G4, (int)np);
-      ++t->launches;
-    }
+    TR_TRY(t, cudaMemsetAsync(t->G + pb.off, 0, G4 * sizeof(float), sd));
+    lstm_seq_backward<<<seq_grid(np), 256, SEQ_BWD_SMEM, sd>>>(q.dh_out, q.gates, q.cbuf, t->P + pk.off + (size_t)K * G4, q.dZ, t->G + pb.off, (int)np);
+    ++t->launches;
     float* gk = t->G + pk.off;
     // dW_x = x_in^T . dZ (all steps at once), dW_h = h_prev^T . dZ, db = column sums
     gemm(true, false, K, G4, (int)rows, q.xin, K, q.dZ, G4, 0.f, gk, G4, sd, &t->launches);
     gemm(true, false, H, G4, (int)rows, q.hbuf, H, q.dZ, G4, 0.f, gk + (size_t)K * G4, G4, sd, &t->launches);
-    TR_TRY(t, cudaMemsetAsync(t->G + pb.off, 0, G4 * sizeof(float), sd));
-    column_sums<<<dim3(blocks_for(G4, 128), 64), 128, 0, sd>>>(q.dZ, rows, G4, t->G + pb.off);
-    ++t->launches;
     if (l == 1) {
       // d(input) = dZ . W_x^T per direction (in its processing order); summed in time order below
       gemm(false, true, (int)rows, K, G4, q.dZ, G4, t->P + pk.off, G4, 0.f, q.dxin, K, sd, &t->launches);
@@ -214,6 +208,11 @@ int clairb_trainer_create(int device, int64_t max_batch, clairb_trainer** out) {
   } while (0)
 #define TC_ALLOC(p, count) TC_TRY(cudaMalloc((void**)&(p), (size_t)(count) * sizeof(*(p))))
   TC_TRY(cudaSetDevice(device));
+  TC_TRY(cudaFuncSetAttribute(l3_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+  TC_TRY(cudaFuncSetAttribute(l3_backward_input, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+  TC_TRY(cudaFuncSetAttribute(l3_backward_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+  TC_TRY(cudaFuncSetAttribute(lstm_seq_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ_FWD_SMEM));
+  TC_TRY(cudaFuncSetAttribute(lstm_seq_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ_BWD_SMEM));
   TC_TRY(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
   TC_TRY(cudaStreamCreateWithFlags(&t->st2, cudaStreamNonBlocking));
   TC_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
@@ -240,8 +239,8 @@ int clairb_trainer_create(int device, int64_t max_batch, clairb_trainer** out) {
       auto& q = t->dir[l][d];
       TC_ALLOC(q.xin, TS * np * K); TC_ALLOC(q.pre, TS * np * G4); TC_ALLOC(q.gates, TS * np * G4);
       TC_ALLOC(q.hbuf, (TS + 1) * np * H); TC_ALLOC(q.cbuf, (TS + 1) * np * H);
-      TC_ALLOC(q.dZ, TS * np * G4); TC_ALLOC(q.dh_out, TS * np * H); TC_ALLOC(q.dh_rec, np * H); TC_ALLOC(q.dc, np * H);
-      TC_ALLOC(q.WhT, (size_t)G4 * H); TC_ALLOC(q.dxin, TS * np * K);
+      TC_ALLOC(q.dZ, TS * np * G4); TC_ALLOC(q.dh_out, TS * np * H);
+      TC_ALLOC(q.dxin, TS * np * K);
     }
   }
   TC_ALLOC(t->a3, np * L3_K); TC_ALLOC(t->da3, np * L3_K);
@@ -362,18 +361,11 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
       const auto& pb = tp(t, lstm_prefix(l, d) + "bias");
       if (d == 0) TR_TRY(t, cudaMemcpyAsync(q.xin, in, (size_t)rows * K * sizeof(float), cudaMemcpyDeviceToDevice, sd));
       else { reverse_time<<<blocks_for(rows * K), 256, 0, sd>>>(in, q.xin, (int)np, K, 0); ++t->launches; }
-      transpose_matrix<<<blocks_for((int64_t)H * G4), 256, 0, sd>>>(t->P + pk.off + (size_t)K * G4, q.WhT, H, G4);
-      fill_rows<<<blocks_for(rows * G4), 256, 0, sd>>>(q.pre, t->P + pb.off, rows, G4);
-      t->launches += 2;
-      gemm(false, false, (int)rows, G4, K, q.xin, K, t->P + pk.off, G4, 1.f, q.pre, G4, sd, &t->launches);
+      gemm(false, false, (int)rows, G4, K, q.xin, K, t->P + pk.off, G4, 0.f, q.pre, G4, sd, &t->launches);
       TR_TRY(t, cudaMemsetAsync(q.hbuf, 0, (size_t)np * H * sizeof(float), sd));
       TR_TRY(t, cudaMemsetAsync(q.cbuf, 0, (size_t)np * H * sizeof(float), sd));
-      for (int s = 0; s < T_STEPS; ++s) {
-        lstm_step_forward<<<(unsigned)(np / ROWS), H, 0, sd>>>(q.pre + (size_t)s * np * G4, t->P + pk.off + (size_t)K * G4, q.hbuf + (size_t)s * np * H,
-                                                                q.cbuf + (size_t)s * np * H, q.gates + (size_t)s * np * G4, q.cbuf + (size_t)(s + 1) * np * H,
-                                                                q.hbuf + (size_t)(s + 1) * np * H, (int)np);
-        ++t->launches;
-      }
+      lstm_seq_forward<<<seq_grid(np), 256, SEQ_FWD_SMEM, sd>>>(q.pre, t->P + pk.off + (size_t)K * G4, t->P + pb.off, q.gates, q.cbuf, q.hbuf, (int)np);
+      ++t->launches;
     }
     TR_TRY(t, cudaEventRecord(t->ev_join, t->st2));
     TR_TRY(t, cudaStreamWaitEvent(st, t->ev_join, 0));
@@ -385,7 +377,9 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
     ++t->launches;
   }
   const auto& p3 = tp(t, "L3/Unit_0/kernel");
-  l3_forward<<<dim3(2 * H, blocks_for(np, 128)), 128, 0, st>>>(t->lout[1], t->P + p3.off, t->a3, (int)np);
+  const int l3_sites = (int)((np + 15) / 16 + 15) / 16 * 16;              // ~16 site chunks x 8 channel groups = 128 CTAs
+  const dim3 l3_grid(2 * H / L3_LANES, (unsigned)((np + l3_sites - 1) / l3_sites));
+  l3_forward<<<l3_grid, 256, L3_SMEM, st>>>(t->lout[1], t->P + p3.off, t->a3, (int)np, l3_sites);
   ++t->launches;
   auto alpha_ab = [](float rate, float* a, float* b) {
     const double q = 1.0 - rate, al = (double)ALPHA_DROPOUT;
@@ -477,8 +471,9 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
   column_sums<<<dim3(blocks_for(L4_UNITS, 128), 16), 128, 0, st>>>(t->da4, np, L4_UNITS, t->G + p4b.off);
   ++t->launches;
   gemm(false, true, (int)np, L3_K, L4_UNITS, t->da4, L4_UNITS, t->P + p4k.off, L4_UNITS, 0.f, t->da3, L3_K, st, &t->launches);
-  l3_backward_input<<<dim3(2 * H, blocks_for(np, 128)), 128, 0, st>>>(t->da3, t->a3, t->P + p3.off, t->dlout[1], (int)np);
-  l3_backward_weights<<<2 * H, 1024, 0, st>>>(t->lout[1], t->da3, t->G + p3.off, (int)np);
+  l3_backward_input<<<l3_grid, 256, L3_SMEM, st>>>(t->da3, t->a3, t->P + p3.off, t->dlout[1], (int)np, l3_sites);
+  TR_TRY(t, cudaMemsetAsync(t->G + p3.off, 0, (size_t)2 * H * L3_STRIDE * sizeof(float), st));
+  l3_backward_weights<<<l3_grid, 352, L3_SMEM, st>>>(t->lout[1], t->da3, t->G + p3.off, (int)np, l3_sites);
   t->launches += 2;
   if (t->rates[0] > 0.f) {
     dropout_scale<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->dlout[1], t->mask[0], 1.f / (1.f - t->rates[0]), rows * 2 * H);

@@ -60,8 +60,9 @@ def device_part(batch=512, steps=8, warm=2, device=0, data_parallel=False):
            "tflops_fp32": world * batch * steps * 3 * FLOP_PER_SITE_FORWARD / dt / 1e12,
            "loss_first_step": first, "loss_last_step": last, "grad_norm_last_step": t.grad_norm,
            "gradient_bytes_all_reduced_per_step": t.num_params * 4 if data_parallel else 0,
-           "note": "fp32 CUDA-core kernels (first correct device path of the row): per-step recurrences as small fused kernels, "
-                   "input projections and weight gradients as one tiled SGEMM over all 33 steps"}
+           "note": "fp32 results throughout: the 33 steps of a direction in ONE launch (clusters of 8 CTAs, h exchanged through distributed "
+                   "shared memory), input projections / weight gradients / L4 as 3xTF32 mma.sync GEMMs over all steps, slice-dense "
+                   "kernels with a lane per channel"}
     t.close()
     return out
 
