@@ -66,6 +66,8 @@ SYMBOLS = {
                                                    _c.c_void_p]),
     "clairb_trainer_backward_lstm": (_c.c_int, [_c.c_void_p]),
     "clairb_trainer_apply": (_c.c_int, [_c.c_void_p, _c.c_float, _c.c_float, _c.c_float, _c.c_int64, _c.POINTER(_c.c_double)]),
+    "clairb_trainer_step": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_uint64, _c.c_float,
+                                       _c.c_float, _c.c_float, _c.c_int64, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double)]),
     "clairb_trainer_get_probabilities": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64]),
     "clairb_trainer_kernel_launches": (_c.c_int64, [_c.c_void_p]),
     "clairb_trainer_last_error": (_c.c_char_p, [_c.c_void_p]),

@@ -42,6 +42,7 @@ struct clairb_trainer {
   double* d_loss = nullptr;                                            // [4 focal sums, L2 sum, gradient sum of squares]
   int64_t last_n = 0, last_np = 0;
   bool lstm_pending = false;
+  bool one_sync = false;                                               // inside clairb_trainer_step: the parts do not synchronise
   float rates[6] = {0.5f, 0.5f, 0.2f, 0.2f, 0.2f, 0.2f};
 };
 
@@ -480,10 +481,11 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
     ++t->launches;
   }
   TR_TRY(t, cudaGetLastError());
+  t->lstm_pending = true;
+  if (t->one_sync) return CLAIRB_OK;
   TR_TRY(t, cudaMemcpyAsync(losses, t->d_loss, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TR_TRY(t, cudaStreamSynchronize(st));
   losses[4] *= 0.5;                                          // sum ||v||^2 / 2 (tf.nn.l2_loss)
-  t->lstm_pending = true;
   return CLAIRB_OK;
 }
 
@@ -495,7 +497,7 @@ int clairb_trainer_backward_lstm(clairb_trainer* t) {
   if (int rc = lstm_layer_backward(t, 1, t->last_np)) return rc;
   if (int rc = lstm_layer_backward(t, 0, t->last_np)) return rc;
   TR_TRY(t, cudaGetLastError());
-  TR_TRY(t, cudaStreamSynchronize(t->st));
+  if (!t->one_sync) TR_TRY(t, cudaStreamSynchronize(t->st));
   t->lstm_pending = false;
   return CLAIRB_OK;
 }
@@ -523,6 +525,24 @@ int clairb_trainer_apply(clairb_trainer* t, float learning_rate, float l2_lambda
   TR_TRY(t, cudaMemcpyAsync(&ss, t->d_loss + 5, sizeof(double), cudaMemcpyDeviceToHost, st));
   TR_TRY(t, cudaStreamSynchronize(st));
   if (grad_norm) *grad_norm = std::sqrt(ss);
+  return CLAIRB_OK;
+}
+
+// The whole optimisation step of Clair.train (clair/model.py:913-945) - the three calls above back to back on the device, ONE
+// synchronisation at the end (the single-GPU path; a data-parallel caller needs the two points in between for its all-reduce).
+int clairb_trainer_step(clairb_trainer* t, const void* x_host, int dtype, const float* y_host, int64_t n, const uint8_t* const* masks, uint64_t seed,
+                        float learning_rate, float l2_lambda, float clip_norm, int64_t step, double* losses, double* grad_norm) {
+  if (!t) return CLAIRB_EINVAL;
+  if (!losses) return tfail(t, CLAIRB_EINVAL, "train step: bad n or buffers");
+  t->one_sync = true;
+  int rc = clairb_trainer_forward_backward(t, x_host, dtype, y_host, n, masks, seed, losses);
+  if (!rc) rc = clairb_trainer_backward_lstm(t);
+  t->one_sync = false;
+  if (rc) { t->lstm_pending = false; return rc; }
+  rc = clairb_trainer_apply(t, learning_rate, l2_lambda, clip_norm, step, grad_norm);      // synchronises
+  if (rc) return rc;
+  TR_TRY(t, cudaMemcpy(losses, t->d_loss, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+  losses[4] *= 0.5;                                          // sum ||v||^2 / 2 (tf.nn.l2_loss)
   return CLAIRB_OK;
 }
 

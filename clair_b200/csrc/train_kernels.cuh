@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace clairb {
 namespace train {
@@ -105,6 +106,29 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+// One k = 8 slab of NT products that share the A fragment, with fp32-grade accuracy, added to acc.  The tensor core adds into its
+// accumulator with truncation (round toward zero): accumulating a long contraction inside the MMA biases every sum the same way,
+// and the 33-step recurrence compounds it - 16 % on one LSTM weight gradient of the Adam parity test.  So each slab is accumulated
+// from zero (correction terms first, three MMAs per tile, term-major so that NT independent MMAs lie between two dependent ones)
+// and joins the running sum through a rounded FADD.
+template <int NT>
+__device__ __forceinline__ void mma_3xtf32(float (&acc)[NT][4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&bh)[NT][2],
+                                           const uint32_t (&bl)[NT][2]) {
+  float v[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(v[j][0]), "=f"(v[j][1]), "=f"(v[j][2]), "=f"(v[j][3])
+                 : "r"(al[0]), "r"(al[1]), "r"(al[2]), "r"(al[3]), "r"(bh[j][0]), "r"(bh[j][1]), "f"(0.f));
+#pragma unroll
+  for (int j = 0; j < NT; ++j) mma_tf32(v[j], ah, bl[j]);
+#pragma unroll
+  for (int j = 0; j < NT; ++j) mma_tf32(v[j], ah, bh[j]);
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[j][q] += v[j][q];
+}
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256, 2) sgemm_big(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                     float beta, float* __restrict__ C, int ldc, int k_per_slice) {
@@ -162,12 +186,7 @@ __global__ void __launch_bounds__(256, 2) sgemm_big(int M, int N, int K, const f
         split_tf32(A_K ? as[(kk + tig) * LD_K + mb + 8] : as[(mb + 8) * LD_R + kk + tig], ah[1], al[1]);
         split_tf32(A_K ? as[(kk + tig + 4) * LD_K + mb] : as[mb * LD_R + kk + tig + 4], ah[2], al[2]);
         split_tf32(A_K ? as[(kk + tig + 4) * LD_K + mb + 8] : as[(mb + 8) * LD_R + kk + tig + 4], ah[3], al[3]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], al, bh[j]);      // the small terms first; term-major so that four
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], ah, bl[j]);      // independent MMAs lie between two on one accumulator
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], ah, bh[j]);
+        mma_3xtf32<4>(acc[i], ah, al, bh, bl);
       }
     }
     if (more) stage(buf ^ 1);
@@ -325,121 +344,175 @@ __global__ void reverse_time(const float* __restrict__ in, float* __restrict__ o
   if (accumulate) out[o] += in[i]; else out[o] = in[i];
 }
 
-// ---- the 33 steps of one LSTM direction, forward: z_s = pre[s] + h_{s-1} . W_h ; gates ; c_s, h_s ------------------------------
+// ---- the 33 steps of one LSTM direction, forward: z_s = x_s W_x (pre) + b + h_{s-1} . W_h ; gates ; c_s, h_s ---------------------
 // (LSTMBlockCell, forget_bias 0; clair/model.py:299-305).  One thread-block CLUSTER of 8 CTAs carries 64 sites through all 33
-// steps: CTA j owns hidden units 16j..16j+15, keeps their 64 gate columns of W_h (32 KB) and the whole h_{s-1} of the 64 sites
-// (transposed, [unit][site]) in shared memory, computes the [64 x 64] gate tile on the FP32 pipe, and writes its 16 new h columns
-// into the NEXT-step buffer of all 8 CTAs through distributed shared memory; one cluster barrier per step.  Thread (ty, tx) owns
-// sites 4 ty..4 ty+3 of unit tx, i.e. the 4 x 4 accumulators (site, gate): the local gate columns are ordered unit-major.
+// steps.  CTA j owns hidden units 16j..16j+15: it keeps their 64 gate columns of W_h and the whole h_{s-1} of the 64 sites
+// ([unit][site], row stride 72) in shared memory and computes the [64 x 128] . [128 x 64] gate tile as 3xTF32 mma.sync (see
+// sgemm_big).  Its 16 new h columns are one contiguous 4.6 KB run of the next step's buffer: one thread sends that run to the same
+// place in the 7 other CTAs with cp.async.bulk over distributed shared memory, each copy completing bytes on the RECEIVER's
+// mbarrier - the receivers wait on their own barrier, there is no cluster-wide barrier in the loop.  (The first version pushed h
+// with st.shared::cluster and ran cluster.sync every step: 1.0 + 0.8 us of a 7.8 us step, the FFMA contraction another 4.3.)
+// Why one buffer pair is enough: a CTA sends h_s only after its own step-s contraction, i.e. after it has every piece of h_{s-1};
+// so when h_s has arrived from everybody, everybody is done reading h_{s-1}'s buffer and has received what was sent from it.
+// Warp (mp, ug) owns sites 32mp..+31 x units 4ug..+3: 2 x 2 MMA tiles whose 8 columns are ordered (unit, gate pair), so that lane
+// (g, tig) ends up with all four gates of unit 4ug+tig for sites g, g+8, g+16, g+24 of its half.
 constexpr int SEQ_ROWS = 64, SEQ_CTAS = 8, SEQ_UNITS = H / SEQ_CTAS;      // 64 sites per cluster, 16 units per CTA
-constexpr int SEQ_FWD_SMEM = (H * 4 * SEQ_UNITS + 2 * H * SEQ_ROWS) * (int)sizeof(float);                                    // 96 KB
-constexpr int SEQ_BWD_SMEM = (4 * SEQ_UNITS * H + 4 * SEQ_UNITS * SEQ_ROWS + 2 * SEQ_CTAS * SEQ_UNITS * SEQ_ROWS) * (int)sizeof(float);   // 112 KB
+constexpr int SEQ_LD = SEQ_ROWS + 8;                                      // 72 = 8 (mod 32): conflict-free fragment loads
+constexpr int SEQ_SLICE_BYTES = SEQ_UNITS * SEQ_LD * (int)sizeof(float);  // 4608: the h columns (or dh partial sums) of one CTA
+constexpr int SEQ_FWD_SMEM = (H * SEQ_LD + 2 * H * SEQ_LD) * (int)sizeof(float) + 16;                                         // 110,608 B
+constexpr int SEQ_BWD_LDW = H + 8;                                        // 136
+constexpr int SEQ_BWD_SMEM = (4 * SEQ_UNITS * SEQ_BWD_LDW + 4 * SEQ_UNITS * SEQ_LD + 2 * H * SEQ_LD + 2 * SEQ_CTAS * SEQ_UNITS * SEQ_LD) * (int)sizeof(float) + 16;   // 200,720 B
+
+// local shared memory -> the same offset in CTA `rank` of the cluster, completing `bytes` on that CTA's mbarrier
+__device__ __forceinline__ void bulk_to_cta(const void* src, void* dst_same_offset, uint64_t* bar_same_offset, uint32_t rank, uint32_t bytes) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   tc::map_to_cta(tc::smem_u32(dst_same_offset), rank)),
+               "r"(tc::smem_u32(src)), "r"(bytes), "r"(tc::map_to_cta(tc::smem_u32(bar_same_offset), rank))
+               : "memory");
+}
 
 __global__ void __cluster_dims__(SEQ_CTAS, 1, 1) __launch_bounds__(256)
 lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, const float* __restrict__ bias, float* __restrict__ gates,
                  float* __restrict__ cbuf, float* __restrict__ hbuf, int n) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) float seq_smem[];
-  float* Ws = seq_smem;                                  // [128 k][64 local columns = unit * 4 + gate]
-  float* hT = seq_smem + H * 4 * SEQ_UNITS;              // [2][128 unit][64 site]
-  const int j = (int)cluster.block_rank();
+  float* Ws = seq_smem;                                  // [128 units of h_{s-1}][72: 64 local gate columns]
+  float* hT = Ws + H * SEQ_LD;                           // [2][128 units][72: 64 sites]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hT + 2 * H * SEQ_LD);      // [2]: "h of this buffer has arrived from the 7 other CTAs"
+  const int j = (int)tc::cluster_ctarank();
   const int r0 = (int)(blockIdx.x / SEQ_CTAS) * SEQ_ROWS;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int unit = j * SEQ_UNITS + tx;
-  const int row = r0 + 4 * ty;
-  const bool live = row < n;                             // n is a multiple of 8: a group of 4 sites is in or out as a whole
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+  const int mp = warp >> 2, ug = warp & 3;
+  const int unit = j * SEQ_UNITS + 4 * ug + tig;         // this lane's hidden unit
+  // local gate column lc = 16 ug' + 8 nt + nin  <->  unit 4 ug' + (nin >> 1), gate 2 nt + (nin & 1)
   for (int i = threadIdx.x; i < H * 4 * SEQ_UNITS; i += 256) {
     const int k = i >> 6, lc = i & 63;
-    Ws[i] = Wh[(size_t)k * G4 + (lc & 3) * H + j * SEQ_UNITS + (lc >> 2)];
+    const int u = 4 * (lc >> 4) + ((lc & 7) >> 1), gate = 2 * ((lc >> 3) & 1) + (lc & 1);
+    Ws[k * SEQ_LD + lc] = Wh[(size_t)k * G4 + gate * H + j * SEQ_UNITS + u];
   }
-  for (int i = threadIdx.x; i < H * SEQ_ROWS; i += 256) hT[i] = 0.f;      // h_0 = 0
-  float* remote[SEQ_CTAS];
-#pragma unroll
-  for (int d = 0; d < SEQ_CTAS; ++d) remote[d] = cluster.map_shared_rank(hT, d);
-  float c[4] = {0.f, 0.f, 0.f, 0.f};
-  const float2 b01 = make_float2(bias[unit], bias[H + unit]), b23 = make_float2(bias[2 * H + unit], bias[3 * H + unit]);
-  float2 z[4][2];                                        // site i: (i, g) and (f, o) pre-activations = x_s W_x (pre) + b + h_{s-1} W_h
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float* q = pre + (size_t)(row + i) * G4 + unit;
-    z[i][0] = live ? make_float2(q[0] + b01.x, q[H] + b01.y) : make_float2(0.f, 0.f);
-    z[i][1] = live ? make_float2(q[2 * H] + b23.x, q[3 * H] + b23.y) : make_float2(0.f, 0.f);
+  for (int i = threadIdx.x; i < H * SEQ_LD; i += 256) hT[i] = 0.f;        // h_0 = 0
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_barrier_init();
   }
-  cluster.sync();                                        // every CTA of the cluster runs and has its buffers initialised
+  float bz[2][2];                                        // bias of (gate 2 nt + e) of this lane's unit
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) bz[nt][e] = bias[(2 * nt + e) * H + unit];
+  // accumulators acc[mi][nt][2 half + e]: site 32 mp + 16 mi + 8 half + g, gate 2 nt + e; they start as pre + bias
+  float acc[2][2][4], c[2][2] = {};
+  auto fetch = [&](int s, float (&z)[2][2][4]) {
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = r0 + 32 * mp + 16 * mi + 8 * half + g;
+        const float* q = pre + ((size_t)s * n + row) * G4 + unit;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) z[mi][nt][2 * half + e] = row < n ? q[(2 * nt + e) * H] + bz[nt][e] : 0.f;
+      }
+  };
+  fetch(0, acc);
+  tc::cluster_sync_all();                                // every CTA of the cluster runs and has its barriers initialised
   for (int s = 0; s < T_STEPS; ++s) {
-    const float* hc = hT + (s & 1) * H * SEQ_ROWS;
-    float2 zn[4][2];                                     // the next step's input projection, requested before the contraction
+    const float* hc = hT + (s & 1) * H * SEQ_LD;
+    float* hn = hT + ((s + 1) & 1) * H * SEQ_LD;
+    float nxt[2][2][4];                                  // the next step's input projection, requested before the contraction
+    if (s + 1 < T_STEPS) fetch(s + 1, nxt);
+    if (s > 0) tc::mbar_wait(&bars[s & 1], ((s - 1) >> 1) & 1);
+#pragma unroll 4
+    for (int kk = 0; kk < H; kk += 8) {
+      uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        split_tf32(Ws[(kk + tig) * SEQ_LD + 16 * ug + 8 * nt + g], bh[nt][0], bl[nt][0]);
+        split_tf32(Ws[(kk + tig + 4) * SEQ_LD + 16 * ug + 8 * nt + g], bh[nt][1], bl[nt][1]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int mb = 32 * mp + 16 * mi + g;
+        uint32_t ah[4], al[4];
+        split_tf32(hc[(kk + tig) * SEQ_LD + mb], ah[0], al[0]);
+        split_tf32(hc[(kk + tig) * SEQ_LD + mb + 8], ah[1], al[1]);
+        split_tf32(hc[(kk + tig + 4) * SEQ_LD + mb], ah[2], al[2]);
+        split_tf32(hc[(kk + tig + 4) * SEQ_LD + mb + 8], ah[3], al[3]);
+        mma_3xtf32<2>(acc[mi], ah, al, bh, bl);
+      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int rl = 32 * mp + 16 * mi + 8 * half + g;
+        const float ig = sigmoidf_(acc[mi][0][2 * half]), gg = tanhf(acc[mi][0][2 * half + 1]);
+        const float fg = sigmoidf_(acc[mi][1][2 * half]), og = sigmoidf_(acc[mi][1][2 * half + 1]);
+        const float cv = gg * ig + c[mi][half] * fg;
+        const float hv = tanhf(cv) * og;
+        c[mi][half] = cv;
+        hn[unit * SEQ_LD + rl] = hv;
+        if (r0 + rl < n) {
+          const size_t r = (size_t)s * n + r0 + rl;
+          gates[r * G4 + unit] = ig; gates[r * G4 + H + unit] = gg; gates[r * G4 + 2 * H + unit] = fg; gates[r * G4 + 3 * H + unit] = og;
+          cbuf[(r + n) * H + unit] = cv;
+          hbuf[(r + n) * H + unit] = hv;
+        }
+      }
     if (s + 1 < T_STEPS) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float* q = pre + ((size_t)(s + 1) * n + row + i) * G4 + unit;
-        zn[i][0] = live ? make_float2(q[0] + b01.x, q[H] + b01.y) : make_float2(0.f, 0.f);
-        zn[i][1] = live ? make_float2(q[2 * H] + b23.x, q[3 * H] + b23.y) : make_float2(0.f, 0.f);
+      tc::fence_proxy_async();                           // the h columns just written are read by the bulk copies
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tc::mbar_expect_tx(&bars[(s + 1) & 1], (SEQ_CTAS - 1) * SEQ_SLICE_BYTES);
+        float* mine = hn + j * SEQ_UNITS * SEQ_LD;
+#pragma unroll 1
+        for (int d = 1; d < SEQ_CTAS; ++d) bulk_to_cta(mine, mine, &bars[(s + 1) & 1], (uint32_t)((j + d) & (SEQ_CTAS - 1)), SEQ_SLICE_BYTES);
       }
-    }
-#pragma unroll 8
-    for (int k = 0; k < H; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(hc + k * SEQ_ROWS + 4 * ty);
-      const float4 b = *reinterpret_cast<const float4*>(Ws + k * 4 * SEQ_UNITS + 4 * tx);
-      const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        z[i][0] = fma2(av[i], make_float2(b.x, b.y), z[i][0]);
-        z[i][1] = fma2(av[i], make_float2(b.z, b.w), z[i][1]);
-      }
-    }
-    float hv[4];
+      for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float ig = sigmoidf_(z[i][0].x), gg = tanhf(z[i][0].y), fg = sigmoidf_(z[i][1].x), og = sigmoidf_(z[i][1].y);
-      c[i] = gg * ig + c[i] * fg;
-      hv[i] = tanhf(c[i]) * og;
-      if (live) {
-        const size_t r = (size_t)s * n + row + i;
-        gates[r * G4 + unit] = ig; gates[r * G4 + H + unit] = gg; gates[r * G4 + 2 * H + unit] = fg; gates[r * G4 + 3 * H + unit] = og;
-        cbuf[(r + n) * H + unit] = c[i];
-        hbuf[(r + n) * H + unit] = hv[i];
-      }
-    }
-    const int off = ((s + 1) & 1) * H * SEQ_ROWS + unit * SEQ_ROWS + 4 * ty;
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-    for (int d = 0; d < SEQ_CTAS; ++d) *reinterpret_cast<float4*>(remote[d] + off) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-    if (s + 1 < T_STEPS) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { z[i][0] = zn[i][0]; z[i][1] = zn[i][1]; }
+          for (int q = 0; q < 4; ++q) acc[mi][nt][q] = nxt[mi][nt][q];
     }
-    cluster.sync();                                      // h_s is complete in every CTA; nobody still reads h_{s-1}'s other buffer
   }
+  tc::cluster_sync_all();                                // nobody leaves while a copy from or into its shared memory may be in flight
 }
 
 // ---- the 33 steps of one LSTM direction, backward: dh = dh_out[s] + dh_rec ; gate gradients dZ[s] ; dc_{s-1} ; dh_rec <- dZ[s] . W_h^T
-// Same cluster shape.  CTA j produces the 64 gate-gradient columns of its 16 units, multiplies them by its 64 rows of W_h^T
-// ([64 x 64] . [64 x 128], a partial sum of dh_rec for ALL 128 units), and scatters the partial columns to the CTA that owns each
-// unit (slot j of that CTA, double-buffered); after the barrier every CTA adds its 8 slots in a fixed order.
+// Same cluster shape and the same exchange.  CTA j produces the 64 gate-gradient columns of its 16 units (thread (ty, tx): sites
+// 4ty..+3 of unit tx), multiplies them by its 64 rows of W_h^T - [64 x 64] . [64 x 128] on the tensor cores, a partial sum of
+// dh_rec for ALL 128 units - and sends the 16 columns each other CTA owns into slot j of that CTA; when its own 7 slots have
+// arrived it adds the 8 partial sums in a fixed order.  The partial sums are double-buffered at the sender: a slot copy of step s
+// is known to be complete only when the receiver's answer of step s - 1 has arrived.  Also accumulates the bias gradient.
 __global__ void __cluster_dims__(SEQ_CTAS, 1, 1) __launch_bounds__(256)
 lstm_seq_backward(const float* __restrict__ dh_out, const float* __restrict__ gates, const float* __restrict__ cbuf, const float* __restrict__ Wh,
                   float* __restrict__ dZ, float* __restrict__ dbias, int n) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) float seq_smem[];
-  float* Wt = seq_smem;                                  // [64 local gate columns][128 units of h_{s-1}]
-  float* dzT = Wt + 4 * SEQ_UNITS * H;                   // [64 local gate columns][64 sites]
-  float* slots = dzT + 4 * SEQ_UNITS * SEQ_ROWS;         // [2][8 source CTAs][16 units][64 sites]
-  constexpr int SLOT = SEQ_UNITS * SEQ_ROWS;
-  const int j = (int)cluster.block_rank();
+  float* Wt = seq_smem;                                  // [64 local gate columns][136: 128 units of h_{s-1}]
+  float* dzs = Wt + 4 * SEQ_UNITS * SEQ_BWD_LDW;         // [64 local gate columns][72: 64 sites]
+  float* part = dzs + 4 * SEQ_UNITS * SEQ_LD;            // [2][128 units][72: 64 sites]   this CTA's partial sums of dh_rec
+  float* slots = part + 2 * H * SEQ_LD;                  // [2][8 source CTAs][16 units][72]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slots + 2 * SEQ_CTAS * SEQ_UNITS * SEQ_LD);
+  constexpr int SLOT = SEQ_UNITS * SEQ_LD;
+  const int j = (int)tc::cluster_ctarank();
   const int r0 = (int)(blockIdx.x / SEQ_CTAS) * SEQ_ROWS;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+  const int mp = warp >> 2, nq = warp & 3;               // MMA role: sites 32 mp..+31  x  units 32 nq..+31 of the partial sums
   const int unit = j * SEQ_UNITS + tx;
   const int row = r0 + 4 * ty;
   const bool live = row < n;
   for (int i = threadIdx.x; i < 4 * SEQ_UNITS * H; i += 256) {
-    const int lc = i >> 7, k = i & 127;
-    Wt[i] = Wh[(size_t)k * G4 + (lc & 3) * H + j * SEQ_UNITS + (lc >> 2)];
+    const int lc = i >> 7, k = i & 127;                  // local gate column lc = 4 unit + gate
+    Wt[lc * SEQ_BWD_LDW + k] = Wh[(size_t)k * G4 + (lc & 3) * H + j * SEQ_UNITS + (lc >> 2)];
   }
-  float* remote[2];                                      // the two CTAs that own the units of this thread's partial columns
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) remote[hh] = cluster.map_shared_rank(slots, hh * 4 + (tx >> 2));
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_barrier_init();
+  }
   float dc[4] = {0.f, 0.f, 0.f, 0.f}, dh_rec[4] = {0.f, 0.f, 0.f, 0.f};
   float db[4] = {0.f, 0.f, 0.f, 0.f};                   // bias gradient of this unit's four gates over the thread's sites and all steps
   float gi[4][4], cs[4], cp[4], dho[4];
@@ -448,78 +521,102 @@ lstm_seq_backward(const float* __restrict__ dh_out, const float* __restrict__ ga
     for (int i = 0; i < 4; ++i) {
       const size_t r = (size_t)s * n + row + i;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) gi[i][g] = live ? gates[r * G4 + g * H + unit] : 0.f;
+      for (int q = 0; q < 4; ++q) gi[i][q] = live ? gates[r * G4 + q * H + unit] : 0.f;
       cs[i] = live ? cbuf[(r + n) * H + unit] : 0.f;
       cp[i] = live ? cbuf[r * H + unit] : 0.f;
       dho[i] = live ? dh_out[r * H + unit] : 0.f;
     }
   };
   fetch(T_STEPS - 1);
-  cluster.sync();
+  tc::cluster_sync_all();
   for (int s = T_STEPS - 1; s >= 0; --s) {
     const int p = s & 1;
     float dz[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float ig = gi[i][0], gg = gi[i][1], fg = gi[i][2], og = gi[i][3];
-      const float tc = tanhf(cs[i]);
+      const float tch = tanhf(cs[i]);
       const float dh = dho[i] + dh_rec[i];
-      const float dcs = dc[i] + dh * og * (1.f - tc * tc);
+      const float dcs = dc[i] + dh * og * (1.f - tch * tch);
       dz[i][0] = dcs * gg * ig * (1.f - ig);
       dz[i][1] = dcs * ig * (1.f - gg * gg);
       dz[i][2] = dcs * cp[i] * fg * (1.f - fg);
-      dz[i][3] = dh * tc * og * (1.f - og);
+      dz[i][3] = dh * tch * og * (1.f - og);
       dc[i] = dcs * fg;
       if (live) {
         const size_t r = (size_t)s * n + row + i;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) { dZ[r * G4 + g * H + unit] = dz[i][g]; db[g] += dz[i][g]; }
+        for (int q = 0; q < 4; ++q) { dZ[r * G4 + q * H + unit] = dz[i][q]; db[q] += dz[i][q]; }
       }
     }
+    if (s == 0) break;                                   // dh_rec of step -1 is not needed
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      *reinterpret_cast<float4*>(dzT + (4 * tx + g) * SEQ_ROWS + 4 * ty) = make_float4(dz[0][g], dz[1][g], dz[2][g], dz[3][g]);
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(dzs + (4 * tx + q) * SEQ_LD + 4 * ty) = make_float4(dz[0][q], dz[1][q], dz[2][q], dz[3][q]);
     __syncthreads();
-    if (s > 0) fetch(s - 1);                             // independent of the recurrence: in flight during the contraction
-    float2 acc[4][4] = {};                               // sites 4 ty..+3  x  units 4 tx..+3 and 64 + 4 tx..+3
-#pragma unroll 8
-    for (int k = 0; k < 4 * SEQ_UNITS; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(dzT + k * SEQ_ROWS + 4 * ty);
-      const float4 b0 = *reinterpret_cast<const float4*>(Wt + k * H + 4 * tx);
-      const float4 b1 = *reinterpret_cast<const float4*>(Wt + k * H + 64 + 4 * tx);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+    fetch(s - 1);                                        // independent of the recurrence: in flight during the contraction
+    float acc[2][4][4] = {};                             // [mi][nt][2 half + e]: site 32 mp + 16 mi + 8 half + g, unit 32 nq + 8 nt + 2 tig + e
+#pragma unroll 2
+    for (int kk = 0; kk < 4 * SEQ_UNITS; kk += 8) {
+      uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int nt = 0; nt < 4; ++nt) {
+        split_tf32(Wt[(kk + tig) * SEQ_BWD_LDW + 32 * nq + 8 * nt + g], bh[nt][0], bl[nt][0]);
+        split_tf32(Wt[(kk + tig + 4) * SEQ_BWD_LDW + 32 * nq + 8 * nt + g], bh[nt][1], bl[nt][1]);
+      }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[i][q] = fma2(av[i], bv[q], acc[i][q]);
+      for (int mi = 0; mi < 2; ++mi) {
+        const int mb = 32 * mp + 16 * mi + g;
+        uint32_t ah[4], al[4];
+        split_tf32(dzs[(kk + tig) * SEQ_LD + mb], ah[0], al[0]);
+        split_tf32(dzs[(kk + tig) * SEQ_LD + mb + 8], ah[1], al[1]);
+        split_tf32(dzs[(kk + tig + 4) * SEQ_LD + mb], ah[2], al[2]);
+        split_tf32(dzs[(kk + tig + 4) * SEQ_LD + mb + 8], ah[3], al[3]);
+        mma_3xtf32<4>(acc[mi], ah, al, bh, bl);
+      }
     }
+    float* pp = part + p * H * SEQ_LD;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh)
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4*>(remote[hh] + (p * SEQ_CTAS + j) * SLOT + ((tx & 3) * 4 + q) * SEQ_ROWS + 4 * ty) =
-            (q & 1) ? make_float4(acc[0][hh * 2 + (q >> 1)].y, acc[1][hh * 2 + (q >> 1)].y, acc[2][hh * 2 + (q >> 1)].y, acc[3][hh * 2 + (q >> 1)].y)
-                    : make_float4(acc[0][hh * 2 + (q >> 1)].x, acc[1][hh * 2 + (q >> 1)].x, acc[2][hh * 2 + (q >> 1)].x, acc[3][hh * 2 + (q >> 1)].x);
-    cluster.sync();                                      // all partial sums of this step have landed; dzT may be overwritten
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pp[(32 * nq + 8 * nt + 2 * tig + (q & 1)) * SEQ_LD + 32 * mp + 16 * mi + 8 * (q >> 1) + g] = acc[mi][nt][q];
+    tc::fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc::mbar_expect_tx(&bars[p], (SEQ_CTAS - 1) * SEQ_SLICE_BYTES);
+      float* slot = slots + (p * SEQ_CTAS + j) * SLOT;   // slot j of the receiver
+#pragma unroll 1
+      for (int d = 1; d < SEQ_CTAS; ++d) {
+        const int to = (j + d) & (SEQ_CTAS - 1);
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         tc::map_to_cta(tc::smem_u32(slot), (uint32_t)to)),
+                     "r"(tc::smem_u32(pp + to * SLOT)), "r"((uint32_t)SEQ_SLICE_BYTES), "r"(tc::map_to_cta(tc::smem_u32(&bars[p]), (uint32_t)to))
+                     : "memory");
+      }
+    }
+    tc::mbar_wait(&bars[p], ((T_STEPS - 1 - s) >> 1) & 1);
     float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int src = 0; src < SEQ_CTAS; ++src) {
-      const float4 v = *reinterpret_cast<const float4*>(slots + (p * SEQ_CTAS + src) * SLOT + tx * SEQ_ROWS + 4 * ty);
+      const float* from = src == j ? pp + j * SLOT : slots + (p * SEQ_CTAS + src) * SLOT;
+      const float4 v = *reinterpret_cast<const float4*>(from + tx * SEQ_LD + 4 * ty);
       sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) dh_rec[i] = sum[i];
   }
-  cluster.sync();                                        // no CTA leaves while its slots may still be written
+  tc::cluster_sync_all();                                // nobody leaves while a copy from or into its shared memory may be in flight
   // bias gradient: the 16 site groups of the CTA are added up through shared memory, then one atomic per (gate, unit) and cluster
+  __syncthreads();
 #pragma unroll
-  for (int g = 0; g < 4; ++g) dzT[(4 * tx + g) * SEQ_ROWS + ty] = db[g];
+  for (int q = 0; q < 4; ++q) dzs[(4 * tx + q) * SEQ_LD + ty] = db[q];
   __syncthreads();
   if (threadIdx.x < 4 * SEQ_UNITS) {
     float sum = 0.f;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) sum += dzT[threadIdx.x * SEQ_ROWS + q];
+    for (int q = 0; q < 16; ++q) sum += dzs[threadIdx.x * SEQ_LD + q];
     atomicAdd(dbias + (threadIdx.x & 3) * H + j * SEQ_UNITS + (threadIdx.x >> 2), sum);
   }
 }

@@ -78,9 +78,7 @@ class Trainer(object):
         self.dropout_rates = tuple(float(x) for x in rates)
 
     # ---- one step, in its three parts ------------------------------------------------------------------------------------
-    def forward_backward(self, batchX, batchY, masks=None):
-        """Forward, loss and the backward pass through the dense layers -> [gt21, genotype, length 1, length 2] focal-loss sums
-        and the L2 sum without lambda.  masks: {name in DROPOUTS: uint8 keep-mask} (parity tests) or None (drawn on the device)."""
+    def _inputs(self, batchX, batchY, masks):
         X = np.asarray(batchX)
         if X.ndim == 2:
             X = X.reshape(-1, 33, 8, 4)
@@ -95,7 +93,7 @@ class Trainer(object):
         if Y.shape != (n, _lib.N_OUT):
             raise ValueError("batchY must be [n,90]")
         ptrs = None
-        keep = []
+        keep = [X, Y]
         if masks is not None:
             shapes = {"lstm2": (33, n, 256), "l4": (n, 192), "l5_1": (n, 96), "l5_2": (n, 96), "l5_3": (n, 96), "l5_4": (n, 96)}
             arr = (ctypes.c_void_p * 6)()
@@ -106,13 +104,18 @@ class Trainer(object):
                 keep.append(m)
                 arr[i] = m.ctypes.data
             ptrs = arr
-        losses = (ctypes.c_double * 5)()
         self.step += 1
-        rc = self._lib.clairb_trainer_forward_backward(self._t, X.ctypes.data_as(ctypes.c_void_p), dtype, Y.ctypes.data_as(ctypes.c_void_p), n,
-                                                       ptrs, ctypes.c_uint64((self.seed * 1000003 + self.step) & (2 ** 64 - 1)), losses)
-        self._check(rc, "clairb_trainer_forward_backward")
-        self.loss_parts = [float(v) for v in losses]
         self._n = n
+        seed = ctypes.c_uint64((self.seed * 1000003 + self.step) & (2 ** 64 - 1))
+        return X.ctypes.data_as(ctypes.c_void_p), dtype, Y.ctypes.data_as(ctypes.c_void_p), n, ptrs, seed, keep
+
+    def forward_backward(self, batchX, batchY, masks=None):
+        """Forward, loss and the backward pass through the dense layers -> [gt21, genotype, length 1, length 2] focal-loss sums
+        and the L2 sum without lambda.  masks: {name in DROPOUTS: uint8 keep-mask} (parity tests) or None (drawn on the device)."""
+        x, dtype, y, n, ptrs, seed, keep = self._inputs(batchX, batchY, masks)
+        losses = (ctypes.c_double * 5)()
+        self._check(self._lib.clairb_trainer_forward_backward(self._t, x, dtype, y, n, ptrs, seed, losses), "clairb_trainer_forward_backward")
+        self.loss_parts = [float(v) for v in losses]
         return self.loss_parts
 
     def backward_lstm(self):
@@ -132,10 +135,15 @@ class Trainer(object):
         return p[0] + p[1] + p[2] + p[3] + self.l2_regularization_lambda_value * p[4]
 
     def train(self, batchX, batchY, masks=None):
-        """Reference clair/model.py:913-945: one optimisation step -> the training loss of the batch."""
-        self.forward_backward(batchX, batchY, masks)
-        self.backward_lstm()
-        self.grad_norm = self.apply()
+        """Reference clair/model.py:913-945: one optimisation step -> the training loss of the batch.  One library call
+        (clairb_trainer_step: forward_backward, backward_lstm and apply with a single synchronisation)."""
+        x, dtype, y, n, ptrs, seed, keep = self._inputs(batchX, batchY, masks)
+        losses, norm = (ctypes.c_double * 5)(), ctypes.c_double()
+        rc = self._lib.clairb_trainer_step(self._t, x, dtype, y, n, ptrs, seed, self.learning_rate_value, self.l2_regularization_lambda_value,
+                                           CLIP_NORM, self.step, losses, ctypes.byref(norm))
+        self._check(rc, "clairb_trainer_step")
+        self.loss_parts = [float(v) for v in losses]
+        self.grad_norm = norm.value
         self.training_loss_on_one_batch = self.total_loss()
         return self.training_loss_on_one_batch
 

@@ -310,6 +310,7 @@ int clairb_destroy(clairb_engine* e);
  *                                     sums and sum ||kernel||^2 / 2
  *   clairb_trainer_backward_lstm    : BPTT through LSTM2 and LSTM1 (offsets < dense_offset)
  *   clairb_trainer_apply            : g += lambda * w on kernels, clip by global norm, Adam step `step` (1-based)
+ *   clairb_trainer_step             : the three above back to back, one synchronisation (single GPU)
  * masks: NULL (drawn on the device from `seed`, one stream per dropout) or six uint8 keep-masks [33][n][256], [n][192],
  * 4 x [n][96] (parity tests: TensorFlow's random stream cannot be reproduced, both sides are handed the same masks).
  * clairb_trainer_get: which = 0 weights, 1 gradients of the last step, 2 / 3 Adam moments, by TF variable name. */
@@ -326,6 +327,11 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
 int clairb_trainer_backward_lstm(clairb_trainer* t);
 int clairb_trainer_apply(clairb_trainer* t, float learning_rate, float l2_lambda, float clip_norm, int64_t step,
                          double* grad_norm);
+/* The three calls above as ONE call with one device synchronisation: what Clair.train(batchX, batchY) does per batch
+ * (clair/model.py:913-945) on one GPU.  losses[5] and grad_norm as above. */
+int clairb_trainer_step(clairb_trainer* t, const void* x_host, int dtype, const float* y_host, int64_t n,
+                        const uint8_t* const* masks, uint64_t seed, float learning_rate, float l2_lambda, float clip_norm,
+                        int64_t step, double* losses, double* grad_norm);
 int clairb_trainer_get_probabilities(clairb_trainer* t, float* out, int64_t n);
 int64_t clairb_trainer_kernel_launches(const clairb_trainer* t);
 const char* clairb_trainer_last_error(const clairb_trainer* t);
