@@ -322,9 +322,22 @@ constexpr int F_SUBTRACT = 2;       // write channels 1..3 minus channel 0 (clai
 // SITES_PER_BLOCK sites per block, each with its own 4.2 KB of counters; only warp-level synchronisation.
 constexpr int SITES_PER_BLOCK = THREADS / 32;
 
+// Every op must carry a known code and stay inside `seq` (create_tensors reads it unguarded).  bad[0] / bad[1] receive the index of
+// an op with an unknown code / an op that reads past the end of SEQ (-1: none); create_tensors does nothing when either is set.
+// 10^7 ops per region: on the host this check was 8 of the call's 21 ms, here it is one pass over 8 bytes per op.
+__global__ void validate_ops(const int32_t* __restrict__ op_qry, const int32_t* __restrict__ op_len, int n_ops, int64_t seq_len,
+                             int* __restrict__ bad) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_ops; k += gridDim.x * blockDim.x) {
+    const int len = op_len[k] >> 2, code = op_len[k] & 3;
+    if (code != OP_D && code != OP_M && code != OP_I) atomicMax(&bad[0], k);
+    else if (len < 0 || (code != OP_D && (op_qry[k] < 0 || (int64_t)op_qry[k] + len > seq_len))) atomicMax(&bad[1], k);
+  }
+}
+
 __global__ void __launch_bounds__(THREADS) create_tensors(Alignments a, const int32_t* __restrict__ centers, int n_centers,
                                                           int flags, int16_t* __restrict__ x_out, int32_t* __restrict__ meta,
-                                                          int* __restrict__ overflow) {
+                                                          int* __restrict__ overflow, const int* __restrict__ bad) {
+  if (bad[0] >= 0 || bad[1] >= 0) return;                // validate_ops (same stream, just before) found a malformed op
   __shared__ int cnt_all[SITES_PER_BLOCK][ELEMS];
   __shared__ uint8_t win_all[SITES_PER_BLOCK][N_POS + 3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

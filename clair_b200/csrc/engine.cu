@@ -1163,23 +1163,6 @@ int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const in
   }
   for (int64_t i = 1; i < n_centers; ++i)
     if (centers[i] <= centers[i - 1]) return fail(e, CLAIRB_EINVAL, "create_tensors: candidate positions must be strictly ascending");
-  {
-    // every op must stay inside `seq` (the kernel reads it unguarded); 10^7 ops per region, so on the host threads
-    static const int threads = getenv("CLAIRB_DECODE_THREADS") ? atoi(getenv("CLAIRB_DECODE_THREADS")) : 4;
-    constexpr int64_t CHUNK = 1 << 16;
-    std::atomic<int64_t> bad_code(-1), bad_seq(-1);
-    sam::parallel_for((O + CHUNK - 1) / CHUNK, threads, [&](int64_t c) {
-      const int64_t hi = (c + 1) * CHUNK < O ? (c + 1) * CHUNK : O;
-      for (int64_t k = c * CHUNK; k < hi; ++k) {
-        const int len = a->op_len[k] >> 2, code = a->op_len[k] & 3;
-        if (code != ct::OP_D && code != ct::OP_M && code != ct::OP_I) bad_code.store(k);
-        else if (len < 0 || (code != ct::OP_D && (a->op_qry[k] < 0 || (int64_t)a->op_qry[k] + len > a->seq_len))) bad_seq.store(k);
-      }
-    });
-    if (bad_code.load() >= 0) return fail(e, CLAIRB_EINVAL, "create_tensors: op %lld has an unknown code", (long long)bad_code.load());
-    if (bad_seq.load() >= 0)
-      return fail(e, CLAIRB_EINVAL, "create_tensors: op %lld reads past the end of its SEQ (the reference raises IndexError)", (long long)bad_seq.load());
-  }
   CU_TRY(e, cudaSetDevice(e->device));
   cudaStream_t st = e->s_comp;
   const void* src[9] = {a->read_pos, a->read_end, maxend.data(), a->read_op0, a->read_strand, a->op_ref, a->op_qry, a->op_len, a->seq};
@@ -1195,8 +1178,9 @@ int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const in
   CU_TRY(e, cudaMemcpyAsync(e->ct_in[10].p, centers, (size_t)n_centers * 4, cudaMemcpyHostToDevice, st));
   if (int rc = grow(e, e->ct_x, (size_t)n_centers * ct::ELEMS * sizeof(int16_t))) return rc;
   if (int rc = grow(e, e->ct_meta, (size_t)n_centers * 2 * sizeof(int32_t))) return rc;
-  if (!e->ct_overflow) CU_TRY(e, cudaMalloc((void**)&e->ct_overflow, sizeof(int)));
+  if (!e->ct_overflow) CU_TRY(e, cudaMalloc((void**)&e->ct_overflow, 3 * sizeof(int)));      // [overflow, bad code op, bad SEQ op]
   CU_TRY(e, cudaMemsetAsync(e->ct_overflow, 0, sizeof(int), st));
+  CU_TRY(e, cudaMemsetAsync(e->ct_overflow + 1, 0xff, 2 * sizeof(int), st));
   e->ct_rows = 0;
   ct::Alignments da;
   da.read_pos = (const int32_t*)e->ct_in[0].p;  da.read_end = (const int32_t*)e->ct_in[1].p;
@@ -1210,20 +1194,25 @@ int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const in
   // persistent grid: 13 blocks of 4 warps (4 sites, 16.9 KB of counters) fit an SM's shared memory
   const int64_t resident = (int64_t)sms * 13, blocks = (n_centers + ct::SITES_PER_BLOCK - 1) / ct::SITES_PER_BLOCK;
   const unsigned grid = (unsigned)(blocks < resident ? blocks : resident);
+  if (O) ct::validate_ops<<<(unsigned)(sms * 8), 256, 0, st>>>(da.op_qry, da.op_len, (int)O, a->seq_len, e->ct_overflow + 1);
   {
     ProfScope ps(e, 14, st);
     ct::create_tensors<<<grid, ct::THREADS, 0, st>>>(da, (const int32_t*)e->ct_in[10].p, (int)n_centers, flags,
-                                                     (int16_t*)e->ct_x.p, (int32_t*)e->ct_meta.p, e->ct_overflow);
+                                                     (int16_t*)e->ct_x.p, (int32_t*)e->ct_meta.p, e->ct_overflow, e->ct_overflow + 1);
   }
   cudaError_t lst = cudaGetLastError();
   if (lst != cudaSuccess) return fail(e, CLAIRB_ECUDA, "create_tensors launch failed: %s", cudaGetErrorString(lst));
-  e->launches += 1;
-  int overflow = 0;
+  e->launches += O ? 2 : 1;
+  int status[3] = {0, -1, -1};
+  int& overflow = status[0];
+  CU_TRY(e, cudaMemcpyAsync(status, e->ct_overflow, sizeof status, cudaMemcpyDeviceToHost, st));
   CU_TRY(e, cudaMemcpyAsync(meta_host, e->ct_meta.p, (size_t)n_centers * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CU_TRY(e, cudaMemcpyAsync(&overflow, e->ct_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
   if (x_host)
     CU_TRY(e, cudaMemcpyAsync(x_host, e->ct_x.p, (size_t)n_centers * ct::ELEMS * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   CU_TRY(e, cudaStreamSynchronize(st));
+  if (status[1] >= 0) return fail(e, CLAIRB_EINVAL, "create_tensors: op %d has an unknown code", status[1]);
+  if (status[2] >= 0)
+    return fail(e, CLAIRB_EINVAL, "create_tensors: op %d reads past the end of its SEQ (the reference raises IndexError)", status[2]);
   if (overflow) return fail(e, CLAIRB_EINVAL, "create_tensors: a count does not fit int16 (depth above 32767)");
   e->ct_rows = n_centers;
   e->ct_subtracted = (flags & ct::F_SUBTRACT) != 0;

@@ -209,6 +209,10 @@ int clairb_trainer_create(int device, int64_t max_batch, clairb_trainer** out) {
   } while (0)
 #define TC_ALLOC(p, count) TC_TRY(cudaMalloc((void**)&(p), (size_t)(count) * sizeof(*(p))))
   TC_TRY(cudaSetDevice(device));
+  TC_TRY(cudaFuncSetAttribute(sgemm_big<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
+  TC_TRY(cudaFuncSetAttribute(sgemm_big<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
+  TC_TRY(cudaFuncSetAttribute(sgemm_big<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
+  TC_TRY(cudaFuncSetAttribute(sgemm_big<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
   TC_TRY(cudaFuncSetAttribute(l3_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
   TC_TRY(cudaFuncSetAttribute(l3_backward_input, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
   TC_TRY(cudaFuncSetAttribute(l3_backward_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));

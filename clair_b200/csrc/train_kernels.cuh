@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) sgemm(int M, int N, int K, float alpha, c
 // product).  Measured on B200: 275 TFLOP/s of TF32 mma.sync = 92 TFLOP/s of such products, against 35 for the FFMA version of this
 // tile (tools/probes/mma_rate.cu).  8 warps, a warp owns 64 x 32 of the tile (4 x 4 MMA tiles).  An operand whose global layout has
 // k outermost is staged [k][136], the other kind [row][20]: both are stored with plain 16-byte stores and both give conflict-free
-// fragment loads.  Two shared-memory stages; the next tile's global loads are in flight during the current tile's MMAs.
+// fragment loads.  Three shared-memory stages filled by cp.async: two tiles are in flight while one is multiplied.
 // Requires M, N, K, lda, ldb, ldc and k_per_slice to be multiples of 4 and 16-byte aligned bases (gemm() checks).
 constexpr int BM = 128, BN = 128, BK = 16, LD_K = BM + 8, LD_R = BK + 4, STAGE_FLOATS = BM * LD_R;      // 2560 >= 16 * 136
 // hi = x rounded to TF32's 10 mantissa bits in integer arithmetic (half away from zero); lo = x - hi is exact in fp32, has either
@@ -129,46 +129,63 @@ __device__ __forceinline__ void mma_3xtf32(float (&acc)[NT][4], const uint32_t (
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[j][q] += v[j][q];
 }
+constexpr int BIG_STAGES = 3;
+constexpr int BIG_SMEM = BIG_STAGES * 2 * STAGE_FLOATS * (int)sizeof(float);      // 61,440 B
+// 16 bytes global -> shared without a register hop; `ok` false writes zeros (no bytes are read)
+__device__ __forceinline__ void cp_async16_or_zero(float* smem_dst, const float* gmem_src, bool ok) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(ok ? 16 : 0));
+}
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256, 2) sgemm_big(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                     float beta, float* __restrict__ C, int ldc, int k_per_slice) {
   constexpr bool A_K = TA, B_K = !TB;                    // operand stored with k outermost in global memory
-  __shared__ __align__(16) float As[2][STAGE_FLOATS], Bs[2][STAGE_FLOATS];
+  extern __shared__ __align__(16) float big_smem[];      // [stage][A tile | B tile]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tig = lane & 3;
   const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.z * k_per_slice;
   const int k_end = min(K, k_begin + k_per_slice);
-  float4 ra[2], rb[2];
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto load = [&](int k0) {
+  const int iters = (k_end - k_begin + BK - 1) / BK;
+  // three stages of cp.async: tile it + 2 is requested while tile it is multiplied; one barrier per tile
+  auto request = [&](int it) {
+    if (it < iters) {
+      const int k0 = k_begin + it * BK;
+      float* as = big_smem + (it % BIG_STAGES) * 2 * STAGE_FLOATS;
+      float* bs = as + STAGE_FLOATS;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const int f = tid + 256 * p;
-      if (A_K) { const int k = f >> 5, m = (f & 31) * 4; ra[p] = (m0 + m < M && k0 + k < k_end) ? *reinterpret_cast<const float4*>(A + (size_t)(k0 + k) * lda + m0 + m) : zero4; }
-      else { const int m = f >> 2, k = (f & 3) * 4; ra[p] = (m0 + m < M && k0 + k < k_end) ? *reinterpret_cast<const float4*>(A + (size_t)(m0 + m) * lda + k0 + k) : zero4; }
-      if (B_K) { const int k = f >> 5, nn = (f & 31) * 4; rb[p] = (n0 + nn < N && k0 + k < k_end) ? *reinterpret_cast<const float4*>(B + (size_t)(k0 + k) * ldb + n0 + nn) : zero4; }
-      else { const int nn = f >> 2, k = (f & 3) * 4; rb[p] = (n0 + nn < N && k0 + k < k_end) ? *reinterpret_cast<const float4*>(B + (size_t)(n0 + nn) * ldb + k0 + k) : zero4; }
+      for (int p = 0; p < 2; ++p) {
+        const int f = tid + 256 * p;
+        if (A_K) {
+          const int k = f >> 5, m = (f & 31) * 4;
+          const bool ok = m0 + m < M && k0 + k < k_end;
+          cp_async16_or_zero(as + k * LD_K + m, ok ? A + (size_t)(k0 + k) * lda + m0 + m : A, ok);
+        } else {
+          const int m = f >> 2, k = (f & 3) * 4;
+          const bool ok = m0 + m < M && k0 + k < k_end;
+          cp_async16_or_zero(as + m * LD_R + k, ok ? A + (size_t)(m0 + m) * lda + k0 + k : A, ok);
+        }
+        if (B_K) {
+          const int k = f >> 5, nn = (f & 31) * 4;
+          const bool ok = n0 + nn < N && k0 + k < k_end;
+          cp_async16_or_zero(bs + k * LD_K + nn, ok ? B + (size_t)(k0 + k) * ldb + n0 + nn : B, ok);
+        } else {
+          const int nn = f >> 2, k = (f & 3) * 4;
+          const bool ok = n0 + nn < N && k0 + k < k_end;
+          cp_async16_or_zero(bs + nn * LD_R + k, ok ? B + (size_t)(n0 + nn) * ldb + k0 + k : B, ok);
+        }
+      }
     }
-  };
-  auto stage = [&](int buf) {
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const int f = tid + 256 * p;
-      *reinterpret_cast<float4*>(&As[buf][A_K ? (f >> 5) * LD_K + (f & 31) * 4 : (f >> 2) * LD_R + (f & 3) * 4]) = ra[p];
-      *reinterpret_cast<float4*>(&Bs[buf][B_K ? (f >> 5) * LD_K + (f & 31) * 4 : (f >> 2) * LD_R + (f & 3) * 4]) = rb[p];
-    }
+    cp_async_commit();                                   // an empty group when there is nothing left keeps the counting uniform
   };
   float acc[4][4][4] = {};                               // [m tile][n tile][c0..c3]
-  load(k_begin);
-  stage(0);
-  __syncthreads();
-  int buf = 0;
-  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-    const bool more = k0 + BK < k_end;
-    if (more) load(k0 + BK);
-    const float* as = As[buf];
-    const float* bs = Bs[buf];
+  request(0);
+  request(1);
+  for (int it = 0; it < iters; ++it) {
+    cp_async_wait<1>();                                  // tile it has landed (this thread's part)
+    __syncthreads();                                     // ... everybody's part; and everybody is done with tile it - 1
+    request(it + 2);                                     // into the buffer tile it - 1 occupied
+    const float* as = big_smem + (it % BIG_STAGES) * 2 * STAGE_FLOATS;
+    const float* bs = as + STAGE_FLOATS;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 8) {
       uint32_t bh[4][2], bl[4][2];
@@ -189,9 +206,6 @@ __global__ void __launch_bounds__(256, 2) sgemm_big(int M, int N, int K, const f
         mma_3xtf32<4>(acc[i], ah, al, bh, bl);
       }
     }
-    if (more) stage(buf ^ 1);
-    __syncthreads();
-    buf ^= 1;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -246,10 +260,10 @@ inline void gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda,
     ++*launches;
   }
   if (big) {
-    if (!ta && !tb) sgemm_big<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, beta, C, ldc, k_per_slice);
-    else if (ta && !tb) sgemm_big<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, beta, C, ldc, k_per_slice);
-    else if (!ta && tb) sgemm_big<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, beta, C, ldc, k_per_slice);
-    else sgemm_big<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, beta, C, ldc, k_per_slice);
+    if (!ta && !tb) sgemm_big<false, false><<<grid, 256, BIG_SMEM, st>>>(M, N, K, A, lda, B, ldb, beta, C, ldc, k_per_slice);
+    else if (ta && !tb) sgemm_big<true, false><<<grid, 256, BIG_SMEM, st>>>(M, N, K, A, lda, B, ldb, beta, C, ldc, k_per_slice);
+    else if (!ta && tb) sgemm_big<false, true><<<grid, 256, BIG_SMEM, st>>>(M, N, K, A, lda, B, ldb, beta, C, ldc, k_per_slice);
+    else sgemm_big<true, true><<<grid, 256, BIG_SMEM, st>>>(M, N, K, A, lda, B, ldb, beta, C, ldc, k_per_slice);
   } else if (!ta && !tb) sgemm<false, false><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, k_per_slice);
   else if (ta && !tb) sgemm<true, false><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, k_per_slice);
   else if (!ta && tb) sgemm<false, true><<<grid, 256, 0, st>>>(M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, k_per_slice);

@@ -433,3 +433,18 @@ def test_device_argument_errors(model):
     aln.read_pos = aln.read_pos[::-1].copy()
     with pytest.raises(ValueError):
         CT.create_tensors(model, aln, candidates_of(case), seq, start0)
+    # malformed ops are found on the device (validate_ops) before the counting kernel reads SEQ through them
+    aln = CT.encode_alignments(case["sam"])
+    aligned = np.flatnonzero((aln.op_len & 3) != 2)                      # ops that read SEQ (M = 0, I = 1; D = 2 does not)
+    bad = CT.encode_alignments(case["sam"])
+    bad.op_qry = aln.op_qry.copy()
+    bad.op_qry[aligned[-1]] = aln.seq.size                              # starts at the end of SEQ
+    with pytest.raises(ValueError, match="past the end of its SEQ"):
+        CT.create_tensors(model, bad, candidates_of(case), seq, start0)
+    bad = CT.encode_alignments(case["sam"])
+    bad.op_len = aln.op_len.copy()
+    bad.op_len[0] = aln.op_len[0] | 3                                   # the encoder only writes codes 0..2
+    with pytest.raises(ValueError, match="unknown code"):
+        CT.create_tensors(model, bad, candidates_of(case), seq, start0)
+    # and the handle still works afterwards
+    assert device_block(model, case).text_rows() == case["expected"]
