@@ -8,6 +8,7 @@ expandReferenceRegion = 1000000      # shared/param.py:5 (CreateTensor.py:131)
 SAMTOOLS_VIEW_FILTER_FLAG = 2316     # shared/param.py:6 (CreateTensor.py:174)
 trainBatchSize = 10000        # shared/param.py:15
 initialLearningRate = 1e-3    # shared/param.py:17
+learningRateDecay = 0.1        # shared/param.py:18 (applied by the training loop, clair/train.py:201-215)
 l2RegularizationLambda = 0.005    # shared/param.py:23
 NUM_THREADS = 12              # shared/param.py:3 (kept for callers that mutate it: call_var.py:182-189)
 
