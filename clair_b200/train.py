@@ -167,11 +167,41 @@ class Trainer(object):
             pass
 
 
+class GradientExchange(object):
+    """The all-reduce of one flat gradient buffer in two pieces: `dense()` starts the tail [dense_offset:] - complete once the
+    backward pass has left the dense layers -, `head()` the LSTM part [:dense_offset] after BPTT, `wait()` returns when both
+    sums are in place on every rank.  SUM, not mean: the reference's loss is a sum over the batch (clair/model.py:696-709, 783-805),
+    so the gradient of the global batch is the sum of the ranks' gradients.  Works on any torch.distributed backend (the CPU
+    tests run it over gloo); `stream` is the communication stream on CUDA."""
+
+    def __init__(self, grad, dense_offset, dist, stream=None):
+        self.grad, self.dense_offset, self.dist, self.stream = grad, int(dense_offset), dist, stream
+        self._work = []
+
+    def _start(self, piece):
+        if self.stream is not None:
+            import torch
+            with torch.cuda.stream(self.stream):
+                self._work.append(self.dist.all_reduce(piece, op=self.dist.ReduceOp.SUM, async_op=True))
+        else:
+            self._work.append(self.dist.all_reduce(piece, op=self.dist.ReduceOp.SUM, async_op=True))
+
+    def dense(self):
+        self._start(self.grad[self.dense_offset:])
+
+    def head(self):
+        self._start(self.grad[:self.dense_offset])
+
+    def wait(self):
+        for w in self._work:
+            w.wait()
+        self._work = []
+
+
 class DataParallelTrainer(Trainer):
-    """One process per GPU (torch.distributed, NCCL): every rank runs the step on its own batch, the gradient of the global
-    batch is the SUM over ranks (the reference's loss sums over the batch: clair/model.py:696-709, 783-805).  The flat gradient
-    buffer is a torch tensor; its dense tail is all-reduced while the LSTM backward runs, the LSTM head after it, then every
-    rank applies the same update.  Weights must start identical on all ranks (set_weights with the same blob / seed)."""
+    """One process per GPU (torch.distributed, NCCL): every rank runs the step on its own batch.  The flat gradient buffer is a
+    torch tensor; its dense tail is all-reduced while the LSTM backward runs, the LSTM head after it (GradientExchange), then
+    every rank applies the same update.  Weights must start identical on all ranks (set_weights with the same blob / seed)."""
 
     def __init__(self, **kw):
         import torch
@@ -181,18 +211,15 @@ class DataParallelTrainer(Trainer):
         Trainer.__init__(self, **kw)
         self._grad = torch.zeros(self.num_params, dtype=torch.float32, device="cuda:%d" % self.device)
         self._check(self._lib.clairb_trainer_set_grad_buffer(self._t, ctypes.c_void_p(self._grad.data_ptr())), "clairb_trainer_set_grad_buffer")
-        self._comm = torch.cuda.Stream(device=self.device)
+        self._exchange = GradientExchange(self._grad, self.dense_offset, dist, torch.cuda.Stream(device=self.device))
 
     def train(self, batchX, batchY, masks=None):
         torch, dist = self._torch, self._dist
         parts = self.forward_backward(batchX, batchY, masks)          # returns with the dense gradients complete
-        with torch.cuda.stream(self._comm):
-            dense = dist.all_reduce(self._grad[self.dense_offset:], op=dist.ReduceOp.SUM, async_op=True)
+        self._exchange.dense()
         self.backward_lstm()                                          # BPTT runs while the 8.3 MB dense piece travels
-        with torch.cuda.stream(self._comm):
-            head = dist.all_reduce(self._grad[:self.dense_offset], op=dist.ReduceOp.SUM, async_op=True)
-        dense.wait()
-        head.wait()
+        self._exchange.head()
+        self._exchange.wait()
         torch.cuda.synchronize(self.device)
         sums = torch.tensor(parts[:4], dtype=torch.float64, device="cuda:%d" % self.device)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)

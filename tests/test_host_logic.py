@@ -128,6 +128,44 @@ def test_sharded_predict_two_ranks_gloo(n):
     assert all(results)
 
 
+def _gradient_exchange_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from clair_b200.train import GradientExchange
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, dense_offset = 1000, 377
+        mine = torch.arange(n, dtype=torch.float32) * (rank + 1) + rank
+        want = sum(torch.arange(n, dtype=torch.float32) * (r + 1) + r for r in range(world))
+        ex = GradientExchange(mine, dense_offset, dist)
+        ex.dense()                                             # the tail first ...
+        ex.wait()
+        tail_done = torch.equal(mine[dense_offset:], want[dense_offset:]) and not torch.equal(mine[:dense_offset], want[:dense_offset])
+        ex.head()                                              # ... then the LSTM part
+        ex.wait()
+        q.put(bool(tail_done and torch.equal(mine, want)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_exchange_two_ranks_gloo():
+    """The data-parallel trainer's all-reduce of the flat gradient buffer (SUM, two pieces) on world_size 2 over gloo."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gradient_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(results)
+
+
 def test_run_batches_with_decision_hands_over_matching_records():
     from clair_b200 import decision
 
