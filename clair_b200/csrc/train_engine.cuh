@@ -33,8 +33,8 @@ struct clairb_trainer {
   uint8_t* is_kernel = nullptr;
   bool weights_set = false;
   // activations / gradients (sized for np_max sites)
-  float *x_tm = nullptr, *xin = nullptr, *lout[2] = {nullptr, nullptr}, *dlout[2] = {nullptr, nullptr};
-  struct Dir { float *xin, *pre, *gates, *hbuf, *cbuf, *dZ, *dh_out, *dxin; } dir[2][2] = {};
+  float *x_tm = nullptr, *lout[2] = {nullptr, nullptr}, *dlout[2] = {nullptr, nullptr};
+  struct Dir { float *pre, *gates, *hbuf, *cbuf, *dZ; } dir[2][2] = {};      // hbuf / cbuf: 35 slabs (train_kernels.cuh)
   float *a3 = nullptr, *da3 = nullptr, *a4 = nullptr, *a4d = nullptr, *da4 = nullptr, *a5[4] = {}, *a5d[4] = {}, *da5[4] = {};
   float *zall = nullptr, *dzall = nullptr, *probs = nullptr, *target = nullptr;
   void* x_in = nullptr;
@@ -122,7 +122,7 @@ void trainer_free(clairb_trainer* t) {
   for (int l = 0; l < 2; ++l)
     for (int d = 0; d < 2; ++d) {
       auto& q = t->dir[l][d];
-      drop(q.xin); drop(q.pre); drop(q.gates); drop(q.hbuf); drop(q.cbuf); drop(q.dZ); drop(q.dh_out); drop(q.dxin);
+      drop(q.pre); drop(q.gates); drop(q.hbuf); drop(q.cbuf); drop(q.dZ);
     }
   drop(t->a3); drop(t->da3); drop(t->a4); drop(t->a4d); drop(t->da4);
   for (int k = 0; k < 4; ++k) { drop(t->a5[k]); drop(t->a5d[k]); drop(t->da5[k]); }
@@ -142,8 +142,7 @@ int lstm_layer_backward(clairb_trainer* t, int l, int64_t np) {
   cudaStream_t st = t->st;
   const int K = l ? 2 * H : F_IN;
   const int64_t rows = (int64_t)T_STEPS * np;
-  split_bidirectional<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->dlout[l], t->dir[l][0].dh_out, t->dir[l][1].dh_out, (int)np);
-  ++t->launches;
+  const float* in = l ? t->lout[0] : t->x_tm;
   TR_TRY(t, cudaEventRecord(t->ev_fork, st));
   TR_TRY(t, cudaStreamWaitEvent(t->st2, t->ev_fork, 0));
   for (int d = 0; d < 2; ++d) {
@@ -152,23 +151,21 @@ int lstm_layer_backward(clairb_trainer* t, int l, int64_t np) {
     const auto& pk = tp(t, lstm_prefix(l, d) + "kernel");
     const auto& pb = tp(t, lstm_prefix(l, d) + "bias");
     TR_TRY(t, cudaMemsetAsync(t->G + pb.off, 0, G4 * sizeof(float), sd));
-    lstm_seq_backward<<<seq_grid(np), 256, SEQ_BWD_SMEM, sd>>>(q.dh_out, q.gates, q.cbuf, t->P + pk.off + (size_t)K * G4, q.dZ, t->G + pb.off, (int)np);
+    lstm_seq_backward<<<seq_grid(np), 256, SEQ_BWD_SMEM, sd>>>(t->dlout[l], d * H, q.gates, q.cbuf, t->P + pk.off + (size_t)K * G4, q.dZ, t->G + pb.off,
+                                                                (int)np, d);
     ++t->launches;
     float* gk = t->G + pk.off;
-    // dW_x = x_in^T . dZ (all steps at once), dW_h = h_prev^T . dZ, db = column sums
-    gemm(true, false, K, G4, (int)rows, q.xin, K, q.dZ, G4, 0.f, gk, G4, sd, &t->launches);
-    gemm(true, false, H, G4, (int)rows, q.hbuf, H, q.dZ, G4, 0.f, gk + (size_t)K * G4, G4, sd, &t->launches);
-    if (l == 1) {
-      // d(input) = dZ . W_x^T per direction (in its processing order); summed in time order below
-      gemm(false, true, (int)rows, K, G4, q.dZ, G4, t->P + pk.off, G4, 0.f, q.dxin, K, sd, &t->launches);
-    }
+    // dW_x = in^T . dZ (all steps at once, both in time order), dW_h = h_prev^T . dZ: h of the step before time t is slab t (fw) / t + 2 (bw)
+    gemm(true, false, K, G4, (int)rows, in, K, q.dZ, G4, 0.f, gk, G4, sd, &t->launches);
+    gemm(true, false, H, G4, (int)rows, q.hbuf + (d ? 2 : 0) * (size_t)np * H, H, q.dZ, G4, 0.f, gk + (size_t)K * G4, G4, sd, &t->launches);
+    // d(input) = dZ . W_x^T, the two directions added: fw writes dlout[0] on its stream, bw adds to it behind the join
+    if (l == 1 && d == 0) gemm(false, true, (int)rows, K, G4, q.dZ, G4, t->P + pk.off, G4, 0.f, t->dlout[0], K, sd, &t->launches);
   }
   TR_TRY(t, cudaEventRecord(t->ev_join, t->st2));
   TR_TRY(t, cudaStreamWaitEvent(st, t->ev_join, 0));
   if (l == 1) {
-    TR_TRY(t, cudaMemcpyAsync(t->dlout[0], t->dir[1][0].dxin, (size_t)rows * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    reverse_time<<<blocks_for(rows * K), 256, 0, st>>>(t->dir[1][1].dxin, t->dlout[0], (int)np, K, 1);
-    ++t->launches;
+    const auto& pk = tp(t, lstm_prefix(1, 1) + "kernel");
+    gemm(false, true, (int)rows, K, G4, t->dir[1][1].dZ, G4, t->P + pk.off, G4, 1.f, t->dlout[0], K, st, &t->launches);
   }
   return CLAIRB_OK;
 }
@@ -239,13 +236,11 @@ int clairb_trainer_create(int device, int64_t max_batch, clairb_trainer** out) {
   for (int l = 0; l < 2; ++l) {
     TC_ALLOC(t->lout[l], TS * np * 2 * H);
     TC_ALLOC(t->dlout[l], TS * np * 2 * H);
-    const size_t K = l ? 2 * H : F_IN;
     for (int d = 0; d < 2; ++d) {
       auto& q = t->dir[l][d];
-      TC_ALLOC(q.xin, TS * np * K); TC_ALLOC(q.pre, TS * np * G4); TC_ALLOC(q.gates, TS * np * G4);
-      TC_ALLOC(q.hbuf, (TS + 1) * np * H); TC_ALLOC(q.cbuf, (TS + 1) * np * H);
-      TC_ALLOC(q.dZ, TS * np * G4); TC_ALLOC(q.dh_out, TS * np * H);
-      TC_ALLOC(q.dxin, TS * np * K);
+      TC_ALLOC(q.pre, TS * np * G4); TC_ALLOC(q.gates, TS * np * G4);
+      TC_ALLOC(q.hbuf, (TS + 2) * np * H); TC_ALLOC(q.cbuf, (TS + 2) * np * H);
+      TC_ALLOC(q.dZ, TS * np * G4);
     }
   }
   TC_ALLOC(t->a3, np * L3_K); TC_ALLOC(t->da3, np * L3_K);
@@ -364,18 +359,16 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
       auto& q = t->dir[l][d];
       const auto& pk = tp(t, lstm_prefix(l, d) + "kernel");
       const auto& pb = tp(t, lstm_prefix(l, d) + "bias");
-      if (d == 0) TR_TRY(t, cudaMemcpyAsync(q.xin, in, (size_t)rows * K * sizeof(float), cudaMemcpyDeviceToDevice, sd));
-      else { reverse_time<<<blocks_for(rows * K), 256, 0, sd>>>(in, q.xin, (int)np, K, 0); ++t->launches; }
-      gemm(false, false, (int)rows, G4, K, q.xin, K, t->P + pk.off, G4, 0.f, q.pre, G4, sd, &t->launches);
-      TR_TRY(t, cudaMemsetAsync(q.hbuf, 0, (size_t)np * H * sizeof(float), sd));
-      TR_TRY(t, cudaMemsetAsync(q.cbuf, 0, (size_t)np * H * sizeof(float), sd));
-      lstm_seq_forward<<<seq_grid(np), 256, SEQ_FWD_SMEM, sd>>>(q.pre, t->P + pk.off + (size_t)K * G4, t->P + pb.off, q.gates, q.cbuf, q.hbuf, (int)np);
+      gemm(false, false, (int)rows, G4, K, in, K, t->P + pk.off, G4, 0.f, q.pre, G4, sd, &t->launches);
+      // the state before the first step: slab 0 (fw walks t = 0..32) and slab 34 (bw walks t = 32..0)
+      TR_TRY(t, cudaMemsetAsync(q.hbuf + (d ? 34 : 0) * (size_t)np * H, 0, (size_t)np * H * sizeof(float), sd));
+      TR_TRY(t, cudaMemsetAsync(q.cbuf + (d ? 34 : 0) * (size_t)np * H, 0, (size_t)np * H * sizeof(float), sd));
+      lstm_seq_forward<<<seq_grid(np), 256, SEQ_FWD_SMEM, sd>>>(q.pre, t->P + pk.off + (size_t)K * G4, t->P + pb.off, q.gates, q.cbuf, q.hbuf, t->lout[l],
+                                                                 d * H, (int)np, d);
       ++t->launches;
     }
     TR_TRY(t, cudaEventRecord(t->ev_join, t->st2));
     TR_TRY(t, cudaStreamWaitEvent(st, t->ev_join, 0));
-    assemble_bidirectional<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->dir[l][0].hbuf + (size_t)np * H, t->dir[l][1].hbuf + (size_t)np * H, t->lout[l], (int)np);
-    ++t->launches;
   }
   if (t->rates[0] > 0.f) {
     dropout_scale<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->lout[1], t->mask[0], 1.f / (1.f - t->rates[0]), rows * 2 * H);

@@ -5,16 +5,18 @@
 //   forward in training phase   :400-622, tf.layers.dropout :434-459, selu.dropout_selu clair/selu.py:43-74
 //   focal loss                  :783-805        L2 :689-694        total :696-709
 //   clip_by_global_norm(5.0) + AdamOptimizer    :717-728
-// Everything here is fp32 on the CUDA cores - the reference trains in fp32 (float_type is forced to tf.float32, :165-170) and
-// the parity tests compare gradients with a float64 autograd restatement (oracle/train_oracle.py).  This is the first correct
-// device path of the row: the per-step recurrences are small fused kernels (one CTA per 8 sites), every large contraction
-// (input projections, weight gradients) is one tiled SGEMM over all 33 steps.  The tensor-core kernels of the inference
-// path do not save the gate activations BPTT needs and are not used here.
+// Every result is fp32-grade - the reference trains in fp32 (float_type is forced to tf.float32, :165-170) and the parity tests
+// compare gradients with a float64 autograd restatement (oracle/train_oracle.py).  The 33 steps of an LSTM direction are ONE
+// launch (thread-block clusters, h exchanged through distributed shared memory); every large contraction (recurrences, input
+// projections, weight gradients, L4) runs on the tensor cores as 3xTF32 mma.sync with the slabs accumulated in fp32 outside
+// the MMA; the small ones (L5, heads) and the elementwise work on the CUDA cores.  The tcgen05 kernels of the inference path
+// do not save the gate activations BPTT needs and are not used here.
 //
-// Layouts (row-major fp32): activations of a layer in time-major order [33][n][...]; per direction the recurrent kernels work
-// in PROCESSING order s = 0..32 (s = t for fw, s = 32 - t for bw); gate columns in TF order i, c(candidate), f, o.
+// Layouts (row-major fp32): everything in global memory is time-major [33][n][...] in TIME order for both directions; the
+// sequence kernels walk processing steps s = 0..32 and address time t = s (fw) or 32 - s (bw), so no array is ever reversed or
+// copied per direction.  h and c of a direction live in 35 slabs, time t at slab t + 1, slabs 0 and 34 zero: the state before
+// a step is slab t (fw) / t + 2 (bw).  Gate columns in TF order i, c(candidate), f, o.
 #pragma once
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,7 +30,9 @@ constexpr int ROWS = 8;                  // batches are padded to a multiple of 
 constexpr float ALPHA_DROPOUT = -1.7580993408473766f;     // clair/selu.py:43
 
 // Two independent fp32 FMAs in one instruction (FFMA2, scalar a broadcast over the pair): c + a * b, each half rounded like fmaf.
-// A three-register FFMA issues every second cycle per scheduler on this part; the paired form is what reaches 128 FMA/clk/SM.
+// Halves the instruction count of an outer-product inner loop; measured here it is throughput-neutral against plain FFMA
+// (tools/probes/mma_rate.cu: FFMA 72 TFLOP/s with two register operands, 55 as an outer product; the large contractions moved
+// to the tensor cores instead, sgemm_big).
 __device__ __forceinline__ float2 fma2(float a, float2 b, float2 c) { return __ffma2_rn(make_float2(a, a), b, c); }
 
 // ---- C[M,N] = alpha * op(A)[M,K] . op(B)[K,N] + beta * C     (row-major; TA: A is stored [K][M]; TB: B is stored [N][K]) ----
@@ -327,36 +331,6 @@ __global__ void make_mask(uint8_t* __restrict__ mask, int64_t count, float rate,
   const float u = (float)(h >> 40) * (1.f / 16777216.f);
   mask[i] = u >= rate;
 }
-// layer output [33][n][256] <- the two directions' h in processing order ([33][n][128] each; hbuf has a leading zero block)
-__global__ void assemble_bidirectional(const float* __restrict__ h_fw, const float* __restrict__ h_bw, float* __restrict__ out, int n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)T_STEPS * n * 2 * H) return;
-  const int f = (int)(i % (2 * H));
-  const int64_t tb = i / (2 * H);
-  const int t = (int)(tb / n);
-  const int64_t b = tb % n;
-  out[i] = f < H ? h_fw[((size_t)t * n + b) * H + f] : h_bw[((size_t)(T_STEPS - 1 - t) * n + b) * H + (f - H)];
-}
-// the reverse: d(layer output) [33][n][256] -> per-direction dh in processing order
-__global__ void split_bidirectional(const float* __restrict__ dout, float* __restrict__ dh_fw, float* __restrict__ dh_bw, int n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)T_STEPS * n * 2 * H) return;
-  const int f = (int)(i % (2 * H));
-  const int64_t tb = i / (2 * H);
-  const int t = (int)(tb / n);
-  const int64_t b = tb % n;
-  if (f < H) dh_fw[((size_t)t * n + b) * H + f] = dout[i];
-  else dh_bw[((size_t)(T_STEPS - 1 - t) * n + b) * H + (f - H)] = dout[i];
-}
-// x [33][n][K] -> the same rows in reversed time order (input of a backward direction in processing order), or accumulate back
-__global__ void reverse_time(const float* __restrict__ in, float* __restrict__ out, int n, int K, int accumulate) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)T_STEPS * n * K) return;
-  const int64_t per = (int64_t)n * K;
-  const int t = (int)(i / per);
-  const int64_t o = (int64_t)(T_STEPS - 1 - t) * per + i % per;
-  if (accumulate) out[o] += in[i]; else out[o] = in[i];
-}
 
 // ---- the 33 steps of one LSTM direction, forward: z_s = x_s W_x (pre) + b + h_{s-1} . W_h ; gates ; c_s, h_s ---------------------
 // (LSTMBlockCell, forget_bias 0; clair/model.py:299-305).  One thread-block CLUSTER of 8 CTAs carries 64 sites through all 33
@@ -387,7 +361,7 @@ __device__ __forceinline__ void bulk_to_cta(const void* src, void* dst_same_offs
 
 __global__ void __cluster_dims__(SEQ_CTAS, 1, 1) __launch_bounds__(256)
 lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, const float* __restrict__ bias, float* __restrict__ gates,
-                 float* __restrict__ cbuf, float* __restrict__ hbuf, int n) {
+                 float* __restrict__ cbuf, float* __restrict__ hbuf, float* __restrict__ lout, int col0, int n, int reverse) {
   extern __shared__ __align__(16) float seq_smem[];
   float* Ws = seq_smem;                                  // [128 units of h_{s-1}][72: 64 local gate columns]
   float* hT = Ws + H * SEQ_LD;                           // [2][128 units][72: 64 sites]
@@ -417,12 +391,13 @@ lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, co
   // accumulators acc[mi][nt][2 half + e]: site 32 mp + 16 mi + 8 half + g, gate 2 nt + e; they start as pre + bias
   float acc[2][2][4], c[2][2] = {};
   auto fetch = [&](int s, float (&z)[2][2][4]) {
+    const int t = reverse ? T_STEPS - 1 - s : s;         // everything in global memory is in TIME order
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int row = r0 + 32 * mp + 16 * mi + 8 * half + g;
-        const float* q = pre + ((size_t)s * n + row) * G4 + unit;
+        const float* q = pre + ((size_t)t * n + row) * G4 + unit;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -468,10 +443,11 @@ lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, co
         c[mi][half] = cv;
         hn[unit * SEQ_LD + rl] = hv;
         if (r0 + rl < n) {
-          const size_t r = (size_t)s * n + r0 + rl;
+          const size_t r = (size_t)(reverse ? T_STEPS - 1 - s : s) * n + r0 + rl;
           gates[r * G4 + unit] = ig; gates[r * G4 + H + unit] = gg; gates[r * G4 + 2 * H + unit] = fg; gates[r * G4 + 3 * H + unit] = og;
-          cbuf[(r + n) * H + unit] = cv;
+          cbuf[(r + n) * H + unit] = cv;                 // slab t + 1 of 35: slabs 0 and 34 stay zero (the state before the first step)
           hbuf[(r + n) * H + unit] = hv;
+          lout[r * 2 * H + col0 + unit] = hv;            // the layer's output [t][site][fw | bw]
         }
       }
     if (s + 1 < T_STEPS) {
@@ -501,8 +477,8 @@ lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, co
 // arrived it adds the 8 partial sums in a fixed order.  The partial sums are double-buffered at the sender: a slot copy of step s
 // is known to be complete only when the receiver's answer of step s - 1 has arrived.  Also accumulates the bias gradient.
 __global__ void __cluster_dims__(SEQ_CTAS, 1, 1) __launch_bounds__(256)
-lstm_seq_backward(const float* __restrict__ dh_out, const float* __restrict__ gates, const float* __restrict__ cbuf, const float* __restrict__ Wh,
-                  float* __restrict__ dZ, float* __restrict__ dbias, int n) {
+lstm_seq_backward(const float* __restrict__ dlout, int col0, const float* __restrict__ gates, const float* __restrict__ cbuf,
+                  const float* __restrict__ Wh, float* __restrict__ dZ, float* __restrict__ dbias, int n, int reverse) {
   extern __shared__ __align__(16) float seq_smem[];
   float* Wt = seq_smem;                                  // [64 local gate columns][136: 128 units of h_{s-1}]
   float* dzs = Wt + 4 * SEQ_UNITS * SEQ_BWD_LDW;         // [64 local gate columns][72: 64 sites]
@@ -531,14 +507,15 @@ lstm_seq_backward(const float* __restrict__ dh_out, const float* __restrict__ ga
   float db[4] = {0.f, 0.f, 0.f, 0.f};                   // bias gradient of this unit's four gates over the thread's sites and all steps
   float gi[4][4], cs[4], cp[4], dho[4];
   auto fetch = [&](int s) {
+    const int t = reverse ? T_STEPS - 1 - s : s;         // time of processing step s; the step before it is time t -+ 1
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const size_t r = (size_t)s * n + row + i;
+      const size_t r = (size_t)t * n + row + i;
 #pragma unroll
       for (int q = 0; q < 4; ++q) gi[i][q] = live ? gates[r * G4 + q * H + unit] : 0.f;
-      cs[i] = live ? cbuf[(r + n) * H + unit] : 0.f;
-      cp[i] = live ? cbuf[r * H + unit] : 0.f;
-      dho[i] = live ? dh_out[r * H + unit] : 0.f;
+      cs[i] = live ? cbuf[(r + n) * H + unit] : 0.f;                                   // slab t + 1
+      cp[i] = live ? cbuf[(r + (reverse ? 2 * (size_t)n : 0)) * H + unit] : 0.f;       // slab t + 2 (bw) or t (fw)
+      dho[i] = live ? dlout[r * 2 * H + col0 + unit] : 0.f;
     }
   };
   fetch(T_STEPS - 1);
@@ -558,7 +535,7 @@ lstm_seq_backward(const float* __restrict__ dh_out, const float* __restrict__ ga
       dz[i][3] = dh * tch * og * (1.f - og);
       dc[i] = dcs * fg;
       if (live) {
-        const size_t r = (size_t)s * n + row + i;
+        const size_t r = (size_t)(reverse ? T_STEPS - 1 - s : s) * n + row + i;
 #pragma unroll
         for (int q = 0; q < 4; ++q) { dZ[r * G4 + q * H + unit] = dz[i][q]; db[q] += dz[i][q]; }
       }
