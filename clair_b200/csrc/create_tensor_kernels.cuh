@@ -19,6 +19,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Build switches (A/B, all parity-green on host and device): default = each lane follows its read's ops from global memory
+// (0.58 ms on the 2 Mb ONT-like region of tools/ct_bench.py); -DCLAIRB_CT_FLAT = position-major walk from global memory
+// (0.97 ms); -DCLAIRB_CT_STAGED = operands staged in shared memory, then all lanes walk the 33 positions together (0.75 ms).
+
 namespace clairb {
 namespace ct {
 
@@ -237,6 +241,143 @@ __host__ __device__ __forceinline__ bool fold_read_flat(const Alignments& a, int
   return true;
 }
 
+// ---- the same rule from STAGED operands (-DCLAIRB_CT_STAGED; measured, not the default) -----------------------------------------
+// fold_read_ops follows each read's own ops: the lanes of a warp sit in different op types and loop lengths (8.9 of 32 threads
+// active per instruction, 9.3 k warp instructions per site).  Here a read is first staged for its window - the (length, code)
+// words of the ops under the window and the query bytes they use, copied to shared memory once, with plain independent loads -
+// and then all lanes step through the 33 window positions TOGETHER, the op cursor advancing from shared memory as a side branch.
+// Result on B200 (ncu, profiles/r02_ct_staged_walk.txt): the positions are walked converged (20 of 32 lanes at the loop head:
+// 40 reads are 32 + 8), but the kernel executes MORE warp instructions (10.8 k per site) and takes 0.75 ms against 0.58: staging
+// and its consistency checks cost what the walk saves; inserted bases are still counted by one lane at a time (an indel every
+// ~8 bases in the bench region: 10 % of the instructions at 1.0 threads each); fetching a query byte out of the staged words and
+// turning it into a row is 30 % of the instructions; and converged lanes hit the SAME counter with their shared-memory atomics.
+// Kept, parity-green on the host (tests/harness) and on the device, as the record of the attempt.
+constexpr int STAGE_OPS = 20;             // ops kept per read (an ONT window of 33 bases holds 2 x Poisson(4) + 1 ops)
+constexpr int STAGE_WORDS = 16;           // 64 query bytes per read, from a 4-byte aligned address
+struct Staged {
+  int q;                                  // first counted reference position
+  int p0;                                 // reference position of the first staged op
+  int qi;                                 // index, within the staged bytes, of the first staged op's first query base (can be < 0)
+  int n_ops;
+};
+// -> 0: the read does not open the window (fold_read_ops would return false); 1: staged; 2: needs fold_read_ops - more ops or query
+// bytes under the window than are staged, or op_ref / op_qry are not the running sums of the lengths before them (the staged walk
+// rebuilds positions from lengths; the arrays of the host encoder always are, a foreign caller's may not be).
+// Store: put_op(j, length_code), put_word(w, four query bytes).
+template <typename Store>
+__host__ __device__ __forceinline__ int stage_read(const Alignments& a, int r, int center, bool left_edge, Store& st, Staged& out) {
+  const int w0 = center - (FLANK + 1);
+  const int pos = a.read_pos[r], end = a.read_end[r];
+  int q;
+  if (left_edge) {
+    if (pos > w0 + 2 * FLANK + 1 || end <= w0) return 0;
+    q = pos > w0 ? pos : w0;
+  } else {
+    if (pos > w0 || end <= w0) return 0;
+    q = w0;
+  }
+  if (q >= end) return 0;
+  const int wend = w0 + N_POS;
+  int lo = a.read_op0[r], hi = a.read_op0[r + 1];
+  const int op_end = hi;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int lc = a.op_len[mid];
+    const int e = a.op_ref[mid] + (((lc & 3) == OP_I) ? 0 : (lc >> 2));
+    if (e > q) hi = mid; else lo = mid + 1;
+  }
+  out.q = q;
+  out.n_ops = 0;
+  out.p0 = 0;
+  out.qi = 0;
+  if (lo >= op_end) return 1;
+  int run_p = a.op_ref[lo], run_q = a.op_qry[lo];
+  const int lc0 = a.op_len[lo];
+  // the first query byte the window can use: the base under q of an aligned op, or the next base behind a deletion
+  const int first_byte = run_q + (((lc0 & 3) == OP_M) ? q - run_p : 0);
+  const int base = first_byte & ~3;
+  int need_end = first_byte;
+  out.p0 = run_p;
+  out.qi = run_q - base;
+  int n = 0;
+  for (int j0 = 0; j0 < STAGE_OPS; j0 += 4) {            // four ops' fields requested at a time
+    int lc[4], pr[4], qq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = lo + j0 + u < op_end ? lo + j0 + u : op_end - 1;
+      lc[u] = a.op_len[idx]; pr[u] = a.op_ref[idx]; qq[u] = a.op_qry[idx];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (lo + j0 + u >= op_end || run_p >= wend) { j0 = STAGE_OPS; break; }      // no more ops / the window is covered
+      if (pr[u] != run_p || qq[u] != run_q) return 2;
+      st.put_op(j0 + u, lc[u]);
+      n = j0 + u + 1;
+      const int len = lc[u] >> 2, code = lc[u] & 3;
+      if (code == OP_M) { const int t = run_p + len < wend ? len : wend - run_p; if (run_q + t > need_end) need_end = run_q + t; }
+      else if (code == OP_I && run_p > q && run_q + len > need_end) need_end = run_q + len;
+      if (code != OP_I) run_p += len;
+      if (code != OP_D) run_q += len;
+    }
+  }
+  if (n == STAGE_OPS && lo + n < op_end && run_p < wend) return 2;
+  if (need_end - base > 4 * STAGE_WORDS) return 2;
+  out.n_ops = n;
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(a.seq + base);       // `seq` carries 64 bytes of slack behind its end
+  const int n_words = (need_end - base + 3) >> 2;
+#pragma unroll 4
+  for (int w = 0; w < STAGE_WORDS; ++w)
+    if (w < n_words) st.put_word(w, words[w]);
+  return 1;
+}
+
+// The walk of fold_read_flat over staged operands.  Load: op(j), byte(i).  Written so that the lanes of a warp stay in lockstep over
+// the 33 positions (uniform loop bounds, the lane's own range as a predicate).
+template <typename Add, typename Load>
+__host__ __device__ __forceinline__ void fold_read_staged(const Staged& s, int center, int strand16, const uint8_t* win, Load& ld, Add& add) {
+  const int w0 = center - (FLANK + 1), wend = w0 + N_POS, q = s.q;
+  bool live = s.n_ops > 0;
+  int k = 0, p0 = s.p0, qi = s.qi;
+  int lc = live ? ld.op(0) : 0;
+  int len = lc >> 2, code = lc & 3;
+  for (int p = w0; p < wend; ++p) {
+    ld.converge();                                       // the lanes that walk (uniform loop bounds) meet here every position ...
+    const bool on = live && p >= q;
+    if (on) {
+      while (code == OP_I || p >= p0 + len) {            // move the cursor to the op that covers p
+        if (code == OP_I && p0 > q) {                    // inserted bases sit before reference position p0 == p
+          const int i0 = p0 - w0;
+          for (int t = 0; t < len; ++t) {
+            const int qb = base_row(ld.byte(qi + t));
+            if (qb == 255) continue;
+            const int idx = i0 + t < N_POS - 1 ? i0 + t : N_POS - 1;
+            add.add(idx * 32 + strand16 + qb * 4 + SLOT_INS);
+          }
+        }
+        if (code != OP_D) qi += len;
+        if (code != OP_I) p0 += len;
+        if (++k >= s.n_ops) { live = false; break; }
+        lc = ld.op(k);
+        len = lc >> 2; code = lc & 3;
+      }
+    }
+    ld.converge();                                       // ... and again behind the cursor moves, which only some lanes make
+    if (on && live) {
+      const int rb = win[p - w0];
+      if (code == OP_M) {
+        const int qb = base_row(ld.byte(qi + (p - p0)));
+        if (rb != 255 && qb != 255) {
+          const int cell = (p - w0) * 32 + strand16;
+          add.add(cell + rb * 4 + SLOT_MREF);
+          add.add(cell + qb * 4 + SLOT_MQRY);
+        }
+      } else if (p > q && rb != 255) {
+        add.add((p - w0) * 32 + strand16 + rb * 4 + SLOT_DEL);
+      }
+    }
+  }
+}
+
 template <typename Add>
 __host__ __device__ __forceinline__ bool fold_read(const Alignments& a, int r, int center, bool left_edge, const uint8_t* win, Add& add) {
 #ifdef CLAIRB_CT_FLAT
@@ -310,6 +451,18 @@ struct SharedAdd {
   int* cnt;
   __device__ __forceinline__ void add(int i) { atomicAdd(cnt + i, 1); }
 };
+// a lane's staged operands: ops [STAGE_OPS][32 lanes], query words [STAGE_WORDS][32 lanes] (a lane's column: no bank conflicts)
+struct SharedStage {
+  int* ops;
+  uint32_t* words;
+  int lane;
+  unsigned walkers;                                      // lanes inside fold_read_staged in this round
+  __device__ __forceinline__ void converge() const { __syncwarp(walkers); }
+  __device__ __forceinline__ void put_op(int j, int lc) { ops[j * 32 + lane] = lc; }
+  __device__ __forceinline__ void put_word(int w, uint32_t v) { words[w * 32 + lane] = v; }
+  __device__ __forceinline__ int op(int j) const { return ops[j * 32 + lane]; }
+  __device__ __forceinline__ uint8_t byte(int i) const { return (uint8_t)(words[(i >> 2) * 32 + lane] >> (8 * (i & 3))); }
+};
 
 // flags
 constexpr int F_LEFT_EDGE = 1;      // default of the reference (absence of --stop_consider_left_edge)
@@ -343,6 +496,11 @@ __global__ void __launch_bounds__(THREADS) create_tensors(Alignments a, const in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* cnt = cnt_all[warp];
   uint8_t* win = win_all[warp];
+#ifdef CLAIRB_CT_STAGED
+  __shared__ int ops_all[SITES_PER_BLOCK][STAGE_OPS * 32];
+  __shared__ uint32_t words_all[SITES_PER_BLOCK][STAGE_WORDS * 32];
+  SharedStage stage{ops_all[warp], words_all[warp], lane, 0u};
+#endif
   const bool left_edge = flags & F_LEFT_EDGE;
   for (int ci = blockIdx.x * SITES_PER_BLOCK + warp; ci < n_centers; ci += gridDim.x * SITES_PER_BLOCK) {
     const int center = centers[ci];
@@ -353,7 +511,20 @@ __global__ void __launch_bounds__(THREADS) create_tensors(Alignments a, const in
     __syncwarp();
     SharedAdd add{cnt};
     int opened = 0;
+#ifndef CLAIRB_CT_STAGED
     for (int r = first + lane; r < last; r += 32) opened += fold_read(a, r, center, left_edge, win, add) ? 1 : 0;
+#else
+    for (int r0 = first; r0 < last; r0 += 32) {            // 32 reads per round: stage each, then walk the window together
+      const int r = r0 + lane;
+      Staged sg;
+      const int state = r < last ? stage_read(a, r, center, left_edge, stage, sg) : 0;
+      opened += state != 0;
+      stage.walkers = __ballot_sync(0xffffffffu, state == 1);
+      if (state == 1) fold_read_staged(sg, center, a.read_strand[r] ? 16 : 0, win, stage, add);
+      else if (state == 2) fold_read_ops(a, r, center, left_edge, win, add);
+      __syncwarp();
+    }
+#endif
     opened = __reduce_add_sync(0xffffffffu, opened);
     __syncwarp();
     // one row out: 528 words of two int16 = channels (0,1) or (2,3) of a cell

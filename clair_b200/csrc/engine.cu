@@ -1169,7 +1169,7 @@ int clairb_create_tensors(clairb_engine* e, const clairb_alignments* a, const in
   const size_t bytes[9] = {(size_t)R * 4, (size_t)R * 4, (size_t)R * 4, (size_t)(R + 1) * 4, (size_t)R, (size_t)O * 4, (size_t)O * 4, (size_t)O * 4,
                            (size_t)a->seq_len};
   for (int i = 0; i < 9; ++i) {
-    if (int rc = grow(e, e->ct_in[i], bytes[i] ? bytes[i] : 4)) return rc;
+    if (int rc = grow(e, e->ct_in[i], (bytes[i] ? bytes[i] : 4) + (i == 8 ? 64 : 0))) return rc;      // seq: slack for the staged word loads
     if (bytes[i] && src[i]) CU_TRY(e, cudaMemcpyAsync(e->ct_in[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, st));
   }
   if (int rc = grow(e, e->ct_in[9], (size_t)a->ref_len)) return rc;

@@ -62,7 +62,11 @@ def test_oracle_reproduces_reference_rows(case):
 
 
 # ---- the kernel's rule, compiled for the host ------------------------------------------------------------------------
-@pytest.fixture(scope="module", params=["op-major walk", "position-major walk (-DCLAIRB_CT_FLAT)"])
+WALKS = {"staged": [0, 0]}                      # (site, read) pairs that took the staged / the general walk, over the module
+
+
+@pytest.fixture(scope="module", params=["staged walk (-DCLAIRB_CT_STAGED)", "op-major walk (the kernel's default)",
+                                        "position-major walk (-DCLAIRB_CT_FLAT)"])
 def host_rule(request, tmp_path_factory):
     out = str(tmp_path_factory.mktemp("ct_harness") / "ct_host.so")
     src = os.path.join(ROOT, "tests", "harness", "create_tensor_host.cu")
@@ -72,6 +76,8 @@ def host_rule(request, tmp_path_factory):
                    ["-o", out, src], check=True)
     lib = ctypes.CDLL(out)
     lib.ct_host_sites.restype = ctypes.c_int
+    lib.ct_host_sites_staged.restype = ctypes.c_int
+    lib.staged = request.param.startswith("staged")
     return lib
 
 
@@ -94,10 +100,21 @@ def host_rule_rows(lib, case):
     def p(arr):
         return arr.ctypes.data_as(ctypes.c_void_p)
 
-    rc = lib.ct_host_sites(p(aln.read_pos), p(aln.read_end), p(maxend), p(aln.read_op0), p(aln.read_strand),
-                           ctypes.c_int32(aln.n_reads), p(aln.op_ref), p(aln.op_qry), p(aln.op_len), p(aln.seq), p(ref),
-                           ctypes.c_int32(start0), ctypes.c_int32(ref.shape[0]), p(centers), ctypes.c_int32(n),
-                           ctypes.c_int(0 if a["stop_consider_left_edge"] else 1), p(counts), p(opened))
+    args = [p(aln.read_pos), p(aln.read_end), p(maxend), p(aln.read_op0), p(aln.read_strand),
+            ctypes.c_int32(aln.n_reads), p(aln.op_ref), p(aln.op_qry), p(aln.op_len), p(aln.seq), p(ref),
+            ctypes.c_int32(start0), ctypes.c_int32(ref.shape[0]), p(centers), ctypes.c_int32(n),
+            ctypes.c_int(0 if a["stop_consider_left_edge"] else 1), p(counts), p(opened)]
+    if lib.staged:
+        padded = np.zeros(aln.seq.shape[0] + 64, np.uint8)            # the device buffer carries the same slack behind SEQ
+        padded[:aln.seq.shape[0]] = aln.seq
+        assert padded.ctypes.data % 4 == 0
+        args[9] = p(padded)
+        took = (ctypes.c_int64 * 2)()
+        rc = lib.ct_host_sites_staged(*args, ctypes.byref(took, 0), ctypes.byref(took, 8))
+        WALKS["staged"][0] += took[0]
+        WALKS["staged"][1] += took[1]
+    else:
+        rc = lib.ct_host_sites(*args)
     assert rc == 0, "a read outside the searched range opens site %d" % (rc - 1)
     rows = []
     for i in range(n):
@@ -123,6 +140,13 @@ def test_kernel_rule_on_host_random_regions(host_rule):
         assert len(got) == len(want)
         for g, w in zip(got, want):
             assert g[:3] == w[:3] and np.array_equal(g[3], w[3].reshape(-1))
+
+
+def test_staged_and_general_walks_were_both_taken():
+    """Runs after the host-rule tests above (file order): the golden regions and the random ones must have sent reads down both
+    walks of the staged variant - windows that fit the stage, and windows with more ops / inserted bases than it holds."""
+    staged, general = WALKS["staged"]
+    assert staged > 1000 and general > 0, (staged, general)
 
 
 @pytest.mark.parametrize("shape", [dict(depth=60, read_len=150, ops_per_read=3, site_spacing=40),       # short reads, few ops
