@@ -66,6 +66,9 @@ SYMBOLS = {
                                                    _c.c_void_p]),
     "clairb_trainer_backward_lstm": (_c.c_int, [_c.c_void_p]),
     "clairb_trainer_apply": (_c.c_int, [_c.c_void_p, _c.c_float, _c.c_float, _c.c_float, _c.c_int64, _c.POINTER(_c.c_double)]),
+    "clairb_trainer_stream": (_c.c_void_p, [_c.c_void_p]),
+    "clairb_trainer_set_deferred": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p]),
+    "clairb_trainer_read_losses": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_double)]),
     "clairb_trainer_step": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_uint64, _c.c_float,
                                        _c.c_float, _c.c_float, _c.c_int64, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double)]),
     "clairb_trainer_get_probabilities": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64]),

@@ -42,7 +42,9 @@ struct clairb_trainer {
   double* d_loss = nullptr;                                            // [4 focal sums, L2 sum, gradient sum of squares]
   int64_t last_n = 0, last_np = 0;
   bool lstm_pending = false;
-  bool one_sync = false;                                               // inside clairb_trainer_step: the parts do not synchronise
+  bool one_sync = false;                                               // inside clairb_trainer_step / deferred mode: the parts do not synchronise
+  bool deferred = false;                                               // clairb_trainer_set_deferred
+  float* loss_tail = nullptr;                                          // caller-owned [4] floats: the focal sums, written by forward_backward
   float rates[6] = {0.5f, 0.5f, 0.2f, 0.2f, 0.2f, 0.2f};
 };
 
@@ -295,6 +297,30 @@ int clairb_trainer_set_grad_buffer(clairb_trainer* t, float* dev_ptr) {
   return CLAIRB_OK;
 }
 
+// Data-parallel plumbing without host synchronisation between the parts of a step.  `stream` is the CUDA stream every part is
+// enqueued on (the second direction's stream is joined back into it before a part returns): a caller makes its communication
+// stream wait on it and makes it wait on the collectives.  In deferred mode forward_backward / backward_lstm only enqueue (the
+// `losses` argument is not written; read them with clairb_trainer_read_losses after clairb_trainer_apply, which synchronises).
+// `loss_tail`: 4 caller-owned device floats that receive the focal-loss sums at the end of forward_backward - placed right
+// behind the gradient buffer they are summed over the ranks by the same all-reduce.
+void* clairb_trainer_stream(clairb_trainer* t) { return t ? (void*)t->st : nullptr; }
+
+int clairb_trainer_set_deferred(clairb_trainer* t, int on, float* loss_tail) {
+  if (!t) return CLAIRB_EINVAL;
+  t->deferred = on != 0;
+  t->loss_tail = on ? loss_tail : nullptr;
+  return CLAIRB_OK;
+}
+
+int clairb_trainer_read_losses(clairb_trainer* t, double* losses) {
+  if (!t || !losses) return CLAIRB_EINVAL;
+  TR_TRY(t, cudaSetDevice(t->device));
+  TR_TRY(t, cudaStreamSynchronize(t->st));
+  TR_TRY(t, cudaMemcpy(losses, t->d_loss, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+  losses[4] *= 0.5;                                          // sum ||v||^2 / 2 (tf.nn.l2_loss)
+  return CLAIRB_OK;
+}
+
 int clairb_trainer_set_dropout_rates(clairb_trainer* t, const float* rates6) {
   if (!t || !rates6) return CLAIRB_EINVAL;
   for (int i = 0; i < 6; ++i) {
@@ -312,7 +338,7 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
   using namespace clairb::train;
   if (!t) return CLAIRB_EINVAL;
   if (!t->weights_set) return tfail(t, CLAIRB_EINVAL, "train step before the weights were set");
-  if (!x_host || !y_host || !losses || n <= 0 || n > t->max_batch) return tfail(t, CLAIRB_EINVAL, "train step: bad n or buffers");
+  if (!x_host || !y_host || (!losses && !t->deferred) || n <= 0 || n > t->max_batch) return tfail(t, CLAIRB_EINVAL, "train step: bad n or buffers");
   if (dtype != CLAIRB_DTYPE_F32 && dtype != CLAIRB_DTYPE_I16) return tfail(t, CLAIRB_EINVAL, "unknown dtype %d", dtype);
   TR_TRY(t, cudaSetDevice(t->device));
   cudaStream_t st = t->st;
@@ -477,9 +503,13 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
     dropout_scale<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->dlout[1], t->mask[0], 1.f / (1.f - t->rates[0]), rows * 2 * H);
     ++t->launches;
   }
+  if (t->loss_tail) {
+    store_loss_sums<<<1, 32, 0, st>>>(t->d_loss, t->loss_tail);
+    ++t->launches;
+  }
   TR_TRY(t, cudaGetLastError());
   t->lstm_pending = true;
-  if (t->one_sync) return CLAIRB_OK;
+  if (t->one_sync || t->deferred) return CLAIRB_OK;
   TR_TRY(t, cudaMemcpyAsync(losses, t->d_loss, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TR_TRY(t, cudaStreamSynchronize(st));
   losses[4] *= 0.5;                                          // sum ||v||^2 / 2 (tf.nn.l2_loss)
@@ -494,7 +524,7 @@ int clairb_trainer_backward_lstm(clairb_trainer* t) {
   if (int rc = lstm_layer_backward(t, 1, t->last_np)) return rc;
   if (int rc = lstm_layer_backward(t, 0, t->last_np)) return rc;
   TR_TRY(t, cudaGetLastError());
-  if (!t->one_sync) TR_TRY(t, cudaStreamSynchronize(t->st));
+  if (!t->one_sync && !t->deferred) TR_TRY(t, cudaStreamSynchronize(t->st));
   t->lstm_pending = false;
   return CLAIRB_OK;
 }

@@ -775,5 +775,10 @@ __global__ void adam_update(float* __restrict__ w, const float* __restrict__ g, 
   w[i] -= lr_t * mi / (sqrtf(vi) + 1e-8f);
 }
 
+// the four focal-loss sums as floats behind a data-parallel caller's gradient buffer: they travel with the gradient all-reduce
+__global__ void store_loss_sums(const double* __restrict__ d_loss, float* __restrict__ out) {
+  if (threadIdx.x < 4) out[threadIdx.x] = (float)d_loss[threadIdx.x];
+}
+
 }  // namespace train
 }  // namespace clairb

@@ -172,16 +172,18 @@ class GradientExchange(object):
     backward pass has left the dense layers -, `head()` the LSTM part [:dense_offset] after BPTT, `wait()` returns when both
     sums are in place on every rank.  SUM, not mean: the reference's loss is a sum over the batch (clair/model.py:696-709, 783-805),
     so the gradient of the global batch is the sum of the ranks' gradients.  Works on any torch.distributed backend (the CPU
-    tests run it over gloo); `stream` is the communication stream on CUDA."""
+    tests run it over gloo).  On CUDA, `compute` is the stream the gradients are produced on and `comm` the communication stream:
+    a piece starts when `compute` has reached this point, and wait() makes `compute` (not the host) wait for the sums."""
 
-    def __init__(self, grad, dense_offset, dist, stream=None):
-        self.grad, self.dense_offset, self.dist, self.stream = grad, int(dense_offset), dist, stream
+    def __init__(self, grad, dense_offset, dist, compute=None, comm=None):
+        self.grad, self.dense_offset, self.dist, self.compute, self.comm = grad, int(dense_offset), dist, compute, comm
         self._work = []
 
     def _start(self, piece):
-        if self.stream is not None:
+        if self.comm is not None:
             import torch
-            with torch.cuda.stream(self.stream):
+            self.comm.wait_stream(self.compute)
+            with torch.cuda.stream(self.comm):
                 self._work.append(self.dist.all_reduce(piece, op=self.dist.ReduceOp.SUM, async_op=True))
         else:
             self._work.append(self.dist.all_reduce(piece, op=self.dist.ReduceOp.SUM, async_op=True))
@@ -193,15 +195,23 @@ class GradientExchange(object):
         self._start(self.grad[:self.dense_offset])
 
     def wait(self):
-        for w in self._work:
-            w.wait()
+        if self.comm is not None:
+            import torch
+            with torch.cuda.stream(self.compute):
+                for w in self._work:
+                    w.wait()                                         # NCCL: blocks the current STREAM, not the host
+        else:
+            for w in self._work:
+                w.wait()
         self._work = []
 
 
 class DataParallelTrainer(Trainer):
     """One process per GPU (torch.distributed, NCCL): every rank runs the step on its own batch.  The flat gradient buffer is a
-    torch tensor; its dense tail is all-reduced while the LSTM backward runs, the LSTM head after it (GradientExchange), then
-    every rank applies the same update.  Weights must start identical on all ranks (set_weights with the same blob / seed)."""
+    torch tensor with four extra floats behind it that receive the rank's focal-loss sums; its dense tail (and the loss sums) is
+    all-reduced while the LSTM backward runs, the LSTM head after it (GradientExchange), then every rank applies the same update.
+    The parts of the step are only enqueued (deferred mode): the library's stream waits for the collectives, the host
+    synchronises once, in apply().  Weights must start identical on all ranks (set_weights with the same blob / seed)."""
 
     def __init__(self, **kw):
         import torch
@@ -209,21 +219,24 @@ class DataParallelTrainer(Trainer):
         self._dist, self._torch = dist, torch
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         Trainer.__init__(self, **kw)
-        self._grad = torch.zeros(self.num_params, dtype=torch.float32, device="cuda:%d" % self.device)
-        self._check(self._lib.clairb_trainer_set_grad_buffer(self._t, ctypes.c_void_p(self._grad.data_ptr())), "clairb_trainer_set_grad_buffer")
-        self._exchange = GradientExchange(self._grad, self.dense_offset, dist, torch.cuda.Stream(device=self.device))
+        self._buf = torch.zeros(self.num_params + 4, dtype=torch.float32, device="cuda:%d" % self.device)
+        self._grad = self._buf[:self.num_params]
+        self._check(self._lib.clairb_trainer_set_grad_buffer(self._t, ctypes.c_void_p(self._buf.data_ptr())), "clairb_trainer_set_grad_buffer")
+        tail = ctypes.c_void_p(self._buf.data_ptr() + 4 * self.num_params)
+        self._check(self._lib.clairb_trainer_set_deferred(self._t, 1, tail), "clairb_trainer_set_deferred")
+        compute = torch.cuda.ExternalStream(self._lib.clairb_trainer_stream(self._t), device=self.device)
+        self._exchange = GradientExchange(self._buf, self.dense_offset, dist, compute, torch.cuda.Stream(device=self.device))
 
     def train(self, batchX, batchY, masks=None):
-        torch, dist = self._torch, self._dist
-        parts = self.forward_backward(batchX, batchY, masks)          # returns with the dense gradients complete
-        self._exchange.dense()
-        self.backward_lstm()                                          # BPTT runs while the 8.3 MB dense piece travels
+        x, dtype, y, n, ptrs, seed, keep = self._inputs(batchX, batchY, masks)
+        self._check(self._lib.clairb_trainer_forward_backward(self._t, x, dtype, y, n, ptrs, seed, None), "clairb_trainer_forward_backward")
+        self._exchange.dense()                                        # 8.3 MB + the loss sums travel while BPTT runs
+        self.backward_lstm()
         self._exchange.head()
         self._exchange.wait()
-        torch.cuda.synchronize(self.device)
-        sums = torch.tensor(parts[:4], dtype=torch.float64, device="cuda:%d" % self.device)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        self.loss_parts = sums.tolist() + [parts[4]]
-        self.grad_norm = self.apply()
+        self.grad_norm = self.apply()                                 # the one host synchronisation of the step
+        own = (ctypes.c_double * 5)()
+        self._check(self._lib.clairb_trainer_read_losses(self._t, own), "clairb_trainer_read_losses")
+        self.loss_parts = [float(v) for v in self._buf[self.num_params:].tolist()] + [float(own[4])]
         self.training_loss_on_one_batch = self.total_loss()
         return self.training_loss_on_one_batch

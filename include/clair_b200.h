@@ -332,6 +332,14 @@ int clairb_trainer_apply(clairb_trainer* t, float learning_rate, float l2_lambda
 int clairb_trainer_step(clairb_trainer* t, const void* x_host, int dtype, const float* y_host, int64_t n,
                         const uint8_t* const* masks, uint64_t seed, float learning_rate, float l2_lambda, float clip_norm,
                         int64_t step, double* losses, double* grad_norm);
+/* Data-parallel plumbing without a host synchronisation between the parts of a step: the stream the parts are enqueued on
+ * (cudaStream_t; a caller makes its communication stream wait on it, and it wait on the collectives); deferred mode, in which
+ * forward_backward / backward_lstm only enqueue (losses are not written - clairb_trainer_read_losses after clairb_trainer_apply);
+ * loss_tail = 4 caller-owned device floats that receive the focal-loss sums at the end of forward_backward, e.g. right behind
+ * the gradient buffer so that the gradient all-reduce sums them over the ranks too. */
+void* clairb_trainer_stream(clairb_trainer* t);
+int clairb_trainer_set_deferred(clairb_trainer* t, int on, float* loss_tail);
+int clairb_trainer_read_losses(clairb_trainer* t, double* losses);
 int clairb_trainer_get_probabilities(clairb_trainer* t, float* out, int64_t n);
 int64_t clairb_trainer_kernel_launches(const clairb_trainer* t);
 const char* clairb_trainer_last_error(const clairb_trainer* t);

@@ -1,5 +1,5 @@
-"""Training-step throughput (BASELINE.json configs[4]: batch 512 per GPU, data-parallel): python tools/train_bench.py
-bench.py adds the result to its JSON line as `train_stage`; `cpu_part` is the only piece that touches oracle/."""
+"""Training-step throughput (BASELINE.json configs[4]: batch 512 per GPU, data-parallel): python tools/train_bench.py [batch]
+(or under torchrun for the data-parallel step).  bench.py adds the result to its JSON line as `train_stage`; `cpu_part` is the only piece that touches oracle/."""
 import json
 import os
 import sys
@@ -81,6 +81,18 @@ def cpu_part(report, n=32):
 
 
 if __name__ == "__main__":
-    r = device_part(int(sys.argv[1]) if len(sys.argv) > 1 else 512)
-    cpu_part(r)
-    print(json.dumps(r))
+    batch = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    if "RANK" in os.environ:                             # under torchrun: the data-parallel step, one rank per GPU
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        r = device_part(batch, steps=12, warm=3, device=local, data_parallel=True)
+        if dist.get_rank() == 0:
+            print(json.dumps(r))
+        dist.destroy_process_group()
+    else:
+        r = device_part(batch)
+        cpu_part(r)
+        print(json.dumps(r))
