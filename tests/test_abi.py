@@ -55,6 +55,23 @@ def test_create_fails_loudly_without_a_b200():
         Clair()
 
 
+def test_trainer_fails_loudly_without_a_b200():
+    """The training step has no CPU path either: the handle refuses to exist without an sm_100 device."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible; the refusal path is for the CPU box")
+    lib = _lib.load()
+    t = ctypes.c_void_p()
+    rc = lib.clairb_trainer_create(0, 512, ctypes.byref(t))
+    assert rc == _lib.ENODEVICE and not t.value
+    msg = lib.clairb_trainer_last_error(None)
+    assert msg and (b"not available" in msg or b"compute capability" in msg)
+    from clair_b200.train import Trainer
+    with pytest.raises(RuntimeError):
+        Trainer()
+    assert lib.clairb_trainer_stream(None) is None and lib.clairb_trainer_num_params(None) in (0, -1)
+
+
 def test_bad_arguments_are_rejected_not_crashed():
     lib = _lib.load()
     h = ctypes.c_void_p()
