@@ -47,3 +47,34 @@ def test_one_step_moves_the_loss_down(weights1234):
     again = TO.train_step(X, Y, r["new_weights"], masks)
     assert again["loss"] < r["loss"]
     assert set(r["grads"]) == set(weights1234) and all(np.isfinite(g).all() for g in r["grads"].values())
+
+
+def test_three_term_tf32_split_is_fp32_grade():
+    """The arithmetic of the training GEMMs (csrc/train_kernels.cuh: split_tf32 + mma_3xtf32), restated in numpy: an operand is
+    hi (rounded to TF32's 10 mantissa bits in integer arithmetic) + lo (exact remainder, of which the tensor core reads the top
+    19 bits), a product is a_lo.b_hi + a_hi.b_lo + a_hi.b_hi.  Its error stays below 2^-20 of |a.b| - the fp32 rounding of a
+    single product is 2^-24 - and is not biased, which is what the near-cancelling sums of weight gradients need."""
+    rng = np.random.default_rng(11)
+    a = (rng.standard_normal(200000) * 10.0 ** rng.uniform(-6, 3, 200000)).astype(np.float32)
+    b = (rng.standard_normal(200000) * 10.0 ** rng.uniform(-6, 3, 200000)).astype(np.float32)
+
+    def split(x):
+        bits = x.view(np.uint32)
+        hi = ((bits + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(np.float32)
+        lo = (x - hi).astype(np.float32)                                  # exact in fp32
+        assert np.array_equal(lo.astype(np.float64), x.astype(np.float64) - hi.astype(np.float64))
+        lo_seen = (lo.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)      # what the MMA reads of the register
+        return hi.astype(np.float64), lo_seen.astype(np.float64)
+
+    ah, al = split(a)
+    bh, bl = split(b)
+    got = al * bh + ah * bl + ah * bh
+    exact = a.astype(np.float64) * b.astype(np.float64)
+    rel = (got - exact) / np.abs(exact)
+    assert np.abs(rel).max() < 2.0 ** -20
+    assert abs(rel.mean()) < 2.0 ** -26                                   # unbiased (measured 2^-33; worst single product 2^-21.1)
+    # the rejected variant: hi cut instead of rounded biases every product the same way (mean error 2^-21.8 of the product)
+    hi_cut = (a.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32).astype(np.float64)
+    lo_cut = ((a - hi_cut.astype(np.float32)).astype(np.float32).view(np.uint32) & np.uint32(0xffffe000)).view(np.float32).astype(np.float64)
+    rel_cut = ((lo_cut * bh + hi_cut * bl + hi_cut * bh) - exact) / exact
+    assert abs(rel_cut.mean()) > 10 * abs(rel.mean())
