@@ -247,7 +247,10 @@ __global__ void scale_matrix(float* __restrict__ C, int M, int N, int ldc, float
 
 inline void gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc,
                  cudaStream_t st, int64_t* launches) {
-  const bool big = M >= 96 && N >= 96 && !((M | N | K | lda | ldb | ldc) & 3) && !(((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15);
+  // the tensor-core tile for everything large; a long contraction is worth it even when only a quarter of the tile's rows exist
+  // (layer 1's dW_x: 32 x 512 over 33 n rows)
+  const bool big = (M >= 96 || (M >= 32 && K >= 4096)) && N >= 96 && !((M | N | K | lda | ldb | ldc) & 3) &&
+                   !(((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15);
   const int tm = big ? BM : GM, tn = big ? BN : GN, tk = big ? BK : GK;
   dim3 grid((N + tn - 1) / tn, (M + tm - 1) / tm);
   // split the contraction when the output tiles alone cannot fill the machine (148 SMs, 2 resident CTAs of the large kernel, 4 of
