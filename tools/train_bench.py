@@ -35,7 +35,14 @@ def device_part(batch=512, steps=8, warm=2, device=0, data_parallel=False):
         t = Trainer(device=device, max_batch=batch)
         rank = 0
     t.set_weights(W.random_weights(seed=1234))
-    pool = [(synth.synthetic_tensors(batch, seed=900 + 10 * rank + i).astype(np.int16), labels(batch, 10 * rank + i)) for i in range(4)]
+    # tensors and labels of a step come from page-locked host memory (the staging a loader fills), copied to the device every step
+    from clair_b200.model import pinned_empty
+    pool = []
+    for i in range(4):
+        X, Y = pinned_empty((batch, 33, 8, 4), np.int16), pinned_empty((batch, 90), np.float32)
+        X[...] = synth.synthetic_tensors(batch, seed=900 + 10 * rank + i).astype(np.int16)
+        Y[...] = labels(batch, 10 * rank + i)
+        pool.append((X, Y))
     for i in range(warm):
         t.train(*pool[i % 4])
     torch.cuda.synchronize(device)
@@ -54,7 +61,7 @@ def device_part(batch=512, steps=8, warm=2, device=0, data_parallel=False):
         v = torch.tensor([dt], dtype=torch.float64, device="cuda:%d" % device)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         dt = float(v.item())
-    out = {"workload": "training step, batch %d per GPU x %d GPU(s), synthetic (tensor, label) pairs, int16 host input" % (batch, world),
+    out = {"workload": "training step, batch %d per GPU x %d GPU(s), synthetic (tensor, label) pairs, int16 tensors and labels from pinned host memory every step" % (batch, world),
            "sites_per_s": world * batch * steps / dt, "ms_per_step": dt / steps * 1e3, "steps": steps,
            "gpu_launches_per_step": (t.kernel_launches() - l0) / steps,
            "tflops_fp32": world * batch * steps * 3 * FLOP_PER_SITE_FORWARD / dt / 1e12,
@@ -64,6 +71,10 @@ def device_part(batch=512, steps=8, warm=2, device=0, data_parallel=False):
                    "shared memory), input projections / weight gradients / L4 as 3xTF32 mma.sync GEMMs over all steps, slice-dense "
                    "kernels with a lane per channel"}
     t.close()
+    from clair_b200.model import pinned_free
+    for X, Y in pool:
+        pinned_free(X)
+        pinned_free(Y)
     return out
 
 
