@@ -72,8 +72,9 @@ int tfail(clairb_trainer* t, int code, const char* fmt, ...) {
   } while (0)
 
 inline unsigned blocks_for(int64_t count, int threads = 256) { return (unsigned)((count + threads - 1) / threads); }
-// one cluster of SEQ_CTAS CTAs per SEQ_ROWS sites (lstm_seq_forward / lstm_seq_backward)
-inline unsigned seq_grid(int64_t np) { return (unsigned)((np + clairb::train::SEQ_ROWS - 1) / clairb::train::SEQ_ROWS * clairb::train::SEQ_CTAS); }
+// one cluster of SEQ_CTAS CTAs per `rows` sites (lstm_seq_forward<rows> / lstm_seq_backward: 64)
+inline unsigned seq_grid(int64_t np, int rows = clairb::train::SEQ_ROWS) { return (unsigned)((np + rows - 1) / rows * clairb::train::SEQ_CTAS); }
+constexpr int SEQ_FWD_ROWS = 32;
 
 void trainer_layout(clairb_trainer* t) {
   const int head_n[4] = {21, 3, 33, 33};
@@ -215,7 +216,7 @@ int clairb_trainer_create(int device, int64_t max_batch, clairb_trainer** out) {
   TC_TRY(cudaFuncSetAttribute(l3_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
   TC_TRY(cudaFuncSetAttribute(l3_backward_input, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
   TC_TRY(cudaFuncSetAttribute(l3_backward_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-  TC_TRY(cudaFuncSetAttribute(lstm_seq_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ_FWD_SMEM));
+  TC_TRY(cudaFuncSetAttribute(lstm_seq_forward<SEQ_FWD_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_fwd_smem(SEQ_FWD_ROWS)));
   TC_TRY(cudaFuncSetAttribute(lstm_seq_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ_BWD_SMEM));
   TC_TRY(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
   TC_TRY(cudaStreamCreateWithFlags(&t->st2, cudaStreamNonBlocking));
@@ -389,7 +390,7 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
       // the state before the first step: slab 0 (fw walks t = 0..32) and slab 34 (bw walks t = 32..0)
       TR_TRY(t, cudaMemsetAsync(q.hbuf + (d ? 34 : 0) * (size_t)np * H, 0, (size_t)np * H * sizeof(float), sd));
       TR_TRY(t, cudaMemsetAsync(q.cbuf + (d ? 34 : 0) * (size_t)np * H, 0, (size_t)np * H * sizeof(float), sd));
-      lstm_seq_forward<<<seq_grid(np), 256, SEQ_FWD_SMEM, sd>>>(q.pre, t->P + pk.off + (size_t)K * G4, t->P + pb.off, q.gates, q.cbuf, q.hbuf, t->lout[l],
+      lstm_seq_forward<SEQ_FWD_ROWS><<<seq_grid(np, SEQ_FWD_ROWS), 256, seq_fwd_smem(SEQ_FWD_ROWS), sd>>>(q.pre, t->P + pk.off + (size_t)K * G4, t->P + pb.off, q.gates, q.cbuf, q.hbuf, t->lout[l],
                                                                  d * H, (int)np, d);
       ++t->launches;
     }

@@ -350,7 +350,7 @@ __global__ void make_mask(uint8_t* __restrict__ mask, int64_t count, float rate,
 constexpr int SEQ_ROWS = 64, SEQ_CTAS = 8, SEQ_UNITS = H / SEQ_CTAS;      // 64 sites per cluster, 16 units per CTA
 constexpr int SEQ_LD = SEQ_ROWS + 8;                                      // 72 = 8 (mod 32): conflict-free fragment loads
 constexpr int SEQ_SLICE_BYTES = SEQ_UNITS * SEQ_LD * (int)sizeof(float);  // 4608: the h columns (or dh partial sums) of one CTA
-constexpr int SEQ_FWD_SMEM = (H * SEQ_LD + 2 * H * SEQ_LD) * (int)sizeof(float) + 16;                                         // 110,608 B
+constexpr int seq_fwd_smem(int rb) { return (H * SEQ_LD + 2 * H * (rb + 8)) * (int)sizeof(float) + 16; }      // 110,608 B (64 sites), 77,840 B (32)
 constexpr int SEQ_BWD_LDW = H + 8;                                        // 136
 constexpr int SEQ_BWD_SMEM = (4 * SEQ_UNITS * SEQ_BWD_LDW + 4 * SEQ_UNITS * SEQ_LD + 2 * H * SEQ_LD + 2 * SEQ_CTAS * SEQ_UNITS * SEQ_LD) * (int)sizeof(float) + 16;   // 200,720 B
 
@@ -362,15 +362,19 @@ __device__ __forceinline__ void bulk_to_cta(const void* src, void* dst_same_offs
                : "memory");
 }
 
+// RB = sites per cluster: 64 (a warp owns 2 x 2 MMA tiles) or 32 (1 x 2; half the work and half the exchange per CTA and step, so
+// that two CTAs - of different clusters - share an SM and one computes while the other waits for its h to arrive).
+template <int RB>
 __global__ void __cluster_dims__(SEQ_CTAS, 1, 1) __launch_bounds__(256)
 lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, const float* __restrict__ bias, float* __restrict__ gates,
                  float* __restrict__ cbuf, float* __restrict__ hbuf, float* __restrict__ lout, int col0, int n, int reverse) {
+  constexpr int MI = RB / 32, LD = RB + 8, SLICE_BYTES = SEQ_UNITS * LD * (int)sizeof(float);      // LD = 8 (mod 32) for both
   extern __shared__ __align__(16) float seq_smem[];
   float* Ws = seq_smem;                                  // [128 units of h_{s-1}][72: 64 local gate columns]
-  float* hT = Ws + H * SEQ_LD;                           // [2][128 units][72: 64 sites]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hT + 2 * H * SEQ_LD);      // [2]: "h of this buffer has arrived from the 7 other CTAs"
+  float* hT = Ws + H * SEQ_LD;                           // [2][128 units][LD: RB sites]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hT + 2 * H * LD);      // [2]: "h of this buffer has arrived from the 7 other CTAs"
   const int j = (int)tc::cluster_ctarank();
-  const int r0 = (int)(blockIdx.x / SEQ_CTAS) * SEQ_ROWS;
+  const int r0 = (int)(blockIdx.x / SEQ_CTAS) * RB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
   const int mp = warp >> 2, ug = warp & 3;
   const int unit = j * SEQ_UNITS + 4 * ug + tig;         // this lane's hidden unit
@@ -380,7 +384,7 @@ lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, co
     const int u = 4 * (lc >> 4) + ((lc & 7) >> 1), gate = 2 * ((lc >> 3) & 1) + (lc & 1);
     Ws[k * SEQ_LD + lc] = Wh[(size_t)k * G4 + gate * H + j * SEQ_UNITS + u];
   }
-  for (int i = threadIdx.x; i < H * SEQ_LD; i += 256) hT[i] = 0.f;        // h_0 = 0
+  for (int i = threadIdx.x; i < H * LD; i += 256) hT[i] = 0.f;        // h_0 = 0
   if (threadIdx.x == 0) {
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
@@ -392,14 +396,14 @@ lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, co
 #pragma unroll
     for (int e = 0; e < 2; ++e) bz[nt][e] = bias[(2 * nt + e) * H + unit];
   // accumulators acc[mi][nt][2 half + e]: site 32 mp + 16 mi + 8 half + g, gate 2 nt + e; they start as pre + bias
-  float acc[2][2][4], c[2][2] = {};
-  auto fetch = [&](int s, float (&z)[2][2][4]) {
+  float acc[MI][2][4], c[MI][2] = {};
+  auto fetch = [&](int s, float (&z)[MI][2][4]) {
     const int t = reverse ? T_STEPS - 1 - s : s;         // everything in global memory is in TIME order
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const int row = r0 + 32 * mp + 16 * mi + 8 * half + g;
+        const int row = r0 + 16 * MI * mp + 16 * mi + 8 * half + g;
         const float* q = pre + ((size_t)t * n + row) * G4 + unit;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
@@ -410,9 +414,9 @@ lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, co
   fetch(0, acc);
   tc::cluster_sync_all();                                // every CTA of the cluster runs and has its barriers initialised
   for (int s = 0; s < T_STEPS; ++s) {
-    const float* hc = hT + (s & 1) * H * SEQ_LD;
-    float* hn = hT + ((s + 1) & 1) * H * SEQ_LD;
-    float nxt[2][2][4];                                  // the next step's input projection, requested before the contraction
+    const float* hc = hT + (s & 1) * H * LD;
+    float* hn = hT + ((s + 1) & 1) * H * LD;
+    float nxt[MI][2][4];                                  // the next step's input projection, requested before the contraction
     if (s + 1 < T_STEPS) fetch(s + 1, nxt);
     if (s > 0) tc::mbar_wait(&bars[s & 1], ((s - 1) >> 1) & 1);
 #pragma unroll 4
@@ -424,27 +428,27 @@ lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, co
         split_tf32(Ws[(kk + tig + 4) * SEQ_LD + 16 * ug + 8 * nt + g], bh[nt][1], bl[nt][1]);
       }
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi) {
-        const int mb = 32 * mp + 16 * mi + g;
+      for (int mi = 0; mi < MI; ++mi) {
+        const int mb = 16 * MI * mp + 16 * mi + g;
         uint32_t ah[4], al[4];
-        split_tf32(hc[(kk + tig) * SEQ_LD + mb], ah[0], al[0]);
-        split_tf32(hc[(kk + tig) * SEQ_LD + mb + 8], ah[1], al[1]);
-        split_tf32(hc[(kk + tig + 4) * SEQ_LD + mb], ah[2], al[2]);
-        split_tf32(hc[(kk + tig + 4) * SEQ_LD + mb + 8], ah[3], al[3]);
+        split_tf32(hc[(kk + tig) * LD + mb], ah[0], al[0]);
+        split_tf32(hc[(kk + tig) * LD + mb + 8], ah[1], al[1]);
+        split_tf32(hc[(kk + tig + 4) * LD + mb], ah[2], al[2]);
+        split_tf32(hc[(kk + tig + 4) * LD + mb + 8], ah[3], al[3]);
         mma_3xtf32<2>(acc[mi], ah, al, bh, bl);
       }
     }
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const int rl = 32 * mp + 16 * mi + 8 * half + g;
+        const int rl = 16 * MI * mp + 16 * mi + 8 * half + g;
         const float ig = sigmoidf_(acc[mi][0][2 * half]), gg = tanhf(acc[mi][0][2 * half + 1]);
         const float fg = sigmoidf_(acc[mi][1][2 * half]), og = sigmoidf_(acc[mi][1][2 * half + 1]);
         const float cv = gg * ig + c[mi][half] * fg;
         const float hv = tanhf(cv) * og;
         c[mi][half] = cv;
-        hn[unit * SEQ_LD + rl] = hv;
+        hn[unit * LD + rl] = hv;
         if (r0 + rl < n) {
           const size_t r = (size_t)(reverse ? T_STEPS - 1 - s : s) * n + r0 + rl;
           gates[r * G4 + unit] = ig; gates[r * G4 + H + unit] = gg; gates[r * G4 + 2 * H + unit] = fg; gates[r * G4 + 3 * H + unit] = og;
@@ -457,13 +461,13 @@ lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, co
       tc::fence_proxy_async();                           // the h columns just written are read by the bulk copies
       __syncthreads();
       if (threadIdx.x == 0) {
-        tc::mbar_expect_tx(&bars[(s + 1) & 1], (SEQ_CTAS - 1) * SEQ_SLICE_BYTES);
-        float* mine = hn + j * SEQ_UNITS * SEQ_LD;
+        tc::mbar_expect_tx(&bars[(s + 1) & 1], (SEQ_CTAS - 1) * SLICE_BYTES);
+        float* mine = hn + j * SEQ_UNITS * LD;
 #pragma unroll 1
-        for (int d = 1; d < SEQ_CTAS; ++d) bulk_to_cta(mine, mine, &bars[(s + 1) & 1], (uint32_t)((j + d) & (SEQ_CTAS - 1)), SEQ_SLICE_BYTES);
+        for (int d = 1; d < SEQ_CTAS; ++d) bulk_to_cta(mine, mine, &bars[(s + 1) & 1], (uint32_t)((j + d) & (SEQ_CTAS - 1)), SLICE_BYTES);
       }
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
+      for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
