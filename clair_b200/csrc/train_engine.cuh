@@ -74,7 +74,11 @@ int tfail(clairb_trainer* t, int code, const char* fmt, ...) {
 inline unsigned blocks_for(int64_t count, int threads = 256) { return (unsigned)((count + threads - 1) / threads); }
 // one cluster of SEQ_CTAS CTAs per `rows` sites (lstm_seq_forward<rows> / lstm_seq_backward: 64)
 inline unsigned seq_grid(int64_t np, int rows = clairb::train::SEQ_ROWS) { return (unsigned)((np + rows - 1) / rows * clairb::train::SEQ_CTAS); }
-constexpr int SEQ_FWD_ROWS = 32;
+// Sites per cluster of the sequence kernels.  Forward: always 32 - two CTAs per SM, one computes while the other waits for its
+// exchange (measured at 512 and 2048 sites: 3.00 / 8.45 ms per step against 3.26 / 8.83 with 64).  Backward: 32 while both
+// directions' clusters fit the machine at two CTAs per SM, 64 beyond (its [64 x 128] weight tile is loaded per CTA and its
+// fragments are reused over fewer sites at 32: 8.63 against 8.45 ms at 2048 sites).
+inline int seq_rows_backward(int64_t np) { return seq_grid(np, 32) * 2 <= 2 * 148 ? 32 : 64; }
 
 void trainer_layout(clairb_trainer* t) {
   const int head_n[4] = {21, 3, 33, 33};
@@ -154,8 +158,12 @@ int lstm_layer_backward(clairb_trainer* t, int l, int64_t np) {
     const auto& pk = tp(t, lstm_prefix(l, d) + "kernel");
     const auto& pb = tp(t, lstm_prefix(l, d) + "bias");
     TR_TRY(t, cudaMemsetAsync(t->G + pb.off, 0, G4 * sizeof(float), sd));
-    lstm_seq_backward<<<seq_grid(np), 256, SEQ_BWD_SMEM, sd>>>(t->dlout[l], d * H, q.gates, q.cbuf, t->P + pk.off + (size_t)K * G4, q.dZ, t->G + pb.off,
-                                                                (int)np, d);
+    if (seq_rows_backward(np) == 32)
+      lstm_seq_backward<32><<<seq_grid(np, 32), 256, seq_bwd_smem(32), sd>>>(t->dlout[l], d * H, q.gates, q.cbuf, t->P + pk.off + (size_t)K * G4, q.dZ,
+                                                                               t->G + pb.off, (int)np, d);
+    else
+      lstm_seq_backward<64><<<seq_grid(np, 64), 256, seq_bwd_smem(64), sd>>>(t->dlout[l], d * H, q.gates, q.cbuf, t->P + pk.off + (size_t)K * G4, q.dZ,
+                                                                               t->G + pb.off, (int)np, d);
     ++t->launches;
     float* gk = t->G + pk.off;
     // dW_x = in^T . dZ (all steps at once, both in time order), dW_h = h_prev^T . dZ: h of the step before time t is slab t (fw) / t + 2 (bw)
@@ -216,8 +224,9 @@ int clairb_trainer_create(int device, int64_t max_batch, clairb_trainer** out) {
   TC_TRY(cudaFuncSetAttribute(l3_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
   TC_TRY(cudaFuncSetAttribute(l3_backward_input, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
   TC_TRY(cudaFuncSetAttribute(l3_backward_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-  TC_TRY(cudaFuncSetAttribute(lstm_seq_forward<SEQ_FWD_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_fwd_smem(SEQ_FWD_ROWS)));
-  TC_TRY(cudaFuncSetAttribute(lstm_seq_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ_BWD_SMEM));
+  TC_TRY(cudaFuncSetAttribute(lstm_seq_forward<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_fwd_smem(32)));
+  TC_TRY(cudaFuncSetAttribute(lstm_seq_backward<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_bwd_smem(32)));
+  TC_TRY(cudaFuncSetAttribute(lstm_seq_backward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_bwd_smem(64)));
   TC_TRY(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
   TC_TRY(cudaStreamCreateWithFlags(&t->st2, cudaStreamNonBlocking));
   TC_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
@@ -390,8 +399,8 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
       // the state before the first step: slab 0 (fw walks t = 0..32) and slab 34 (bw walks t = 32..0)
       TR_TRY(t, cudaMemsetAsync(q.hbuf + (d ? 34 : 0) * (size_t)np * H, 0, (size_t)np * H * sizeof(float), sd));
       TR_TRY(t, cudaMemsetAsync(q.cbuf + (d ? 34 : 0) * (size_t)np * H, 0, (size_t)np * H * sizeof(float), sd));
-      lstm_seq_forward<SEQ_FWD_ROWS><<<seq_grid(np, SEQ_FWD_ROWS), 256, seq_fwd_smem(SEQ_FWD_ROWS), sd>>>(q.pre, t->P + pk.off + (size_t)K * G4, t->P + pb.off, q.gates, q.cbuf, q.hbuf, t->lout[l],
-                                                                 d * H, (int)np, d);
+      lstm_seq_forward<32><<<seq_grid(np, 32), 256, seq_fwd_smem(32), sd>>>(q.pre, t->P + pk.off + (size_t)K * G4, t->P + pb.off, q.gates, q.cbuf, q.hbuf,
+                                                                              t->lout[l], d * H, (int)np, d);
       ++t->launches;
     }
     TR_TRY(t, cudaEventRecord(t->ev_join, t->st2));

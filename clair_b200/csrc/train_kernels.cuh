@@ -352,7 +352,9 @@ constexpr int SEQ_LD = SEQ_ROWS + 8;                                      // 72 
 constexpr int SEQ_SLICE_BYTES = SEQ_UNITS * SEQ_LD * (int)sizeof(float);  // 4608: the h columns (or dh partial sums) of one CTA
 constexpr int seq_fwd_smem(int rb) { return (H * SEQ_LD + 2 * H * (rb + 8)) * (int)sizeof(float) + 16; }      // 110,608 B (64 sites), 77,840 B (32)
 constexpr int SEQ_BWD_LDW = H + 8;                                        // 136
-constexpr int SEQ_BWD_SMEM = (4 * SEQ_UNITS * SEQ_BWD_LDW + 4 * SEQ_UNITS * SEQ_LD + 2 * H * SEQ_LD + 2 * SEQ_CTAS * SEQ_UNITS * SEQ_LD) * (int)sizeof(float) + 16;   // 200,720 B
+constexpr int seq_bwd_smem(int rb) {                                      // 163,864 B (64 sites), 106,520 B (32)
+  return (4 * SEQ_UNITS * SEQ_BWD_LDW + 4 * SEQ_UNITS * (rb + 8) + H * (rb + 8) + 2 * SEQ_CTAS * SEQ_UNITS * (rb + 8)) * (int)sizeof(float) + 24;
+}
 
 // local shared memory -> the same offset in CTA `rank` of the cluster, completing `bytes` on that CTA's mbarrier
 __device__ __forceinline__ void bulk_to_cta(const void* src, void* dst_same_offset, uint64_t* bar_same_offset, uint32_t rank, uint32_t bytes) {
@@ -479,28 +481,32 @@ lstm_seq_forward(const float* __restrict__ pre, const float* __restrict__ Wh, co
 
 // ---- the 33 steps of one LSTM direction, backward: dh = dh_out[s] + dh_rec ; gate gradients dZ[s] ; dc_{s-1} ; dh_rec <- dZ[s] . W_h^T
 // Same cluster shape and the same exchange.  CTA j produces the 64 gate-gradient columns of its 16 units (thread (ty, tx): sites
-// 4ty..+3 of unit tx), multiplies them by its 64 rows of W_h^T - [64 x 64] . [64 x 128] on the tensor cores, a partial sum of
-// dh_rec for ALL 128 units - and sends the 16 columns each other CTA owns into slot j of that CTA; when its own 7 slots have
-// arrived it adds the 8 partial sums in a fixed order.  The partial sums are double-buffered at the sender: a slot copy of step s
-// is known to be complete only when the receiver's answer of step s - 1 has arrived.  Also accumulates the bias gradient.
+// RPT ty..+RPT-1 of unit tx), multiplies them by its 64 rows of W_h^T - [RB x 64] . [64 x 128] on the tensor cores, a partial sum
+// of dh_rec for ALL 128 units - and sends the 16 columns each other CTA owns into slot j of that CTA; when its own 7 slots have
+// arrived it adds the 8 partial sums in a fixed order.  A slot copy reads the sender's partial sums asynchronously: every
+// receiver acknowledges on the sender's `ack` barrier once its slots are complete, and the sender waits for the 7
+// acknowledgements of a step before it overwrites the partial sums in the next (one step later: the wait is never felt).
+// With RB = 32 sites per cluster the kernel needs 104 KB of shared memory and two CTAs share an SM, as in the forward kernel.
+// Also accumulates the bias gradient.
+template <int RB>
 __global__ void __cluster_dims__(SEQ_CTAS, 1, 1) __launch_bounds__(256)
 lstm_seq_backward(const float* __restrict__ dlout, int col0, const float* __restrict__ gates, const float* __restrict__ cbuf,
                   const float* __restrict__ Wh, float* __restrict__ dZ, float* __restrict__ dbias, int n, int reverse) {
+  constexpr int MI = RB / 32, LD = RB + 8, RPT = RB / 16, SLOT = SEQ_UNITS * LD, SLICE_BYTES = SLOT * (int)sizeof(float);
   extern __shared__ __align__(16) float seq_smem[];
   float* Wt = seq_smem;                                  // [64 local gate columns][136: 128 units of h_{s-1}]
-  float* dzs = Wt + 4 * SEQ_UNITS * SEQ_BWD_LDW;         // [64 local gate columns][72: 64 sites]
-  float* part = dzs + 4 * SEQ_UNITS * SEQ_LD;            // [2][128 units][72: 64 sites]   this CTA's partial sums of dh_rec
-  float* slots = part + 2 * H * SEQ_LD;                  // [2][8 source CTAs][16 units][72]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slots + 2 * SEQ_CTAS * SEQ_UNITS * SEQ_LD);
-  constexpr int SLOT = SEQ_UNITS * SEQ_LD;
+  float* dzs = Wt + 4 * SEQ_UNITS * SEQ_BWD_LDW;         // [64 local gate columns][LD: RB sites]
+  float* part = dzs + 4 * SEQ_UNITS * LD;                // [128 units][LD]   this CTA's partial sums of dh_rec
+  float* slots = part + H * LD;                          // [2][8 source CTAs][16 units][LD]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slots + 2 * SEQ_CTAS * SLOT);     // [0], [1]: slots of that parity complete; [2]: ack
   const int j = (int)tc::cluster_ctarank();
-  const int r0 = (int)(blockIdx.x / SEQ_CTAS) * SEQ_ROWS;
+  const int r0 = (int)(blockIdx.x / SEQ_CTAS) * RB;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
-  const int mp = warp >> 2, nq = warp & 3;               // MMA role: sites 32 mp..+31  x  units 32 nq..+31 of the partial sums
+  const int mp = warp >> 2, nq = warp & 3;               // MMA role: sites 16 MI mp..  x  units 32 nq..+31 of the partial sums
   const int unit = j * SEQ_UNITS + tx;
-  const int row = r0 + 4 * ty;
-  const bool live = row < n;
+  const int row = r0 + RPT * ty;
+  const bool live = row < n;                             // n is a multiple of 8 >= RPT: a thread's sites are in or out together
   for (int i = threadIdx.x; i < 4 * SEQ_UNITS * H; i += 256) {
     const int lc = i >> 7, k = i & 127;                  // local gate column lc = 4 unit + gate
     Wt[lc * SEQ_BWD_LDW + k] = Wh[(size_t)k * G4 + (lc & 3) * H + j * SEQ_UNITS + (lc >> 2)];
@@ -508,15 +514,16 @@ lstm_seq_backward(const float* __restrict__ dlout, int col0, const float* __rest
   if (threadIdx.x == 0) {
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
+    tc::mbar_init(&bars[2], SEQ_CTAS - 1);
     tc::fence_barrier_init();
   }
-  float dc[4] = {0.f, 0.f, 0.f, 0.f}, dh_rec[4] = {0.f, 0.f, 0.f, 0.f};
+  float dc[RPT] = {}, dh_rec[RPT] = {};
   float db[4] = {0.f, 0.f, 0.f, 0.f};                   // bias gradient of this unit's four gates over the thread's sites and all steps
-  float gi[4][4], cs[4], cp[4], dho[4];
+  float gi[RPT][4], cs[RPT], cp[RPT], dho[RPT];
   auto fetch = [&](int s) {
     const int t = reverse ? T_STEPS - 1 - s : s;         // time of processing step s; the step before it is time t -+ 1
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < RPT; ++i) {
       const size_t r = (size_t)t * n + row + i;
 #pragma unroll
       for (int q = 0; q < 4; ++q) gi[i][q] = live ? gates[r * G4 + q * H + unit] : 0.f;
@@ -529,9 +536,9 @@ lstm_seq_backward(const float* __restrict__ dlout, int col0, const float* __rest
   tc::cluster_sync_all();
   for (int s = T_STEPS - 1; s >= 0; --s) {
     const int p = s & 1;
-    float dz[4][4];
+    float dz[RPT][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < RPT; ++i) {
       const float ig = gi[i][0], gg = gi[i][1], fg = gi[i][2], og = gi[i][3];
       const float tch = tanhf(cs[i]);
       const float dh = dho[i] + dh_rec[i];
@@ -550,10 +557,11 @@ lstm_seq_backward(const float* __restrict__ dlout, int col0, const float* __rest
     if (s == 0) break;                                   // dh_rec of step -1 is not needed
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<float4*>(dzs + (4 * tx + q) * SEQ_LD + 4 * ty) = make_float4(dz[0][q], dz[1][q], dz[2][q], dz[3][q]);
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) dzs[(4 * tx + q) * LD + RPT * ty + i] = dz[i][q];
     __syncthreads();
     fetch(s - 1);                                        // independent of the recurrence: in flight during the contraction
-    float acc[2][4][4] = {};                             // [mi][nt][2 half + e]: site 32 mp + 16 mi + 8 half + g, unit 32 nq + 8 nt + 2 tig + e
+    float acc[MI][4][4] = {};                            // [mi][nt][2 half + e]: site 16 MI mp + 16 mi + 8 half + g, unit 32 nq + 8 nt + 2 tig + e
 #pragma unroll 2
     for (int kk = 0; kk < 4 * SEQ_UNITS; kk += 8) {
       uint32_t bh[4][2], bl[4][2];
@@ -563,58 +571,63 @@ lstm_seq_backward(const float* __restrict__ dlout, int col0, const float* __rest
         split_tf32(Wt[(kk + tig + 4) * SEQ_BWD_LDW + 32 * nq + 8 * nt + g], bh[nt][1], bl[nt][1]);
       }
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi) {
-        const int mb = 32 * mp + 16 * mi + g;
+      for (int mi = 0; mi < MI; ++mi) {
+        const int mb = 16 * MI * mp + 16 * mi + g;
         uint32_t ah[4], al[4];
-        split_tf32(dzs[(kk + tig) * SEQ_LD + mb], ah[0], al[0]);
-        split_tf32(dzs[(kk + tig) * SEQ_LD + mb + 8], ah[1], al[1]);
-        split_tf32(dzs[(kk + tig + 4) * SEQ_LD + mb], ah[2], al[2]);
-        split_tf32(dzs[(kk + tig + 4) * SEQ_LD + mb + 8], ah[3], al[3]);
+        split_tf32(dzs[(kk + tig) * LD + mb], ah[0], al[0]);
+        split_tf32(dzs[(kk + tig) * LD + mb + 8], ah[1], al[1]);
+        split_tf32(dzs[(kk + tig + 4) * LD + mb], ah[2], al[2]);
+        split_tf32(dzs[(kk + tig + 4) * LD + mb + 8], ah[3], al[3]);
         mma_3xtf32<4>(acc[mi], ah, al, bh, bl);
       }
     }
-    float* pp = part + p * H * SEQ_LD;
+    // the slot copies of the previous exchange have read `part`: all 7 receivers said so
+    if (s < T_STEPS - 1) tc::mbar_wait_cluster(&bars[2], (T_STEPS - 2 - s) & 1);
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) pp[(32 * nq + 8 * nt + 2 * tig + (q & 1)) * SEQ_LD + 32 * mp + 16 * mi + 8 * (q >> 1) + g] = acc[mi][nt][q];
+        for (int q = 0; q < 4; ++q) part[(32 * nq + 8 * nt + 2 * tig + (q & 1)) * LD + 16 * MI * mp + 16 * mi + 8 * (q >> 1) + g] = acc[mi][nt][q];
     tc::fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) {
-      tc::mbar_expect_tx(&bars[p], (SEQ_CTAS - 1) * SEQ_SLICE_BYTES);
+      tc::mbar_expect_tx(&bars[p], (SEQ_CTAS - 1) * SLICE_BYTES);
       float* slot = slots + (p * SEQ_CTAS + j) * SLOT;   // slot j of the receiver
 #pragma unroll 1
       for (int d = 1; d < SEQ_CTAS; ++d) {
         const int to = (j + d) & (SEQ_CTAS - 1);
         asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          tc::map_to_cta(tc::smem_u32(slot), (uint32_t)to)),
-                     "r"(tc::smem_u32(pp + to * SLOT)), "r"((uint32_t)SEQ_SLICE_BYTES), "r"(tc::map_to_cta(tc::smem_u32(&bars[p]), (uint32_t)to))
+                     "r"(tc::smem_u32(part + to * SLOT)), "r"((uint32_t)SLICE_BYTES), "r"(tc::map_to_cta(tc::smem_u32(&bars[p]), (uint32_t)to))
                      : "memory");
       }
     }
     tc::mbar_wait(&bars[p], ((T_STEPS - 1 - s) >> 1) & 1);
-    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+    if (threadIdx.x == 0) {                              // my 7 slots are complete: their senders may reuse their partial sums
+#pragma unroll 1
+      for (int d = 1; d < SEQ_CTAS; ++d) tc::mbar_arrive_cluster(tc::map_to_cta(tc::smem_u32(&bars[2]), (uint32_t)((j + d) & (SEQ_CTAS - 1))));
+    }
+    float sum[RPT] = {};
 #pragma unroll
     for (int src = 0; src < SEQ_CTAS; ++src) {
-      const float* from = src == j ? pp + j * SLOT : slots + (p * SEQ_CTAS + src) * SLOT;
-      const float4 v = *reinterpret_cast<const float4*>(from + tx * SEQ_LD + 4 * ty);
-      sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
+      const float* from = (src == j ? part + j * SLOT : slots + (p * SEQ_CTAS + src) * SLOT) + tx * LD + RPT * ty;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) sum[i] += from[i];
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) dh_rec[i] = sum[i];
+    for (int i = 0; i < RPT; ++i) dh_rec[i] = sum[i];
   }
   tc::cluster_sync_all();                                // nobody leaves while a copy from or into its shared memory may be in flight
   // bias gradient: the 16 site groups of the CTA are added up through shared memory, then one atomic per (gate, unit) and cluster
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) dzs[(4 * tx + q) * SEQ_LD + ty] = db[q];
+  for (int q = 0; q < 4; ++q) dzs[(4 * tx + q) * LD + ty] = db[q];
   __syncthreads();
   if (threadIdx.x < 4 * SEQ_UNITS) {
     float sum = 0.f;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) sum += dzs[threadIdx.x * SEQ_LD + q];
+    for (int q = 0; q < 16; ++q) sum += dzs[threadIdx.x * LD + q];
     atomicAdd(dbias + (threadIdx.x & 3) * H + j * SEQ_UNITS + (threadIdx.x >> 2), sum);
   }
 }
