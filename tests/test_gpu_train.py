@@ -53,6 +53,34 @@ def test_losses_and_gradients_equal_autograd(weights1234, n):
     t2.close()
 
 
+def test_a_batch_beyond_the_machine_takes_the_64_site_backward_kernel(weights1234):
+    """Up to ~590 sites both sequence kernels run 32 sites per cluster; beyond, the backward kernel runs 64 (train_engine.cuh:
+    seq_rows_backward).  The loss and every gradient are sums over the sites of a batch, so the step on 620 sites (64-site
+    kernel, ragged: ends inside a cluster) must equal the sum of the steps on its two halves (32-site kernel, the path the tests
+    above hold against the oracle) - the float64 oracle itself needs a minute and a half for a batch of this size."""
+    from clair_b200.train import Trainer
+    n = 620
+    X, Y = batch(n, 11)
+    masks = TO.make_masks(n, seed=9)
+    t = Trainer(max_batch=640)
+    t.set_weights(weights1234)
+
+    def run(lo, hi):
+        m = {k: (v[:, lo:hi] if k == "lstm2" else v[lo:hi]) for k, v in masks.items()}
+        parts = t.forward_backward(X[lo:hi], Y[lo:hi], m)
+        t.backward_lstm()
+        return np.array(parts[:4]), {k: v.astype(np.float64) for k, v in t.gradients().items()}
+
+    whole_parts, whole = run(0, n)
+    a_parts, a = run(0, n // 2)
+    b_parts, b = run(n // 2, n)
+    np.testing.assert_allclose(whole_parts, a_parts + b_parts, rtol=1e-5)
+    worst = {k: rel(whole[k], a[k] + b[k]) for k in whole}
+    bad = {k: v for k, v in worst.items() if v > 5e-5}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:5]
+    t.close()
+
+
 def test_two_adam_steps_equal_the_restatement(weights1234):
     from clair_b200.train import Trainer
     n = 16
