@@ -24,7 +24,8 @@ struct clairb_trainer {
   std::string err;
   int64_t launches = 0;
   cudaStream_t st = nullptr, st2 = nullptr;          // the two directions of a BiLSTM layer run side by side (st: fw, st2: bw)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t st_head[4] = {};                      // the four heads (L5_k -> head k and back) side by side: [0] = st, [1] = st2
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_head[4] = {};
   struct Param { std::string name; int64_t off, rows, cols; };       // bias: rows = 1
   std::vector<Param> params;
   std::map<std::string, int> index;
@@ -138,6 +139,10 @@ void trainer_free(clairb_trainer* t) {
   for (int i = 0; i < 6; ++i) drop(t->mask[i]);
   if (t->st) cudaStreamDestroy(t->st);
   if (t->st2) cudaStreamDestroy(t->st2);
+  for (int k = 2; k < 4; ++k)
+    if (t->st_head[k]) cudaStreamDestroy(t->st_head[k]);
+  for (int k = 0; k < 4; ++k)
+    if (t->ev_head[k]) cudaEventDestroy(t->ev_head[k]);
   if (t->ev_fork) cudaEventDestroy(t->ev_fork);
   if (t->ev_join) cudaEventDestroy(t->ev_join);
 }
@@ -229,6 +234,10 @@ int clairb_trainer_create(int device, int64_t max_batch, clairb_trainer** out) {
   TC_TRY(cudaFuncSetAttribute(lstm_seq_backward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_bwd_smem(64)));
   TC_TRY(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
   TC_TRY(cudaStreamCreateWithFlags(&t->st2, cudaStreamNonBlocking));
+  t->st_head[0] = t->st;
+  t->st_head[1] = t->st2;
+  for (int k = 2; k < 4; ++k) TC_TRY(cudaStreamCreateWithFlags(&t->st_head[k], cudaStreamNonBlocking));
+  for (int k = 0; k < 4; ++k) TC_TRY(cudaEventCreateWithFlags(&t->ev_head[k], cudaEventDisableTiming));
   TC_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
   TC_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
   TC_ALLOC(t->P, t->n_params); TC_ALLOC(t->G_own, t->n_params); TC_ALLOC(t->M1, t->n_params); TC_ALLOC(t->M2, t->n_params);
@@ -435,64 +444,87 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
   const int head_n[4] = {21, 3, 33, 33}, head_off[4] = {0, 21, 24, 57};
   const char* head_names[4] = {"Y_base_change_logits", "Y_genotype_logits", "Y_indel_length_logits_1", "Y_indel_length_logits_2"};
   float* zk[4];
+  // the four heads are independent chains of small kernels (launch-bound): each on its own stream, forked behind L4 and joined
+  // in front of the loss; the same again for their backward chains
+  auto fork_heads = [&]() -> int {
+    TR_TRY(t, cudaEventRecord(t->ev_fork, st));
+    for (int k = 1; k < 4; ++k) TR_TRY(t, cudaStreamWaitEvent(t->st_head[k], t->ev_fork, 0));
+    return CLAIRB_OK;
+  };
+  auto join_heads = [&]() -> int {
+    for (int k = 1; k < 4; ++k) {
+      TR_TRY(t, cudaEventRecord(t->ev_head[k], t->st_head[k]));
+      TR_TRY(t, cudaStreamWaitEvent(st, t->ev_head[k], 0));
+    }
+    return CLAIRB_OK;
+  };
+  if (int rc = fork_heads()) return rc;
   for (int k = 0; k < 4; ++k) {
+    cudaStream_t sh = t->st_head[k];
     const auto& p5k = tp(t, "L5_" + std::to_string(k + 1) + "/kernel");
     const auto& p5b = tp(t, "L5_" + std::to_string(k + 1) + "/bias");
     const auto& phk = tp(t, std::string("Prediction/") + head_names[k] + "/kernel");
     const auto& phb = tp(t, std::string("Prediction/") + head_names[k] + "/bias");
-    gemm(false, false, (int)np, L5_UNITS, L4_UNITS, t->a4d, L4_UNITS, t->P + p5k.off, L5_UNITS, 0.f, t->a5[k], L5_UNITS, st, &t->launches);
-    bias_selu<<<blocks_for(np * L5_UNITS), 256, 0, st>>>(t->a5[k], t->P + p5b.off, np, L5_UNITS);
-    TR_TRY(t, cudaMemcpyAsync(t->a5d[k], t->a5[k], (size_t)np * L5_UNITS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    gemm(false, false, (int)np, L5_UNITS, L4_UNITS, t->a4d, L4_UNITS, t->P + p5k.off, L5_UNITS, 0.f, t->a5[k], L5_UNITS, sh, &t->launches);
+    bias_selu<<<blocks_for(np * L5_UNITS), 256, 0, sh>>>(t->a5[k], t->P + p5b.off, np, L5_UNITS);
+    TR_TRY(t, cudaMemcpyAsync(t->a5d[k], t->a5[k], (size_t)np * L5_UNITS * sizeof(float), cudaMemcpyDeviceToDevice, sh));
     ++t->launches;
     if (t->rates[2 + k] > 0.f) {
       float a, b;
       alpha_ab(t->rates[2 + k], &a, &b);
-      alpha_dropout_forward<<<blocks_for(np * L5_UNITS), 256, 0, st>>>(t->a5d[k], t->mask[2 + k], a, b, np * L5_UNITS);
+      alpha_dropout_forward<<<blocks_for(np * L5_UNITS), 256, 0, sh>>>(t->a5d[k], t->mask[2 + k], a, b, np * L5_UNITS);
       ++t->launches;
     }
     // head k: its post-SELU logits live in their own [np][n_k] block of da5-sized scratch (da3 is free until the backward)
     zk[k] = t->da3 + (size_t)np * head_off[k];
-    gemm(false, false, (int)np, head_n[k], L5_UNITS, t->a5d[k], L5_UNITS, t->P + phk.off, head_n[k], 0.f, zk[k], head_n[k], st, &t->launches);
-    bias_selu<<<blocks_for(np * head_n[k]), 256, 0, st>>>(zk[k], t->P + phb.off, np, head_n[k]);
+    gemm(false, false, (int)np, head_n[k], L5_UNITS, t->a5d[k], L5_UNITS, t->P + phk.off, head_n[k], 0.f, zk[k], head_n[k], sh, &t->launches);
+    bias_selu<<<blocks_for(np * head_n[k]), 256, 0, sh>>>(zk[k], t->P + phb.off, np, head_n[k]);
     ++t->launches;
     // side by side in zall [np][90] for the loss kernel
     TR_TRY(t, cudaMemcpy2DAsync(t->zall + head_off[k], N_OUT * sizeof(float), zk[k], head_n[k] * sizeof(float), head_n[k] * sizeof(float), (size_t)np,
-                                cudaMemcpyDeviceToDevice, st));
+                                cudaMemcpyDeviceToDevice, sh));
   }
+  if (int rc = join_heads()) return rc;
   TR_TRY(t, cudaMemsetAsync(t->dzall, 0, (size_t)np * N_OUT * sizeof(float), st));      // padding sites: no gradient
   focal_loss_heads<<<blocks_for(np, 128), 128, 0, st>>>(t->zall, t->target, t->probs, t->dzall, t->d_loss, (int)n);
   sum_squares<<<256, 256, 0, st>>>(t->P, t->is_kernel, t->n_params, t->d_loss + 4);
   t->launches += 2;
   // ---- backward: heads, L5, L4, slice-dense ----
   TR_TRY(t, cudaMemsetAsync(t->G + t->dense_off, 0, (size_t)(t->n_params - t->dense_off) * sizeof(float), st));
-  float* dzk = t->da3 + (size_t)np * N_OUT;                  // scratch behind the four logit blocks
+  if (int rc = fork_heads()) return rc;
   for (int k = 0; k < 4; ++k) {
+    cudaStream_t sh = t->st_head[k];
+    float* dzk = t->da3 + (size_t)np * (N_OUT + head_off[k]);          // scratch behind the four logit blocks, one block per head
+    float* da4k = t->da3 + (size_t)np * (2 * N_OUT + k * L4_UNITS);    // this head's share of d(a4); added up behind the join
     const auto& p5k = tp(t, "L5_" + std::to_string(k + 1) + "/kernel");
     const auto& p5b = tp(t, "L5_" + std::to_string(k + 1) + "/bias");
     const auto& phk = tp(t, std::string("Prediction/") + head_names[k] + "/kernel");
     const auto& phb = tp(t, std::string("Prediction/") + head_names[k] + "/bias");
     // gradient w.r.t. the head's pre-activation: dz (from the loss, in dzall) * selu'(z)
     TR_TRY(t, cudaMemcpy2DAsync(dzk, head_n[k] * sizeof(float), t->dzall + head_off[k], N_OUT * sizeof(float), head_n[k] * sizeof(float), (size_t)np,
-                                cudaMemcpyDeviceToDevice, st));
-    selu_backward<<<blocks_for(np * head_n[k]), 256, 0, st>>>(dzk, zk[k], np * head_n[k]);
+                                cudaMemcpyDeviceToDevice, sh));
+    selu_backward<<<blocks_for(np * head_n[k]), 256, 0, sh>>>(dzk, zk[k], np * head_n[k]);
     ++t->launches;
-    gemm(true, false, L5_UNITS, head_n[k], (int)np, t->a5d[k], L5_UNITS, dzk, head_n[k], 0.f, t->G + phk.off, head_n[k], st, &t->launches);
-    column_sums<<<dim3(blocks_for(head_n[k], 128), 16), 128, 0, st>>>(dzk, np, head_n[k], t->G + phb.off);
-    gemm(false, true, (int)np, L5_UNITS, head_n[k], dzk, head_n[k], t->P + phk.off, head_n[k], 0.f, t->da5[k], L5_UNITS, st, &t->launches);
+    gemm(true, false, L5_UNITS, head_n[k], (int)np, t->a5d[k], L5_UNITS, dzk, head_n[k], 0.f, t->G + phk.off, head_n[k], sh, &t->launches);
+    column_sums<<<dim3(blocks_for(head_n[k], 128), 16), 128, 0, sh>>>(dzk, np, head_n[k], t->G + phb.off);
+    gemm(false, true, (int)np, L5_UNITS, head_n[k], dzk, head_n[k], t->P + phk.off, head_n[k], 0.f, t->da5[k], L5_UNITS, sh, &t->launches);
     ++t->launches;
     if (t->rates[2 + k] > 0.f) {
       float a, b;
       alpha_ab(t->rates[2 + k], &a, &b);
-      alpha_dropout_backward<<<blocks_for(np * L5_UNITS), 256, 0, st>>>(t->da5[k], t->mask[2 + k], a, np * L5_UNITS);
+      alpha_dropout_backward<<<blocks_for(np * L5_UNITS), 256, 0, sh>>>(t->da5[k], t->mask[2 + k], a, np * L5_UNITS);
       ++t->launches;
     }
-    selu_backward<<<blocks_for(np * L5_UNITS), 256, 0, st>>>(t->da5[k], t->a5[k], np * L5_UNITS);
+    selu_backward<<<blocks_for(np * L5_UNITS), 256, 0, sh>>>(t->da5[k], t->a5[k], np * L5_UNITS);
     ++t->launches;
-    gemm(true, false, L4_UNITS, L5_UNITS, (int)np, t->a4d, L4_UNITS, t->da5[k], L5_UNITS, 0.f, t->G + p5k.off, L5_UNITS, st, &t->launches);
-    column_sums<<<dim3(blocks_for(L5_UNITS, 128), 16), 128, 0, st>>>(t->da5[k], np, L5_UNITS, t->G + p5b.off);
+    gemm(true, false, L4_UNITS, L5_UNITS, (int)np, t->a4d, L4_UNITS, t->da5[k], L5_UNITS, 0.f, t->G + p5k.off, L5_UNITS, sh, &t->launches);
+    column_sums<<<dim3(blocks_for(L5_UNITS, 128), 16), 128, 0, sh>>>(t->da5[k], np, L5_UNITS, t->G + p5b.off);
     ++t->launches;
-    gemm(false, true, (int)np, L4_UNITS, L5_UNITS, t->da5[k], L5_UNITS, t->P + p5k.off, L5_UNITS, k ? 1.f : 0.f, t->da4, L4_UNITS, st, &t->launches);
+    gemm(false, true, (int)np, L4_UNITS, L5_UNITS, t->da5[k], L5_UNITS, t->P + p5k.off, L5_UNITS, 0.f, da4k, L4_UNITS, sh, &t->launches);
   }
+  if (int rc = join_heads()) return rc;
+  sum_four<<<blocks_for(np * L4_UNITS), 256, 0, st>>>(t->da3 + (size_t)np * 2 * N_OUT, np * L4_UNITS, t->da4);
+  ++t->launches;
   if (t->rates[1] > 0.f) {
     float a, b;
     alpha_ab(t->rates[1], &a, &b);

@@ -795,6 +795,12 @@ __global__ void adam_update(float* __restrict__ w, const float* __restrict__ g, 
   w[i] -= lr_t * mi / (sqrtf(vi) + 1e-8f);
 }
 
+// out = in[0] + in[1] + in[2] + in[3] (four blocks of `count` floats back to back): the heads' shares of d(a4)
+__global__ void sum_four(const float* __restrict__ in, int64_t count, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = (in[i] + in[count + i]) + (in[2 * count + i] + in[3 * count + i]);
+}
+
 // the four focal-loss sums as floats behind a data-parallel caller's gradient buffer: they travel with the gradient all-reduce
 __global__ void store_loss_sums(const double* __restrict__ d_loss, float* __restrict__ out) {
   if (threadIdx.x < 4) out[threadIdx.x] = (float)d_loss[threadIdx.x];
