@@ -162,7 +162,6 @@ int lstm_layer_backward(clairb_trainer* t, int l, int64_t np) {
     auto& q = t->dir[l][d];
     const auto& pk = tp(t, lstm_prefix(l, d) + "kernel");
     const auto& pb = tp(t, lstm_prefix(l, d) + "bias");
-    TR_TRY(t, cudaMemsetAsync(t->G + pb.off, 0, G4 * sizeof(float), sd));
     if (seq_rows_backward(np) == 32)
       lstm_seq_backward<32><<<seq_grid(np, 32), 256, seq_bwd_smem(32), sd>>>(t->dlout[l], d * H, q.gates, q.cbuf, t->P + pk.off + (size_t)K * G4, q.dZ,
                                                                                t->G + pb.off, (int)np, d);
@@ -172,8 +171,8 @@ int lstm_layer_backward(clairb_trainer* t, int l, int64_t np) {
     ++t->launches;
     float* gk = t->G + pk.off;
     // dW_x = in^T . dZ (all steps at once, both in time order), dW_h = h_prev^T . dZ: h of the step before time t is slab t (fw) / t + 2 (bw)
-    gemm(true, false, K, G4, (int)rows, in, K, q.dZ, G4, 0.f, gk, G4, sd, &t->launches);
-    gemm(true, false, H, G4, (int)rows, q.hbuf + (d ? 2 : 0) * (size_t)np * H, H, q.dZ, G4, 0.f, gk + (size_t)K * G4, G4, sd, &t->launches);
+    gemm(true, false, K, G4, (int)rows, in, K, q.dZ, G4, 0.f, gk, G4, sd, &t->launches, true);
+    gemm(true, false, H, G4, (int)rows, q.hbuf + (d ? 2 : 0) * (size_t)np * H, H, q.dZ, G4, 0.f, gk + (size_t)K * G4, G4, sd, &t->launches, true);
     // d(input) = dZ . W_x^T, the two directions added: fw writes dlout[0] on its stream, bw adds to it behind the join
     if (l == 1 && d == 0) gemm(false, true, (int)rows, K, G4, q.dZ, G4, t->P + pk.off, G4, 0.f, t->dlout[0], K, sd, &t->launches);
   }
@@ -377,6 +376,7 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
   // dropout masks: the caller's (parity tests) or drawn from the seed
   const int64_t mask_count[6] = {rows * 2 * H, np * L4_UNITS, np * L5_UNITS, np * L5_UNITS, np * L5_UNITS, np * L5_UNITS};
   const int64_t mask_real[6] = {0, n * L4_UNITS, n * L5_UNITS, n * L5_UNITS, n * L5_UNITS, n * L5_UNITS};
+  bool masks_forked = false;
   for (int i = 0; i < 6; ++i) {
     if (masks && masks[i]) {
       if (i == 0) {
@@ -388,10 +388,17 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
         TR_TRY(t, cudaMemcpyAsync(t->mask[i], masks[i], (size_t)mask_real[i], cudaMemcpyHostToDevice, st));
       }
     } else {
-      make_mask<<<blocks_for(mask_count[i]), 256, 0, st>>>(t->mask[i], mask_count[i], t->rates[i], seed, (uint64_t)i);
+      // drawn on a side stream while the LSTMs run; joined in front of the first consumer (the dropout behind LSTM2)
+      if (!masks_forked) {
+        TR_TRY(t, cudaEventRecord(t->ev_head[0], st));
+        TR_TRY(t, cudaStreamWaitEvent(t->st_head[2], t->ev_head[0], 0));
+        masks_forked = true;
+      }
+      make_mask<<<blocks_for(mask_count[i]), 256, 0, t->st_head[2]>>>(t->mask[i], mask_count[i], t->rates[i], seed, (uint64_t)i);
       ++t->launches;
     }
   }
+  if (masks_forked) TR_TRY(t, cudaEventRecord(t->ev_head[0], t->st_head[2]));
   TR_TRY(t, cudaMemsetAsync(t->d_loss, 0, 8 * sizeof(double), st));
   // ---- forward ----
   for (int l = 0; l < 2; ++l) {
@@ -415,6 +422,7 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
     TR_TRY(t, cudaEventRecord(t->ev_join, t->st2));
     TR_TRY(t, cudaStreamWaitEvent(st, t->ev_join, 0));
   }
+  if (masks_forked) TR_TRY(t, cudaStreamWaitEvent(st, t->ev_head[0], 0));
   if (t->rates[0] > 0.f) {
     dropout_scale<<<blocks_for(rows * 2 * H), 256, 0, st>>>(t->lout[1], t->mask[0], 1.f / (1.f - t->rates[0]), rows * 2 * H);
     ++t->launches;
@@ -505,7 +513,7 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
                                 cudaMemcpyDeviceToDevice, sh));
     selu_backward<<<blocks_for(np * head_n[k]), 256, 0, sh>>>(dzk, zk[k], np * head_n[k]);
     ++t->launches;
-    gemm(true, false, L5_UNITS, head_n[k], (int)np, t->a5d[k], L5_UNITS, dzk, head_n[k], 0.f, t->G + phk.off, head_n[k], sh, &t->launches);
+    gemm(true, false, L5_UNITS, head_n[k], (int)np, t->a5d[k], L5_UNITS, dzk, head_n[k], 0.f, t->G + phk.off, head_n[k], sh, &t->launches, true);
     column_sums<<<dim3(blocks_for(head_n[k], 128), 16), 128, 0, sh>>>(dzk, np, head_n[k], t->G + phb.off);
     gemm(false, true, (int)np, L5_UNITS, head_n[k], dzk, head_n[k], t->P + phk.off, head_n[k], 0.f, t->da5[k], L5_UNITS, sh, &t->launches);
     ++t->launches;
@@ -517,7 +525,7 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
     }
     selu_backward<<<blocks_for(np * L5_UNITS), 256, 0, sh>>>(t->da5[k], t->a5[k], np * L5_UNITS);
     ++t->launches;
-    gemm(true, false, L4_UNITS, L5_UNITS, (int)np, t->a4d, L4_UNITS, t->da5[k], L5_UNITS, 0.f, t->G + p5k.off, L5_UNITS, sh, &t->launches);
+    gemm(true, false, L4_UNITS, L5_UNITS, (int)np, t->a4d, L4_UNITS, t->da5[k], L5_UNITS, 0.f, t->G + p5k.off, L5_UNITS, sh, &t->launches, true);
     column_sums<<<dim3(blocks_for(L5_UNITS, 128), 16), 128, 0, sh>>>(t->da5[k], np, L5_UNITS, t->G + p5b.off);
     ++t->launches;
     gemm(false, true, (int)np, L4_UNITS, L5_UNITS, t->da5[k], L5_UNITS, t->P + p5k.off, L5_UNITS, 0.f, da4k, L4_UNITS, sh, &t->launches);
@@ -533,12 +541,11 @@ int clairb_trainer_forward_backward(clairb_trainer* t, const void* x_host, int d
   }
   selu_backward<<<blocks_for(np * L4_UNITS), 256, 0, st>>>(t->da4, t->a4, np * L4_UNITS);
   ++t->launches;
-  gemm(true, false, L3_K, L4_UNITS, (int)np, t->a3, L3_K, t->da4, L4_UNITS, 0.f, t->G + p4k.off, L4_UNITS, st, &t->launches);
+  gemm(true, false, L3_K, L4_UNITS, (int)np, t->a3, L3_K, t->da4, L4_UNITS, 0.f, t->G + p4k.off, L4_UNITS, st, &t->launches, true);
   column_sums<<<dim3(blocks_for(L4_UNITS, 128), 16), 128, 0, st>>>(t->da4, np, L4_UNITS, t->G + p4b.off);
   ++t->launches;
   gemm(false, true, (int)np, L3_K, L4_UNITS, t->da4, L4_UNITS, t->P + p4k.off, L4_UNITS, 0.f, t->da3, L3_K, st, &t->launches);
   l3_backward_input<<<l3_grid, 256, L3_SMEM, st>>>(t->da3, t->a3, t->P + p3.off, t->dlout[1], (int)np, l3_sites);
-  TR_TRY(t, cudaMemsetAsync(t->G + p3.off, 0, (size_t)2 * H * L3_STRIDE * sizeof(float), st));
   l3_backward_weights<<<l3_grid, 352, L3_SMEM, st>>>(t->lout[1], t->da3, t->G + p3.off, (int)np, l3_sites);
   t->launches += 2;
   if (t->rates[0] > 0.f) {
@@ -563,6 +570,8 @@ int clairb_trainer_backward_lstm(clairb_trainer* t) {
   if (!t) return CLAIRB_EINVAL;
   if (!t->lstm_pending) return tfail(t, CLAIRB_EINVAL, "backward_lstm: no forward_backward call is pending");
   TR_TRY(t, cudaSetDevice(t->device));
+  // the LSTM block of the gradient buffer starts from zero: bias gradients and split contractions are added into it
+  TR_TRY(t, cudaMemsetAsync(t->G, 0, (size_t)t->dense_off * sizeof(float), t->st));
   if (int rc = lstm_layer_backward(t, 1, t->last_np)) return rc;
   if (int rc = lstm_layer_backward(t, 0, t->last_np)) return rc;
   TR_TRY(t, cudaGetLastError());

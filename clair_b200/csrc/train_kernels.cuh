@@ -245,8 +245,10 @@ __global__ void scale_matrix(float* __restrict__ C, int M, int N, int ldc, float
   }
 }
 
+// c_zeroed: C is known to hold zeros (a gradient block behind the step's memset): a split contraction with beta = 0 then needs no
+// scaling pass in front of its atomics.
 inline void gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc,
-                 cudaStream_t st, int64_t* launches) {
+                 cudaStream_t st, int64_t* launches, bool c_zeroed = false) {
   // the tensor-core tile for everything large; a long contraction is worth it even when only a quarter of the tile's rows exist
   // (layer 1's dW_x: 32 x 512 over 33 n rows)
   const bool big = (M >= 96 || (M >= 32 && K >= 4096)) && N >= 96 && !((M | N | K | lda | ldb | ldc) & 3) &&
@@ -262,7 +264,7 @@ inline void gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda,
   int k_per_slice = ((K + slices - 1) / slices + tk - 1) / tk * tk;
   slices = (K + k_per_slice - 1) / k_per_slice;
   grid.z = slices;
-  if (slices > 1) {
+  if (slices > 1 && !(c_zeroed && beta == 0.f)) {
     scale_matrix<<<(unsigned)(((int64_t)M * N + 255) / 256), 256, 0, st>>>(C, M, N, ldc, beta);
     ++*launches;
   }
