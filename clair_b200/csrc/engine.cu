@@ -414,9 +414,9 @@ extern "C" {
 
 const char* clairb_version(void) {
 #ifdef CLAIRB_CROSSCHECK
-  return "clair_b200 0.5 sm_100a cross-check build (tcgen05 engine + fp32 CUDA-core engines)";
+  return "clair_b200 0.6 sm_100a cross-check build (tcgen05 engine + fp32 CUDA-core engines)";
 #else
-  return "clair_b200 0.5 sm_100a (tcgen05 BiLSTM, streamed layer-2 projection, async batch queue, decision stage, create_tensors)";
+  return "clair_b200 0.6 sm_100a (tcgen05 BiLSTM, streamed layer-2 projection, async batch queue, decision stage, create_tensors, training step)";
 #endif
 }
 
