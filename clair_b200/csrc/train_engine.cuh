@@ -73,7 +73,7 @@ int tfail(clairb_trainer* t, int code, const char* fmt, ...) {
   } while (0)
 
 inline unsigned blocks_for(int64_t count, int threads = 256) { return (unsigned)((count + threads - 1) / threads); }
-// one cluster of SEQ_CTAS CTAs per `rows` sites (lstm_seq_forward<rows> / lstm_seq_backward: 64)
+// one cluster of SEQ_CTAS CTAs per `rows` sites (lstm_seq_forward<rows> / lstm_seq_backward<rows>)
 inline unsigned seq_grid(int64_t np, int rows = clairb::train::SEQ_ROWS) { return (unsigned)((np + rows - 1) / rows * clairb::train::SEQ_CTAS); }
 // Sites per cluster of the sequence kernels.  Forward: always 32 - two CTAs per SM, one computes while the other waits for its
 // exchange (measured at 512 and 2048 sites: 3.00 / 8.45 ms per step against 3.26 / 8.83 with 64).  Backward: 32 while both
