@@ -3,8 +3,9 @@
 Mirrors what `Clair.train(batchX, batchY)` does per call (reference clair/model.py:913-945 with the graph of :400-740):
 forward in training phase (dropout behind LSTM2, alpha-dropout behind L4 / L5_k), focal loss of the four heads + L2,
 gradients of every trainable variable, clip_by_global_norm(5.0), Adam.  Underneath: `clairb_trainer_*` of the C-ABI
-library (csrc/train_kernels.cuh, fp32 CUDA kernels).  `Trainer` drives one GPU; `DataParallelTrainer` is the config-5
-shape (one process per GPU, NCCL all-reduce of the flat gradient buffer in two pieces that overlap the backward pass).
+library (csrc/train_kernels.cuh: fp32 results; sequence kernels on thread-block clusters, 3xTF32 tensor-core GEMMs).  `Trainer`
+drives one GPU; `DataParallelTrainer` is the config-5 shape (one process per GPU, NCCL all-reduce of the flat gradient buffer in
+two pieces that overlap the backward pass, ordered stream to stream).
 The training loop around it (learning-rate schedule, validation, checkpoints: clair/train.py:78-263) stays with the caller.
 """
 import ctypes
